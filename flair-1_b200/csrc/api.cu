@@ -1,0 +1,878 @@
+// C ABI of libflairb200 (include/flair_b200.h): context, checkpoint folding/packing, the U-Net
+// (ResNet34 encoder) layer graph, and the zone_detect / patch-predict loops built from the kernels in
+// conv_igemm.cu and elementwise.cu. Topology restated from segmentation-models-pytorch 0.3.3
+// `Unet(resnet34)` (un-vendored dependency of the reference, setup.py:36).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/flair_b200.h"
+#include "conv_igemm.cuh"
+#include "elementwise.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct ConvLayer {
+  __nv_bfloat16* w = nullptr;  // device [Cout][Kpad]
+  float* bias = nullptr;       // device [Cout]
+  int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
+};
+
+struct Act {  // a named NHWC bf16 (or fp32) activation in the arena
+  void* ptr = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  int elem = 2;
+};
+
+struct ProfRec {
+  int cat;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct fb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  std::string err;
+  int64_t launches = 0;
+  bool force_gather = false;
+
+  // model
+  bool loaded = false;
+  int in_ch = 0, ncls = 0, use_meta = 0;
+  std::map<std::string, ConvLayer> conv;
+  float* mlp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<void*> owned;  // device allocations freed at destroy
+
+  // normalisation
+  bool norm_set = false;
+  __nv_bfloat16* lut = nullptr;  // device [8][256]
+
+  // raster
+  const uint8_t* raster = nullptr;
+  uint8_t* raster_own = nullptr;
+  size_t raster_own_bytes = 0;
+  int bands_total = 0, rc = 0, layout = 0;
+  int64_t W = 0, H = 0, row0 = 0, rows = 0;
+  int* band_idx_dev = nullptr;
+
+  // activation arena
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  int arena_n = 0, arena_T = 0;
+  std::map<std::string, Act> acts;
+  int* tile_xy_dev = nullptr;  // [cap][2]
+  int* tiles_dev = nullptr;    // [cap][6]
+  int tile_cap = 0;
+  float* meta_dev = nullptr;   // [n][45]
+  float* menc_dev = nullptr;   // [n][16]
+  int meta_cap = 0;
+
+  // profiling
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
+};
+
+namespace {
+
+int fail(fb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(fb_ctx* c, cudaError_t e, const char* what) {
+  return fail(c, static_cast<int>(e), std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define FB_CUDA(c, call)                                     \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); \
+  } while (0)
+#define FB_TRY(expr)              \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != 0) return rc__;   \
+  } while (0)
+
+struct ProfScope {
+  fb_ctx* c;
+  ProfRec r;
+  bool on;
+  ProfScope(fb_ctx* c_, int cat) : c(c_), on(c_->prof) {
+    if (on) {
+      r.cat = cat;
+      cudaEventCreate(&r.a);
+      cudaEventCreate(&r.b);
+      cudaEventRecord(r.a, c->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(r.b, c->stream);
+      c->prof_recs.push_back(r);
+    }
+  }
+};
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7FFFu + lsb;
+  return static_cast<uint16_t>(u >> 16);
+}
+
+typedef std::unordered_map<std::string, const fb_tensor_desc*> TensorMap;
+
+const fb_tensor_desc* find(const TensorMap& m, const std::string& k) {
+  auto it = m.find(k);
+  return it == m.end() ? nullptr : it->second;
+}
+int64_t numel(const fb_tensor_desc* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+  return n;
+}
+
+// conv weight [Cout][Cin][KH][KW] (+ optional eval-mode BatchNorm `bn.*`, + optional bias) ->
+// bf16 [CoutPad][Kpad] with k = (kh*KW + kw)*CinPad + cin, fp32 bias [CoutPad].
+int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const std::string& wkey,
+               const std::string& bn, const std::string& bkey, int Cin, int Cout, int KH, int stride,
+               int pad) {
+  const fb_tensor_desc* w = find(tm, wkey);
+  if (!w) return fail(c, FB_ERR_WEIGHTS, "missing tensor " + wkey);
+  if (w->ndim != 4 || w->shape[0] != Cout || w->shape[1] != Cin || w->shape[2] != KH || w->shape[3] != KH)
+    return fail(c, FB_ERR_WEIGHTS, "bad shape for " + wkey);
+  std::vector<double> scale(Cout, 1.0), shift(Cout, 0.0);
+  if (!bn.empty()) {
+    const fb_tensor_desc* g = find(tm, bn + ".weight");
+    const fb_tensor_desc* b = find(tm, bn + ".bias");
+    const fb_tensor_desc* mu = find(tm, bn + ".running_mean");
+    const fb_tensor_desc* var = find(tm, bn + ".running_var");
+    if (!g || !b || !mu || !var) return fail(c, FB_ERR_WEIGHTS, "missing BatchNorm tensors " + bn + ".*");
+    if (numel(g) != Cout || numel(b) != Cout || numel(mu) != Cout || numel(var) != Cout)
+      return fail(c, FB_ERR_WEIGHTS, "bad BatchNorm shape " + bn);
+    for (int o = 0; o < Cout; ++o) {
+      // torch: y = (x - mean) / sqrt(var + eps) * gamma + beta, eps = 1e-5
+      const double s = static_cast<double>(g->data[o]) / sqrt(static_cast<double>(var->data[o]) + 1e-5);
+      scale[o] = s;
+      shift[o] = static_cast<double>(b->data[o]) - static_cast<double>(mu->data[o]) * s;
+    }
+  }
+  if (!bkey.empty()) {
+    const fb_tensor_desc* b = find(tm, bkey);
+    if (!b || numel(b) != Cout) return fail(c, FB_ERR_WEIGHTS, "missing/bad tensor " + bkey);
+    for (int o = 0; o < Cout; ++o) shift[o] += static_cast<double>(b->data[o]) * scale[o];
+  }
+  ConvLayer L;
+  const int CinPad = (Cin + 7) / 8 * 8;
+  const int CoutPad = (Cout + 15) / 16 * 16;
+  L.Cin = CinPad; L.Cout = CoutPad; L.KH = KH; L.KW = KH; L.stride = stride; L.pad = pad;
+  L.Ktot = KH * KH * CinPad;
+  L.Kpad = (L.Ktot + 63) / 64 * 64;
+  std::vector<uint16_t> packed(static_cast<size_t>(CoutPad) * L.Kpad, 0);
+  std::vector<float> bias(CoutPad, 0.f);
+  for (int o = 0; o < Cout; ++o) {
+    bias[o] = static_cast<float>(shift[o]);
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int kh = 0; kh < KH; ++kh)
+        for (int kw = 0; kw < KH; ++kw) {
+          const double v = static_cast<double>(w->data[((static_cast<size_t>(o) * Cin + ci) * KH + kh) * KH + kw]) * scale[o];
+          packed[static_cast<size_t>(o) * L.Kpad + (kh * KH + kw) * CinPad + ci] = f32_to_bf16_rne(static_cast<float>(v));
+        }
+  }
+  FB_CUDA(c, cudaMalloc(&L.w, packed.size() * 2));
+  c->owned.push_back(L.w);
+  FB_CUDA(c, cudaMalloc(&L.bias, bias.size() * 4));
+  c->owned.push_back(L.bias);
+  FB_CUDA(c, cudaMemcpyAsync(L.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaMemcpyAsync(L.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors die at scope exit
+  c->conv[name] = L;
+  return 0;
+}
+
+int upload_f32(fb_ctx* c, const TensorMap& tm, const std::string& key, int64_t n, float** out) {
+  const fb_tensor_desc* t = find(tm, key);
+  if (!t || numel(t) != n) return fail(c, FB_ERR_WEIGHTS, "missing/bad tensor " + key);
+  FB_CUDA(c, cudaMalloc(out, n * 4));
+  c->owned.push_back(*out);
+  FB_CUDA(c, cudaMemcpy(*out, t->data, n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- arena
+const int kStageBlocks[4] = {3, 4, 6, 3};
+const int kStageCh[4] = {64, 128, 256, 512};
+const int kDecOut[5] = {256, 128, 64, 32, 16};
+
+int arena_alloc(fb_ctx* c, const std::string& name, int B, int H, int W, int C, int elem, bool dry) {
+  const size_t bytes = (static_cast<size_t>(B) * H * W * C * elem + 1023) / 1024 * 1024;
+  if (!dry) {
+    Act a;
+    a.ptr = c->arena + c->arena_used;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.elem = elem;
+    c->acts[name] = a;
+  }
+  c->arena_used += bytes;
+  return 0;
+}
+
+void arena_plan(fb_ctx* c, int n, int T, bool dry) {
+  c->arena_used = 0;
+  if (!dry) c->acts.clear();
+  arena_alloc(c, "x0", n, T, T, 8, 2, dry);
+  arena_alloc(c, "f1", n, T / 2, T / 2, 64, 2, dry);
+  arena_alloc(c, "pool", n, T / 4, T / 4, 64, 2, dry);
+  int S = T / 4;
+  for (int st = 0; st < 4; ++st) {
+    const int C = kStageCh[st];
+    char buf[64];
+    snprintf(buf, sizeof buf, "layer%d.tmp", st + 1);
+    arena_alloc(c, buf, n, S, S, C, 2, dry);
+    if (st > 0) {
+      snprintf(buf, sizeof buf, "layer%d.ds", st + 1);
+      arena_alloc(c, buf, n, S, S, C, 2, dry);
+    }
+    for (int b = 0; b < kStageBlocks[st]; ++b) {
+      snprintf(buf, sizeof buf, "layer%d.%d.out", st + 1, b);
+      arena_alloc(c, buf, n, S, S, C, 2, dry);
+    }
+    S /= 2;
+  }
+  S = T / 16;
+  for (int d = 0; d < 5; ++d) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "dec%d.mid", d);
+    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry);
+    snprintf(buf, sizeof buf, "dec%d", d);
+    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry);
+    S *= 2;
+  }
+  arena_alloc(c, "logits", n, T, T, 16, 4, dry);
+}
+
+int ensure_arena(fb_ctx* c, int n, int T) {
+  if (c->arena && c->arena_n == n && c->arena_T == T) return 0;
+  arena_plan(c, n, T, true);
+  const size_t need = c->arena_used;
+  if (need > c->arena_bytes) {
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->arena) cudaFree(c->arena);
+    c->arena = nullptr;
+    c->arena_bytes = 0;
+    cudaError_t e = cudaMalloc(&c->arena, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, FB_ERR_OOM, "activation arena: cudaMalloc of " + std::to_string(need) + " bytes failed");
+    }
+    c->arena_bytes = need;
+  }
+  arena_plan(c, n, T, false);
+  c->arena_n = n;
+  c->arena_T = T;
+  return 0;
+}
+
+int ensure_tile_buffers(fb_ctx* c, int n) {
+  if (n <= c->tile_cap) return 0;
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->tile_xy_dev) cudaFree(c->tile_xy_dev);
+  if (c->tiles_dev) cudaFree(c->tiles_dev);
+  c->tile_xy_dev = nullptr; c->tiles_dev = nullptr; c->tile_cap = 0;
+  FB_CUDA(c, cudaMalloc(&c->tile_xy_dev, static_cast<size_t>(n) * 2 * sizeof(int)));
+  FB_CUDA(c, cudaMalloc(&c->tiles_dev, static_cast<size_t>(n) * 6 * sizeof(int)));
+  c->tile_cap = n;
+  return 0;
+}
+
+int ensure_meta_buffers(fb_ctx* c, int n) {
+  if (n <= c->meta_cap) return 0;
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->meta_dev) cudaFree(c->meta_dev);
+  if (c->menc_dev) cudaFree(c->menc_dev);
+  c->meta_dev = nullptr; c->menc_dev = nullptr; c->meta_cap = 0;
+  FB_CUDA(c, cudaMalloc(&c->meta_dev, static_cast<size_t>(n) * FB_METADATA_DIM * sizeof(float)));
+  FB_CUDA(c, cudaMalloc(&c->menc_dev, static_cast<size_t>(n) * 16 * sizeof(float)));
+  c->meta_cap = n;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- graph
+int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, bool up1, const Act* res,
+             const float* rowbias, bool relu, const Act& out) {
+  fb::ConvArgs a;
+  memset(&a, 0, sizeof a);
+  a.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
+  a.x2 = x2 ? static_cast<const __nv_bfloat16*>(x2->ptr) : nullptr;
+  a.C1 = x1.C;
+  a.C2 = x2 ? x2->C : 0;
+  a.up1 = up1 ? 1 : 0;
+  a.B = x1.B;
+  a.Hin = up1 ? x1.H * 2 : x1.H;
+  a.Win = up1 ? x1.W * 2 : x1.W;
+  a.Hout = out.H; a.Wout = out.W;
+  a.KH = L.KH; a.KW = L.KW; a.stride = L.stride; a.pad = L.pad;
+  a.Cout = L.Cout;
+  a.Ktot = L.Ktot;
+  a.bias = L.bias;
+  a.residual = res ? static_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
+  a.rowbias = rowbias;
+  a.relu = relu ? 1 : 0;
+  if (out.elem == 4) a.out_f32 = static_cast<float*>(out.ptr); else a.out = static_cast<__nv_bfloat16*>(out.ptr);
+  if (a.C1 + a.C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
+  const bool tma = !c->force_gather && L.KH == 3 && L.stride == 1 && L.pad == 1 && !x2 && !up1 &&
+                   a.C1 % 64 == 0 && a.Hout % 8 == 0 && a.Wout % 16 == 0;
+  ProfScope ps(c, 1);
+  const int rc = fb::launch_conv(a, L.w, L.Kpad, tma, c->num_sms, c->stream);
+  if (rc != 0) return fail(c, rc, "conv launch failed (code " + std::to_string(rc) + ")");
+  c->launches++;
+  return 0;
+}
+
+// x0 (normalised tiles) must already be in the arena; enqueues encoder + decoder + head.
+int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
+  auto A = [&](const std::string& k) -> Act& { return c->acts[k]; };
+  auto L = [&](const std::string& k) -> const ConvLayer& { return c->conv[k]; };
+  FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, false, nullptr, nullptr, true, A("f1")));
+  {
+    ProfScope ps(c, 2);
+    Act& f1 = A("f1");
+    int rc = fb::launch_maxpool3x3s2(static_cast<const __nv_bfloat16*>(f1.ptr),
+                                     static_cast<__nv_bfloat16*>(A("pool").ptr), n, f1.H, f1.W, 64,
+                                     c->num_sms, c->stream);
+    if (rc) return fail(c, rc, "maxpool launch failed");
+    c->launches++;
+  }
+  std::string cur = "pool";
+  for (int st = 0; st < 4; ++st) {
+    char nm[64], tmp[64], ds[64];
+    snprintf(tmp, sizeof tmp, "layer%d.tmp", st + 1);
+    snprintf(ds, sizeof ds, "layer%d.ds", st + 1);
+    for (int b = 0; b < kStageBlocks[st]; ++b) {
+      snprintf(nm, sizeof nm, "layer%d.%d", st + 1, b);
+      const std::string base(nm);
+      const std::string outn = base + ".out";
+      const Act* res = &A(cur);
+      FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), nullptr, false, nullptr, nullptr, true, A(tmp)));
+      if (st > 0 && b == 0) {
+        FB_TRY(run_conv(c, L(base + ".downsample"), A(cur), nullptr, false, nullptr, nullptr, false, A(ds)));
+        res = &A(ds);
+      }
+      const bool last = (st == 3 && b == kStageBlocks[st] - 1);
+      FB_TRY(run_conv(c, L(base + ".conv2"), A(tmp), nullptr, false, res, last ? menc_dev : nullptr, true, A(outn)));
+      cur = outn;
+    }
+  }
+  const char* skips[5] = {"layer3.5.out", "layer2.3.out", "layer1.2.out", "f1", nullptr};
+  for (int d = 0; d < 5; ++d) {
+    char nm[64];
+    snprintf(nm, sizeof nm, "dec%d", d);
+    const std::string base(nm);
+    FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, true, nullptr, nullptr, true, A(base + ".mid")));
+    FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, false, nullptr, nullptr, true, A(base)));
+    cur = base;
+  }
+  FB_TRY(run_conv(c, L("head"), A(cur), nullptr, false, nullptr, nullptr, false, A("logits")));
+  return 0;
+}
+
+int run_extract(fb_ctx* c, const uint8_t* raster, int layout, int bands_total, const int* band_idx_dev,
+                int rc_, int64_t W, int64_t H, int64_t row0, int64_t rows, const int* xy_dev, int n, int T) {
+  ProfScope ps(c, 0);
+  int rc = fb::launch_extract_normalise(raster, layout, bands_total, band_idx_dev, rc_, W, H, row0, rows,
+                                        xy_dev, n, T, c->lut,
+                                        static_cast<__nv_bfloat16*>(c->acts["x0"].ptr), c->num_sms, c->stream);
+  if (rc) return fail(c, rc, "extract launch failed");
+  c->launches++;
+  return 0;
+}
+
+int run_metadata(fb_ctx* c, const float* metadata_host, int n, const float** menc) {
+  *menc = nullptr;
+  if (!c->use_meta) return 0;
+  if (!metadata_host) return fail(c, FB_ERR_INVALID, "model was loaded with use_metadata=1 but metadata is NULL");
+  FB_TRY(ensure_meta_buffers(c, n));
+  FB_CUDA(c, cudaMemcpyAsync(c->meta_dev, metadata_host, static_cast<size_t>(n) * FB_METADATA_DIM * 4,
+                             cudaMemcpyHostToDevice, c->stream));
+  ProfScope ps(c, 2);
+  int rc = fb::launch_metadata_mlp(c->meta_dev, c->mlp, c->menc_dev, n, c->stream);
+  if (rc) return fail(c, rc, "metadata MLP launch failed");
+  c->launches++;
+  *menc = c->menc_dev;
+  return 0;
+}
+
+int check_ready(fb_ctx* c, bool need_raster, int tile) {
+  if (!c) return FB_ERR_INVALID;
+  if (!c->loaded) return fail(c, FB_ERR_STATE, "fb_load_weights has not been called");
+  if (!c->norm_set) return fail(c, FB_ERR_STATE, "fb_set_norm has not been called");
+  if (need_raster && !c->raster) return fail(c, FB_ERR_STATE, "no raster set (fb_set_raster / fb_upload_raster)");
+  if (tile <= 0 || tile % 32 != 0) return fail(c, FB_ERR_INVALID, "tile size must be a positive multiple of 32 (U-Net depth 5)");
+  if (c->use_meta && tile != 512) return fail(c, FB_ERR_INVALID, "the metadata branch is hard-wired to 512x512 inputs (flair/model.py:59)");
+  return 0;
+}
+
+int set_raster_common(fb_ctx* c, int bands_total, const int32_t* band_idx, int rc_, int64_t W, int64_t H,
+                      int64_t row0, int64_t rows, int layout) {
+  if (!c->loaded) return fail(c, FB_ERR_STATE, "fb_load_weights has not been called");
+  if (rc_ != c->in_ch) return fail(c, FB_ERR_INVALID, "number of selected bands differs from the model's in_channels");
+  if (bands_total <= 0 || W <= 0 || H <= 0 || rows < 0 || row0 < 0 || row0 + rows > H)
+    return fail(c, FB_ERR_INVALID, "bad raster geometry");
+  if (layout != FB_LAYOUT_CHW && layout != FB_LAYOUT_HWC) return fail(c, FB_ERR_INVALID, "bad raster layout");
+  for (int i = 0; i < rc_; ++i)
+    if (band_idx[i] < 0 || band_idx[i] >= bands_total) return fail(c, FB_ERR_INVALID, "band index out of range");
+  if (!c->band_idx_dev) FB_CUDA(c, cudaMalloc(&c->band_idx_dev, 8 * sizeof(int)));
+  int tmp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < rc_; ++i) tmp[i] = band_idx[i];
+  FB_CUDA(c, cudaMemcpyAsync(c->band_idx_dev, tmp, sizeof tmp, cudaMemcpyHostToDevice, c->stream));
+  c->bands_total = bands_total; c->rc = rc_; c->layout = layout;
+  c->W = W; c->H = H; c->row0 = row0; c->rows = rows;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_api_version(void) { return FB_API_VERSION; }
+
+const char* fb_last_error(const fb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int fb_create(int device, void* cuda_stream, fb_ctx** out) {
+  if (!out) return FB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(nullptr, FB_ERR_NO_DEVICE, "no CUDA device available; libflairb200 has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(nullptr, FB_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, FB_ERR_NO_DEVICE, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, FB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not compute capability 10.x; this library is sm_100a only");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, FB_ERR_NO_DEVICE, "cudaSetDevice failed");
+  if (fb::init_tma_encoder() != 0) return fail(nullptr, FB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available from the driver");
+  fb_ctx* c = new fb_ctx();
+  c->device = device;
+  c->stream = static_cast<cudaStream_t>(cuda_stream);
+  c->num_sms = prop.multiProcessorCount;
+  const char* fg = getenv("FB_FORCE_GATHER");
+  c->force_gather = fg && fg[0] == '1';
+  *out = c;
+  return 0;
+}
+
+void fb_destroy(fb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (void* p : c->owned) cudaFree(p);
+  if (c->lut) cudaFree(c->lut);
+  if (c->raster_own) cudaFree(c->raster_own);
+  if (c->band_idx_dev) cudaFree(c->band_idx_dev);
+  if (c->arena) cudaFree(c->arena);
+  if (c->tile_xy_dev) cudaFree(c->tile_xy_dev);
+  if (c->tiles_dev) cudaFree(c->tiles_dev);
+  if (c->meta_dev) cudaFree(c->meta_dev);
+  if (c->menc_dev) cudaFree(c->menc_dev);
+  delete c;
+}
+
+int fb_synchronize(fb_ctx* c) {
+  if (!c) return FB_ERR_INVALID;
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int64_t fb_launch_count(const fb_ctx* c) { return c ? c->launches : 0; }
+
+int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int in_channels,
+                    int n_classes, int use_metadata) {
+  if (!c || !tensors || n_tensors <= 0) return FB_ERR_INVALID;
+  if (in_channels < 1 || in_channels > 8) return fail(c, FB_ERR_INVALID, "in_channels must be in 1..8");
+  if (n_classes < 1 || n_classes > 16) return fail(c, FB_ERR_INVALID, "n_classes must be in 1..16");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  TensorMap tm;
+  for (int i = 0; i < n_tensors; ++i)
+    if (tensors[i].name && tensors[i].data) tm[tensors[i].name] = &tensors[i];
+  for (void* p : c->owned) cudaFree(p);
+  c->owned.clear();
+  c->conv.clear();
+  c->loaded = false;
+
+  FB_TRY(build_conv(c, tm, "stem", "encoder.conv1.weight", "encoder.bn1", "", in_channels, 64, 7, 2, 3));
+  int cin = 64;
+  for (int st = 0; st < 4; ++st) {
+    const int C = kStageCh[st];
+    for (int b = 0; b < kStageBlocks[st]; ++b) {
+      char pre[96], nm[64];
+      snprintf(pre, sizeof pre, "encoder.layer%d.%d", st + 1, b);
+      snprintf(nm, sizeof nm, "layer%d.%d", st + 1, b);
+      const std::string P(pre), N(nm);
+      const int s = (st > 0 && b == 0) ? 2 : 1;
+      FB_TRY(build_conv(c, tm, N + ".conv1", P + ".conv1.weight", P + ".bn1", "", cin, C, 3, s, 1));
+      FB_TRY(build_conv(c, tm, N + ".conv2", P + ".conv2.weight", P + ".bn2", "", C, C, 3, 1, 1));
+      if (st > 0 && b == 0)
+        FB_TRY(build_conv(c, tm, N + ".downsample", P + ".downsample.0.weight", P + ".downsample.1", "", cin, C, 1, 2, 0));
+      cin = C;
+    }
+  }
+  const int dec_in[5] = {512 + 256, 256 + 128, 128 + 64, 64 + 64, 32};
+  for (int d = 0; d < 5; ++d) {
+    char pre[96], nm[64];
+    snprintf(pre, sizeof pre, "decoder.blocks.%d", d);
+    snprintf(nm, sizeof nm, "dec%d", d);
+    const std::string P(pre), N(nm);
+    FB_TRY(build_conv(c, tm, N + ".conv1", P + ".conv1.0.weight", P + ".conv1.1", "", dec_in[d], kDecOut[d], 3, 1, 1));
+    FB_TRY(build_conv(c, tm, N + ".conv2", P + ".conv2.0.weight", P + ".conv2.1", "", kDecOut[d], kDecOut[d], 3, 1, 1));
+  }
+  FB_TRY(build_conv(c, tm, "head", "segmentation_head.0.weight", "", "segmentation_head.0.bias", 16, n_classes, 3, 1, 1));
+  if (use_metadata) {
+    FB_TRY(upload_f32(c, tm, "enc.enc_mlp.0.weight", 64 * 45, &c->mlp[0]));
+    FB_TRY(upload_f32(c, tm, "enc.enc_mlp.0.bias", 64, &c->mlp[1]));
+    FB_TRY(upload_f32(c, tm, "enc.enc_mlp.3.weight", 32 * 64, &c->mlp[2]));
+    FB_TRY(upload_f32(c, tm, "enc.enc_mlp.3.bias", 32, &c->mlp[3]));
+    FB_TRY(upload_f32(c, tm, "enc.enc_mlp.6.weight", 16 * 32, &c->mlp[4]));
+    FB_TRY(upload_f32(c, tm, "enc.enc_mlp.6.bias", 16, &c->mlp[5]));
+  }
+  c->in_ch = in_channels;
+  c->ncls = n_classes;
+  c->use_meta = use_metadata ? 1 : 0;
+  c->loaded = true;
+  return 0;
+}
+
+int fb_set_norm(fb_ctx* c, int mode, const double* mean, const double* std, int nc) {
+  if (!c) return FB_ERR_INVALID;
+  if (nc < 1 || nc > 8) return fail(c, FB_ERR_INVALID, "norm: channel count must be in 1..8");
+  if (mode != FB_NORM_CUSTOM && mode != FB_NORM_SCALING && mode != FB_NORM_WITHOUT)
+    return fail(c, FB_ERR_INVALID, "norm: unknown mode");
+  if (mode == FB_NORM_CUSTOM && (!mean || !std)) return fail(c, FB_ERR_INVALID, "norm: custom mode needs means and stds");
+  std::vector<uint16_t> lut(8 * 256, 0);
+  for (int ch = 0; ch < nc; ++ch)
+    for (int v = 0; v < 256; ++v) {
+      double d;
+      if (mode == FB_NORM_CUSTOM) d = (static_cast<double>(v) - mean[ch]) / std[ch];
+      else if (mode == FB_NORM_SCALING) d = static_cast<double>(v) / 255.0;
+      else d = static_cast<double>(v);
+      lut[ch * 256 + v] = f32_to_bf16_rne(static_cast<float>(d));  // float64 -> float32 -> bf16
+    }
+  FB_CUDA(c, cudaSetDevice(c->device));
+  if (!c->lut) FB_CUDA(c, cudaMalloc(&c->lut, lut.size() * 2));
+  FB_CUDA(c, cudaMemcpyAsync(c->lut, lut.data(), lut.size() * 2, cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->norm_set = true;
+  return 0;
+}
+
+int fb_set_raster(fb_ctx* c, const uint8_t* dev_raster, int bands_total, const int32_t* band_idx, int nc,
+                  int64_t W, int64_t H, int64_t row0, int64_t rows, int layout) {
+  if (!c || !dev_raster || !band_idx) return FB_ERR_INVALID;
+  FB_TRY(set_raster_common(c, bands_total, band_idx, nc, W, H, row0, rows, layout));
+  c->raster = dev_raster;
+  return 0;
+}
+
+int fb_upload_raster(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx, int nc,
+                     int64_t W, int64_t H, int64_t row0, int64_t rows, int layout) {
+  if (!c || !host_raster || !band_idx) return FB_ERR_INVALID;
+  FB_TRY(set_raster_common(c, bands_total, band_idx, nc, W, H, row0, rows, layout));
+  const size_t bytes = static_cast<size_t>(bands_total) * rows * W;
+  if (bytes > c->raster_own_bytes) {
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->raster_own) cudaFree(c->raster_own);
+    c->raster_own = nullptr; c->raster_own_bytes = 0;
+    if (cudaMalloc(&c->raster_own, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, FB_ERR_OOM, "raster upload: cudaMalloc failed");
+    }
+    c->raster_own_bytes = bytes;
+  }
+  FB_CUDA(c, cudaMemcpyAsync(c->raster_own, host_raster, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->raster = c->raster_own;
+  return 0;
+}
+
+int fb_forward_tiles(fb_ctx* c, const int32_t* tile_xy, int n, int tile, const float* metadata,
+                     float* logits_dev) {
+  FB_TRY(check_ready(c, true, tile));
+  if (!tile_xy || n <= 0) return fail(c, FB_ERR_INVALID, "forward: no tiles");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  FB_TRY(ensure_arena(c, n, tile));
+  FB_TRY(ensure_tile_buffers(c, n));
+  FB_CUDA(c, cudaMemcpyAsync(c->tile_xy_dev, tile_xy, static_cast<size_t>(n) * 2 * sizeof(int),
+                             cudaMemcpyHostToDevice, c->stream));
+  const float* menc = nullptr;
+  FB_TRY(run_metadata(c, metadata, n, &menc));
+  FB_TRY(run_extract(c, c->raster, c->layout, c->bands_total, c->band_idx_dev, c->rc, c->W, c->H, c->row0,
+                     c->rows, c->tile_xy_dev, n, tile));
+  FB_TRY(run_network(c, n, tile, menc));
+  if (logits_dev)
+    FB_CUDA(c, cudaMemcpyAsync(logits_dev, c->acts["logits"].ptr, static_cast<size_t>(n) * tile * tile * 16 * 4,
+                               cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int fb_detect_strip(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, uint8_t* cls_map_dev,
+                    uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0) {
+  FB_TRY(check_ready(c, true, tile));
+  if (c->use_meta) return fail(c, FB_ERR_INVALID, "zone detection does not take metadata (zone_detect/model.py:52)");
+  if (!tiles || n < 0 || batch <= 0 || !cls_map_dev) return fail(c, FB_ERR_INVALID, "detect: bad arguments");
+  if (n == 0) return 0;
+  for (int i = 0; i < n; ++i) {
+    const fb_tile& t = tiles[i];
+    if (t.wx1 > t.wx0 && t.wy1 > t.wy0 &&
+        (t.wx0 < t.x0 || t.wy0 < t.y0 || t.wx1 > t.x0 + tile || t.wy1 > t.y0 + tile || t.wx0 < 0 || t.wx1 > map_w || t.wy0 < map_row0))
+      return fail(c, FB_ERR_INVALID, "detect: write rectangle of tile " + std::to_string(i) + " is outside its tile or the map");
+  }
+  FB_CUDA(c, cudaSetDevice(c->device));
+  if (batch > n) batch = n;
+  FB_TRY(ensure_arena(c, batch, tile));
+  FB_TRY(ensure_tile_buffers(c, n));
+  std::vector<int> xy(static_cast<size_t>(n) * 2);
+  for (int i = 0; i < n; ++i) { xy[2 * i] = tiles[i].x0; xy[2 * i + 1] = tiles[i].y0; }
+  FB_CUDA(c, cudaMemcpyAsync(c->tile_xy_dev, xy.data(), xy.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaMemcpyAsync(c->tiles_dev, tiles, static_cast<size_t>(n) * sizeof(fb_tile), cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));  // xy is a local
+  for (int i0 = 0; i0 < n; i0 += batch) {
+    const int nb = (n - i0 < batch) ? n - i0 : batch;
+    if (nb != c->arena_n) FB_TRY(ensure_arena(c, nb, tile));  // ragged last batch: re-plan inside the same block
+    FB_TRY(run_extract(c, c->raster, c->layout, c->bands_total, c->band_idx_dev, c->rc, c->W, c->H, c->row0,
+                       c->rows, c->tile_xy_dev + 2 * i0, nb, tile));
+    FB_TRY(run_network(c, nb, tile, nullptr));
+    ProfScope ps(c, 3);
+    int rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, nb, tile,
+                                      c->tiles_dev + 6 * i0, cls_map_dev, conf_map_dev, map_w, map_row0, c->stream);
+    if (rc) return fail(c, rc, "argmax/stitch launch failed");
+    c->launches++;
+  }
+  return 0;
+}
+
+int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
+                        int nc, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
+                        const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
+                        uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows) {
+  if (!c || !host_cls || map_w <= 0 || map_rows <= 0) return FB_ERR_INVALID;
+  FB_TRY(fb_upload_raster(c, host_raster, bands_total, band_idx, nc, W, H, row0, rows, layout));
+  const size_t mbytes = static_cast<size_t>(map_w) * map_rows;
+  uint8_t* maps = nullptr;
+  if (cudaMalloc(&maps, mbytes * (host_conf ? 2 : 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, FB_ERR_OOM, "class map: cudaMalloc failed");
+  }
+  int rc = 0;
+  cudaError_t e = cudaMemsetAsync(maps, 0, mbytes * (host_conf ? 2 : 1), c->stream);
+  if (e != cudaSuccess) rc = cuda_fail(c, e, "cudaMemsetAsync");
+  if (!rc) rc = fb_detect_strip(c, tiles, n, tile, batch, maps, host_conf ? maps + mbytes : nullptr, map_w, map_row0);
+  if (!rc) {
+    e = cudaMemcpyAsync(host_cls, maps, mbytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && host_conf) e = cudaMemcpyAsync(host_conf, maps + mbytes, mbytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = cuda_fail(c, e, "class map download");
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaFree(maps);
+  return rc;
+}
+
+int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metadata, int n, int tile,
+                       int batch, uint8_t* cls_out_dev) {
+  FB_TRY(check_ready(c, false, tile));
+  if (!dev_patches || !cls_out_dev || n < 0 || batch <= 0) return fail(c, FB_ERR_INVALID, "predict: bad arguments");
+  if (n == 0) return 0;
+  FB_CUDA(c, cudaSetDevice(c->device));
+  if (batch > n) batch = n;
+  FB_TRY(ensure_arena(c, batch, tile));
+  FB_TRY(ensure_tile_buffers(c, batch));
+  if (!c->band_idx_dev) FB_CUDA(c, cudaMalloc(&c->band_idx_dev, 8 * sizeof(int)));
+  // every patch is its own little band-planar raster of c bands; the write rectangle is the whole tile
+  int ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+  int* ident_dev = nullptr;
+  FB_CUDA(c, cudaMalloc(&ident_dev, sizeof ident));
+  FB_CUDA(c, cudaMemcpyAsync(ident_dev, ident, sizeof ident, cudaMemcpyHostToDevice, c->stream));
+  std::vector<int> xy(static_cast<size_t>(batch) * 2), rect(static_cast<size_t>(batch) * 6);
+  for (int i = 0; i < batch; ++i) {
+    xy[2 * i] = 0; xy[2 * i + 1] = i * tile;
+    rect[6 * i] = 0; rect[6 * i + 1] = i * tile; rect[6 * i + 2] = 0; rect[6 * i + 3] = i * tile;
+    rect[6 * i + 4] = tile; rect[6 * i + 5] = (i + 1) * tile;
+  }
+  FB_CUDA(c, cudaMemcpyAsync(c->tile_xy_dev, xy.data(), xy.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaMemcpyAsync(c->tiles_dev, rect.data(), rect.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  int rc = 0;
+  for (int i0 = 0; i0 < n && !rc; i0 += batch) {
+    const int nb = (n - i0 < batch) ? n - i0 : batch;
+    if (nb != c->arena_n) rc = ensure_arena(c, nb, tile);
+    const float* menc = nullptr;
+    if (!rc) rc = run_metadata(c, metadata ? metadata + static_cast<size_t>(i0) * FB_METADATA_DIM : nullptr, nb, &menc);
+    // the batch is seen as one planar raster of width `tile` and height nb*tile per band... but patches are
+    // stored patch-major ([n][c][T][T]), so extract patch by patch view: band stride = T*T inside a patch.
+    // launch_extract_normalise's planar addressing is (band*rows + y)*W + x with rows = raster rows; using
+    // rows = tile and one launch per patch keeps the addressing exact.
+    for (int j = 0; j < nb && !rc; ++j) {
+      const uint8_t* patch = dev_patches + static_cast<size_t>(i0 + j) * c->in_ch * tile * tile;
+      ProfScope ps(c, 0);
+      rc = fb::launch_extract_normalise(patch, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
+                                        c->tile_xy_dev /* (0,0) */, 1, tile, c->lut,
+                                        static_cast<__nv_bfloat16*>(c->acts["x0"].ptr) + static_cast<size_t>(j) * tile * tile * 8,
+                                        c->num_sms, c->stream);
+      if (rc) rc = fail(c, rc, "extract launch failed");
+      c->launches++;
+    }
+    if (!rc) rc = run_network(c, nb, tile, menc);
+    if (!rc) {
+      ProfScope ps(c, 3);
+      rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, nb, tile, c->tiles_dev,
+                                    cls_out_dev + static_cast<size_t>(i0) * tile * tile, nullptr, tile, 0, c->stream);
+      if (rc) rc = fail(c, rc, "argmax launch failed");
+      c->launches++;
+    }
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaFree(ident_dev);
+  return rc;
+}
+
+int fb_confusion(fb_ctx* c, const uint8_t* pred_dev, const uint8_t* truth_dev, int64_t npx, int ncls,
+                 int truth_sub, int64_t* cm_dev) {
+  if (!c || !pred_dev || !truth_dev || !cm_dev || npx < 0) return FB_ERR_INVALID;
+  if (ncls < 1 || ncls > 32) return fail(c, FB_ERR_INVALID, "confusion: ncls must be in 1..32");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  int rc = fb::launch_confusion(pred_dev, truth_dev, npx, ncls, truth_sub & 0xFF, reinterpret_cast<long long*>(cm_dev),
+                                c->num_sms, c->stream);
+  if (rc) return fail(c, rc, "confusion launch failed");
+  c->launches++;
+  return 0;
+}
+
+int fb_conv2d(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, int up1, int B, int Hin, int Win,
+              int KH, int KW, int stride, int pad, int Cout, const void* weights, int Kpad,
+              const float* bias, const void* residual, const float* rowbias, int relu, void* out_bf16,
+              float* out_f32, int mode) {
+  if (!c || !x1 || !weights || !bias || (!out_bf16 == !out_f32)) return FB_ERR_INVALID;
+  FB_CUDA(c, cudaSetDevice(c->device));
+  fb::ConvArgs a;
+  memset(&a, 0, sizeof a);
+  a.x1 = static_cast<const __nv_bfloat16*>(x1);
+  a.x2 = static_cast<const __nv_bfloat16*>(x2);
+  a.C1 = C1; a.C2 = x2 ? C2 : 0; a.up1 = up1;
+  a.B = B; a.Hin = Hin; a.Win = Win;
+  a.Hout = (Hin + 2 * pad - KH) / stride + 1;
+  a.Wout = (Win + 2 * pad - KW) / stride + 1;
+  a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
+  a.Cout = Cout;
+  a.Ktot = KH * KW * (a.C1 + a.C2);
+  a.bias = bias;
+  a.residual = static_cast<const __nv_bfloat16*>(residual);
+  a.rowbias = rowbias;
+  a.relu = relu;
+  a.out = static_cast<__nv_bfloat16*>(out_bf16);
+  a.out_f32 = out_f32;
+  const bool can_tma = KH == 3 && KW == 3 && stride == 1 && pad == 1 && !x2 && !up1 && C1 % 64 == 0 &&
+                       a.Hout % 8 == 0 && a.Wout % 16 == 0;
+  bool tma;
+  if (mode == 1) {
+    if (!can_tma) return fail(c, FB_ERR_INVALID, "conv2d: shape not eligible for the TMA producer");
+    tma = true;
+  } else if (mode == 0) tma = false;
+  else tma = can_tma && !c->force_gather;
+  const int rc = fb::launch_conv(a, static_cast<const __nv_bfloat16*>(weights), Kpad, tma, c->num_sms, c->stream);
+  if (rc) return fail(c, rc, "conv2d launch failed (code " + std::to_string(rc) + ")");
+  c->launches++;
+  return 0;
+}
+
+int fb_debug_activation(fb_ctx* c, const char* name, void* out_dev, int64_t* count, int32_t* dims4) {
+  if (!c || !name) return FB_ERR_INVALID;
+  auto it = c->acts.find(name);
+  if (it == c->acts.end()) return fail(c, FB_ERR_INVALID, std::string("no activation named ") + name);
+  const Act& a = it->second;
+  const int64_t n = static_cast<int64_t>(a.B) * a.H * a.W * a.C;
+  if (count) *count = n;
+  if (dims4) { dims4[0] = a.B; dims4[1] = a.H; dims4[2] = a.W; dims4[3] = a.C; }
+  if (out_dev) FB_CUDA(c, cudaMemcpyAsync(out_dev, a.ptr, static_cast<size_t>(n) * a.elem, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int fb_profile_forward(fb_ctx* c, int n, int tile, int iters, float* ms5) {
+  FB_TRY(check_ready(c, true, tile));
+  if (n <= 0 || iters <= 0 || !ms5) return fail(c, FB_ERR_INVALID, "profile: bad arguments");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  FB_TRY(ensure_arena(c, n, tile));
+  FB_TRY(ensure_tile_buffers(c, n));
+  std::vector<int> xy(static_cast<size_t>(n) * 2), rect(static_cast<size_t>(n) * 6);
+  for (int i = 0; i < n; ++i) {
+    const int x0 = static_cast<int>((static_cast<int64_t>(i) * 256) % (c->W > tile ? c->W - tile : 1));
+    const int y0 = static_cast<int>(c->row0);
+    xy[2 * i] = x0; xy[2 * i + 1] = y0;
+    rect[6 * i] = x0; rect[6 * i + 1] = y0; rect[6 * i + 2] = x0; rect[6 * i + 3] = y0;
+    rect[6 * i + 4] = x0 + tile; rect[6 * i + 5] = y0 + tile;
+  }
+  FB_CUDA(c, cudaMemcpy(c->tile_xy_dev, xy.data(), xy.size() * sizeof(int), cudaMemcpyHostToDevice));
+  FB_CUDA(c, cudaMemcpy(c->tiles_dev, rect.data(), rect.size() * sizeof(int), cudaMemcpyHostToDevice));
+  uint8_t* scratch = nullptr;
+  FB_CUDA(c, cudaMalloc(&scratch, static_cast<size_t>(c->W) * (tile + 1)));
+  const float* menc = nullptr;
+  if (c->use_meta) {
+    std::vector<float> met(static_cast<size_t>(n) * FB_METADATA_DIM, 0.5f);
+    int rc = run_metadata(c, met.data(), n, &menc);
+    if (rc) { cudaFree(scratch); return rc; }
+    cudaStreamSynchronize(c->stream);
+  }
+  double acc[5] = {0, 0, 0, 0, 0};
+  int rc = 0;
+  for (int itn = 0; itn < iters + 1 && !rc; ++itn) {  // first pass is a warm-up
+    c->prof = itn > 0;
+    c->prof_recs.clear();
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, c->stream);
+    rc = run_extract(c, c->raster, c->layout, c->bands_total, c->band_idx_dev, c->rc, c->W, c->H, c->row0, c->rows,
+                     c->tile_xy_dev, n, tile);
+    if (!rc) rc = run_network(c, n, tile, menc);
+    if (!rc) {
+      ProfScope ps(c, 3);
+      rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, n, tile, c->tiles_dev,
+                                    scratch, nullptr, c->W, c->row0, c->stream);
+      c->launches++;
+    }
+    cudaEventRecord(t1, c->stream);
+    cudaStreamSynchronize(c->stream);
+    if (itn > 0) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      acc[4] += ms;
+      for (auto& r : c->prof_recs) {
+        float m = 0;
+        cudaEventElapsedTime(&m, r.a, r.b);
+        acc[r.cat] += m;
+      }
+    }
+    for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->prof_recs.clear();
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+  }
+  c->prof = false;
+  cudaFree(scratch);
+  if (rc) return rc;
+  for (int i = 0; i < 5; ++i) ms5[i] = static_cast<float>(acc[i] / iters);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// Implicit-GEMM convolution kernel for sm_100a (tcgen05.mma + TMEM accumulators + TMA / cp.async
+// operand staging). See conv_igemm.cuh for the role layout and the reference call sites it replaces.
+#include "conv_igemm.cuh"
+
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace fb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kNumProducerThreads = 128;  // warps 0-3
+constexpr int kNumEpilogueThreads = 128;  // warps 4-7
+constexpr int kNumThreads = 288;          // + warp 8 (MMA issuer / TMEM owner)
+constexpr int kGatherLag = 2;             // cp.async groups kept in flight per producer thread
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;  // 16384
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes;
+};
+
+template <int BN, bool TMA_A>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvArgs p) {
+  using C = Cfg<BN>;
+  constexpr int S = C::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SW128 atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t bars = base + S * C::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S * C::kStageBytes + (2 * S + 4) * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(full_bar(s), TMA_A ? 1 : (kNumProducerThreads + 1));
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), kNumEpilogueThreads);
+      }
+      fence_mbar_init();
+      if (TMA_A) tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int nk = p.num_k_iters;
+
+  if (warp < 4) {
+    // ===================================================================== producers
+    if (TMA_A) {
+      if (threadIdx.x == 0) {
+        const int tiles_w = p.Wout >> 4, tiles_h = p.Hout >> 3;
+        const int cchunks = p.C1 >> 6;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+          const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
+          const int b = m_tile / (tiles_w * tiles_h);
+          for (int kit = 0; kit < nk; ++kit, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), C::kStageBytes);
+            const int tap = kit / cchunks, cc = kit - tap * cchunks;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t a_dst = base + s * C::kStageBytes;
+            tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, tw * 16 + kw - 1, th * 8 + kh - 1, b);
+            tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, n_tile * BN);
+          }
+        }
+      }
+    } else {
+      const int tid = threadIdx.x;          // 0..127
+      const int chunk = tid & 7;            // 16-byte chunk (8 channels) within the 128-byte k row
+      const int rbase = tid >> 3;           // rows rbase + 16*j, j = 0..7
+      const int Cin = p.C1 + p.C2;
+      const int HWo = p.Hout * p.Wout;
+      const uint32_t sw_off = static_cast<uint32_t>((chunk ^ (rbase & 7)) << 4);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+        int rb[8], rih[8], riw[8];  // batch index (-1 = row out of range), top-left input coords
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pix = m_tile * kBM + rbase + 16 * j;
+          if (pix < p.M_total) {
+            const int b = pix / HWo, rem = pix - b * HWo;
+            const int oh = rem / p.Wout, ow = rem - oh * p.Wout;
+            rb[j] = b;
+            rih[j] = oh * p.stride - p.pad;
+            riw[j] = ow * p.stride - p.pad;
+          } else {
+            rb[j] = -1; rih[j] = 0; riw[j] = 0;
+          }
+        }
+        for (int kit = 0; kit < nk; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t a_dst = base + s * C::kStageBytes;
+          if (tid == 0) {
+            mbar_expect_tx(full_bar(s), C::kBBytes);
+            tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, n_tile * BN);
+          }
+          const int k0 = kit * kBK + chunk * 8;
+          const bool kvalid = k0 < p.Ktot;
+          const int tap = k0 / Cin, ch = k0 - tap * Cin;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          const bool from1 = ch < p.C1;
+          const __nv_bfloat16* src = from1 ? p.x1 : p.x2;
+          const int Cs = from1 ? p.C1 : p.C2;
+          const int chs = from1 ? ch : ch - p.C1;
+          const int sh = (from1 && p.up1) ? 1 : 0;
+          const int Hs = p.Hin >> sh, Ws = p.Win >> sh;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ih = rih[j] + kh, iw = riw[j] + kw;
+            const bool ok = kvalid && rb[j] >= 0 && ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win;
+            const __nv_bfloat16* g = src;
+            if (ok) {
+              g = src + (static_cast<size_t>(rb[j] * Hs + (ih >> sh)) * Ws + (iw >> sh)) * Cs + chs;
+            }
+            const uint32_t dst = a_dst + static_cast<uint32_t>((rbase + 16 * j) * 128) + sw_off;
+            cp_async_16(dst, g, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (it >= static_cast<uint32_t>(kGatherLag)) {
+            cp_async_wait<kGatherLag>();
+            fence_proxy_async_smem();
+            mbar_arrive(full_bar((it - kGatherLag) % S));
+          }
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      const uint32_t first = it >= static_cast<uint32_t>(kGatherLag) ? it - kGatherLag : 0u;
+      for (uint32_t j = first; j < it; ++j) mbar_arrive(full_bar(j % S));
+    }
+  } else if (warp < 8) {
+    // ===================================================================== epilogue
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // tile row == TMEM lane
+    const int tiles_w = p.Wout >> 4, tiles_h = p.Hout >> 3;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      long long pix;
+      bool valid;
+      int b_idx, oh_idx;
+      if (TMA_A) {
+        const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
+        b_idx = m_tile / (tiles_w * tiles_h);
+        oh_idx = th * 8 + (row >> 4);
+        pix = (static_cast<long long>(b_idx) * p.Hout + oh_idx) * p.Wout + tw * 16 + (row & 15);
+        valid = true;
+      } else {
+        pix = static_cast<long long>(m_tile) * kBM + row;
+        valid = pix < p.M_total;
+        const int HWo = p.Hout * p.Wout;
+        b_idx = static_cast<int>(pix / HWo);
+        oh_idx = static_cast<int>((pix - static_cast<long long>(b_idx) * HWo) / p.Wout);
+      }
+      const float rb = (p.rowbias != nullptr && valid) ? p.rowbias[b_idx * p.Hout + oh_idx] : 0.f;
+      const size_t obase = static_cast<size_t>(pix) * p.Cout + n_tile * BN;
+
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_x16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[16];
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = __ldg(bp + i);
+            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 rr = __ldg(rp + h);
+              const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+                v[8 * h + 2 * i + 0] += __low2float(b2);
+                v[8 * h + 2 * i + 1] += __high2float(b2);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += rb;
+          if (p.out_f32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
+            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(tempty_bar(as));
+    }
+  } else {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const int as = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(as), aph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kit = 0; kit < nk; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after_sync();
+          const uint32_t a_addr = base + s * C::kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is >>4)
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+template <int BN, bool TMA_A>
+int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, int grid,
+             cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, TMA_A>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  conv_igemm_kernel<BN, TMA_A><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+int init_tma_encoder() {
+  if (g_encode != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) return -1;
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+int conv_pick_bn(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  if (Cout % 32 == 0) return 32;
+  if (Cout % 16 == 0) return 16;
+  return 0;
+}
+
+int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bool use_tma_a,
+                int num_sms, cudaStream_t stream) {
+  if (init_tma_encoder() != 0) return -1001;
+  ConvArgs a = a_in;
+  const int BN = conv_pick_bn(a.Cout);
+  if (BN == 0) return -1002;
+  const int Cin = a.C1 + a.C2;
+  if (Cin % 8 != 0 || a.C1 % 8 != 0 || Kpad % kBK != 0 || Kpad < a.Ktot) return -1003;
+  a.M_total = a.B * a.Hout * a.Wout;
+  a.num_n_tiles = a.Cout / BN;
+  a.num_k_iters = (a.Ktot + kBK - 1) / kBK;
+  if (use_tma_a) {
+    if (!(a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.C2 == 0 && a.up1 == 0 &&
+          a.C1 % 64 == 0 && a.Hout % 8 == 0 && a.Wout % 16 == 0 && a.Hin == a.Hout && a.Win == a.Wout))
+      return -1004;
+    a.num_m_tiles = a.B * (a.Hout / 8) * (a.Wout / 16);
+  } else {
+    a.num_m_tiles = (a.M_total + kBM - 1) / kBM;
+  }
+
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  {
+    // weights: [Cout][Kpad] bf16, box = 64 k x BN rows, 128-byte swizzle
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kpad), static_cast<cuuint64_t>(a.Cout)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kpad) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(BN)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(weights),
+                          dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -1100 - static_cast<int>(r);
+  }
+  if (use_tma_a) {
+    // activations: NHWC bf16 seen as (C, W, H, B); box = 64 channels x 16 x 8 pixels; out-of-range
+    // coordinates are zero-filled by the TMA unit, which is exactly the conv's zero padding.
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.C1), static_cast<cuuint64_t>(a.Win),
+                          static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.C1) * 2,
+                             static_cast<cuuint64_t>(a.Win) * a.C1 * 2,
+                             static_cast<cuuint64_t>(a.Hin) * a.Win * a.C1 * 2};
+    cuuint32_t box[4] = {64, 16, 8, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.x1),
+                          dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -1200 - static_cast<int>(r);
+  }
+
+  const int num_tiles = a.num_m_tiles * a.num_n_tiles;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (grid <= 0) return 0;
+
+#define FB_DISPATCH(BN_)                                                               \
+  case BN_:                                                                            \
+    return use_tma_a ? launch_t<BN_, true>(tmA, tmB, a, grid, stream)                  \
+                     : launch_t<BN_, false>(tmA, tmB, a, grid, stream);
+  switch (BN) {
+    FB_DISPATCH(16)
+    FB_DISPATCH(32)
+    FB_DISPATCH(64)
+    FB_DISPATCH(128)
+    FB_DISPATCH(256)
+  }
+#undef FB_DISPATCH
+  return -1005;
+}
+
+}  // namespace fb

@@ -1,0 +1,288 @@
+// HBM-bound kernels of the zone_detect / patch-predict hot path (everything that is not a conv):
+//   K1  tile extraction + per-band normalisation   (src/zone_detect/dataset.py:68-113, src/flair/data_loader.py:9-30)
+//   --  3x3 stride-2 max-pool of the stem           (torchvision ResNet `maxpool`)
+//   K4  metadata MLP 45->64->32->16                 (src/flair/model.py:74-96)
+//   K6  softmax-max / argmax / margin clip / stitch (src/zone_detect/compare.py:35,66-82, dataset.py:11-34)
+//   K9  confusion-matrix histogram                  (src/flair/metrics.py:60-74, src/zone_detect/test/metrics.py:146-163)
+#include "elementwise.cuh"
+
+#include <cuda_bf16.h>
+
+namespace fb {
+
+// ------------------------------------------------------------------------------------------ K1
+// One thread per output pixel: gathers `c` band bytes (coalesced along x for the planar layout),
+// maps each through a 256-entry bf16 table (the host builds it in float64 -> float32 -> bf16 so the
+// result is bit-identical to rounding the reference's float32 tensor), writes 8 bf16 (16 bytes).
+// Pixels outside the raster read raw 0 *before* normalisation (rasterio boundless=True semantics).
+__global__ void __launch_bounds__(256)
+extract_normalise_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int bands_total,
+                         const int* __restrict__ band_idx, int c, long long W, long long H,
+                         long long row0, long long rows, const int* __restrict__ tile_xy, int n,
+                         int T, const __nv_bfloat16* __restrict__ lut, __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 s_lut[8 * 256];
+  __shared__ int s_band[8];
+  for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_lut[i] = lut[i];
+  if (threadIdx.x < 8) s_band[threadIdx.x] = threadIdx.x < c ? band_idx[threadIdx.x] : 0;
+  __syncthreads();
+  const long long total = static_cast<long long>(n) * T * T;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(idx / (static_cast<long long>(T) * T));
+    const int rem = static_cast<int>(idx - static_cast<long long>(t) * T * T);
+    const int y = rem / T, x = rem - y * T;
+    const long long rx = tile_xy[2 * t] + static_cast<long long>(x);
+    const long long ry = tile_xy[2 * t + 1] + static_cast<long long>(y);
+    const bool inside = rx >= 0 && rx < W && ry >= 0 && ry < H && ry >= row0 && ry < row0 + rows;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch < c) {
+        unsigned raw = 0;
+        if (inside) {
+          const long long ly = ry - row0;
+          raw = layout_hwc ? raster[(ly * W + rx) * bands_total + s_band[ch]]
+                           : raster[(static_cast<long long>(s_band[ch]) * rows + ly) * W + rx];
+        }
+        v[ch] = s_lut[ch * 256 + raw];
+      } else {
+        v[ch] = __float2bfloat16(0.f);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+int launch_extract_normalise(const uint8_t* raster, int layout_hwc, int bands_total, const int* band_idx,
+                             int c, long long W, long long H, long long row0, long long rows,
+                             const int* tile_xy, int n, int T, const __nv_bfloat16* lut,
+                             __nv_bfloat16* out, int num_sms, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * T * T;
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  extract_normalise_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      raster, layout_hwc, bands_total, band_idx, c, W, H, row0, rows, tile_xy, n, T, lut, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ maxpool
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H,
+                    int W, int C) {
+  const int Ho = H >> 1, Wo = W >> 1, Cg = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * Cg;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % Cg);
+    long long pix = idx / Cg;
+    const int ow = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int oh = static_cast<int>(pix % Ho);
+    const int b = static_cast<int>(pix / Ho);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -3.0e38f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int ih = 2 * oh + dy;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int iw = 2 * ow + dx;
+        if (iw < 0 || iw >= W) continue;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(
+            in + ((static_cast<long long>(b) * H + ih) * W + iw) * C + g * 8));
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+          m[2 * i] = fmaxf(m[2 * i], __low2float(b2));
+          m[2 * i + 1] = fmaxf(m[2 * i + 1], __high2float(b2));
+        }
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(m[2 * i], m[2 * i + 1]);
+      pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+int launch_maxpool3x3s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C,
+                        int num_sms, cudaStream_t stream) {
+  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return 0;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  maxpool3x3s2_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(in, out, B, H, W, C);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// One 64-thread block per sample; fp32 FMA on CUDA cores (5.4 kMAC: far too small for tensor cores).
+__global__ void __launch_bounds__(64)
+metadata_mlp_kernel(const float* __restrict__ met, const float* __restrict__ w0,
+                    const float* __restrict__ b0, const float* __restrict__ w1,
+                    const float* __restrict__ b1, const float* __restrict__ w2,
+                    const float* __restrict__ b2, float* __restrict__ out) {
+  __shared__ float x[45], h0[64], h1[32];
+  const int s = blockIdx.x, t = threadIdx.x;
+  if (t < 45) x[t] = met[s * 45 + t];
+  __syncthreads();
+  {
+    float acc = b0[t];
+    for (int i = 0; i < 45; ++i) acc = fmaf(w0[t * 45 + i], x[i], acc);
+    h0[t] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  if (t < 32) {
+    float acc = b1[t];
+    for (int i = 0; i < 64; ++i) acc = fmaf(w1[t * 64 + i], h0[i], acc);
+    h1[t] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  if (t < 16) {
+    float acc = b2[t];
+    for (int i = 0; i < 32; ++i) acc = fmaf(w2[t * 32 + i], h1[i], acc);
+    out[s * 16 + t] = fmaxf(acc, 0.f);
+  }
+}
+
+int launch_metadata_mlp(const float* met, const float* const* wb, float* out, int n,
+                        cudaStream_t stream) {
+  if (n == 0) return 0;
+  metadata_mlp_kernel<<<n, 64, 0, stream>>>(met, wb[0], wb[1], wb[2], wb[3], wb[4], wb[5], out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ K6
+// One thread per written pixel. argmax = first maximum (numpy semantics); confidence byte =
+// round-half-up of the max soft-max probability (what a float32 -> uint8 raster write produces).
+__global__ void __launch_bounds__(256)
+argmax_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ tiles,
+                     uint8_t* __restrict__ cls_map, uint8_t* __restrict__ conf_map, long long map_w,
+                     long long map_row0) {
+  const int t = blockIdx.y;
+  const int* tt = tiles + 6 * t;  // x0, y0 (tile origin, raster px), wx0, wy0, wx1, wy1 (write rect)
+  const int x0 = tt[0], y0 = tt[1], wx0 = tt[2], wy0 = tt[3], wx1 = tt[4], wy1 = tt[5];
+  const int rw = wx1 - wx0, rh = wy1 - wy0;
+  if (rw <= 0 || rh <= 0) return;
+  const int total = rw * rh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ry = wy0 + i / rw, rx = wx0 + i % rw;
+    const int ty = ry - y0, tx = rx - x0;
+    const float4* lp = reinterpret_cast<const float4*>(
+        logits + ((static_cast<long long>(t) * T + ty) * T + tx) * 16);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 f = __ldg(lp + k);
+      v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+    }
+    float best = v[0];
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+      if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < ncls) den += __expf(v[k] - best);
+    const float pmax = 1.f / den;
+    const long long o = (static_cast<long long>(ry) - map_row0) * map_w + rx;
+    cls_map[o] = static_cast<uint8_t>(arg);
+    if (conf_map != nullptr) conf_map[o] = static_cast<uint8_t>(pmax + 0.5f);
+  }
+}
+
+int launch_argmax_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* cls_map,
+                         uint8_t* conf_map, long long map_w, long long map_row0, cudaStream_t stream) {
+  if (n == 0) return 0;
+  dim3 grid((T * T + 255) / 256 > 64 ? 64 : (T * T + 255) / 256, n);
+  argmax_stitch_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, cls_map, conf_map, map_w,
+                                                 map_row0);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ K9
+// Confusion matrix cm[truth][pred] (int64, rows = truth) over pairs with both labels < ncls; any other
+// pair is dropped, which is what sklearn.confusion_matrix(labels=range(ncls)) does. `truth_sub` is
+// subtracted from the truth byte with uint8 wrap-around first (the reference computes `mask - 1` on a
+// uint8 array, so 0 wraps to 255 and is dropped). Per-block bins live in shared memory; lanes of a
+// warp that hit the same bin are merged with __match_any_sync so hot bins cost one atomic per warp.
+constexpr int kMaxCls = 32;
+
+__global__ void __launch_bounds__(256)
+confusion_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ truth, long long npx,
+                 int ncls, int truth_sub, unsigned long long* __restrict__ cm) {
+  __shared__ unsigned int bins[kMaxCls * kMaxCls];
+  const int nb = ncls * ncls;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long nvec = npx >> 4;  // 16 pixels per uint4
+  const bool aligned = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(truth)) & 15) == 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long done = 0;
+  if (aligned) {
+    // every lane of a warp runs the same trip count (loop bound is rounded up per warp)
+    const long long first = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    for (long long vbase = first - lane; vbase < nvec; vbase += stride) {
+      const long long v = vbase + lane;
+      const bool active = v < nvec;
+      uint4 pv = make_uint4(0, 0, 0, 0), tv = make_uint4(0, 0, 0, 0);
+      if (active) {
+        pv = __ldg(reinterpret_cast<const uint4*>(pred) + v);
+        tv = __ldg(reinterpret_cast<const uint4*>(truth) + v);
+      }
+      const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+      const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const unsigned pb = (pw[w] >> (8 * b)) & 0xFF;
+          const unsigned tb = ((tw[w] >> (8 * b)) - truth_sub) & 0xFF;
+          const bool ok = active && pb < static_cast<unsigned>(ncls) && tb < static_cast<unsigned>(ncls);
+          const unsigned key = ok ? tb * ncls + pb : 0xFFFFu;
+          const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+          if (ok && lane == __ffs(peers) - 1) atomicAdd(&bins[key], __popc(peers));
+        }
+      }
+    }
+    done = nvec << 4;
+  }
+  // scalar tail (and the whole range when the pointers are not 16-byte aligned)
+  for (long long i = done + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npx;
+       i += stride) {
+    const unsigned pb = pred[i];
+    const unsigned tb = (static_cast<unsigned>(truth[i]) - truth_sub) & 0xFF;
+    if (pb < static_cast<unsigned>(ncls) && tb < static_cast<unsigned>(ncls))
+      atomicAdd(&bins[tb * ncls + pb], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (bins[i] != 0) atomicAdd(&cm[i], static_cast<unsigned long long>(bins[i]));
+}
+
+int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, int ncls, int truth_sub,
+                     long long* cm, int num_sms, cudaStream_t stream) {
+  if (ncls <= 0 || ncls > kMaxCls) return -2001;
+  if (npx <= 0) return 0;
+  // a block handles at most 2^32-1 pixels between flushes: 256 threads * 16 px * trips stays far below
+  long long blocks = (npx / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  confusion_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      pred, truth, npx, ncls, truth_sub, reinterpret_cast<unsigned long long*>(cm));
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace fb

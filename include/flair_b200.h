@@ -1,0 +1,153 @@
+/* libflairb200 -- C ABI of the B200-native zone_detect / patch-predict hot path.
+ *
+ * The reference (Draghoyns/FLAIR-1) is pure Python and has no FFI of its own; its "operator boundary"
+ * for this path is a handful of Python calls. Each entry point below replaces
+ * one of those calls and cites it. A reference maintainer binds these with ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a positive cudaError_t, or a negative library code;
+ *    fb_last_error(ctx) gives a human-readable message for the last failure on that context
+ *    (fb_last_error(NULL) for fb_create failures). No exception ever crosses this boundary.
+ *  - a context is bound to one CUDA device and one stream (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream). It is NOT thread-safe; distinct contexts are independent.
+ *  - "dev" pointers are device pointers on the context's device, "host" pointers are host memory.
+ *  - all work is enqueued on the context's stream; calls that take host output buffers synchronise
+ *    the stream before returning, the others do not.
+ *  - there is no CPU fallback: every call fails with FB_ERR_NO_DEVICE when no sm_100 device exists.
+ */
+#ifndef FLAIR_B200_H_
+#define FLAIR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_API_VERSION 1
+
+#define FB_OK 0
+#define FB_ERR_INVALID (-1)    /* bad argument */
+#define FB_ERR_STATE (-2)      /* call order (weights / norm / raster not set) */
+#define FB_ERR_NO_DEVICE (-3)  /* no CUDA device of compute capability 10.x */
+#define FB_ERR_WEIGHTS (-4)    /* missing / mis-shaped tensor in the state dict */
+#define FB_ERR_OOM (-5)
+
+#define FB_NORM_CUSTOM 0  /* (x - mean) / std, float64 then float32: src/zone_detect/dataset.py:79-86 */
+#define FB_NORM_SCALING 1 /* x / 255 (skimage img_as_float): dataset.py:88, src/flair/data_loader.py:28-29 */
+#define FB_NORM_WITHOUT 2 /* raw values: src/flair/data_loader.py:15 ('without') */
+
+#define FB_LAYOUT_CHW 0 /* band-planar, what rasterio's read() returns */
+#define FB_LAYOUT_HWC 1 /* pixel-interleaved */
+
+#define FB_LOGIT_STRIDE 16 /* logits are written as [n, T, T, 16] fp32; classes >= n_classes are 0 */
+#define FB_METADATA_DIM 45 /* src/flair/tasks_utils.py:158-213 */
+
+typedef struct fb_ctx fb_ctx;
+
+/* One entry of the checkpoint: host fp32 data under its segmentation-models-pytorch key
+ * ("encoder.conv1.weight", "decoder.blocks.0.conv1.1.running_var", "segmentation_head.0.bias",
+ * "enc.enc_mlp.0.weight", ...) after the "model.seg_model." / "model." prefixes were stripped the way
+ * src/zone_detect/model.py:61-76 does. */
+typedef struct fb_tensor_desc {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} fb_tensor_desc;
+
+/* One sliding-window tile of the slicing job (src/zone_detect/slicing_job.py:54-106) in raster pixel
+ * coordinates, y growing downwards. (x0, y0) is the top-left of the margin-expanded square and may
+ * lie outside the raster; [wx0,wx1) x [wy0,wy1) is the part of the class map this tile owns
+ * (interior box after margin clipping, minus what a later tile of the write order overwrites:
+ * src/zone_detect/compare.py:66-82, src/zone_detect/main.py:409-426). */
+typedef struct fb_tile {
+  int32_t x0, y0;
+  int32_t wx0, wy0, wx1, wy1;
+} fb_tile;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int fb_api_version(void);
+int fb_create(int device, void* cuda_stream, fb_ctx** out);
+void fb_destroy(fb_ctx* ctx);
+const char* fb_last_error(const fb_ctx* ctx);
+int fb_synchronize(fb_ctx* ctx);
+
+/* ---- model: replaces smp.create_model + load_state_dict(strict=True)
+ *      (src/zone_detect/model.py:30-39,79-88; src/flair/model.py:20-50, src/flair/main.py:77-146).
+ *      Folds eval-mode BatchNorm into the conv weights in float64, rounds once to bf16, repacks to
+ *      [Cout][kh][kw][Cin] and uploads. in_channels in 1..8, n_classes in 1..16. */
+int fb_load_weights(fb_ctx* ctx, const fb_tensor_desc* tensors, int n_tensors, int in_channels,
+                    int n_classes, int use_metadata);
+
+/* ---- input normalisation: Sliced_Dataset.normalization (dataset.py:68-88) / norm()
+ *      (data_loader.py:9-30). mean/std are per selected band (ignored unless FB_NORM_CUSTOM). */
+int fb_set_norm(fb_ctx* ctx, int mode, const double* mean, const double* std, int c);
+
+/* ---- raster: replaces rasterio.open + windowed boundless read (dataset.py:90-104).
+ *      The buffer holds rows [row0, row0+rows) of a W x H raster with bands_total uint8 bands;
+ *      band_idx[c] are the 0-based bands fed to the network (config "channels" minus 1). Anything
+ *      outside [0,W)x[0,H) -- or outside the resident rows -- reads as raw 0 before normalisation.
+ *      fb_set_raster borrows a device pointer; fb_upload_raster copies from host (pinned or not) into
+ *      a context-owned device buffer on the context's stream. */
+int fb_set_raster(fb_ctx* ctx, const uint8_t* dev_raster, int bands_total, const int32_t* band_idx,
+                  int c, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout);
+int fb_upload_raster(fb_ctx* ctx, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
+                     int c, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout);
+
+/* ---- logits = model(imgs [, met]) (compare.py:27-33; task_module.py:206-210; flair/model.py:52-70)
+ *      for n tiles of tile x tile pixels cut from the current raster at host tile_xy[n][2] = (x0, y0).
+ *      metadata: host [n][45] or NULL. logits_dev: device [n][tile][tile][16] fp32. */
+int fb_forward_tiles(fb_ctx* ctx, const int32_t* tile_xy, int n, int tile, const float* metadata,
+                     float* logits_dev);
+
+/* ---- the zone_detect hot loop (main.py:398-426): for every tile forward -> softmax -> margin crop ->
+ *      argmax / max-probability -> write into the class map, `batch` tiles per forward pass.
+ *      cls_map_dev / conf_map_dev (conf may be NULL): device uint8 [map_rows][map_w]; a raster pixel
+ *      (x, y) lands at (y - map_row0) * map_w + x. */
+int fb_detect_strip(fb_ctx* ctx, const fb_tile* tiles, int n, int tile, int batch, uint8_t* cls_map_dev,
+                    uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0);
+
+/* ---- same loop, host buffers in and out (upload raster rows, detect, download class map); this is
+ *      the call the end-to-end benchmark times. host_cls / host_conf: [map_rows][map_w] uint8. */
+int fb_detect_zone_host(fb_ctx* ctx, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
+                        int c, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
+                        const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
+                        uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows);
+
+/* ---- patch predict (flair/task_module.py:206-213 + data_loader.py:130-144): n whole patches,
+ *      dev_patches uint8 [n][c][tile][tile] (band-planar per patch, already restricted to the selected
+ *      bands), metadata host [n][45] or NULL, cls_out_dev uint8 [n][tile][tile] (0-based classes). */
+int fb_predict_patches(fb_ctx* ctx, const uint8_t* dev_patches, const float* metadata, int n, int tile,
+                       int batch, uint8_t* cls_out_dev);
+
+/* ---- confusion matrix (sklearn.metrics.confusion_matrix(labels=range(ncls)) at
+ *      flair/metrics.py:67-71 and zone_detect/test/metrics.py:161-163,229-231):
+ *      cm_dev[t*ncls + p] += #{ i : (uint8)(truth[i] - truth_sub) == t, pred[i] == p, t,p < ncls }.
+ *      int64 device accumulator, caller zeroes it; ncls <= 32. */
+int fb_confusion(fb_ctx* ctx, const uint8_t* pred_dev, const uint8_t* truth_dev, int64_t npx, int ncls,
+                 int truth_sub, int64_t* cm_dev);
+
+/* ---- test / profiling hooks (used by tests/ and bench.py, not by the pipelines) --------------- */
+/* Single convolution: NHWC bf16 in/out, weights [Cout][Kpad] bf16 (k = (kh*KW+kw)*Cin + c, Kpad a
+ * multiple of 64), fp32 bias. x2/C2: optional second (skip) source concatenated after x1's channels;
+ * up1: x1 is read through a nearest x2 upsample. mode: 0 = cp.async gather producer, 1 = TMA producer
+ * (3x3 stride 1 only), -1 = automatic. Exactly one of out_bf16 / out_f32 is non-NULL. */
+int fb_conv2d(fb_ctx* ctx, const void* x1, const void* x2, int C1, int C2, int up1, int B, int Hin,
+              int Win, int KH, int KW, int stride, int pad, int Cout, const void* weights, int Kpad,
+              const float* bias, const void* residual, const float* rowbias, int relu, void* out_bf16,
+              float* out_f32, int mode);
+/* Copy a named intermediate of the last fb_forward_tiles call (e.g. "f1", "layer2.0.out", "dec3")
+ * to a device buffer as bf16 NHWC. Returns its element count through *count (also when out is NULL). */
+int fb_debug_activation(fb_ctx* ctx, const char* name, void* out_dev, int64_t* count, int32_t* dims4);
+/* Run fb_forward_tiles-equivalent work `iters` times and report the mean device time per kernel
+ * family in ms (CUDA events on the context's stream): [0]=extract [1]=conv(all) [2]=maxpool+mlp
+ * [3]=argmax/stitch [4]=total. */
+int fb_profile_forward(fb_ctx* ctx, int n, int tile, int iters, float* ms5);
+/* Number of kernels this library has launched on the context since creation. */
+int64_t fb_launch_count(const fb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAIR_B200_H_ */

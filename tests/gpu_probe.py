@@ -1,0 +1,159 @@
+"""Diagnostic runner for the CUDA kernels (not a pytest module): runs each kernel against a plain
+PyTorch fp32 reference on the same inputs and prints one line per case, flushing as it goes so that a
+hang still leaves a readable log. Usage (on a GPU box):
+
+    timeout 600 python tests/gpu_probe.py [case-substring ...] > gpurun_out/probe.log 2>&1
+"""
+from __future__ import annotations
+
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import flair1_b200._native as nat  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+RESULTS = []
+
+
+def log(*a):
+    print(*a, flush=True)
+
+
+def ref_conv(x1, w, bias, stride, pad, x2=None, up1=False, residual=None, rowbias=None, relu=False):
+    """fp32 reference on bf16-rounded operands; NHWC in / NHWC out."""
+    a = x1.float().permute(0, 3, 1, 2)
+    if up1:
+        a = F.interpolate(a, scale_factor=2, mode="nearest")
+    if x2 is not None:
+        a = torch.cat([a, x2.float().permute(0, 3, 1, 2)], dim=1)
+    y = F.conv2d(a, w.to(torch.bfloat16).float(), bias=bias, stride=stride, padding=pad)
+    if residual is not None:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    if relu:
+        y = torch.relu(y)
+    if rowbias is not None:
+        y = y + rowbias[:, None, :, None]
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=False, res=False, rowb=False,
+              relu=True, out_f32=False, seed=0, identity=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = ctx.device
+    h1, w1 = (H // 2, W // 2) if up1 else (H, W)
+    x1 = torch.randn((B, h1, w1, C1), generator=g).to(torch.bfloat16).to(dev)
+    x2 = torch.randn((B, H, W, C2), generator=g).to(torch.bfloat16).to(dev) if C2 else None
+    Cin = C1 + C2
+    w = torch.randn((Cout, Cin, k, k), generator=g) / np.sqrt(Cin * k * k)
+    if identity:  # centre tap identity: out[..., n] = x[..., n]
+        w.zero_()
+        for o in range(min(Cout, Cin)):
+            w[o, o, k // 2, k // 2] = 1.0
+    bias = (torch.randn((Cout,), generator=g) * 0.1).to(dev)
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    residual = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).to(dev) if res else None
+    rowbias = torch.randn((B, Ho), generator=g).to(dev) if rowb else None
+    wp = nat.pack_conv_weight(w, cin_pad=Cin, cout_pad=Cout).to(dev)
+    t0 = time.time()
+    try:
+        y = ctx.conv2d(x1, wp, bias, k, k, stride, pad, x2=x2, up1=up1, residual=residual, rowbias=rowbias,
+                       relu=relu, out_f32=out_f32, mode=mode)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        log(f"CASE {name}: EXCEPTION {e}")
+        RESULTS.append({"case": name, "ok": False, "error": str(e)})
+        return False
+    dt = time.time() - t0
+    yr = ref_conv(x1, w.to(dev), bias, stride, pad, x2=x2, up1=up1, residual=residual, rowbias=rowbias, relu=relu)
+    err = (y.float() - yr).abs()
+    scale = yr.abs().max().item() + 1e-9
+    tol = 2e-5 if out_f32 else 1.0 / 128  # bf16 output: half-ulp relative 2^-9, allow 2x
+    rel = (err / (yr.abs() + 0.05 * scale)).max().item()
+    ok = bool(rel < tol * 2 + 1e-4) and bool(torch.isfinite(y.float()).all())
+    bad = (err / (yr.abs() + 0.05 * scale) > tol * 2 + 1e-4)
+    info = ""
+    if not ok:
+        idx = bad.nonzero()
+        info = f" nbad={idx.shape[0]}/{bad.numel()} first_bad={idx[:4].tolist()} " \
+               f"rows_bad={sorted(set((idx[:, 1] * Wo + idx[:, 2]).tolist()))[:16]} chans_bad={sorted(set(idx[:, 3].tolist()))[:16]}"
+    log(f"CASE {name}: {'OK ' if ok else 'FAIL'} maxabs={err.max().item():.4e} rel={rel:.4e} refmax={scale:.3f} t={dt*1e3:.1f}ms{info}")
+    RESULTS.append({"case": name, "ok": ok, "maxabs": err.max().item(), "rel": rel})
+    return ok
+
+
+def main():
+    want = sys.argv[1:]
+    log("device:", torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
+    ctx = nat.Context(0)
+
+    def sel(name):
+        return not want or any(s in name for s in want)
+
+    G, T = 0, 1
+    cases = [
+        # name, B, H, W, C1, Cout, k, stride, pad, mode, kwargs
+        ("g_ident_64_64_8x16", 1, 8, 16, 64, 64, 3, 1, 1, G, dict(identity=True, relu=False)),
+        ("g_3x3_64_64_8x16", 1, 8, 16, 64, 64, 3, 1, 1, G, {}),
+        ("t_ident_64_64_8x16", 1, 8, 16, 64, 64, 3, 1, 1, T, dict(identity=True, relu=False)),
+        ("t_3x3_64_64_8x16", 1, 8, 16, 64, 64, 3, 1, 1, T, {}),
+        ("g_3x3_64_64_32x32_b2", 2, 32, 32, 64, 64, 3, 1, 1, G, {}),
+        ("t_3x3_64_64_32x32_b2", 2, 32, 32, 64, 64, 3, 1, 1, T, {}),
+        ("g_3x3_128_128_res", 2, 16, 16, 128, 128, 3, 1, 1, G, dict(res=True)),
+        ("t_3x3_128_128_res", 2, 16, 16, 128, 128, 3, 1, 1, T, dict(res=True)),
+        ("t_3x3_256_256", 3, 32, 32, 256, 256, 3, 1, 1, T, {}),
+        ("t_3x3_512_512_rowb", 4, 16, 16, 512, 512, 3, 1, 1, T, dict(res=True, rowb=True)),
+        ("g_3x3_512_512", 2, 16, 16, 512, 512, 3, 1, 1, G, {}),
+        ("g_7x7s2_8_64", 2, 64, 64, 8, 64, 7, 2, 3, G, {}),
+        ("g_3x3s2_64_128", 2, 32, 32, 64, 128, 3, 2, 1, G, {}),
+        ("g_1x1s2_64_128", 2, 32, 32, 64, 128, 1, 2, 0, G, dict(relu=False)),
+        ("g_up_cat_512_256_256", 1, 32, 32, 512, 256, 3, 1, 1, G, dict(C2=256, up1=True)),
+        ("g_up_cat_64_64_32", 1, 64, 64, 64, 32, 3, 1, 1, G, dict(C2=64, up1=True)),
+        ("g_up_32_16", 1, 64, 64, 32, 16, 3, 1, 1, G, dict(up1=True)),
+        ("g_3x3_16_16", 1, 64, 64, 16, 16, 3, 1, 1, G, {}),
+        ("g_3x3_32_32", 1, 64, 64, 32, 32, 3, 1, 1, G, {}),
+        ("g_head_16_16_f32", 1, 64, 64, 16, 16, 3, 1, 1, G, dict(relu=False, out_f32=True)),
+        ("g_ragged_m", 1, 20, 20, 64, 64, 3, 1, 1, G, {}),
+        ("t_many_tiles", 8, 128, 128, 64, 64, 3, 1, 1, T, {}),
+        ("g_many_tiles", 8, 128, 128, 64, 64, 3, 1, 1, G, {}),
+    ]
+    for c in cases:
+        name = c[0]
+        if sel(name):
+            conv_case(ctx, name, *c[1:10], **c[10])
+
+    if sel("confusion"):
+        g = torch.Generator().manual_seed(1)
+        for npx in (1, 15, 16, 1000, 1 << 20, (1 << 22) + 7):
+            pred = torch.randint(0, 21, (npx,), generator=g, dtype=torch.uint8)
+            truth = torch.randint(0, 21, (npx,), generator=g, dtype=torch.uint8)
+            cm = ctx.confusion(pred.cuda(), truth.cuda(), 19, truth_sub=1).cpu().numpy()
+            t = (truth.numpy().astype(np.int64) - 1) & 0xFF
+            p = pred.numpy().astype(np.int64)
+            m = (t < 19) & (p < 19)
+            ref = np.bincount(t[m] * 19 + p[m], minlength=361).reshape(19, 19)
+            ok = bool((cm == ref).all())
+            log(f"CASE confusion_{npx}: {'OK ' if ok else 'FAIL'} sum={cm.sum()} ref={ref.sum()}")
+            RESULTS.append({"case": f"confusion_{npx}", "ok": ok})
+
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "probe.json").write_text(json.dumps(RESULTS, indent=1))
+    nfail = sum(1 for r in RESULTS if not r["ok"])
+    log(f"DONE {len(RESULTS)} cases, {nfail} failed")
+    return 1 if nfail else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
