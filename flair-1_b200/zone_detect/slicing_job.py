@@ -1,0 +1,96 @@
+"""Tile grid of the sliding-window job, in integer pixel space.
+
+Replaces `slice_extent` (src/zone_detect/slicing_job.py:19-118). The reference works in geographic
+floats and builds a GeoDataFrame of shapely boxes; for a north-up, pixel-aligned raster the same grid
+is exact integer arithmetic, which is what the GPU tile table needs:
+
+  x_k  = -margin + k*stride  for k = 0.. while x_k < W + margin      (np.arange at :51)
+  x_k := W + margin - size   when x_k + size > W + margin            (:57-58, last column clamp)
+  y is measured from the raster's BOTTOM edge the same way           (:52, :62-63)
+  interior = [x+m, min(x+size-m, W)) x [yb+m, min(yb+size-m, H))     (:67-70)
+  rows are appended x-major / y-minor, duplicates (same interior) dropped (:78-86)
+
+The write order of the reference's hot loop is the row order and later writes overwrite earlier ones
+(main.py:409-426), so every pixel belongs to the LAST tile whose interior covers it. The ownership is
+separable per axis and is resolved here once, giving each tile a half-open write rectangle.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+TILE_FIELDS = ("x0", "y0", "wx0", "wy0", "wx1", "wy1")
+
+
+def _axis_origins(extent: int, size: int, margin: int, stride: int) -> List[int]:
+    """Unique tile origins along one axis in first-appearance order (slicing_job.py:51-63, 78-86)."""
+    out: List[int] = []
+    k = -margin
+    while k < extent + margin:
+        o = extent + margin - size if k + size > extent + margin else k
+        if o not in out:
+            out.append(o)
+        k += stride
+    return out
+
+
+def _axis_ownership(origins: List[int], extent: int, size: int, margin: int) -> List[Tuple[int, int]]:
+    """For each origin (in write order) the half-open interval of [0, extent) it owns: the interior
+    [o+m, min(o+size-m, extent)) minus everything a later origin's interior covers."""
+    owner = np.full(extent, -1, dtype=np.int64)
+    for i, o in enumerate(origins):
+        a, b = max(o + margin, 0), min(o + size - margin, extent)
+        if b > a:
+            owner[a:b] = i
+    res = []
+    for i in range(len(origins)):
+        idx = np.flatnonzero(owner == i)
+        if idx.size == 0:
+            res.append((0, 0))
+            continue
+        if idx[-1] - idx[0] + 1 != idx.size:
+            raise ValueError("non-contiguous tile ownership (tile grid with stride > interior is not supported)")
+        res.append((int(idx[0]), int(idx[-1]) + 1))
+    return res
+
+
+def tile_table(width: int, height: int, size: int, margin: int, stride: int = 0) -> np.ndarray:
+    """int32 [n, 6] rows (x0, y0, wx0, wy0, wx1, wy1) in the reference's write order; pixel
+    coordinates with y growing downwards; (x0, y0) = top-left of the margin-expanded tile."""
+    if stride <= 0:
+        stride = size - 2 * margin
+    if stride <= 0:
+        raise ValueError("stride must be positive (2*margin < img_pixels_detection)")
+    xs = _axis_origins(width, size, margin, stride)
+    ybs = _axis_origins(height, size, margin, stride)       # measured from the bottom edge
+    own_x = _axis_ownership(xs, width, size, margin)
+    own_yb = _axis_ownership(ybs, height, size, margin)
+    rows = []
+    for ix, x in enumerate(xs):
+        for iy, yb in enumerate(ybs):
+            wx0, wx1 = own_x[ix]
+            b0, b1 = own_yb[iy]                              # from-bottom interval
+            rows.append((x, height - (yb + size), wx0, height - b1, wx1, height - b0))
+    return np.asarray(rows, dtype=np.int32).reshape(-1, 6)
+
+
+def tile_interiors(width: int, height: int, size: int, margin: int, stride: int = 0) -> np.ndarray:
+    """int64 [n, 4] (left, bottom, right, top) interior boxes in pixel units from the raster's
+    bottom-left corner, same order as tile_table -- the `left/bottom/right/top` columns of the
+    reference dataframe divided by the resolution."""
+    if stride <= 0:
+        stride = size - 2 * margin
+    xs = _axis_origins(width, size, margin, stride)
+    ybs = _axis_origins(height, size, margin, stride)
+    return np.asarray([(x + margin, yb + margin, min(x + size - margin, width), min(yb + size - margin, height))
+                       for x in xs for yb in ybs], dtype=np.int64).reshape(-1, 4)
+
+
+def split_rows_across_ranks(tiles: np.ndarray, world_size: int) -> List[np.ndarray]:
+    """Shard the tile table by tile *rows* (equal y0) into `world_size` contiguous groups balanced by
+    tile count; each rank then needs raster rows [min y0, max y0 + size) only. Returns index arrays
+    into `tiles` that keep the original (write) order inside each shard."""
+    y_vals = np.unique(tiles[:, 1])
+    groups = np.array_split(y_vals, world_size)
+    return [np.flatnonzero(np.isin(tiles[:, 1], g)) for g in groups]
