@@ -66,6 +66,8 @@ _SIGNATURES = {
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "fb_debug_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "fb_profile_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "fb_profile_begin": (C.c_int, [C.c_void_p]),
+    "fb_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fb_launch_count": (C.c_int64, [C.c_void_p]),
 }
 
@@ -291,6 +293,14 @@ class Context:
         out = torch.empty(tuple(dims), dtype=dt, device=self.device)
         self._check(self._lib.fb_debug_activation(self._h, name.encode(), out.data_ptr(), C.byref(cnt), dims))
         return out
+
+    def profile_begin(self) -> None:
+        self._check(self._lib.fb_profile_begin(self._h))
+
+    def profile_end(self) -> dict:
+        ms = (C.c_float * 4)()
+        self._check(self._lib.fb_profile_end(self._h, ms))
+        return {"extract_ms": ms[0], "conv_ms": ms[1], "pool_mlp_ms": ms[2], "stitch_ms": ms[3]}
 
     def profile_forward(self, n: int, tile: int, iters: int = 3) -> dict:
         ms = (C.c_float * 5)()

@@ -335,7 +335,6 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, bool u
   if (a.C1 + a.C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
   const bool tma = !c->force_gather && L.KH == 3 && L.stride == 1 && L.pad == 1 && !x2 && !up1 &&
                    a.C1 % 64 == 0 && a.Hout % 8 == 0 && a.Wout % 16 == 0;
-  ProfScope ps(c, 1);
   const int rc = fb::launch_conv(a, L.w, L.Kpad, tma, c->num_sms, c->stream);
   if (rc != 0) return fail(c, rc, "conv launch failed (code " + std::to_string(rc) + ")");
   c->launches++;
@@ -346,7 +345,10 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, bool u
 int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
   auto A = [&](const std::string& k) -> Act& { return c->acts[k]; };
   auto L = [&](const std::string& k) -> const ConvLayer& { return c->conv[k]; };
-  FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, false, nullptr, nullptr, true, A("f1")));
+  {
+    ProfScope ps(c, 1);
+    FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, false, nullptr, nullptr, true, A("f1")));
+  }
   {
     ProfScope ps(c, 2);
     Act& f1 = A("f1");
@@ -356,6 +358,7 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
     if (rc) return fail(c, rc, "maxpool launch failed");
     c->launches++;
   }
+  ProfScope ps_convs(c, 1);  // every launch from here to the end of the function is a conv
   std::string cur = "pool";
   for (int st = 0; st < 4; ++st) {
     char nm[64], tmp[64], ds[64];
@@ -807,6 +810,30 @@ int fb_debug_activation(fb_ctx* c, const char* name, void* out_dev, int64_t* cou
   if (count) *count = n;
   if (dims4) { dims4[0] = a.B; dims4[1] = a.H; dims4[2] = a.W; dims4[3] = a.C; }
   if (out_dev) FB_CUDA(c, cudaMemcpyAsync(out_dev, a.ptr, static_cast<size_t>(n) * a.elem, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int fb_profile_begin(fb_ctx* c) {
+  if (!c) return FB_ERR_INVALID;
+  for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  c->prof_recs.clear();
+  c->prof = true;
+  return 0;
+}
+
+int fb_profile_end(fb_ctx* c, float* ms4) {
+  if (!c || !ms4) return FB_ERR_INVALID;
+  c->prof = false;
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  double acc[4] = {0, 0, 0, 0};
+  for (auto& r : c->prof_recs) {
+    float m = 0;
+    if (cudaEventElapsedTime(&m, r.a, r.b) == cudaSuccess && r.cat >= 0 && r.cat < 4) acc[r.cat] += m;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c->prof_recs.clear();
+  for (int i = 0; i < 4; ++i) ms4[i] = static_cast<float>(acc[i]);
   return 0;
 }
 

@@ -144,6 +144,12 @@ int fb_debug_activation(fb_ctx* ctx, const char* name, void* out_dev, int64_t* c
  * family in ms (CUDA events on the context's stream): [0]=extract [1]=conv(all) [2]=maxpool+mlp
  * [3]=argmax/stitch [4]=total. */
 int fb_profile_forward(fb_ctx* ctx, int n, int tile, int iters, float* ms5);
+/* Device-time accounting over any region of calls on this context: between fb_profile_begin and
+ * fb_profile_end every kernel family is bracketed by CUDA events on the context's stream (two events
+ * per family per batch, not per launch). ms4: [0]=extract [1]=conv kernels [2]=maxpool+mlp
+ * [3]=argmax/stitch, summed over the region. fb_profile_end synchronises the stream. */
+int fb_profile_begin(fb_ctx* ctx);
+int fb_profile_end(fb_ctx* ctx, float* ms4);
 /* Number of kernels this library has launched on the context since creation. */
 int64_t fb_launch_count(const fb_ctx* ctx);
 

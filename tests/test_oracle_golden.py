@@ -1,0 +1,177 @@
+"""The oracle against vectors produced by the reference's own code (tests/golden/make_golden.py),
+and the product's integer tile grid against the same vectors. CPU only."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import flair_ref, metrics_ref, tiles_ref, zone_detect_ref as zref
+from flair1_b200.zone_detect import slicing_job, tiles as ptiles
+
+
+def _case_rows(case):
+    spec = case["spec"]
+    W, H, res, ox, oy = spec
+    rows = zref.slice_extent((ox, oy, ox + W * res, oy + H * res), (res, res), case["size"], case["margin"], case["stride"])
+    return np.array([[r["left"], r["bottom"], r["right"], r["top"], *r["geometry"]] for r in rows], dtype=np.float64)
+
+
+def test_slice_extent_oracle_matches_reference(golden):
+    for case in golden["slice_extent"]:
+        arr = _case_rows(case)
+        assert len(arr) == case["n"], case["spec"]
+        if "rows" in case:
+            np.testing.assert_allclose(arr, np.array(case["rows"]), rtol=0, atol=1e-6)
+        else:
+            np.testing.assert_allclose(arr[:50], np.array(case["rows_head"]), rtol=0, atol=1e-6)
+            np.testing.assert_allclose(arr[-50:], np.array(case["rows_tail"]), rtol=0, atol=1e-6)
+            np.testing.assert_allclose(arr.sum(axis=0), np.array(case["rows_sum"]), rtol=1e-12)
+
+
+def test_integer_tile_grid_matches_reference(golden):
+    """The product's pixel-space grid reproduces the reference dataframe (interior boxes, tile
+    geometry, order, de-duplication) for every pixel-aligned golden raster."""
+    for case in golden["slice_extent"]:
+        W, H, res, ox, oy = case["spec"]
+        size, margin = case["size"], case["margin"]
+        t = slicing_job.tile_table(int(W), int(H), size, margin, case["stride"])
+        ints = slicing_job.tile_interiors(int(W), int(H), size, margin, case["stride"])
+        assert len(t) == case["n"], (case["spec"], size, margin)
+        ref = np.array(case["rows"]) if "rows" in case else None
+        if ref is None:
+            head = np.array(case["rows_head"])
+            geo = np.stack([(head[:, 0] - ox) / res, (head[:, 1] - oy) / res, (head[:, 2] - ox) / res, (head[:, 3] - oy) / res], 1)
+            np.testing.assert_allclose(ints[:50], geo, atol=1e-3)
+            continue
+        geo = np.stack([(ref[:, 0] - ox) / res, (ref[:, 1] - oy) / res, (ref[:, 2] - ox) / res, (ref[:, 3] - oy) / res], 1)
+        np.testing.assert_allclose(ints, geo, atol=1e-3)
+        # tile origin (top-left, y down) against the margin-expanded geometry bounds
+        x0 = (ref[:, 4] - ox) / res
+        y0 = H - (ref[:, 7] - oy) / res
+        np.testing.assert_allclose(t[:, 0], x0, atol=1e-3)
+        np.testing.assert_allclose(t[:, 1], y0, atol=1e-3)
+
+
+def test_write_rects_replay_reference_write_order(golden):
+    """Painting interiors in row order with later tiles overwriting (main.py:409-426) must give the
+    same owner per pixel as the precomputed write rectangles."""
+    for case in golden["slice_extent"]:
+        W, H = int(case["spec"][0]), int(case["spec"][1])
+        if W * H > 4_000_000 or "rows" not in case:
+            continue
+        size, margin = case["size"], case["margin"]
+        t = slicing_job.tile_table(W, H, size, margin, case["stride"])
+        ints = slicing_job.tile_interiors(W, H, size, margin, case["stride"])
+        owner = np.full((H, W), -1, np.int32)
+        for i, (l, b, r, tp) in enumerate(ints):
+            owner[max(H - tp, 0):H - b, max(l, 0):r] = i
+        mine = np.full((H, W), -1, np.int32)
+        for i, (x0, y0, wx0, wy0, wx1, wy1) in enumerate(t):
+            assert (mine[wy0:wy1, wx0:wx1] == -1).all()
+            mine[wy0:wy1, wx0:wx1] = i
+        assert (mine == owner).all() and (mine >= 0).all()
+
+
+def test_get_stride_and_weights(golden):
+    for g in golden["get_stride"]:
+        assert zref.get_stride(g["config"]) == g["stride"]
+        assert ptiles.get_stride(g["config"]) == g["stride"]
+    z = np.load(GOLDEN / "tiles_weights.npz")
+    for n, k in ((512, "w512"), (128, "w128"), (7, "w7")):
+        np.testing.assert_array_equal(tiles_ref.patch_weights(n, 0.5), z[k])
+        np.testing.assert_array_equal(ptiles.patch_weights(n, 0.5), z[k])
+    np.testing.assert_array_equal(tiles_ref.total_weights((1000, 700), 256, [100, 600, 50, 500], 128), z["tw_a"])
+    np.testing.assert_array_equal(tiles_ref.total_weights((64, 64), 16, [0, 64, 0, 64], 8), z["tw_b"])
+    np.testing.assert_array_equal(tiles_ref.patch_overlap((1000, 700), 256, [100, 600, 50, 500], 128), z["ov_a"])
+    np.testing.assert_array_equal(tiles_ref.patch_overlap((64, 64), 16, [0, 64, 0, 64], 8), z["ov_b"])
+    for g in golden["get_tile_coord"]:
+        assert sorted(tiles_ref.get_tile_coord(*g["args"])) == g["coords"]
+
+
+def test_convert_and_normalisation():
+    z = np.load(GOLDEN / "convert_norm.npz")
+    np.testing.assert_array_equal(zref.convert(z["probs"], "argmax"), z["argmax"])
+    np.testing.assert_array_equal(zref.convert(z["probs"], "class_prob"), z["class_prob"])
+    means, stds = list(z["means"]), list(z["stds"])
+    np.testing.assert_array_equal(zref.normalization(z["img"], "custom", means, stds), z["zone_custom"])
+    np.testing.assert_array_equal(zref.normalization(z["img"], "scaling", means, stds), z["zone_scaling"])
+    np.testing.assert_array_equal(flair_ref.norm(z["img"].copy(), "custom", means, stds), z["flair_custom"])
+    np.testing.assert_array_equal(flair_ref.norm(z["img"].copy(), "scaling"), z["flair_scaling"])
+    np.testing.assert_array_equal(flair_ref.norm(z["img"].copy(), "without"), z["flair_without"])
+    with pytest.raises(SystemExit):
+        flair_ref.norm(z["img"].copy(), "bogus")
+
+
+def test_metric_formulas(golden):
+    for name in ("kat", "rand19"):
+        g = golden["metrics"][name]
+        cm = np.array(g["cm"])
+        iou, miou = metrics_ref.class_IoU(cm)
+        p, ap = metrics_ref.class_precision(cm)
+        r, ar = metrics_ref.class_recall(cm)
+        f, af = metrics_ref.class_fscore(p, r)
+        np.testing.assert_array_equal(iou, np.array(g["iou"]))
+        assert miou == g["miou"] == g["z_miou"]
+        assert metrics_ref.overall_accuracy(cm) == g["oa"] == g["z_oa"]
+        np.testing.assert_array_equal(p, np.array(g["precision"]))
+        np.testing.assert_array_equal(r, np.array(g["recall"]))
+        np.testing.assert_array_equal(f, np.array(g["fscore"]))
+        np.testing.assert_array_equal(f, np.array(g["z_fscore"]))
+        assert [ap, ar, af] == g["avg"]
+    g = golden["metrics"]["kat"]  # hand-computable known answer
+    np.testing.assert_allclose(g["iou"], [62.5, 50.0, 0.0])
+    assert abs(g["miou"] - 37.5) < 1e-12 and abs(g["oa"] - 72.72727272727273) < 1e-9
+    classes = {int(k): v for k, v in golden["classes19"].items()}
+    cleaned = metrics_ref.clean_confmat(np.array(golden["metrics"]["rand19"]["cm"]), classes)
+    np.testing.assert_array_equal(cleaned, np.array(golden["metrics"]["clean_confmat_rand19"]))
+
+
+def test_confusion_matrix_restatements():
+    z = np.load(GOLDEN / "confusion.npz")
+    np.testing.assert_array_equal(metrics_ref.confusion_numpy(z["truth"], z["pred"], 19, 1), z["cm"])
+    np.testing.assert_array_equal(metrics_ref.patch_confusion(z["truth"] - 1, z["pred"], 19), z["cm"])
+    assert z["cm"].dtype == np.int64
+
+
+def test_metadata_encoding(golden):
+    md = json.loads((GOLDEN / "metadata_aerial.json").read_text())
+    g = golden["parsing_metadata"]
+    enc = flair_ref.parsing_metadata(g["images"], md)
+    assert np.array(enc).shape == (3, 45)
+    np.testing.assert_array_equal(np.array(enc), np.array(g["encoded"]))
+
+
+def test_checkpoint_key_handling(golden):
+    import torch
+    g = golden["checkpoint"]
+    sd = {"model.seg_model.encoder.conv1.weight": torch.ones(1), "model.seg_model.segmentation_head.0.bias": torch.zeros(2),
+          "model.enc.enc_mlp.0.weight": torch.ones(3), "criterion.weight": torch.ones(2)}
+    assert sorted(flair_ref.get_module(sd, False).keys()) == g["pth_prefixed"]
+    assert sorted(flair_ref.get_module({"state_dict": sd}, True).keys()) == g["ckpt_prefixed"]
+    assert sorted(flair_ref.get_module({"encoder.conv1.weight": torch.ones(1)}, False).keys()) == g["pth_bare"]
+    s = g["surgery"]
+    src = {k: torch.tensor(v) for k, v in s["src"].items()}
+    dst_shapes = {"head.weight": torch.zeros(3, 4, 3, 3), "head.bias": torch.zeros(3), "criterion.weight": torch.zeros(3)}
+    out = flair_ref.load_checkpoint_state(src, dst_shapes, {int(k): v for k, v in s["classes"].items()})
+    for k, v in s["dst"].items():
+        np.testing.assert_array_equal(np.asarray(out[k]), np.array(v, dtype=np.float32))
+
+
+def test_unet_restatement_pins():
+    """What can be pinned about the un-vendored network: key set, parameter count (README.md:91),
+    output shape, divisibility check."""
+    import torch
+    from oracle.unet_smp033 import Unet
+    from flair1_b200.zone_detect.model import expected_keys
+    m = Unet(3, 15)
+    sd = m.state_dict()
+    assert len(sd) == 278
+    assert sum(p.numel() for p in m.parameters()) == 24_438_399
+    assert {k for k in sd if not k.endswith("num_batches_tracked")} == expected_keys()
+    m.eval()
+    with torch.no_grad():
+        assert m(torch.zeros(1, 3, 64, 64)).shape == (1, 15, 64, 64)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 65, 64))
+    assert Unet(5, 19).state_dict()["encoder.conv1.weight"].shape == (64, 5, 7, 7)
