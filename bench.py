@@ -47,7 +47,7 @@ def synth_rows_gpu(width: int, height: int, y0: int, y1: int, seed: int, device)
     the family the synthetic checkpoint was trained on). Row blocks of 512 are generated from
     (seed, block index) so any rank materialises identical bytes for the same global rows."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    lh, lw = height // 64 + 4, width // 64 + 4
+    lh, lw = (height + 511) // 512 * 8 + 4, (width + 63) // 64 + 4
     low = torch.randn((1, BANDS, lh, lw), generator=g).to(device)
     out = torch.empty((BANDS, y1 - y0, width), dtype=torch.uint8, device=device)
     blk = 512

@@ -69,6 +69,9 @@ _SIGNATURES = {
     "fb_profile_begin": (C.c_int, [C.c_void_p]),
     "fb_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fb_launch_count": (C.c_int64, [C.c_void_p]),
+    "fb_lzw_bound": (C.c_int64, [C.c_int64]),
+    "fb_lzw_encode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
+    "fb_lzw_decode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -320,3 +323,26 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: Optional[int] = None, cout_pad: O
     out = torch.zeros((cout_pad, kpad), dtype=torch.float32)
     out[:, :ktot] = p.reshape(cout_pad, ktot)
     return out.to(torch.bfloat16)
+
+
+def lzw_encode(data: bytes | np.ndarray) -> bytes:
+    """TIFF-LZW encode a byte block (host codec in libflairb200, GIL released during the call)."""
+    lib = load_library()
+    src = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8).ravel()
+    cap = int(lib.fb_lzw_bound(src.size))
+    dst = np.empty(cap, np.uint8)
+    n = lib.fb_lzw_encode(src.ctypes.data, src.size, dst.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("fb_lzw_encode failed")
+    return dst[:n].tobytes()
+
+
+def lzw_decode(data: bytes, expected: int) -> np.ndarray:
+    """TIFF-LZW decode into exactly `expected` bytes (short streams are zero-padded like libtiff)."""
+    lib = load_library()
+    src = np.frombuffer(data, dtype=np.uint8)
+    dst = np.zeros(expected, np.uint8)
+    n = lib.fb_lzw_decode(src.ctypes.data, src.size, dst.ctypes.data, expected)
+    if n < 0:
+        raise RuntimeError("corrupt LZW stream")
+    return dst

@@ -18,7 +18,7 @@ INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libflairb200.so"
 STAMP = PKG_DIR / ".libflairb200.stamp"
 
-SOURCES = ["conv_igemm.cu", "elementwise.cu", "api.cu"]
+SOURCES = ["conv_igemm.cu", "elementwise.cu", "api.cu", "host_codec.cu"]
 HEADERS = ["ptx.cuh", "conv_igemm.cuh", "elementwise.cuh"]
 
 NVCC_FLAGS = [

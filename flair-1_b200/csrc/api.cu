@@ -754,7 +754,9 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
 
 int fb_confusion(fb_ctx* c, const uint8_t* pred_dev, const uint8_t* truth_dev, int64_t npx, int ncls,
                  int truth_sub, int64_t* cm_dev) {
-  if (!c || !pred_dev || !truth_dev || !cm_dev || npx < 0) return FB_ERR_INVALID;
+  if (!c) return FB_ERR_INVALID;
+  if (npx == 0) return 0;
+  if (!pred_dev || !truth_dev || !cm_dev || npx < 0) return fail(c, FB_ERR_INVALID, "confusion: null pointer or negative size");
   if (ncls < 1 || ncls > 32) return fail(c, FB_ERR_INVALID, "confusion: ncls must be in 1..32");
   FB_CUDA(c, cudaSetDevice(c->device));
   int rc = fb::launch_confusion(pred_dev, truth_dev, npx, ncls, truth_sub & 0xFF, reinterpret_cast<long long*>(cm_dev),

@@ -153,6 +153,13 @@ int fb_profile_end(fb_ctx* ctx, float* ms4);
 /* Number of kernels this library has launched on the context since creation. */
 int64_t fb_launch_count(const fb_ctx* ctx);
 
+/* ---- host-side TIFF LZW codec (compression 5, libtiff/GDAL-compatible) used by the GeoTIFF
+ *      reader/writer that stands in for rasterio (main.py:218-232, 421-426; writer.py:38-50).
+ *      encode/decode return the number of bytes produced, or -1 (buffer too small / corrupt). */
+int64_t fb_lzw_bound(int64_t n);
+int64_t fb_lzw_encode(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
+int64_t fb_lzw_decode(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif
