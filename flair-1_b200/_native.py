@@ -64,6 +64,8 @@ _SIGNATURES = {
     "fb_conv2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "fb_conv2d_halo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fb_debug_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "fb_profile_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "fb_profile_begin": (C.c_int, [C.c_void_p]),
@@ -286,6 +288,23 @@ class Context:
         self._check(self._lib.fb_conv2d(self._h, x1.data_ptr(), _ptr(x2), C1, C2, int(up1), B, Hin, Win, KH, KW, stride, pad,
                                         Cout, weights.data_ptr(), Kpad, bias.data_ptr(), _ptr(residual), _ptr(rowbias),
                                         int(relu), None if out_f32 else out.data_ptr(), out.data_ptr() if out_f32 else None, mode))
+        return out
+
+    def conv2d_halo(self, x1: torch.Tensor, w_oihw: torch.Tensor, bias: torch.Tensor, KH: int, stride: int,
+                    x2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, relu: bool = False,
+                    up2_out: bool = False, out_f32: bool = False) -> torch.Tensor:
+        """Test hook: halo-staged conv. w_oihw: host fp32 [Cout, C1+C2, KH, KH] (folded weights)."""
+        B, H, W, C1 = x1.shape
+        C2 = 0 if x2 is None else x2.shape[3]
+        Cout = w_oihw.shape[0]
+        pad = KH // 2
+        Hout, Wout = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KH) // stride + 1
+        m = 2 if up2_out else 1
+        out = torch.empty((B, Hout * m, Wout * m, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
+        w = np.ascontiguousarray(w_oihw.detach().cpu().float().numpy())
+        self._check(self._lib.fb_conv2d_halo(self._h, x1.data_ptr(), _ptr(x2), C1, C2, B, H, W, KH, stride, Cout, w.ctypes.data,
+                                             bias.data_ptr(), _ptr(residual), int(relu), int(up2_out),
+                                             None if out_f32 else out.data_ptr(), out.data_ptr() if out_f32 else None))
         return out
 
     def debug_activation(self, name: str) -> torch.Tensor:

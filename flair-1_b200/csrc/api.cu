@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/flair_b200.h"
+#include "conv_halo.cuh"
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
 
@@ -23,15 +24,18 @@ namespace {
 std::string g_create_error;
 
 struct ConvLayer {
-  __nv_bfloat16* w = nullptr;  // device [Cout][Kpad]
-  float* bias = nullptr;       // device [Cout]
+  __nv_bfloat16* w = nullptr;       // device [Cout][Kpad] (im2col order, TMA / gather producers)
+  __nv_bfloat16* w_halo = nullptr;  // device, K-step order of the halo-staged kernel (or null)
+  float* bias = nullptr;            // device [Cout]
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
+  int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
 };
 
 struct Act {  // a named NHWC bf16 (or fp32) activation in the arena
   void* ptr = nullptr;
-  int B = 0, H = 0, W = 0, C = 0;
+  int B = 0, H = 0, W = 0, C = 0;   // stored dims (already doubled when up2)
   int elem = 2;
+  bool up2 = false;                 // producer writes it 2x2-replicated (decoder nearest x2 upsample)
 };
 
 struct ProfRec {
@@ -47,7 +51,8 @@ struct fb_ctx {
   int num_sms = 148;
   std::string err;
   int64_t launches = 0;
-  bool force_gather = false;
+  bool force_gather = false;  // FB_FORCE_GATHER=1: cp.async im2col producer everywhere (debug / A-B tests)
+  bool no_halo = false;       // FB_NO_HALO=1: skip the halo-staged kernel
 
   // model
   bool loaded = false;
@@ -150,7 +155,7 @@ int64_t numel(const fb_tensor_desc* t) {
 // bf16 [CoutPad][Kpad] with k = (kh*KW + kw)*CinPad + cin, fp32 bias [CoutPad].
 int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const std::string& wkey,
                const std::string& bn, const std::string& bkey, int Cin, int Cout, int KH, int stride,
-               int pad) {
+               int pad, int C2 = 0) {
   const fb_tensor_desc* w = find(tm, wkey);
   if (!w) return fail(c, FB_ERR_WEIGHTS, "missing tensor " + wkey);
   if (w->ndim != 4 || w->shape[0] != Cout || w->shape[1] != Cin || w->shape[2] != KH || w->shape[3] != KH)
@@ -182,16 +187,30 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
   L.Cin = CinPad; L.Cout = CoutPad; L.KH = KH; L.KW = KH; L.stride = stride; L.pad = pad;
   L.Ktot = KH * KH * CinPad;
   L.Kpad = (L.Ktot + 63) / 64 * 64;
+  L.C2 = C2;
+  L.C1 = CinPad - C2;
   std::vector<uint16_t> packed(static_cast<size_t>(CoutPad) * L.Kpad, 0);
   std::vector<float> bias(CoutPad, 0.f);
+  std::vector<float> folded(static_cast<size_t>(Cout) * Cin * KH * KH);
   for (int o = 0; o < Cout; ++o) {
     bias[o] = static_cast<float>(shift[o]);
     for (int ci = 0; ci < Cin; ++ci)
       for (int kh = 0; kh < KH; ++kh)
         for (int kw = 0; kw < KH; ++kw) {
-          const double v = static_cast<double>(w->data[((static_cast<size_t>(o) * Cin + ci) * KH + kh) * KH + kw]) * scale[o];
-          packed[static_cast<size_t>(o) * L.Kpad + (kh * KH + kw) * CinPad + ci] = f32_to_bf16_rne(static_cast<float>(v));
+          const size_t wi = ((static_cast<size_t>(o) * Cin + ci) * KH + kh) * KH + kw;
+          const float v = static_cast<float>(static_cast<double>(w->data[wi]) * scale[o]);
+          folded[wi] = v;
+          packed[static_cast<size_t>(o) * L.Kpad + (kh * KH + kw) * CinPad + ci] = f32_to_bf16_rne(v);
         }
+  }
+  // second packing for the halo-staged kernel when the channel configuration has an instantiation
+  if (fb::halo_supported(KH, stride, L.C1, L.C2, CoutPad, 16, 8)) {
+    const size_t n = fb::pack_halo_weights(folded.data(), Cout, CoutPad, Cin, CinPad, KH, stride, L.C1, L.C2, nullptr);
+    std::vector<uint16_t> hp(n);
+    fb::pack_halo_weights(folded.data(), Cout, CoutPad, Cin, CinPad, KH, stride, L.C1, L.C2, hp.data());
+    FB_CUDA(c, cudaMalloc(&L.w_halo, n * 2));
+    c->owned.push_back(L.w_halo);
+    FB_CUDA(c, cudaMemcpy(L.w_halo, hp.data(), n * 2, cudaMemcpyHostToDevice));
   }
   FB_CUDA(c, cudaMalloc(&L.w, packed.size() * 2));
   c->owned.push_back(L.w);
@@ -218,12 +237,14 @@ const int kStageBlocks[4] = {3, 4, 6, 3};
 const int kStageCh[4] = {64, 128, 256, 512};
 const int kDecOut[5] = {256, 128, 64, 32, 16};
 
-int arena_alloc(fb_ctx* c, const std::string& name, int B, int H, int W, int C, int elem, bool dry) {
+int arena_alloc(fb_ctx* c, const std::string& name, int B, int H, int W, int C, int elem, bool dry,
+                bool up2 = false) {
+  if (up2) { H *= 2; W *= 2; }
   const size_t bytes = (static_cast<size_t>(B) * H * W * C * elem + 1023) / 1024 * 1024;
   if (!dry) {
     Act a;
     a.ptr = c->arena + c->arena_used;
-    a.B = B; a.H = H; a.W = W; a.C = C; a.elem = elem;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.elem = elem; a.up2 = up2;
     c->acts[name] = a;
   }
   c->arena_used += bytes;
@@ -248,7 +269,8 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     }
     for (int b = 0; b < kStageBlocks[st]; ++b) {
       snprintf(buf, sizeof buf, "layer%d.%d.out", st + 1, b);
-      arena_alloc(c, buf, n, S, S, C, 2, dry);
+      // the bottleneck feature only feeds decoder block 0, which reads it through the x2 upsample
+      arena_alloc(c, buf, n, S, S, C, 2, dry, st == 3 && b == kStageBlocks[st] - 1);
     }
     S /= 2;
   }
@@ -258,7 +280,7 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     snprintf(buf, sizeof buf, "dec%d.mid", d);
     arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry);
     snprintf(buf, sizeof buf, "dec%d", d);
-    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry);
+    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry, d < 4);  // dec0..3 feed the next block upsampled
     S *= 2;
   }
   arena_alloc(c, "logits", n, T, T, 16, 4, dry);
@@ -311,31 +333,53 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 }
 
 // ---------------------------------------------------------------------------------- graph
-int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, bool up1, const Act* res,
+int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const Act* res,
              const float* rowbias, bool relu, const Act& out) {
-  fb::ConvArgs a;
-  memset(&a, 0, sizeof a);
-  a.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
-  a.x2 = x2 ? static_cast<const __nv_bfloat16*>(x2->ptr) : nullptr;
-  a.C1 = x1.C;
-  a.C2 = x2 ? x2->C : 0;
-  a.up1 = up1 ? 1 : 0;
-  a.B = x1.B;
-  a.Hin = up1 ? x1.H * 2 : x1.H;
-  a.Win = up1 ? x1.W * 2 : x1.W;
-  a.Hout = out.H; a.Wout = out.W;
-  a.KH = L.KH; a.KW = L.KW; a.stride = L.stride; a.pad = L.pad;
-  a.Cout = L.Cout;
-  a.Ktot = L.Ktot;
-  a.bias = L.bias;
-  a.residual = res ? static_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
-  a.rowbias = rowbias;
-  a.relu = relu ? 1 : 0;
-  if (out.elem == 4) a.out_f32 = static_cast<float*>(out.ptr); else a.out = static_cast<__nv_bfloat16*>(out.ptr);
-  if (a.C1 + a.C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
-  const bool tma = !c->force_gather && L.KH == 3 && L.stride == 1 && L.pad == 1 && !x2 && !up1 &&
-                   a.C1 % 64 == 0 && a.Hout % 8 == 0 && a.Wout % 16 == 0;
-  const int rc = fb::launch_conv(a, L.w, L.Kpad, tma, c->num_sms, c->stream);
+  // `out` may be stored 2x2-replicated (Act::up2): the conv itself runs at half those dims
+  const int Hout = out.up2 ? out.H / 2 : out.H, Wout = out.up2 ? out.W / 2 : out.W;
+  const int C1 = x1.C, C2 = x2 ? x2->C : 0;
+  if (C1 + C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
+  if (x2 && (x2->H != x1.H || x2->W != x1.W)) return fail(c, FB_ERR_INVALID, "internal: skip tensor shape mismatch");
+  int rc;
+  if (!c->force_gather && !c->no_halo && L.w_halo && L.C1 == C1 && L.C2 == C2 &&
+      fb::halo_supported(L.KH, L.stride, C1, C2, L.Cout, Hout, Wout)) {
+    fb::HaloArgs h;
+    memset(&h, 0, sizeof h);
+    h.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
+    h.x2 = x2 ? static_cast<const __nv_bfloat16*>(x2->ptr) : nullptr;
+    h.C1 = C1; h.C2 = C2;
+    h.B = x1.B; h.Hin = x1.H; h.Win = x1.W; h.Hout = Hout; h.Wout = Wout;
+    h.Cout = L.Cout;
+    h.bias = L.bias;
+    h.residual = res ? static_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
+    h.rowbias = rowbias;
+    h.relu = relu ? 1 : 0;
+    if (out.elem == 4) h.out_f32 = static_cast<float*>(out.ptr); else h.out = static_cast<__nv_bfloat16*>(out.ptr);
+    h.up2_out = out.up2 ? 1 : 0;
+    h.wpacked = L.w_halo;
+    fb::halo_fill_steps(h, L.KH, L.stride);
+    rc = fb::launch_conv_halo(h, L.KH, L.stride, c->num_sms, c->stream);
+  } else {
+    fb::ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
+    a.x2 = x2 ? static_cast<const __nv_bfloat16*>(x2->ptr) : nullptr;
+    a.C1 = C1; a.C2 = C2;
+    a.up1 = 0;
+    a.B = x1.B; a.Hin = x1.H; a.Win = x1.W;
+    a.Hout = Hout; a.Wout = Wout;
+    a.KH = L.KH; a.KW = L.KW; a.stride = L.stride; a.pad = L.pad;
+    a.Cout = L.Cout;
+    a.Ktot = L.Ktot;
+    a.bias = L.bias;
+    a.residual = res ? static_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
+    a.rowbias = rowbias;
+    a.relu = relu ? 1 : 0;
+    if (out.elem == 4) a.out_f32 = static_cast<float*>(out.ptr); else a.out = static_cast<__nv_bfloat16*>(out.ptr);
+    a.up2_out = out.up2 ? 1 : 0;
+    const bool tma = !c->force_gather && fb::conv_tma_eligible(a);
+    rc = fb::launch_conv(a, L.w, L.Kpad, tma, c->num_sms, c->stream);
+  }
   if (rc != 0) return fail(c, rc, "conv launch failed (code " + std::to_string(rc) + ")");
   c->launches++;
   return 0;
@@ -347,7 +391,7 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
   auto L = [&](const std::string& k) -> const ConvLayer& { return c->conv[k]; };
   {
     ProfScope ps(c, 1);
-    FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, false, nullptr, nullptr, true, A("f1")));
+    FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, nullptr, nullptr, true, A("f1")));
   }
   {
     ProfScope ps(c, 2);
@@ -369,13 +413,13 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
       const std::string base(nm);
       const std::string outn = base + ".out";
       const Act* res = &A(cur);
-      FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), nullptr, false, nullptr, nullptr, true, A(tmp)));
+      FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), nullptr, nullptr, nullptr, true, A(tmp)));
       if (st > 0 && b == 0) {
-        FB_TRY(run_conv(c, L(base + ".downsample"), A(cur), nullptr, false, nullptr, nullptr, false, A(ds)));
+        FB_TRY(run_conv(c, L(base + ".downsample"), A(cur), nullptr, nullptr, nullptr, false, A(ds)));
         res = &A(ds);
       }
       const bool last = (st == 3 && b == kStageBlocks[st] - 1);
-      FB_TRY(run_conv(c, L(base + ".conv2"), A(tmp), nullptr, false, res, last ? menc_dev : nullptr, true, A(outn)));
+      FB_TRY(run_conv(c, L(base + ".conv2"), A(tmp), nullptr, res, last ? menc_dev : nullptr, true, A(outn)));
       cur = outn;
     }
   }
@@ -384,11 +428,11 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
     char nm[64];
     snprintf(nm, sizeof nm, "dec%d", d);
     const std::string base(nm);
-    FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, true, nullptr, nullptr, true, A(base + ".mid")));
-    FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, false, nullptr, nullptr, true, A(base)));
+    FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid")));
+    FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base)));
     cur = base;
   }
-  FB_TRY(run_conv(c, L("head"), A(cur), nullptr, false, nullptr, nullptr, false, A("logits")));
+  FB_TRY(run_conv(c, L("head"), A(cur), nullptr, nullptr, nullptr, false, A("logits")));
   return 0;
 }
 
@@ -476,6 +520,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   const char* fg = getenv("FB_FORCE_GATHER");
   c->force_gather = fg && fg[0] == '1';
+  const char* nh = getenv("FB_NO_HALO");
+  c->no_halo = nh && nh[0] == '1';
   *out = c;
   return 0;
 }
@@ -536,12 +582,13 @@ int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int
     }
   }
   const int dec_in[5] = {512 + 256, 256 + 128, 128 + 64, 64 + 64, 32};
+  const int dec_skip[5] = {256, 128, 64, 64, 0};
   for (int d = 0; d < 5; ++d) {
     char pre[96], nm[64];
     snprintf(pre, sizeof pre, "decoder.blocks.%d", d);
     snprintf(nm, sizeof nm, "dec%d", d);
     const std::string P(pre), N(nm);
-    FB_TRY(build_conv(c, tm, N + ".conv1", P + ".conv1.0.weight", P + ".conv1.1", "", dec_in[d], kDecOut[d], 3, 1, 1));
+    FB_TRY(build_conv(c, tm, N + ".conv1", P + ".conv1.0.weight", P + ".conv1.1", "", dec_in[d], kDecOut[d], 3, 1, 1, dec_skip[d]));
     FB_TRY(build_conv(c, tm, N + ".conv2", P + ".conv2.0.weight", P + ".conv2.1", "", kDecOut[d], kDecOut[d], 3, 1, 1));
   }
   FB_TRY(build_conv(c, tm, "head", "segmentation_head.0.weight", "", "segmentation_head.0.bias", 16, n_classes, 3, 1, 1));
@@ -789,8 +836,7 @@ int fb_conv2d(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, int up1
   a.relu = relu;
   a.out = static_cast<__nv_bfloat16*>(out_bf16);
   a.out_f32 = out_f32;
-  const bool can_tma = KH == 3 && KW == 3 && stride == 1 && pad == 1 && !x2 && !up1 && C1 % 64 == 0 &&
-                       a.Hout % 8 == 0 && a.Wout % 16 == 0;
+  const bool can_tma = fb::conv_tma_eligible(a);
   bool tma;
   if (mode == 1) {
     if (!can_tma) return fail(c, FB_ERR_INVALID, "conv2d: shape not eligible for the TMA producer");
@@ -799,6 +845,46 @@ int fb_conv2d(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, int up1
   else tma = can_tma && !c->force_gather;
   const int rc = fb::launch_conv(a, static_cast<const __nv_bfloat16*>(weights), Kpad, tma, c->num_sms, c->stream);
   if (rc) return fail(c, rc, "conv2d launch failed (code " + std::to_string(rc) + ")");
+  c->launches++;
+  return 0;
+}
+
+int fb_conv2d_halo(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, int B, int Hin, int Win, int KH,
+                   int stride, int Cout, const float* w_oihw_host, const float* bias, const void* residual,
+                   int relu, int up2_out, void* out_bf16, float* out_f32) {
+  if (!c || !x1 || !w_oihw_host || !bias || (!out_bf16 == !out_f32)) return FB_ERR_INVALID;
+  FB_CUDA(c, cudaSetDevice(c->device));
+  const int pad = KH / 2;
+  fb::HaloArgs h;
+  memset(&h, 0, sizeof h);
+  h.x1 = static_cast<const __nv_bfloat16*>(x1);
+  h.x2 = static_cast<const __nv_bfloat16*>(x2);
+  h.C1 = C1; h.C2 = x2 ? C2 : 0;
+  h.B = B; h.Hin = Hin; h.Win = Win;
+  h.Hout = (Hin + 2 * pad - KH) / stride + 1;
+  h.Wout = (Win + 2 * pad - KH) / stride + 1;
+  h.Cout = Cout;
+  h.bias = bias;
+  h.residual = static_cast<const __nv_bfloat16*>(residual);
+  h.relu = relu;
+  h.out = static_cast<__nv_bfloat16*>(out_bf16);
+  h.out_f32 = out_f32;
+  h.up2_out = up2_out;
+  if (!fb::halo_supported(KH, stride, h.C1, h.C2, Cout, h.Hout, h.Wout))
+    return fail(c, FB_ERR_INVALID, "conv2d_halo: no instantiation for this shape");
+  const int Cin = h.C1 + h.C2;
+  const size_t n = fb::pack_halo_weights(w_oihw_host, Cout, Cout, Cin, Cin, KH, stride, h.C1, h.C2, nullptr);
+  std::vector<uint16_t> hp(n);
+  fb::pack_halo_weights(w_oihw_host, Cout, Cout, Cin, Cin, KH, stride, h.C1, h.C2, hp.data());
+  __nv_bfloat16* wdev = nullptr;
+  FB_CUDA(c, cudaMalloc(&wdev, n * 2));
+  cudaMemcpy(wdev, hp.data(), n * 2, cudaMemcpyHostToDevice);
+  h.wpacked = wdev;
+  fb::halo_fill_steps(h, KH, stride);
+  const int rc = fb::launch_conv_halo(h, KH, stride, c->num_sms, c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(wdev);
+  if (rc) return fail(c, rc, "conv2d_halo launch failed (code " + std::to_string(rc) + ")");
   c->launches++;
   return 0;
 }

@@ -1,0 +1,326 @@
+// Halo-staged tcgen05 convolution (see conv_halo.cuh for the idea and the layers it serves).
+#include "conv_halo.cuh"
+
+#include <string.h>
+
+#include "conv_epilogue.cuh"
+#include "ptx.cuh"
+
+namespace fb {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kTH = 16, kTW = 8;          // output tile: 16 rows x 8 columns = 128 pixels (UMMA M)
+constexpr int kThreads = 288;             // warps 0-3 producers, 4-7 epilogue, 8 MMA issuer
+constexpr int kProducers = 128;
+constexpr int kStages = 4;
+constexpr int kLag = 2;                   // cp.async groups in flight per producer thread
+
+template <int KH, int STRIDE, int NCH>
+struct Geo {
+  static constexpr int PAD = KH / 2;
+  static constexpr int NP = STRIDE;                                    // w-parity planes
+  static constexpr int PH = STRIDE * (kTH - 1) + KH + (NCH == 1 ? 1 : 0);  // +1: stem pairs taps vertically
+  static constexpr int SPANW = STRIDE * (kTW - 1) + KH;
+  static constexpr int PW = (SPANW + NP - 1) / NP;
+  static constexpr int KWCELLS = NP * PW;
+  static constexpr int PLANE16 = PH * PW;                              // 16-byte cells per plane
+  static constexpr int STAGE = ((NCH * NP * PLANE16 * 16) + 127) / 128 * 128;
+  static constexpr int CELLS = PH * KWCELLS * NCH;
+  static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
+};
+
+// no-swizzle K-major shared-memory descriptor: rows of a core matrix 16 B apart (implicit),
+// LBO = distance between the two 8-element K chunks, SBO = distance between 8-row groups.
+__device__ __forceinline__ uint64_t desc_noswz(uint32_t start16, uint32_t lbo16, uint32_t sbo16) {
+  return static_cast<uint64_t>(start16 & 0x3FFF) | (static_cast<uint64_t>(lbo16 & 0x3FFF) << 16) |
+         (static_cast<uint64_t>(sbo16 & 0x3FFF) << 32) | (static_cast<uint64_t>(1) << 46);
+}
+
+template <int KH, int STRIDE, int NCH, int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ HaloArgs p) {
+  using G = Geo<KH, STRIDE, NCH>;
+  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : 128;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int groups = p.groups1 + p.groups2;
+  const int wbytes = groups * p.nsteps * 2 * BN * 16;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t w_addr = smem_base;
+  const uint32_t stage_addr0 = smem_base + ((wbytes + 127) / 128) * 128;
+  const uint32_t bars = stage_addr0 + kStages * G::STAGE;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + (2 * kStages + 4) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // resident filter bank: plain 16-byte copies, made visible to the async proxy (tcgen05) below
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wpacked);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < wbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(full_bar(s), kProducers);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_w = p.Wout / kTW, tiles_h = p.Hout / kTH;
+
+  if (warp < 4) {
+    // ===================================================================== producers (halo gather)
+    const int tid = threadIdx.x;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
+      const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * kTW * STRIDE - G::PAD;
+      for (int g = 0; g < groups; ++g, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const bool from1 = g < p.groups1;
+        const __nv_bfloat16* src = from1 ? p.x1 : p.x2;
+        const int Cs = from1 ? p.C1 : p.C2;
+        const int coff = (from1 ? g : g - p.groups1) * (NCH * 8);
+        const uint32_t st = stage_addr0 + s * G::STAGE;
+#pragma unroll 4
+        for (int idx = tid; idx < G::CELLS; idx += kProducers) {
+          const int c = idx % NCH;
+          const int k = (idx / NCH) % G::KWCELLS;
+          const int hh = idx / (NCH * G::KWCELLS);
+          const int ih = ih0 + hh, iw = iw0 + k;
+          const bool ok = ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win;
+          const __nv_bfloat16* gp = src;
+          if (ok) gp = src + (static_cast<size_t>(b * p.Hin + ih) * p.Win + iw) * Cs + coff + c * 8;
+          const uint32_t dst = st + static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
+          cp_async_16(dst, gp, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (it >= static_cast<uint32_t>(kLag)) {
+          cp_async_wait<kLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(full_bar((it - kLag) % kStages));
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    const uint32_t first = it >= static_cast<uint32_t>(kLag) ? it - kLag : 0u;
+    for (uint32_t j = first; j < it; ++j) mbar_arrive(full_bar(j % kStages));
+  } else if (warp < 8) {
+    // ===================================================================== epilogue
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      epilogue_pixel<BN>(p, taddr, true, b, th * kTH + (row >> 3), tw * kTW + (row & 7), 0);
+      tc_fence_before_sync();
+      mbar_arrive(tempty_bar(as));
+    }
+  } else if (lane == 0) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    const uint32_t w16 = w_addr >> 4;
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tempty_bar(as), aph ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int g = 0; g < groups; ++g, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after_sync();
+        const uint32_t st16 = (stage_addr0 + s * G::STAGE) >> 4;
+        const uint32_t wg16 = w16 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+#pragma unroll 4
+        for (int k = 0; k < p.nsteps; ++k) {
+          const uint64_t adesc = desc_noswz(st16 + p.a_off[k], p.a_lbo[k], G::SBO16);
+          const uint64_t bdesc = desc_noswz(wg16 + static_cast<uint32_t>(k) * (2 * BN), BN, 8);
+          umma_bf16(d_tmem, adesc, bdesc, idesc, (g | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tfull_bar(as));
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int KH, int STRIDE, int NCH, int BN>
+int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
+  using G = Geo<KH, STRIDE, NCH>;
+  const int groups = a.groups1 + a.groups2;
+  const int wbytes = groups * a.nsteps * 2 * BN * 16;
+  const int smem = ((wbytes + 127) / 128) * 128 + kStages * G::STAGE + (2 * kStages + 4) * 8 + 16;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = smem;
+  }
+  const int grid = a.num_m_tiles < num_sms ? a.num_m_tiles : num_sms;
+  if (grid <= 0) return 0;
+  conv_halo_kernel<KH, STRIDE, NCH, BN><<<grid, kThreads, smem, stream>>>(a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+HaloGeom halo_geom(int KH, int stride, int nch, int bn) {
+  HaloGeom g;
+  g.KH = KH; g.stride = stride; g.nch = nch; g.bn = bn;
+  g.pad = KH / 2;
+  g.np = stride;
+  g.ph = stride * (kTH - 1) + KH + (nch == 1 ? 1 : 0);
+  const int spanw = stride * (kTW - 1) + KH;
+  g.pw = (spanw + g.np - 1) / g.np;
+  g.kw_cells = g.np * g.pw;
+  g.plane16 = g.ph * g.pw;
+  g.stage_bytes = ((nch * g.np * g.plane16 * 16) + 127) / 128 * 128;
+  g.nsteps = (nch == 1) ? KH * ((KH + 1) / 2) : KH * KH * (nch / 2);
+  return g;
+}
+
+int halo_group_channels(int KH, int C1, int C2) {
+  if (KH == 7) return 8;
+  int cg = C1 < 64 ? C1 : 64;
+  return cg;
+}
+
+bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int Wout) {
+  if (Hout % kTH != 0 || Wout % kTW != 0) return false;
+  if (KH == 7) return stride == 2 && C1 == 8 && C2 == 0 && Cout == 64;
+  if (KH != 3 || stride != 1) return false;
+  const int cg = halo_group_channels(KH, C1, C2);
+  if (C1 % cg != 0 || C2 % cg != 0) return false;
+  const int nch = cg / 8;
+  if ((C1 + C2) / cg > 2) return false;
+  return (nch == 2 && Cout == 16) || (nch == 4 && (Cout == 16 || Cout == 32)) ||
+         (nch == 8 && (Cout == 32 || Cout == 64));
+}
+
+void halo_fill_steps(HaloArgs& a, int KH, int stride) {
+  const int cg = halo_group_channels(KH, a.C1, a.C2);
+  const int nch = cg / 8;
+  const HaloGeom g = halo_geom(KH, stride, nch, a.Cout);
+  a.groups1 = a.C1 / cg;
+  a.groups2 = a.C2 / cg;
+  a.nsteps = g.nsteps;
+  memset(a.a_off, 0, sizeof a.a_off);
+  memset(a.a_lbo, 0, sizeof a.a_lbo);
+  if (nch == 1) {
+    // stem: one 8-channel chunk per pixel; a K=16 step pairs filter rows (2*pr, 2*pr+1) of column kw
+    for (int kw = 0; kw < KH; ++kw)
+      for (int pr = 0; pr < (KH + 1) / 2; ++pr) {
+        const int s = kw * ((KH + 1) / 2) + pr;
+        const int par = kw % g.np;
+        a.a_off[s] = static_cast<uint32_t>((par * g.ph + 2 * pr) * g.pw + kw / g.np);
+        a.a_lbo[s] = static_cast<uint32_t>(g.pw);
+      }
+  } else {
+    for (int tap = 0; tap < KH * KH; ++tap)
+      for (int kk = 0; kk < nch / 2; ++kk) {
+        const int s = tap * (nch / 2) + kk;
+        const int kh = tap / KH, kw = tap % KH;
+        const int par = kw % g.np;
+        a.a_off[s] = static_cast<uint32_t>(((2 * kk) * g.np + par) * g.plane16 + kh * g.pw + kw / g.np);
+        a.a_lbo[s] = static_cast<uint32_t>(g.np * g.plane16);
+      }
+  }
+  a.num_m_tiles = a.B * (a.Hout / kTH) * (a.Wout / kTW);
+}
+
+static uint16_t bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x007FFFFFu)) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int CinPad, int KH, int stride,
+                         int C1pad, int C2pad, uint16_t* dst) {
+  const int cg = halo_group_channels(KH, C1pad, C2pad);
+  const int nch = cg / 8;
+  const HaloGeom g = halo_geom(KH, stride, nch, CoutPad);
+  const int groups = CinPad / cg;
+  const size_t total = static_cast<size_t>(groups) * g.nsteps * 2 * CoutPad * 8;
+  if (!dst) return total;
+  memset(dst, 0, total * 2);
+  auto W = [&](int o, int ci, int kh, int kw) -> float {
+    if (o >= Cout || ci >= Cin || kh >= KH || kw >= KH) return 0.f;
+    return w[((static_cast<size_t>(o) * Cin + ci) * KH + kh) * KH + kw];
+  };
+  for (int grp = 0; grp < groups; ++grp)
+    for (int s = 0; s < g.nsteps; ++s)
+      for (int j = 0; j < 2; ++j)
+        for (int n = 0; n < CoutPad; ++n)
+          for (int e = 0; e < 8; ++e) {
+            int ci, kh, kw;
+            if (nch == 1) {
+              kw = s / ((KH + 1) / 2);
+              kh = 2 * (s % ((KH + 1) / 2)) + j;
+              ci = e;
+            } else {
+              const int tap = s / (nch / 2), kk = s % (nch / 2);
+              kh = tap / KH; kw = tap % KH;
+              ci = grp * cg + (2 * kk + j) * 8 + e;
+            }
+            dst[(((static_cast<size_t>(grp) * g.nsteps + s) * 2 + j) * CoutPad + n) * 8 + e] = bf16_rne(W(n, ci, kh, kw));
+          }
+  return total;
+}
+
+int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream) {
+  const int cg = halo_group_channels(KH, a.C1, a.C2);
+  const int nch = cg / 8;
+  if (!halo_supported(KH, stride, a.C1, a.C2, a.Cout, a.Hout, a.Wout)) return -3001;
+  if (a.nsteps <= 0 || a.nsteps > kHaloMaxSteps) return -3002;
+  if (KH == 7) return launch_halo_t<7, 2, 1, 64>(a, num_sms, stream);
+  if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16>(a, num_sms, stream);
+  if (nch == 4 && a.Cout == 16) return launch_halo_t<3, 1, 4, 16>(a, num_sms, stream);
+  if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32>(a, num_sms, stream);
+  if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32>(a, num_sms, stream);
+  if (nch == 8 && a.Cout == 64) return launch_halo_t<3, 1, 8, 64>(a, num_sms, stream);
+  return -3003;
+}
+
+}  // namespace fb

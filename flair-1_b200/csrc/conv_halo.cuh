@@ -1,0 +1,65 @@
+// Halo-staged convolution on tcgen05 (sm_100a) for the layers whose input is spatially large and
+// channel-poor: the stem (7x7 stride 2 on the 8-channel-padded image), layer1 / dec2.conv2 (64 ch at
+// 128^2), dec3 (64+64 / 32 ch at 256^2), dec4 and the segmentation head (32 / 16 ch at 512^2).
+//
+// An im2col operand re-reads every input pixel KH*KW times. Here each CTA copies the (16*s+KH-s) x
+// (8*s+KW-s) input halo of its 16 x 8 output tile into shared memory ONCE, as planes of 16-byte cells
+// [channel-chunk][w-parity][h][w] (no swizzle), and every filter tap is just a different start address
+// of the same UMMA shared-memory descriptor: 8 consecutive output columns are 8 consecutive 16-byte
+// cells (the descriptor's 8-row core matrix), the next output row is `stride` plane rows further (SBO)
+// and the second 8-channel chunk of a K=16 step is one plane (or, for the stem, one input row) further
+// (LBO). The whole filter bank stays resident in shared memory for the CTA's lifetime.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fb {
+
+constexpr int kHaloMaxSteps = 36;
+
+struct HaloArgs {
+  const __nv_bfloat16* x1;
+  const __nv_bfloat16* x2;       // optional second source concatenated after x1's channels
+  int C1, C2;
+  int B, Hin, Win, Hout, Wout;
+  int Cout;                      // == BN of the instantiation
+  // epilogue (same meaning as ConvArgs)
+  const float* bias;
+  const __nv_bfloat16* residual;
+  const float* rowbias;
+  int relu;
+  __nv_bfloat16* out;
+  float* out_f32;
+  int up2_out;
+  // filter bank packed by pack_halo_weights(): [group][step][chunk 0/1][n][8] bf16
+  const __nv_bfloat16* wpacked;
+  int groups1, groups2;          // channel groups (of NCH*8 channels) taken from x1 / x2
+  int nsteps;                    // K=16 MMA steps per group
+  uint32_t a_off[kHaloMaxSteps]; // start offset of the step's first chunk inside a stage, in 16-byte units
+  uint32_t a_lbo[kHaloMaxSteps]; // distance to the step's second chunk, in 16-byte units
+  int num_m_tiles;
+};
+
+// Geometry of one instantiation, shared by host packing and the kernel.
+struct HaloGeom {
+  int KH, stride, nch, bn;
+  int pad, np, ph, pw, kw_cells, plane16, stage_bytes, nsteps;
+};
+HaloGeom halo_geom(int KH, int stride, int nch, int bn);
+
+// True when (KH, stride, channels per group, Cout) has a compiled instantiation and the shape tiles.
+bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int Wout);
+int halo_group_channels(int KH, int C1, int C2);
+
+// Fill a_off / a_lbo / nsteps / groups for the given problem (host).
+void halo_fill_steps(HaloArgs& a, int KH, int stride);
+
+// Pack folded fp32 weights [Cout][Cin][KH][KW] (Cin = C1 + C2, already BN-scaled) into the step order.
+// Returns the number of bf16 elements written to `dst` (dst may be null to query the size).
+size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int CinPad, int KH, int stride,
+                         int C1pad, int C2pad, uint16_t* dst);
+
+int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream);
+
+}  // namespace fb

@@ -3,7 +3,9 @@
 #include "conv_igemm.cuh"
 
 #include <stdio.h>
+#include <string.h>
 
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace fb {
@@ -30,8 +32,8 @@ struct Cfg {
 
 template <int BN, bool TMA_A>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const ConvArgs p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
   using C = Cfg<BN>;
   constexpr int S = C::kStages;
 
@@ -61,7 +63,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_init(tempty_bar(a), kNumEpilogueThreads);
       }
       fence_mbar_init();
-      if (TMA_A) tma_prefetch_desc(&tmA);
+      if (TMA_A) {
+        tma_prefetch_desc(&tmA);
+        if (p.C2 > 0) tma_prefetch_desc(&tmA2);
+      }
       tma_prefetch_desc(&tmB);
     }
     __syncwarp();
@@ -81,7 +86,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (TMA_A) {
       if (threadIdx.x == 0) {
         const int tiles_w = p.Wout >> 4, tiles_h = p.Hout >> 3;
-        const int cchunks = p.C1 >> 6;
+        const int c1chunks = p.C1 >> 6;
+        const int cchunks = (p.C1 + p.C2) >> 6;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
@@ -95,7 +101,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int tap = kit / cchunks, cc = kit - tap * cchunks;
             const int kh = tap / 3, kw = tap - kh * 3;
             const uint32_t a_dst = base + s * C::kStageBytes;
-            tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, tw * 16 + kw - 1, th * 8 + kh - 1, b);
+            if (cc < c1chunks) {
+              tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, tw * 16 + kw - 1, th * 8 + kh - 1, b);
+            } else {  // channels of the concatenated skip tensor
+              tma_load_4d(a_dst, &tmA2, full_bar(s), (cc - c1chunks) * 64, tw * 16 + kw - 1, th * 8 + kh - 1, b);
+            }
             tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, n_tile * BN);
           }
         }
@@ -177,81 +187,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      long long pix;
-      bool valid;
-      int b_idx, oh_idx;
+      bool valid = true;
+      int b_idx, oh_idx, ow_idx;
       if (TMA_A) {
         const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
         b_idx = m_tile / (tiles_w * tiles_h);
         oh_idx = th * 8 + (row >> 4);
-        pix = (static_cast<long long>(b_idx) * p.Hout + oh_idx) * p.Wout + tw * 16 + (row & 15);
-        valid = true;
+        ow_idx = tw * 16 + (row & 15);
       } else {
-        pix = static_cast<long long>(m_tile) * kBM + row;
+        const long long pix = static_cast<long long>(m_tile) * kBM + row;
         valid = pix < p.M_total;
         const int HWo = p.Hout * p.Wout;
         b_idx = static_cast<int>(pix / HWo);
-        oh_idx = static_cast<int>((pix - static_cast<long long>(b_idx) * HWo) / p.Wout);
+        const int rem = static_cast<int>(pix - static_cast<long long>(b_idx) * HWo);
+        oh_idx = rem / p.Wout;
+        ow_idx = rem - oh_idx * p.Wout;
       }
-      const float rb = (p.rowbias != nullptr && valid) ? p.rowbias[b_idx * p.Hout + oh_idx] : 0.f;
-      const size_t obase = static_cast<size_t>(pix) * p.Cout + n_tile * BN;
-
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid) {
-          float v[16];
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n_tile * BN + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = __ldg(bp + i);
-            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
-            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
-            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
-          }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 rr = __ldg(rp + h);
-              const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-                v[8 * h + 2 * i + 0] += __low2float(b2);
-                v[8 * h + 2 * i + 1] += __high2float(b2);
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += rb;
-          if (p.out_f32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-              pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
-            op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
-      }
+      epilogue_pixel<BN>(p, taddr, valid, b_idx, oh_idx, ow_idx, n_tile * BN);
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
     }
@@ -302,8 +257,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 
 template <int BN, bool TMA_A>
-int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, int grid,
-             cudaStream_t stream) {
+int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvArgs& a,
+             int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -312,7 +267,7 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvArgs& a, 
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_igemm_kernel<BN, TMA_A><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, a);
+  conv_igemm_kernel<BN, TMA_A><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -337,6 +292,12 @@ int conv_pick_bn(int Cout) {
   return 0;
 }
 
+bool conv_tma_eligible(const ConvArgs& a) {
+  return a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.up1 == 0 && a.C1 % 64 == 0 &&
+         a.C2 % 64 == 0 && (a.C2 == 0 || a.x2 != nullptr) && a.Hout % 8 == 0 && a.Wout % 16 == 0 &&
+         a.Hin == a.Hout && a.Win == a.Wout;
+}
+
 int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bool use_tma_a,
                 int num_sms, cudaStream_t stream) {
   if (init_tma_encoder() != 0) return -1001;
@@ -349,17 +310,17 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   a.num_n_tiles = a.Cout / BN;
   a.num_k_iters = (a.Ktot + kBK - 1) / kBK;
   if (use_tma_a) {
-    if (!(a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.C2 == 0 && a.up1 == 0 &&
-          a.C1 % 64 == 0 && a.Hout % 8 == 0 && a.Wout % 16 == 0 && a.Hin == a.Hout && a.Win == a.Wout))
-      return -1004;
+    if (!conv_tma_eligible(a)) return -1004;
     a.num_m_tiles = a.B * (a.Hout / 8) * (a.Wout / 16);
   } else {
     a.num_m_tiles = (a.M_total + kBM - 1) / kBM;
   }
 
   alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmA2;
   alignas(64) CUtensorMap tmB;
   memset(&tmA, 0, sizeof(tmA));
+  memset(&tmA2, 0, sizeof(tmA2));
   memset(&tmB, 0, sizeof(tmB));
   {
     // weights: [Cout][Kpad] bf16, box = 64 k x BN rows, 128-byte swizzle
@@ -376,18 +337,21 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   if (use_tma_a) {
     // activations: NHWC bf16 seen as (C, W, H, B); box = 64 channels x 16 x 8 pixels; out-of-range
     // coordinates are zero-filled by the TMA unit, which is exactly the conv's zero padding.
-    cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.C1), static_cast<cuuint64_t>(a.Win),
-                          static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B)};
-    cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.C1) * 2,
-                             static_cast<cuuint64_t>(a.Win) * a.C1 * 2,
-                             static_cast<cuuint64_t>(a.Hin) * a.Win * a.C1 * 2};
-    cuuint32_t box[4] = {64, 16, 8, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.x1),
-                          dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return -1200 - static_cast<int>(r);
+    for (int src = 0; src < (a.C2 > 0 ? 2 : 1); ++src) {
+      const int Cs = src == 0 ? a.C1 : a.C2;
+      const __nv_bfloat16* base = src == 0 ? a.x1 : a.x2;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cs), static_cast<cuuint64_t>(a.Win),
+                            static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cs) * 2, static_cast<cuuint64_t>(a.Win) * Cs * 2,
+                               static_cast<cuuint64_t>(a.Hin) * a.Win * Cs * 2};
+      cuuint32_t box[4] = {64, 16, 8, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = g_encode(src == 0 ? &tmA : &tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                            const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return -1200 - static_cast<int>(r);
+    }
   }
 
   const int num_tiles = a.num_m_tiles * a.num_n_tiles;
@@ -396,8 +360,8 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
 
 #define FB_DISPATCH(BN_)                                                               \
   case BN_:                                                                            \
-    return use_tma_a ? launch_t<BN_, true>(tmA, tmB, a, grid, stream)                  \
-                     : launch_t<BN_, false>(tmA, tmB, a, grid, stream);
+    return use_tma_a ? launch_t<BN_, true>(tmA, tmA2, tmB, a, grid, stream)            \
+                     : launch_t<BN_, false>(tmA, tmA2, tmB, a, grid, stream);
   switch (BN) {
     FB_DISPATCH(16)
     FB_DISPATCH(32)

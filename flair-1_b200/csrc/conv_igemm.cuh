@@ -42,6 +42,7 @@ struct ConvArgs {
   int relu;
   __nv_bfloat16* out;              // [B,Hout,Wout,Cout] bf16 (null when out_f32 is used)
   float* out_f32;                  // [B,Hout,Wout,Cout] fp32 (logits) or null
+  int up2_out;                     // 1: bf16 output is written 2x2-replicated into [B,2*Hout,2*Wout,Cout]
   // tiling
   int M_total;       // B*Hout*Wout
   int num_m_tiles;   // gather: ceil(M_total/128); TMA: B*(Hout/8)*(Wout/16)
@@ -49,8 +50,10 @@ struct ConvArgs {
   int num_k_iters;   // ceil(Ktot/64)
 };
 
-// Launch one convolution. `use_tma_a` requires KH=KW=3, stride=1, pad=1, single source without
-// upsample, C1 % 64 == 0, Hout % 8 == 0, Wout % 16 == 0. Returns cudaError_t as int.
+// Launch one convolution. `use_tma_a` requires KH=KW=3, stride=1, pad=1, no input upsample,
+// C1 % 64 == 0 (and C2 % 64 == 0 when a second source is concatenated), Hout % 8 == 0,
+// Wout % 16 == 0. Returns cudaError_t as int.
+bool conv_tma_eligible(const ConvArgs& a);
 int launch_conv(const ConvArgs& a, const __nv_bfloat16* weights /*[Cout][Kpad] bf16*/, int Kpad,
                 bool use_tma_a, int num_sms, cudaStream_t stream);
 

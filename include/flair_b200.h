@@ -137,6 +137,13 @@ int fb_conv2d(fb_ctx* ctx, const void* x1, const void* x2, int C1, int C2, int u
               int Win, int KH, int KW, int stride, int pad, int Cout, const void* weights, int Kpad,
               const float* bias, const void* residual, const float* rowbias, int relu, void* out_bf16,
               float* out_f32, int mode);
+/* Same convolution through the halo-staged kernel (3x3 stride 1 with <= 64 channels per source and
+ * Cout in {16,32,64}, or the 7x7 stride-2 stem on 8 channels): weights are given as host fp32
+ * [Cout][C1+C2][KH][KH] and packed internally. up2_out: write the bf16 result 2x2-replicated into
+ * [B, 2*Hout, 2*Wout, Cout] (the decoder's nearest x2 upsample). Synchronises the stream. */
+int fb_conv2d_halo(fb_ctx* ctx, const void* x1, const void* x2, int C1, int C2, int B, int Hin, int Win,
+                   int KH, int stride, int Cout, const float* w_oihw_host, const float* bias,
+                   const void* residual, int relu, int up2_out, void* out_bf16, float* out_f32);
 /* Copy a named intermediate of the last fb_forward_tiles call (e.g. "f1", "layer2.0.out", "dec3")
  * to a device buffer as bf16 NHWC. Returns its element count through *count (also when out is NULL). */
 int fb_debug_activation(fb_ctx* ctx, const char* name, void* out_dev, int64_t* count, int32_t* dims4);

@@ -93,6 +93,67 @@ def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=Fals
     return ok
 
 
+def halo_case(ctx, name, B, H, W, C1, Cout, KH, stride, C2=0, res=False, relu=True, up2=False, out_f32=False, seed=0,
+              identity=False):
+    """Halo-staged kernel against the fp32 reference on bf16-rounded operands."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = ctx.device
+    x1 = torch.randn((B, H, W, C1), generator=g).to(torch.bfloat16).to(dev)
+    x2 = torch.randn((B, H, W, C2), generator=g).to(torch.bfloat16).to(dev) if C2 else None
+    Cin = C1 + C2
+    w = torch.randn((Cout, Cin, KH, KH), generator=g) / np.sqrt(Cin * KH * KH)
+    if identity:
+        w.zero_()
+        for o in range(min(Cout, Cin)):
+            w[o, o, KH // 2, KH // 2] = 1.0
+    w = w.to(torch.bfloat16).float()
+    bias = (torch.randn((Cout,), generator=g) * 0.1).to(dev)
+    pad = KH // 2
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KH) // stride + 1
+    residual = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).to(dev) if res else None
+    try:
+        y = ctx.conv2d_halo(x1, w, bias, KH, stride, x2=x2, residual=residual, relu=relu, up2_out=up2, out_f32=out_f32)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        log(f"CASE {name}: EXCEPTION {e}")
+        RESULTS.append({"case": name, "ok": False, "error": str(e)})
+        return False
+    yr = ref_conv(x1, w.to(dev), bias, stride, pad, x2=x2, residual=residual, relu=relu)
+    if up2:
+        yr = yr.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    err = (y.float() - yr).abs()
+    scale = yr.abs().max().item() + 1e-9
+    tol = 2e-5 if out_f32 else 1.0 / 128
+    relm = err / (yr.abs() + 0.05 * scale)
+    rel = relm.max().item()
+    ok = bool(rel < tol * 2 + 1e-4) and bool(torch.isfinite(y.float()).all())
+    info = ""
+    if not ok:
+        idx = (relm > tol * 2 + 1e-4).nonzero()
+        info = f" nbad={idx.shape[0]}/{relm.numel()} first_bad={idx[:6].tolist()} chans_bad={sorted(set(idx[:, 3].tolist()))[:16]}" \
+               f" rows_bad={sorted(set(idx[:, 1].tolist()))[:20]} cols_bad={sorted(set(idx[:, 2].tolist()))[:20]}"
+    log(f"CASE {name}: {'OK ' if ok else 'FAIL'} maxabs={err.max().item():.4e} rel={rel:.4e} refmax={scale:.3f}{info}")
+    RESULTS.append({"case": name, "ok": ok, "maxabs": err.max().item(), "rel": rel})
+    return ok
+
+
+HALO_CASES = [
+    # name, B, H, W, C1, Cout, KH, stride, kwargs
+    ("h_ident_16_16", 1, 16, 8, 16, 16, 3, 1, dict(identity=True, relu=False)),
+    ("h_3x3_16_16", 1, 16, 8, 16, 16, 3, 1, {}),
+    ("h_3x3_16_16_multi", 2, 64, 64, 16, 16, 3, 1, {}),
+    ("h_head_16_16_f32", 1, 32, 32, 16, 16, 3, 1, dict(relu=False, out_f32=True)),
+    ("h_3x3_32_16", 2, 32, 32, 32, 16, 3, 1, {}),
+    ("h_3x3_32_32_up2", 1, 32, 32, 32, 32, 3, 1, dict(up2=True)),
+    ("h_ident_64_64", 1, 16, 8, 64, 64, 3, 1, dict(identity=True, relu=False)),
+    ("h_3x3_64_64_res", 2, 32, 32, 64, 64, 3, 1, dict(res=True)),
+    ("h_3x3_64p64_32", 2, 32, 32, 64, 32, 3, 1, dict(C2=64)),
+    ("h_stem_7x7s2", 2, 64, 64, 8, 64, 7, 2, {}),
+    ("h_stem_big", 3, 256, 128, 8, 64, 7, 2, {}),
+    ("h_many_tiles", 4, 256, 256, 16, 16, 3, 1, {}),
+]
+
+
 def main():
     want = sys.argv[1:]
     log("device:", torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
@@ -132,6 +193,13 @@ def main():
         name = c[0]
         if sel(name):
             conv_case(ctx, name, *c[1:10], **c[10])
+
+    for c in HALO_CASES:
+        if sel(c[0]):
+            halo_case(ctx, c[0], *c[1:8], **c[8])
+    if sel("t_dual"):
+        conv_case(ctx, "t_dual_128p64_64", 2, 32, 32, 128, 64, 3, 1, 1, T, C2=64)
+        conv_case(ctx, "g_dual_128p64_64", 2, 32, 32, 128, 64, 3, 1, 1, G, C2=64)
 
     if sel("confusion"):
         g = torch.Generator().manual_seed(1)

@@ -69,6 +69,8 @@ def main():
     for nme in names:
         ref = acts[nme]
         got = ctx.debug_activation(nme).float().cpu().permute(0, 3, 1, 2)[:, :ref.shape[1]]
+        if got.shape[-1] == 2 * ref.shape[-1]:
+            ref = ref.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
         err = (got - ref).abs().max().item()
         log(f"LAYER {nme:14s} maxabs={err:.4e} refmax={ref.abs().max().item():.3f} rel={err / (ref.abs().max().item() + 1e-9):.4e}")
     ref = acts["logits"]

@@ -49,6 +49,26 @@ def test_conv_kernel_vs_torch_fp32(ctx, case):
     assert gpu_probe.conv_case(ctx, case[0], *case[1:10], **case[10]), gpu_probe.RESULTS[-1]
 
 
+def _halo_cases():
+    import gpu_probe
+    return gpu_probe.HALO_CASES
+
+
+@pytest.mark.parametrize("idx", range(12))
+def test_halo_conv_kernel_vs_torch_fp32(ctx, idx):
+    import gpu_probe
+    case = gpu_probe.HALO_CASES[idx]
+    gpu_probe.RESULTS.clear()
+    assert gpu_probe.halo_case(ctx, case[0], *case[1:8], **case[8]), gpu_probe.RESULTS[-1]
+
+
+def test_dual_source_tma_conv(ctx):
+    import gpu_probe
+    gpu_probe.RESULTS.clear()
+    assert gpu_probe.conv_case(ctx, "t_dual_128p64_64", 2, 32, 32, 128, 64, 3, 1, 1, 1, C2=64), gpu_probe.RESULTS[-1]
+    assert gpu_probe.conv_case(ctx, "t_dual_512p256_256", 1, 32, 32, 512, 256, 3, 1, 1, 1, C2=256), gpu_probe.RESULTS[-1]
+
+
 def test_extract_normalise_bit_exact(ctx, trained_3_15):
     """K1 against the oracle's float64 -> float32 normalisation rounded to bf16, including tiles that
     hang over every edge of the raster (boundless zero fill before normalisation)."""
@@ -152,14 +172,16 @@ def test_forward_logits_and_argmax_vs_oracle(ctx, trained_3_15):
     for name in ("f1", "layer1.2.out", "layer2.3.out", "layer3.5.out", "layer4.2.out", "dec0", "dec2", "dec4"):
         r = acts[name]
         g = ctx.debug_activation(name).float().cpu().permute(0, 3, 1, 2)
+        if g.shape[-1] == 2 * r.shape[-1]:  # stored 2x2-replicated for the next decoder block
+            r = r.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
         e = (g - r).abs().max().item() / r.abs().max().item()
         print(f"  {name:14s} rel err {e:.4e}")
         assert e <= LOGIT_TOL, name
 
 
 def test_gather_and_tma_producers_agree(trained_3_15, monkeypatch):
-    """Same network through the cp.async gather producer only (FB_FORCE_GATHER=1): bit-identical logits
-    (both producers feed the same MMA schedule with the same operands)."""
+    """Same network through the cp.async im2col gather producer only (FB_FORCE_GATHER=1) against the
+    default mix of halo-staged / TMA / gather kernels."""
     from oracle import synth
     nat = _nat()
     sd, _ = trained_3_15
@@ -173,7 +195,11 @@ def test_gather_and_tma_producers_agree(trained_3_15, monkeypatch):
         c.set_raster(raster, [0, 1, 2], 512, 512)
         outs.append(c.forward_tiles(np.array([[0, 0], [-100, 37]], np.int32), 512).cpu())
         c.close()
-    assert torch.equal(outs[0], outs[1])
+    rel = (outs[0] - outs[1]).abs().max().item() / outs[1].abs().max().item()
+    print(f"fast paths vs gather-only: logits rel diff {rel:.3e}")
+    # same bf16 operands and fp32 accumulation, only the summation order inside a K loop differs
+    assert rel < 2e-3
+    assert (outs[0].argmax(-1) == outs[1].argmax(-1)).float().mean().item() > 0.9995
 
 
 def test_five_band_metadata_model_logits(ctx):
