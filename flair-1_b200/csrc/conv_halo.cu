@@ -15,8 +15,6 @@ namespace {
 constexpr int kTH = 16, kTW = 8;          // output tile: 16 rows x 8 columns = 128 pixels (UMMA M)
 constexpr int kThreads = 288;             // warps 0-3 producers, 4-7 epilogue, 8 MMA issuer
 constexpr int kProducers = 128;
-constexpr int kStages = 4;
-constexpr int kLag = 2;                   // cp.async groups in flight per producer thread
 
 template <int KH, int STRIDE, int NCH>
 struct Geo {
@@ -29,19 +27,20 @@ struct Geo {
   static constexpr int PLANE16 = PH * PW;                              // 16-byte cells per plane
   static constexpr int STAGE = ((NCH * NP * PLANE16 * 16) + 127) / 128 * 128;
   static constexpr int CELLS = PH * KWCELLS * NCH;
+  static constexpr int CELLS_PER_THREAD = (CELLS + kProducers - 1) / kProducers;
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
+  // small stages: deeper ring, more cp.async groups in flight, two CTAs per SM
+  static constexpr bool SMALL = STAGE <= 12 * 1024;
+  static constexpr int STAGES = SMALL ? 6 : 4;
+  static constexpr int LAG = SMALL ? 4 : 2;
+  static constexpr int OCC = SMALL ? 2 : 1;
 };
 
-// no-swizzle K-major shared-memory descriptor: rows of a core matrix 16 B apart (implicit),
-// LBO = distance between the two 8-element K chunks, SBO = distance between 8-row groups.
-__device__ __forceinline__ uint64_t desc_noswz(uint32_t start16, uint32_t lbo16, uint32_t sbo16) {
-  return static_cast<uint64_t>(start16 & 0x3FFF) | (static_cast<uint64_t>(lbo16 & 0x3FFF) << 16) |
-         (static_cast<uint64_t>(sbo16 & 0x3FFF) << 32) | (static_cast<uint64_t>(1) << 46);
-}
-
 template <int KH, int STRIDE, int NCH, int BN>
-__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ HaloArgs p) {
+__global__ void __launch_bounds__(kThreads, Geo<KH, STRIDE, NCH>::OCC)
+conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   using G = Geo<KH, STRIDE, NCH>;
+  constexpr int S = G::STAGES;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : 128;
 
   extern __shared__ __align__(128) uint8_t smem[];
@@ -49,25 +48,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   const int wbytes = groups * p.nsteps * 2 * BN * 16;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t w_addr = smem_base;
-  const uint32_t stage_addr0 = smem_base + ((wbytes + 127) / 128) * 128;
-  const uint32_t bars = stage_addr0 + kStages * G::STAGE;
+  const uint32_t bias_off = ((wbytes + 127) / 128) * 128;
+  const uint32_t stage_addr0 = smem_base + bias_off + 256;             // 64 fp32 of bias
+  const uint32_t bars = stage_addr0 + S * G::STAGE;
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + (2 * kStages + 4) * 8);
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + (2 * S + 4) * 8);
+  float* bias_s = reinterpret_cast<float*>(smem + bias_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // resident filter bank: plain 16-byte copies, made visible to the async proxy (tcgen05) below
+  // resident filter bank + bias: plain copies, made visible to the async proxy (tcgen05) below
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.wpacked);
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = threadIdx.x; i < wbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
   if (warp == 8) {
     if (lane == 0) {
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < S; ++s) {
         mbar_init(full_bar(s), kProducers);
         mbar_init(empty_bar(s), 1);
       }
@@ -91,44 +93,66 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
 
   if (warp < 4) {
     // ===================================================================== producers (halo gather)
+    // The cells a thread copies do not depend on the tile: decode them once. cell_dst: byte offset
+    // inside a stage | hh << 16 | k << 24 ; cell_src: element offset from the tile's first halo pixel.
     const int tid = threadIdx.x;
+    uint32_t cell_dst[G::CELLS_PER_THREAD];
+    int cell_src1[G::CELLS_PER_THREAD], cell_src2[G::CELLS_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+      const int idx = tid + j * kProducers;
+      const int c = idx % NCH;
+      const int k = (idx / NCH) % G::KWCELLS;
+      const int hh = idx / (NCH * G::KWCELLS);
+      const uint32_t dst = static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
+      cell_dst[j] = idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
+      cell_src1[j] = (hh * p.Win + k) * p.C1 + c * 8;
+      cell_src2[j] = (hh * p.Win + k) * p.C2 + c * 8;
+    }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * kTW * STRIDE - G::PAD;
+      const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
+      const long long origin = (static_cast<long long>(b) * p.Hin + ih0) * p.Win + iw0;  // may be "negative"
       for (int g = 0; g < groups; ++g, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         const bool from1 = g < p.groups1;
-        const __nv_bfloat16* src = from1 ? p.x1 : p.x2;
         const int Cs = from1 ? p.C1 : p.C2;
-        const int coff = (from1 ? g : g - p.groups1) * (NCH * 8);
+        const __nv_bfloat16* src = (from1 ? p.x1 : p.x2) + origin * Cs + (from1 ? g : g - p.groups1) * (NCH * 8);
         const uint32_t st = stage_addr0 + s * G::STAGE;
-#pragma unroll 4
-        for (int idx = tid; idx < G::CELLS; idx += kProducers) {
-          const int c = idx % NCH;
-          const int k = (idx / NCH) % G::KWCELLS;
-          const int hh = idx / (NCH * G::KWCELLS);
-          const int ih = ih0 + hh, iw = iw0 + k;
-          const bool ok = ih >= 0 && ih < p.Hin && iw >= 0 && iw < p.Win;
-          const __nv_bfloat16* gp = src;
-          if (ok) gp = src + (static_cast<size_t>(b * p.Hin + ih) * p.Win + iw) * Cs + coff + c * 8;
-          const uint32_t dst = st + static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
-          cp_async_16(dst, gp, ok ? 16u : 0u);
+        if (interior) {
+#pragma unroll
+          for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+            if (cell_dst[j] != 0xFFFFFFFFu)
+              cp_async_16(st + (cell_dst[j] & 0xFFFFu), src + (from1 ? cell_src1[j] : cell_src2[j]), 16u);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+            if (cell_dst[j] != 0xFFFFFFFFu) {
+              const int hh = (cell_dst[j] >> 16) & 0xFF, k = cell_dst[j] >> 24;
+              const bool ok = static_cast<unsigned>(ih0 + hh) < static_cast<unsigned>(p.Hin) &&
+                              static_cast<unsigned>(iw0 + k) < static_cast<unsigned>(p.Win);
+              const __nv_bfloat16* gp = ok ? src + (from1 ? cell_src1[j] : cell_src2[j]) : p.x1;
+              cp_async_16(st + (cell_dst[j] & 0xFFFFu), gp, ok ? 16u : 0u);
+            }
+          }
         }
         cp_async_commit();
-        if (it >= static_cast<uint32_t>(kLag)) {
-          cp_async_wait<kLag>();
+        if (it >= static_cast<uint32_t>(G::LAG)) {
+          cp_async_wait<G::LAG>();
           fence_proxy_async_smem();
-          mbar_arrive(full_bar((it - kLag) % kStages));
+          mbar_arrive(full_bar((it - G::LAG) % S));
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async_smem();
-    const uint32_t first = it >= static_cast<uint32_t>(kLag) ? it - kLag : 0u;
-    for (uint32_t j = first; j < it; ++j) mbar_arrive(full_bar(j % kStages));
+    const uint32_t first = it >= static_cast<uint32_t>(G::LAG) ? it - G::LAG : 0u;
+    for (uint32_t j = first; j < it; ++j) mbar_arrive(full_bar(j % S));
   } else if (warp < 8) {
     // ===================================================================== epilogue
     const int q = warp & 3;
@@ -138,17 +162,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      epilogue_pixel<BN>(p, taddr, true, b, th * kTH + (row >> 3), tw * kTW + (row & 7), 0);
+      epilogue_pixel<BN, true, true>(p, bias_s, taddr, tfull_bar(as), aph, true, b, th * kTH + (row >> 3),
+                                     tw * kTW + (row & 7), 0);
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
     }
   } else if (lane == 0) {
     // ===================================================================== MMA issuer
+    // Only the low descriptor word (start address, LBO) changes between instructions; the high word
+    // (SBO, descriptor version 1, no swizzle) is a constant per operand.
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-    const uint32_t w16 = w_addr >> 4;
+    constexpr uint32_t a_hi = static_cast<uint32_t>(G::SBO16) | (1u << 14);
+    constexpr uint32_t b_hi = 8u | (1u << 14);
+    const uint32_t b_lo0 = (w_addr >> 4) | (static_cast<uint32_t>(BN) << 16);
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
       const int as = tcount & 1;
@@ -157,17 +184,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int g = 0; g < groups; ++g, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after_sync();
         const uint32_t st16 = (stage_addr0 + s * G::STAGE) >> 4;
-        const uint32_t wg16 = w16 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
 #pragma unroll 4
         for (int k = 0; k < p.nsteps; ++k) {
-          const uint64_t adesc = desc_noswz(st16 + p.a_off[k], p.a_lbo[k], G::SBO16);
-          const uint64_t bdesc = desc_noswz(wg16 + static_cast<uint32_t>(k) * (2 * BN), BN, 8);
-          umma_bf16(d_tmem, adesc, bdesc, idesc, (g | k) != 0 ? 1u : 0u);
+          umma_bf16_lohi(d_tmem, p.a_lo[k] + st16, a_hi, b_lo, b_hi, idesc, (g | k) != 0 ? 1u : 0u);
+          b_lo += 2 * BN;
         }
         umma_commit(empty_bar(s));
       }
@@ -188,15 +214,20 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   using G = Geo<KH, STRIDE, NCH>;
   const int groups = a.groups1 + a.groups2;
   const int wbytes = groups * a.nsteps * 2 * BN * 16;
-  const int smem = ((wbytes + 127) / 128) * 128 + kStages * G::STAGE + (2 * kStages + 4) * 8 + 16;
+  const int smem = ((wbytes + 127) / 128) * 128 + 256 + G::STAGES * G::STAGE + (2 * G::STAGES + 4) * 8 + 16;
   static int configured = 0;
+  static int occ = 1;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN>, kThreads, smem) == cudaSuccess && nb > 0)
+      occ = nb < G::OCC ? nb : G::OCC;
   }
-  const int grid = a.num_m_tiles < num_sms ? a.num_m_tiles : num_sms;
+  const int cap = num_sms * occ;
+  const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
   if (grid <= 0) return 0;
   conv_halo_kernel<KH, STRIDE, NCH, BN><<<grid, kThreads, smem, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
@@ -230,7 +261,7 @@ bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int 
   if (KH == 7) return stride == 2 && C1 == 8 && C2 == 0 && Cout == 64;
   if (KH != 3 || stride != 1) return false;
   const int cg = halo_group_channels(KH, C1, C2);
-  if (C1 % cg != 0 || C2 % cg != 0) return false;
+  if (cg < 16 || C1 % cg != 0 || C2 % cg != 0) return false;
   const int nch = cg / 8;
   if ((C1 + C2) / cg > 2) return false;
   return (nch == 2 && Cout == 16) || (nch == 4 && (Cout == 16 || Cout == 32)) ||
@@ -244,16 +275,16 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride) {
   a.groups1 = a.C1 / cg;
   a.groups2 = a.C2 / cg;
   a.nsteps = g.nsteps;
-  memset(a.a_off, 0, sizeof a.a_off);
-  memset(a.a_lbo, 0, sizeof a.a_lbo);
+  memset(a.a_lo, 0, sizeof a.a_lo);
   if (nch == 1) {
     // stem: one 8-channel chunk per pixel; a K=16 step pairs filter rows (2*pr, 2*pr+1) of column kw
     for (int kw = 0; kw < KH; ++kw)
       for (int pr = 0; pr < (KH + 1) / 2; ++pr) {
         const int s = kw * ((KH + 1) / 2) + pr;
         const int par = kw % g.np;
-        a.a_off[s] = static_cast<uint32_t>((par * g.ph + 2 * pr) * g.pw + kw / g.np);
-        a.a_lbo[s] = static_cast<uint32_t>(g.pw);
+        const uint32_t off = static_cast<uint32_t>((par * g.ph + 2 * pr) * g.pw + kw / g.np);
+        const uint32_t lbo = static_cast<uint32_t>(g.pw);
+        a.a_lo[s] = off | (lbo << 16);
       }
   } else {
     for (int tap = 0; tap < KH * KH; ++tap)
@@ -261,8 +292,9 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride) {
         const int s = tap * (nch / 2) + kk;
         const int kh = tap / KH, kw = tap % KH;
         const int par = kw % g.np;
-        a.a_off[s] = static_cast<uint32_t>(((2 * kk) * g.np + par) * g.plane16 + kh * g.pw + kw / g.np);
-        a.a_lbo[s] = static_cast<uint32_t>(g.np * g.plane16);
+        const uint32_t off = static_cast<uint32_t>(((2 * kk) * g.np + par) * g.plane16 + kh * g.pw + kw / g.np);
+        const uint32_t lbo = static_cast<uint32_t>(g.np * g.plane16);
+        a.a_lo[s] = off | (lbo << 16);
       }
   }
   a.num_m_tiles = a.B * (a.Hout / kTH) * (a.Wout / kTW);

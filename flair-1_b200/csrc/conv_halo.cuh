@@ -36,8 +36,9 @@ struct HaloArgs {
   const __nv_bfloat16* wpacked;
   int groups1, groups2;          // channel groups (of NCH*8 channels) taken from x1 / x2
   int nsteps;                    // K=16 MMA steps per group
-  uint32_t a_off[kHaloMaxSteps]; // start offset of the step's first chunk inside a stage, in 16-byte units
-  uint32_t a_lbo[kHaloMaxSteps]; // distance to the step's second chunk, in 16-byte units
+  // low word of the A descriptor of each K-step, relative to the stage base: start offset of the
+  // step's first 8-channel chunk (16-byte units, bits 0-13) | distance to its second chunk << 16 (LBO)
+  uint32_t a_lo[kHaloMaxSteps];
   int num_m_tiles;
 };
 
@@ -52,7 +53,7 @@ HaloGeom halo_geom(int KH, int stride, int nch, int bn);
 bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int Wout);
 int halo_group_channels(int KH, int C1, int C2);
 
-// Fill a_off / a_lbo / nsteps / groups for the given problem (host).
+// Fill a_lo / nsteps / groups / num_m_tiles for the given problem (host).
 void halo_fill_steps(HaloArgs& a, int KH, int stride);
 
 // Pack folded fp32 weights [Cout][Cin][KH][KW] (Cin = C1 + C2, already BN-scaled) into the step order.

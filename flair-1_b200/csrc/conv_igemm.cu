@@ -203,10 +203,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         oh_idx = rem / p.Wout;
         ow_idx = rem - oh_idx * p.Wout;
       }
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      epilogue_pixel<BN>(p, taddr, valid, b_idx, oh_idx, ow_idx, n_tile * BN);
+      epilogue_pixel<BN, (BN <= 64), false>(p, p.bias, taddr, tfull_bar(as), aph, valid, b_idx, oh_idx, ow_idx,
+                                            n_tile * BN);
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
     }
