@@ -204,7 +204,7 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
         }
   }
   // second packing for the halo-staged kernel when the channel configuration has an instantiation
-  if (fb::halo_supported(KH, stride, L.C1, L.C2, CoutPad, 16, 8)) {
+  if (fb::halo_supported(KH, stride, L.C1, L.C2, CoutPad, 16, 64)) {
     const size_t n = fb::pack_halo_weights(folded.data(), Cout, CoutPad, Cin, CinPad, KH, stride, L.C1, L.C2, nullptr);
     std::vector<uint16_t> hp(n);
     fb::pack_halo_weights(folded.data(), Cout, CoutPad, Cin, CinPad, KH, stride, L.C1, L.C2, hp.data());

@@ -1,10 +1,19 @@
-// Shared epilogue of the tcgen05 convolution kernels: one thread owns one output pixel (= one TMEM
-// lane), walks its BN accumulator columns in chunks of 16, applies folded-BN bias (+ residual) (+ ReLU)
-// (+ per-row metadata bias), rounds once to bf16 and stores NHWC -- optionally replicated 2x2 so that
-// the consumer sees the decoder's nearest-neighbour x2 upsample (smp DecoderBlock) already materialised.
+// Shared epilogue of the tcgen05 convolution kernels.
 //
-// The function also performs the wait on the "accumulator full" mbarrier itself so that, with
-// PREFETCH, the residual row of the pixel is already in flight while the MMAs of the tile still run.
+// One thread owns one output pixel (= one TMEM lane): it walks its BN accumulator columns in chunks of
+// 16, applies folded-BN bias (+ residual) (+ ReLU) (+ per-row metadata bias) and rounds once to bf16.
+// A lane's result row (<= 128 bytes per column group) goes to a per-warp staging buffer in shared
+// memory; the warp then copies the 32 staged rows to global memory cooperatively, RUN/16 lanes per
+// pixel, so every store instruction writes whole contiguous runs instead of 32 scattered 16-byte
+// pieces. With up2_out each run is written to the 2x2 replicated positions, which materialises the
+// decoder's nearest-neighbour x2 upsample (smp DecoderBlock).
+//
+// Where the tile-row -> pixel mapping does not depend on the tile (TMA 8x16 boxes, halo 16x8 blocks) the
+// per-lane destination offsets of the copy-out rounds are computed once per kernel (EpiLane) so that a
+// round costs one LDS, one 64-bit add and the store(s).
+//
+// The function performs the wait on the "accumulator full" mbarrier itself so that, with PREFETCH, the
+// residual row of the pixel is already in flight while the MMAs of the tile still run.
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -13,21 +22,101 @@
 
 namespace fb {
 
+constexpr int kStgPitch = 144;                 // bytes per staged pixel row (128 + 16: conflict-free 16 B stores)
+constexpr int kStgWarpBytes = 32 * kStgPitch;  // staging bytes per epilogue warp
+
+template <int BN>
+struct EpiRun {  // bytes staged per pixel per copy-out
+  static constexpr int GC_BF16 = BN < 64 ? BN : 64;
+  static constexpr int GC_F32 = BN < 32 ? BN : 32;
+};
+
+// Tile-invariant per-lane geometry. dh/dw = position of a tile row inside the tile.
+struct EpiLane {
+  int own_dh, own_dw;   // this lane's own row
+  int rnd_rel[8];       // copy-out round rd: pixel offset of the row this lane helps to write
+                        // (dh*Wout + dw, or (2dh)*(2Wout) + 2dw when the output is 2x2 replicated)
+};
+
+// rowpos(r, dh, dw): position of tile row r. run_bytes: bytes staged per pixel (RUN).
+template <typename RowPos>
+__device__ __forceinline__ EpiLane make_epi_lane(int warp_q, int lane, int run_bytes, int Wout, int up2, RowPos rowpos) {
+  EpiLane L;
+  rowpos(warp_q * 32 + lane, L.own_dh, L.own_dw);
+  const int lpp = run_bytes / 16, ppr = 32 / lpp;
+#pragma unroll
+  for (int rd = 0; rd < 8; ++rd) {
+    int dh = 0, dw = 0;
+    if (rd < lpp) rowpos(warp_q * 32 + rd * ppr + lane / lpp, dh, dw);
+    L.rnd_rel[rd] = up2 ? (2 * dh) * (2 * Wout) + 2 * dw : dh * Wout + dw;
+  }
+  return L;
+}
+
+// Cooperative copy-out with precomputed offsets. dst0: byte address of (tile origin pixel, first staged column).
+template <int RUN>
+__device__ __forceinline__ void warp_copy_out_fast(const uint8_t* stg, int lane, const EpiLane& L, uint8_t* dst0,
+                                                   size_t pixel_bytes, int up2, size_t up_row_bytes) {
+  constexpr int LPP = RUN / 16, PPR = 32 / LPP;
+  const int sub = lane % LPP;
+  const uint8_t* s = stg + (lane / LPP) * kStgPitch + sub * 16;
+  uint8_t* d0 = dst0 + sub * 16;
+#pragma unroll
+  for (int rd = 0; rd < LPP; ++rd) {
+    const uint4 v = *reinterpret_cast<const uint4*>(s + rd * PPR * kStgPitch);
+    uint8_t* d = d0 + static_cast<size_t>(L.rnd_rel[rd]) * pixel_bytes;
+    *reinterpret_cast<uint4*>(d) = v;
+    if (up2) {
+      *reinterpret_cast<uint4*>(d + pixel_bytes) = v;
+      *reinterpret_cast<uint4*>(d + up_row_bytes) = v;
+      *reinterpret_cast<uint4*>(d + up_row_bytes + pixel_bytes) = v;
+    }
+  }
+}
+
+// Generic copy-out: rowfn(r, b, oh, ow) -> valid for tile row r (any mapping, ragged tiles).
+template <int RUN, typename Args, typename RowFn>
+__device__ __forceinline__ void warp_copy_out(const Args& p, const uint8_t* stg, int warp_q, int lane, int col0, int elem,
+                                              uint8_t* out_bytes, RowFn rowfn) {
+  constexpr int LPP = RUN / 16;   // lanes per pixel
+  constexpr int PPR = 32 / LPP;   // pixels per round
+  const int sub = lane % LPP;
+#pragma unroll
+  for (int rd = 0; rd < LPP; ++rd) {
+    const int pr = rd * PPR + lane / LPP;
+    int b, oh, ow;
+    const bool valid = rowfn(warp_q * 32 + pr, b, oh, ow);
+    if (valid) {
+      const uint4 v = *reinterpret_cast<const uint4*>(stg + pr * kStgPitch + sub * 16);
+      if (p.up2_out) {
+        const size_t rowpitch = static_cast<size_t>(2 * p.Wout) * p.Cout * elem;
+        uint8_t* d = out_bytes + (((static_cast<size_t>(b) * 2 * p.Hout + 2 * oh) * 2 * p.Wout + 2 * ow) * p.Cout + col0) * elem + sub * 16;
+        const size_t px = static_cast<size_t>(p.Cout) * elem;
+        *reinterpret_cast<uint4*>(d) = v;
+        *reinterpret_cast<uint4*>(d + px) = v;
+        *reinterpret_cast<uint4*>(d + rowpitch) = v;
+        *reinterpret_cast<uint4*>(d + rowpitch + px) = v;
+      } else {
+        uint8_t* d = out_bytes + (((static_cast<size_t>(b) * p.Hout + oh) * p.Wout + ow) * p.Cout + col0) * elem + sub * 16;
+        *reinterpret_cast<uint4*>(d) = v;
+      }
+    }
+  }
+}
+
 // Args must provide: residual, rowbias, relu, out, out_f32, Cout, Hout, Wout, up2_out.
 // bias: fp32 [>= n0 + BN]; BIAS_SMEM selects plain (shared-memory) loads instead of the read-only path.
-template <int BN, bool PREFETCH, bool BIAS_SMEM, typename Args>
-__device__ __forceinline__ void epilogue_pixel(const Args& p, const float* bias, uint32_t taddr, uint32_t tfull_bar,
-                                               uint32_t tfull_parity, bool valid, int b, int oh, int ow, int n0) {
+// stg: this warp's staging buffer (kStgWarpBytes, 16-byte aligned).
+// own_valid / own_pix / own_rb: this lane's row: in range?, linear output pixel index, rowbias index.
+// copy(run_tag, col0, elem): cooperative copy-out of the staged column group starting at column col0.
+template <int BN, bool PREFETCH, bool BIAS_SMEM, typename Args, typename CopyFn>
+__device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, uint32_t taddr, uint32_t tfull_bar,
+                                              uint32_t tfull_parity, int lane, int n0, uint8_t* stg, bool own_valid,
+                                              long long own_pix, int own_rb, CopyFn copy) {
   using namespace ptx;
-  const long long pix = (static_cast<long long>(b) * p.Hout + oh) * p.Wout + ow;
-  const float rb = (p.rowbias != nullptr && valid) ? p.rowbias[b * p.Hout + oh] : 0.f;
-  const size_t obase = static_cast<size_t>(pix) * p.Cout + n0;
-  size_t ubase = 0, urow = 0;
-  if (p.up2_out) {
-    urow = static_cast<size_t>(2 * p.Wout) * p.Cout;
-    ubase = ((static_cast<size_t>(b) * 2 * p.Hout + 2 * oh) * 2 * p.Wout + 2 * ow) * p.Cout + n0;
-  }
-  const bool has_res = p.residual != nullptr && valid;
+  const float rb = (p.rowbias != nullptr && own_valid) ? p.rowbias[own_rb] : 0.f;
+  const size_t obase = static_cast<size_t>(own_pix) * p.Cout + n0;
+  const bool has_res = p.residual != nullptr && own_valid;
   constexpr int NRES = PREFETCH ? BN / 8 : 1;
   uint4 res[NRES];
   if (PREFETCH) {
@@ -42,6 +131,10 @@ __device__ __forceinline__ void epilogue_pixel(const Args& p, const float* bias,
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after_sync();
 
+  const bool f32 = p.out_f32 != nullptr;
+  uint8_t* my_row = stg + lane * kStgPitch;
+  constexpr int GC_BF16 = EpiRun<BN>::GC_BF16;
+  constexpr int GC_F32 = EpiRun<BN>::GC_F32;
 #pragma unroll(PREFETCH ? BN / 16 : 2)
   for (int c0 = 0; c0 < BN; c0 += 16) {
     uint32_t r[16];
@@ -60,59 +153,56 @@ __device__ __forceinline__ void epilogue_pixel(const Args& p, const float* bias,
 #pragma unroll
     for (int i = 0; i < 4; ++i) bb[i] = BIAS_SMEM ? bp[i] : __ldg(bp + i);
     tmem_ld_wait();
-    if (valid) {
-      float v[16];
+    float v[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb[i].x;
-        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb[i].y;
-        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb[i].z;
-        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb[i].w;
-      }
-      if (has_res) {
+    for (int i = 0; i < 4; ++i) {
+      v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb[i].x;
+      v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb[i].y;
+      v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb[i].z;
+      v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb[i].w;
+    }
+    if (has_res) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t w[4] = {rr[h].x, rr[h].y, rr[h].z, rr[h].w};
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t w[4] = {rr[h].x, rr[h].y, rr[h].z, rr[h].w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-            v[8 * h + 2 * i + 0] += __low2float(b2);
-            v[8 * h + 2 * i + 1] += __high2float(b2);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+          v[8 * h + 2 * i + 0] += __low2float(b2);
+          v[8 * h + 2 * i + 1] += __high2float(b2);
         }
       }
-      if (p.relu) {
+    }
+    if (p.relu) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += rb;
+
+    if (f32) {
+      float4* sp = reinterpret_cast<float4*>(my_row + (c0 % GC_F32) * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if ((c0 + 16) % GC_F32 == 0) {
+        __syncwarp();
+        copy(ptx::Int<GC_F32 * 4>{}, n0 + c0 + 16 - GC_F32, 4);
+        __syncwarp();
       }
+    } else {
+      uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += rb;
-      if (p.out_f32 != nullptr) {
-        float4* op = reinterpret_cast<float4*>(p.out_f32 + obase + c0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      } else {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
-        }
-        const uint4 lo = make_uint4(pk[0], pk[1], pk[2], pk[3]), hi = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (p.up2_out) {
-#pragma unroll
-          for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-              uint4* op = reinterpret_cast<uint4*>(p.out + ubase + dy * urow + static_cast<size_t>(dx) * p.Cout + c0);
-              op[0] = lo;
-              op[1] = hi;
-            }
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(p.out + obase + c0);
-          op[0] = lo;
-          op[1] = hi;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+      uint4* sp = reinterpret_cast<uint4*>(my_row + (c0 % GC_BF16) * 2);
+      sp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      sp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      if ((c0 + 16) % GC_BF16 == 0) {
+        __syncwarp();
+        copy(ptx::Int<GC_BF16 * 2>{}, n0 + c0 + 16 - GC_BF16, 2);
+        __syncwarp();
       }
     }
   }

@@ -1,6 +1,8 @@
 // Halo-staged tcgen05 convolution (see conv_halo.cuh for the idea and the layers it serves).
 #include "conv_halo.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_epilogue.cuh"
@@ -12,16 +14,20 @@ using namespace ptx;
 
 namespace {
 
-constexpr int kTH = 16, kTW = 8;          // output tile: 16 rows x 8 columns = 128 pixels (UMMA M)
-constexpr int kThreads = 288;             // warps 0-3 producers, 4-7 epilogue, 8 MMA issuer
-constexpr int kProducers = 128;
+constexpr int kTH = 16;                  // output tile: 16 rows x (8*MB) columns = MB blocks of 128 pixels (UMMA M)
+// 8 warps: 0-2 producers, 3 MMA issuer / TMEM owner, 4-7 epilogue. Two such CTAs fit one SM at
+// <= 128 registers per thread (16 warps, 4 per scheduler), which is what the small layers need.
+constexpr int kThreads = 256;
+constexpr int kProducers = 96;
+constexpr int kMmaWarp = 3;
 
-template <int KH, int STRIDE, int NCH>
+template <int KH, int STRIDE, int NCH, int MB, int BN = 64>
 struct Geo {
+  static constexpr int TW = 8 * MB;
   static constexpr int PAD = KH / 2;
   static constexpr int NP = STRIDE;                                    // w-parity planes
   static constexpr int PH = STRIDE * (kTH - 1) + KH + (NCH == 1 ? 1 : 0);  // +1: stem pairs taps vertically
-  static constexpr int SPANW = STRIDE * (kTW - 1) + KH;
+  static constexpr int SPANW = STRIDE * (TW - 1) + KH;
   static constexpr int PW = (SPANW + NP - 1) / NP;
   static constexpr int KWCELLS = NP * PW;
   static constexpr int PLANE16 = PH * PW;                              // 16-byte cells per plane
@@ -29,19 +35,22 @@ struct Geo {
   static constexpr int CELLS = PH * KWCELLS * NCH;
   static constexpr int CELLS_PER_THREAD = (CELLS + kProducers - 1) / kProducers;
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
-  // small stages: deeper ring, more cp.async groups in flight, two CTAs per SM
-  static constexpr bool SMALL = STAGE <= 12 * 1024;
-  static constexpr int STAGES = SMALL ? 6 : 4;
-  static constexpr int LAG = SMALL ? 4 : 2;
-  static constexpr int OCC = SMALL ? 2 : 1;
+  // ring depth / cp.async groups in flight / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
+  // memory (filter bank + stages + 18 KB epilogue staging): the 16/32-channel layers run two CTAs per SM
+  static constexpr bool TWO = KH == 3 && NCH <= 4;
+  static constexpr int STAGES = (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
+  static constexpr int LAG = STAGES == 4 ? 2 : 1;
+  static constexpr int OCC = TWO ? 2 : 1;
 };
 
-template <int KH, int STRIDE, int NCH, int BN>
-__global__ void __launch_bounds__(kThreads, Geo<KH, STRIDE, NCH>::OCC)
+template <int KH, int STRIDE, int NCH, int BN, int MB>
+__global__ void __launch_bounds__(kThreads, Geo<KH, STRIDE, NCH, MB, BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
-  using G = Geo<KH, STRIDE, NCH>;
+  using G = Geo<KH, STRIDE, NCH, MB, BN>;
   constexpr int S = G::STAGES;
-  constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : 128;
+  constexpr int kBarBytes = ((2 * S + 4) * 8 + 16 + 127) / 128 * 128;
+  constexpr int ACC = MB * BN;  // TMEM columns of one accumulator buffer (MB blocks of 128 x BN)
+  constexpr int TMEM_COLS = (2 * ACC <= 32) ? 32 : (2 * ACC <= 64) ? 64 : (2 * ACC <= 128) ? 128 : (2 * ACC <= 256) ? 256 : 512;
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int groups = p.groups1 + p.groups2;
@@ -67,7 +76,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     for (int i = threadIdx.x; i < wbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
     if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(full_bar(s), kProducers);
@@ -89,15 +98,17 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_w = p.Wout / kTW, tiles_h = p.Hout / kTH;
+  const int tiles_w = p.Wout / G::TW, tiles_h = p.Hout / kTH;
 
-  if (warp < 4) {
+  if (warp < kMmaWarp) {
     // ===================================================================== producers (halo gather)
-    // The cells a thread copies do not depend on the tile: decode them once. cell_dst: byte offset
-    // inside a stage | hh << 16 | k << 24 ; cell_src: element offset from the tile's first halo pixel.
+    // The cells a thread copies do not depend on the tile: decode them once into one word per cell,
+    // byte offset inside a stage | hh << 16 | k << 24. kProducers is a multiple of NCH, so the channel
+    // chunk c of every cell of a thread is the same: tid % NCH.
     const int tid = threadIdx.x;
-    uint32_t cell_dst[G::CELLS_PER_THREAD];
-    int cell_src1[G::CELLS_PER_THREAD], cell_src2[G::CELLS_PER_THREAD];
+    static_assert(kProducers % NCH == 0, "channel chunk must be constant per producer thread");
+    const int c8 = (tid % NCH) * 8;
+    uint32_t cell[G::CELLS_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
       const int idx = tid + j * kProducers;
@@ -105,14 +116,12 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const int k = (idx / NCH) % G::KWCELLS;
       const int hh = idx / (NCH * G::KWCELLS);
       const uint32_t dst = static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
-      cell_dst[j] = idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
-      cell_src1[j] = (hh * p.Win + k) * p.C1 + c * 8;
-      cell_src2[j] = (hh * p.Win + k) * p.C2 + c * 8;
+      cell[j] = idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
     }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
-      const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * kTW * STRIDE - G::PAD;
+      const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
       const long long origin = (static_cast<long long>(b) * p.Hin + ih0) * p.Win + iw0;  // may be "negative"
       for (int g = 0; g < groups; ++g, ++it) {
@@ -121,23 +130,26 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         mbar_wait(empty_bar(s), ph ^ 1);
         const bool from1 = g < p.groups1;
         const int Cs = from1 ? p.C1 : p.C2;
-        const __nv_bfloat16* src = (from1 ? p.x1 : p.x2) + origin * Cs + (from1 ? g : g - p.groups1) * (NCH * 8);
+        const __nv_bfloat16* src = (from1 ? p.x1 : p.x2) + origin * Cs + (from1 ? g : g - p.groups1) * (NCH * 8) + c8;
+        const int row_elems = p.Win * Cs;  // element distance between halo rows
         const uint32_t st = stage_addr0 + s * G::STAGE;
         if (interior) {
 #pragma unroll
           for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
-            if (cell_dst[j] != 0xFFFFFFFFu)
-              cp_async_16(st + (cell_dst[j] & 0xFFFFu), src + (from1 ? cell_src1[j] : cell_src2[j]), 16u);
+            if (cell[j] != 0xFFFFFFFFu) {
+              const int hh = (cell[j] >> 16) & 0xFF, k = cell[j] >> 24;
+              cp_async_16(st + (cell[j] & 0xFFFFu), src + hh * row_elems + k * Cs, 16u);
+            }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
-            if (cell_dst[j] != 0xFFFFFFFFu) {
-              const int hh = (cell_dst[j] >> 16) & 0xFF, k = cell_dst[j] >> 24;
+            if (cell[j] != 0xFFFFFFFFu) {
+              const int hh = (cell[j] >> 16) & 0xFF, k = cell[j] >> 24;
               const bool ok = static_cast<unsigned>(ih0 + hh) < static_cast<unsigned>(p.Hin) &&
                               static_cast<unsigned>(iw0 + k) < static_cast<unsigned>(p.Win);
-              const __nv_bfloat16* gp = ok ? src + (from1 ? cell_src1[j] : cell_src2[j]) : p.x1;
-              cp_async_16(st + (cell_dst[j] & 0xFFFFu), gp, ok ? 16u : 0u);
+              const __nv_bfloat16* gp = ok ? src + hh * row_elems + k * Cs : p.x1;
+              cp_async_16(st + (cell[j] & 0xFFFFu), gp, ok ? 16u : 0u);
             }
           }
         }
@@ -153,18 +165,39 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     fence_proxy_async_smem();
     const uint32_t first = it >= static_cast<uint32_t>(G::LAG) ? it - G::LAG : 0u;
     for (uint32_t j = first; j < it; ++j) mbar_arrive(full_bar(j % S));
-  } else if (warp < 8) {
+  } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int q = warp & 3;
-    const int row = q * 32 + lane;
+    uint8_t* stg = smem + (bars - smem_base) + kBarBytes + q * kStgWarpBytes;
+    const bool f32 = p.out_f32 != nullptr;
+    const int elem = f32 ? 4 : 2;
+    const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
+    const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
+    uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
+    // block rows: row r is pixel (r / 8, r % 8) of the 16 x 8 block
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2, p.Wout, p.up2_out,
+                                    [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
-      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      epilogue_pixel<BN, true, true>(p, bias_s, taddr, tfull_bar(as), aph, true, b, th * kTH + (row >> 3),
-                                     tw * kTW + (row & 7), 0);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
+      const int oh = th * kTH + L.own_dh;
+      const long long pix0 = (static_cast<long long>(tb) * p.Hout + th * kTH) * p.Wout + tw * G::TW;
+      const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * kTH * 2) * (2 * p.Wout) + tw * G::TW * 2;
+      uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
+      const long long own_pix0 = (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + tw * G::TW + L.own_dw;
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {  // block m = columns 8m..8m+7 of the tile
+        uint8_t* blk_dst = tile_dst + static_cast<size_t>(p.up2_out ? 16 * m : 8 * m) * pixel_bytes;
+        auto copy = [&](auto run, int col0, int el) {
+          warp_copy_out_fast<decltype(run)::value>(stg, lane, L, blk_dst + static_cast<size_t>(col0) * el, pixel_bytes,
+                                                   p.up2_out, up_row_bytes);
+        };
+        epilogue_tile<BN, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix0 + 8 * m,
+                                      tb * p.Hout + oh, copy);
+      }
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
     }
@@ -182,18 +215,22 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const uint32_t aph = (tcount >> 1) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);
       tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + as * BN;
+      const uint32_t d_tmem = tmem_base + as * ACC;
       for (int g = 0; g < groups; ++g, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after_sync();
         const uint32_t st16 = (stage_addr0 + s * G::STAGE) >> 4;
-        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {  // block m = output columns 8m..8m+7 of the tile: 8 cells further
+          uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+          const uint32_t a_base = st16 + 8 * m;
 #pragma unroll 4
-        for (int k = 0; k < p.nsteps; ++k) {
-          umma_bf16_lohi(d_tmem, p.a_lo[k] + st16, a_hi, b_lo, b_hi, idesc, (g | k) != 0 ? 1u : 0u);
-          b_lo += 2 * BN;
+          for (int k = 0; k < p.nsteps; ++k) {
+            umma_bf16_lohi(d_tmem + m * BN, p.a_lo[k] + a_base, a_hi, b_lo, b_hi, idesc, (g | k) != 0 ? 1u : 0u);
+            b_lo += 2 * BN;
+          }
         }
         umma_commit(empty_bar(s));
       }
@@ -203,41 +240,58 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int KH, int STRIDE, int NCH, int BN>
+template <int KH, int STRIDE, int NCH, int BN, int MB>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
-  using G = Geo<KH, STRIDE, NCH>;
+  using G = Geo<KH, STRIDE, NCH, MB, BN>;
   const int groups = a.groups1 + a.groups2;
   const int wbytes = groups * a.nsteps * 2 * BN * 16;
-  const int smem = ((wbytes + 127) / 128) * 128 + 256 + G::STAGES * G::STAGE + (2 * G::STAGES + 4) * 8 + 16;
+  const int smem = ((wbytes + 127) / 128) * 128 + 256 + G::STAGES * G::STAGE +
+                   ((2 * G::STAGES + 4) * 8 + 16 + 127) / 128 * 128 + 4 * kStgWarpBytes;
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
+    // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN>, kThreads, smem) == cudaSuccess && nb > 0)
-      occ = nb < G::OCC ? nb : G::OCC;
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB>, kThreads, smem);
+    if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
+    // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
+    // so size the grid for the intended co-residency and let the hardware place what fits.
+    occ = G::OCC;
   }
   const int cap = num_sms * occ;
   const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
   if (grid <= 0) return 0;
-  conv_halo_kernel<KH, STRIDE, NCH, BN><<<grid, kThreads, smem, stream>>>(a);
+  if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
+  conv_halo_kernel<KH, STRIDE, NCH, BN, MB><<<grid, kThreads, smem, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
 
+int halo_blocks(int KH, int nch, int bn) {
+  if (KH == 7) return 2;
+  if (nch == 2) return 4;               // 16 -> 16 @ 512^2: 16 x 32 pixel tiles
+  if (nch == 4 && bn == 16) return 2;   // 32 -> 16 @ 512^2 (two CTAs per SM)
+  return 2;
+}
+
 HaloGeom halo_geom(int KH, int stride, int nch, int bn) {
   HaloGeom g;
   g.KH = KH; g.stride = stride; g.nch = nch; g.bn = bn;
+  g.mb = halo_blocks(KH, nch, bn);
+  const int kTW = 8 * g.mb;
   g.pad = KH / 2;
   g.np = stride;
   g.ph = stride * (kTH - 1) + KH + (nch == 1 ? 1 : 0);
@@ -257,13 +311,14 @@ int halo_group_channels(int KH, int C1, int C2) {
 }
 
 bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int Wout) {
-  if (Hout % kTH != 0 || Wout % kTW != 0) return false;
-  if (KH == 7) return stride == 2 && C1 == 8 && C2 == 0 && Cout == 64;
+  if (Hout % kTH != 0) return false;
+  if (KH == 7) return stride == 2 && C1 == 8 && C2 == 0 && Cout == 64 && Wout % (8 * halo_blocks(7, 1, 64)) == 0;
   if (KH != 3 || stride != 1) return false;
   const int cg = halo_group_channels(KH, C1, C2);
   if (cg < 16 || C1 % cg != 0 || C2 % cg != 0) return false;
   const int nch = cg / 8;
   if ((C1 + C2) / cg > 2) return false;
+  if (Wout % (8 * halo_blocks(KH, nch, Cout)) != 0) return false;
   return (nch == 2 && Cout == 16) || (nch == 4 && (Cout == 16 || Cout == 32)) ||
          (nch == 8 && (Cout == 32 || Cout == 64));
 }
@@ -297,7 +352,7 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride) {
         a.a_lo[s] = off | (lbo << 16);
       }
   }
-  a.num_m_tiles = a.B * (a.Hout / kTH) * (a.Wout / kTW);
+  a.num_m_tiles = a.B * (a.Hout / kTH) * (a.Wout / (8 * g.mb));
 }
 
 static uint16_t bf16_rne(float f) {
@@ -346,12 +401,12 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   const int nch = cg / 8;
   if (!halo_supported(KH, stride, a.C1, a.C2, a.Cout, a.Hout, a.Wout)) return -3001;
   if (a.nsteps <= 0 || a.nsteps > kHaloMaxSteps) return -3002;
-  if (KH == 7) return launch_halo_t<7, 2, 1, 64>(a, num_sms, stream);
-  if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16>(a, num_sms, stream);
-  if (nch == 4 && a.Cout == 16) return launch_halo_t<3, 1, 4, 16>(a, num_sms, stream);
-  if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32>(a, num_sms, stream);
-  if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32>(a, num_sms, stream);
-  if (nch == 8 && a.Cout == 64) return launch_halo_t<3, 1, 8, 64>(a, num_sms, stream);
+  if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2>(a, num_sms, stream);
+  if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4>(a, num_sms, stream);
+  if (nch == 4 && a.Cout == 16) return launch_halo_t<3, 1, 4, 16, 2>(a, num_sms, stream);
+  if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32, 2>(a, num_sms, stream);
+  if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32, 2>(a, num_sms, stream);
+  if (nch == 8 && a.Cout == 64) return launch_halo_t<3, 1, 8, 64, 2>(a, num_sms, stream);
   return -3003;
 }
 

@@ -44,10 +44,11 @@ struct HaloArgs {
 
 // Geometry of one instantiation, shared by host packing and the kernel.
 struct HaloGeom {
-  int KH, stride, nch, bn;
+  int KH, stride, nch, bn, mb;
   int pad, np, ph, pw, kw_cells, plane16, stage_bytes, nsteps;
 };
 HaloGeom halo_geom(int KH, int stride, int nch, int bn);
+int halo_blocks(int KH, int nch, int bn);  // 128-pixel blocks per CTA tile (tile = 16 rows x 8*blocks columns)
 
 // True when (KH, stride, channels per group, Cout) has a compiled instantiation and the shape tiles.
 bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int Wout);

@@ -26,8 +26,8 @@ struct Cfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes;
+  static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + 4 * kStgWarpBytes;
 };
 
 template <int BN, bool TMA_A>
@@ -179,33 +179,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp < 8) {
     // ===================================================================== epilogue
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;     // tile row == TMEM lane
+    const int q = warp & 3;            // TMEM lane quarter this warp may access (tile rows 32q..32q+31)
     const int tiles_w = p.Wout >> 4, tiles_h = p.Hout >> 3;
+    const int HWo = p.Hout * p.Wout;
+    uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + q * kStgWarpBytes;
+    const bool f32 = p.out_f32 != nullptr;
+    const int elem = f32 ? 4 : 2;
+    const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
+    const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
+    uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
+    // TMA tiles are 8 x 16 pixel boxes: row r of the tile is pixel (r / 16, r % 16) of the box
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2, p.Wout, p.up2_out,
+                                    [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      bool valid = true;
-      int b_idx, oh_idx, ow_idx;
-      if (TMA_A) {
-        const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
-        b_idx = m_tile / (tiles_w * tiles_h);
-        oh_idx = th * 8 + (row >> 4);
-        ow_idx = tw * 16 + (row & 15);
-      } else {
-        const long long pix = static_cast<long long>(m_tile) * kBM + row;
-        valid = pix < p.M_total;
-        const int HWo = p.Hout * p.Wout;
-        b_idx = static_cast<int>(pix / HWo);
-        const int rem = static_cast<int>(pix - static_cast<long long>(b_idx) * HWo);
-        oh_idx = rem / p.Wout;
-        ow_idx = rem - oh_idx * p.Wout;
-      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
-      epilogue_pixel<BN, (BN <= 64), false>(p, p.bias, taddr, tfull_bar(as), aph, valid, b_idx, oh_idx, ow_idx,
-                                            n_tile * BN);
+      if (TMA_A) {
+        const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tb = m_tile / (tiles_w * tiles_h);
+        const int oh = th * 8 + L.own_dh, ow = tw * 16 + L.own_dw;
+        const long long pix0 = (static_cast<long long>(tb) * p.Hout + th * 8) * p.Wout + tw * 16;
+        const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * 16) * (2 * p.Wout) + tw * 32;
+        uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
+        auto copy = [&](auto run, int col0, int el) {
+          warp_copy_out_fast<decltype(run)::value>(stg, lane, L, tile_dst + static_cast<size_t>(col0) * el, pixel_bytes,
+                                                   p.up2_out, up_row_bytes);
+        };
+        epilogue_tile<BN, (BN <= 64), false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
+                                             (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
+      } else {
+        // gather tiles are 128 consecutive pixels of the flattened (b, h, w) index space, possibly ragged
+        auto rowfn = [&](int r, int& b, int& oh, int& ow) -> bool {
+          const long long pix = static_cast<long long>(m_tile) * kBM + r;
+          b = static_cast<int>(pix / HWo);
+          const int rem = static_cast<int>(pix - static_cast<long long>(b) * HWo);
+          oh = rem / p.Wout;
+          ow = rem - oh * p.Wout;
+          return pix < p.M_total;
+        };
+        auto copy = [&](auto run, int col0, int el) {
+          warp_copy_out<decltype(run)::value>(p, stg, q, lane, col0, el, out_bytes, rowfn);
+        };
+        int b, oh, ow;
+        const bool valid = rowfn(q * 32 + lane, b, oh, ow);
+        epilogue_tile<BN, (BN <= 64), false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, valid,
+                                             static_cast<long long>(m_tile) * kBM + q * 32 + lane, b * p.Hout + oh, copy);
+      }
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
     }

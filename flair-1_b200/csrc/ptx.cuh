@@ -9,6 +9,11 @@
 namespace fb {
 namespace ptx {
 
+template <int N>
+struct Int {  // compile-time integer tag (lets a generic lambda receive a constant)
+  static constexpr int value = N;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

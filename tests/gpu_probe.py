@@ -139,13 +139,13 @@ def halo_case(ctx, name, B, H, W, C1, Cout, KH, stride, C2=0, res=False, relu=Tr
 
 HALO_CASES = [
     # name, B, H, W, C1, Cout, KH, stride, kwargs
-    ("h_ident_16_16", 1, 16, 8, 16, 16, 3, 1, dict(identity=True, relu=False)),
-    ("h_3x3_16_16", 1, 16, 8, 16, 16, 3, 1, {}),
+    ("h_ident_16_16", 1, 16, 32, 16, 16, 3, 1, dict(identity=True, relu=False)),
+    ("h_3x3_16_16", 1, 16, 32, 16, 16, 3, 1, {}),
     ("h_3x3_16_16_multi", 2, 64, 64, 16, 16, 3, 1, {}),
     ("h_head_16_16_f32", 1, 32, 32, 16, 16, 3, 1, dict(relu=False, out_f32=True)),
     ("h_3x3_32_16", 2, 32, 32, 32, 16, 3, 1, {}),
     ("h_3x3_32_32_up2", 1, 32, 32, 32, 32, 3, 1, dict(up2=True)),
-    ("h_ident_64_64", 1, 16, 8, 64, 64, 3, 1, dict(identity=True, relu=False)),
+    ("h_ident_64_64", 1, 16, 16, 64, 64, 3, 1, dict(identity=True, relu=False)),
     ("h_3x3_64_64_res", 2, 32, 32, 64, 64, 3, 1, dict(res=True)),
     ("h_3x3_64p64_32", 2, 32, 32, 64, 32, 3, 1, dict(C2=64)),
     ("h_stem_7x7s2", 2, 64, 64, 8, 64, 7, 2, {}),
