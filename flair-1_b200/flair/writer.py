@@ -1,0 +1,28 @@
+"""Per-patch prediction writer (mirrors src/flair/writer.py): PRED_<image name>, uint8, 0-based class
+ids, LZW; georeferenced output copies the input's GeoTIFF tags (writer.py:38-43), plain output is a
+striped LZW TIFF like PIL's (writer.py:50)."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from .. import geotiff
+
+
+class predictionwriter:
+    def __init__(self, config, output_dir, write_interval="batch"):
+        self.config = config
+        self.output_dir = str(output_dir)
+        Path(self.output_dir).mkdir(exist_ok=True, parents=True)
+
+    def write_on_batch_end(self, prediction: dict) -> None:
+        preds = prediction["preds"].cpu().numpy().astype("uint8")
+        for pred, filename in zip(preds, prediction["id"]):
+            name = filename.split("/")[-1]
+            output_file = str(self.output_dir + "/" + "PRED_" + name)
+            if self.config["georeferencing_output"]:
+                tags = geotiff.read_info(filename).geo_tags
+                geotiff.write(output_file, pred, geo_tags=tags, compress="lzw", tiled=False, blocksize=64, bigtiff=False)
+            else:
+                geotiff.write(output_file, pred, compress="lzw", tiled=False, blocksize=64, bigtiff=False)

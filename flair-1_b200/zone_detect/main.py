@@ -1,0 +1,295 @@
+"""`flair-detect --conf x.yaml [-c] [-m] [-b]` on B200 (mirrors src/zone_detect/main.py).
+
+Same CLI flags, same YAML keys, same log tee, same output raster (uint8, LZW, tiled at
+img_pixels_detection, 2 bands for `argmax`: class index and max probability), same "never overwrite"
+file naming. The hot loop of the reference (main.py:398-426: DataLoader -> H2D -> forward -> softmax ->
+D2H of all probabilities -> numpy argmax -> per-tile GDAL write) becomes: read the raster once, upload,
+one `fb_detect_strip` per rank, download the uint8 maps, write the GeoTIFF.
+
+Multi-GPU: launched under `torchrun`, every rank takes a contiguous group of tile rows (halo rows are
+re-read, no exchange), rank 0 gathers the class-map strips over NCCL and writes the file; with `-m` the
+per-rank confusion matrices are summed with one all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import json
+import os
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import geotiff
+from .compare import stitching
+from .dataset import Sliced_Dataset
+from .metrics import confusion_matrix_gpu, metrics_from_confmat
+from .model import load_model
+from .slicing_job import slice_extent, split_rows_across_ranks
+from .tiles import get_stride
+from .utils import gen_param_combination, open_images, setup, setup_device, setup_indiv_path, setup_out_path
+
+warnings.simplefilter(action="ignore", category=FutureWarning)
+
+argParser = argparse.ArgumentParser()
+argParser.add_argument("--conf", help="Path to the .yaml config file")
+argParser.add_argument("-c", "--compare", help="Compare different methods", action="store_true")
+argParser.add_argument("-m", "--metrics", help="Compute metrics", action="store_true")
+argParser.add_argument("-b", "--batch_mode", help="Run the pipeline for a batch of images", action="store_true")
+
+
+def _rank_world() -> tuple[int, int]:
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class Logger(object):
+    """main.py:52-64: tee stdout/stderr to a log file (rank 0 only writes the file)."""
+
+    def __init__(self, filename: str = "Default.log") -> None:
+        self.terminal = sys.stdout
+        self.log = open(filename, "w", encoding="utf-8") if _rank_world()[0] == 0 else None
+        self.encoding = self.terminal.encoding
+
+    def write(self, message: str) -> None:
+        self.terminal.write(message)
+        if self.log:
+            self.log.write(message)
+
+    def flush(self) -> None:
+        self.terminal.flush()
+        if self.log:
+            self.log.flush()
+
+
+def conf_log(config: dict, resolution: tuple[float, float], img_size: list[int]) -> None:
+    """main.py:68-119 (the `strategies` block is optional here: the reference raises KeyError on the
+    plain detect YAML)."""
+    strategies = config.get("strategies", {})
+    print(f"""
+    |- output path: {config['output_path']}
+    |- output raster name: {config['output_name']}
+
+    |- input image path: {config['input_img_path']}
+    |- channels: {config['channels']}
+    |- resolution: {resolution}
+    |- image size: {img_size}
+
+    |- output type: {config['output_type']}
+    |- normalization: {config['norma_task'][0]['norm_type']}
+    |- number of classes: {config['n_classes']}
+
+    |- model weights path: {config['model_weights']}
+    |- model template: {config['model_framework']['model_provider']}
+
+    |- device: cuda (B200, libflairb200)
+    |- batch size: {config['batch_size']}
+
+    |- tiling: size {config['img_pixels_detection']}, margin {config['margin']}, strategies {bool(strategies)}
+    \n\n""")
+
+
+# __________Prepare objects___________#
+def prepare_tiles(config: dict, stride: int):
+    """main.py:123-148."""
+    tiles, profile, resolution, img_size = slice_extent(
+        in_img=Path(config["input_img_path"]), patch_size=config["img_pixels_detection"], margin=config["margin"],
+        output_name=config["output_name"], output_path=Path(config["local_out"]), write_dataframe=config["write_dataframe"],
+        stride=stride)
+    if _rank_world()[0] == 0:
+        conf_log(config, resolution, img_size)
+        print(f"""    [x] sliced input raster to {len(tiles)} squares...""")
+    return tiles, profile, resolution
+
+
+def prepare_data(config: dict, stride: int):
+    """main.py:151-183: tile table + the raster rows this rank needs (no DataLoader: tiles are cut on
+    the GPU)."""
+    tiles, profile, resolution = prepare_tiles(config, stride)
+    rank, world = _rank_world()
+    shard = split_rows_across_ranks(tiles, world)[rank]
+    my_tiles = tiles[shard]
+    size = config["img_pixels_detection"]
+    row_range = (int(my_tiles[:, 1].min()), int(my_tiles[:, 1].max()) + size) if len(my_tiles) else (0, 0)
+    dataset = Sliced_Dataset(dataframe=my_tiles, img_path=config["input_img_path"], resolution=resolution,
+                             bands=config["channels"], patch_detection_size=size, norma_dict=config["norma_task"],
+                             row_range=row_range)
+    return dataset, my_tiles, tiles, profile
+
+
+def prepare_model(config: dict, device: torch.device):
+    """main.py:186-203."""
+    if _rank_world()[0] == 0:
+        print(f"""
+    ##############################################
+    ZONE DETECTION
+    ##############################################
+
+    CUDA available? {torch.cuda.is_available()}""")
+    model = load_model(config, device)
+    nt = config["norma_task"][0]
+    model.set_norm(nt["norm_type"], nt.get("norm_means", []), nt.get("norm_stds", []), channels=len(config["channels"]))
+    if _rank_world()[0] == 0:
+        print("""    [x] loaded model and weights...""")
+    return model
+
+
+def prepare_output(config: dict, profile: dict, identifier: str = "") -> tuple[dict, str]:
+    """main.py:206-232: output profile (uint8, LZW, BIGTIFF, tiled at img_pixels_detection, 2 bands for
+    argmax / n_classes bands for class_prob) and a fresh path."""
+    config, path_out = setup_indiv_path(config, identifier)
+    out_profile = dict(profile)
+    out_profile.update({"dtype": "uint8", "compress": "LZW", "driver": "GTiff", "BIGTIFF": "YES", "tiled": True,
+                        "blockxsize": config["img_pixels_detection"], "blockysize": config["img_pixels_detection"]})
+    out_profile["count"] = 2 if config["output_type"] == "argmax" else config["n_classes"]
+    return out_profile, path_out
+
+
+def _write_output(path_out: str, bands: np.ndarray, profile: dict) -> None:
+    block = int(profile["blockxsize"])
+    block = block if block % 16 == 0 else 512
+    geotiff.write(path_out, bands, geo_tags=profile.get("geo_tags"), compress="lzw", tiled=True, blocksize=block, bigtiff=True)
+
+
+# _________PIPELINES__________#
+def run_from_config(config: dict) -> None:
+    device, use_gpu = setup_device(config)
+    run_pipeline(config, device, use_gpu)
+
+
+def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarray, device: torch.device,
+                stitch: str = "exact-clipping"):
+    """One rank's share of the hot loop. Returns (class strip, confidence strip, first row, rows) with the
+    strips on the device."""
+    size = config["img_pixels_detection"]
+    W = dataset.raster_width
+    if len(my_tiles) == 0:
+        e = torch.empty((0, W), dtype=torch.uint8, device=device)
+        return e, e.clone(), 0, 0
+    my0, my1 = int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())
+    raster_dev = dataset.big_image.to(device, non_blocking=True)
+    model.set_raster(raster_dev, list(range(dataset.num_bands)), W, dataset.raster_height, row0=dataset.row0)
+    cls = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
+    conf = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
+    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 32)))
+    stitching(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
+    return cls, conf, my0, my1 - my0
+
+
+def _gather_strips(strip: torch.Tensor, row0: int, H: int, W: int, device) -> np.ndarray | None:
+    """Rank 0 receives every rank's class-map strip (NCCL gather) and returns the full [H, W] map."""
+    rank, world = _rank_world()
+    if world == 1:
+        out = np.zeros((H, W), np.uint8)
+        out[row0:row0 + strip.shape[0]] = strip.cpu().numpy()
+        return out
+    import torch.distributed as dist
+    meta = torch.tensor([row0, strip.shape[0]], dtype=torch.int64, device=device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    rows_max = int(max(m[1].item() for m in metas))
+    padded = torch.zeros((rows_max, W), dtype=torch.uint8, device=device)
+    padded[:strip.shape[0]] = strip
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, bufs, dst=0)
+    if rank != 0:
+        return None
+    out = np.zeros((H, W), np.uint8)
+    for m, b in zip(metas, bufs):
+        r0, n = int(m[0].item()), int(m[1].item())
+        out[r0:r0 + n] = b[:n].cpu().numpy()
+    return out
+
+
+def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
+    """main.py:244-437, default branch (exact clipping, default tiling) plus `-m` whole-raster metrics;
+    with `-c` the same loop runs once per exact-clipping entry of the strategy grid."""
+    rank, world = _rank_world()
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+    config = setup_out_path(config)
+    local_out = Path(config["local_out"])
+    log_filename = local_out / Path(f"{config['output_name']}_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}.log")
+    old_out, old_err = sys.stdout, sys.stderr
+    sys.stdout = Logger(filename=str(log_filename))
+    sys.stderr = sys.stdout
+    result = {}
+    try:
+        if rank == 0:
+            print(f"    [LOGGER] Writing logs to: {log_filename}")
+        model = prepare_model(config, device)
+        truth_array, metrics_json = open_images(config, local_out, config["metrics"])
+
+        if config["compare"]:
+            settings = [c for c in gen_param_combination(config) if c["stitching"] == "exact-clipping"]
+            skipped = len(gen_param_combination(config)) - len(settings)
+            if skipped and rank == 0:
+                print(f"    [x] {skipped} strategy combination(s) use a weighted stitching the reference cannot execute; skipped")
+        else:
+            settings = [{"img_pixels_detection": config["img_pixels_detection"], "margin": config["margin"],
+                         "padding": "no-padding", "stitching": "exact-clipping", "stride": get_stride(config)[0]}]
+
+        method_metrics = []
+        for combi in settings:
+            cfg = dict(config)
+            cfg.update({"img_pixels_detection": combi["img_pixels_detection"], "margin": combi["margin"],
+                        "padding": combi["padding"], "stride": combi["stride"], "stitching": combi["stitching"]})
+            method = (f"size={combi['img_pixels_detection']}_stride={combi['stride']}_margin={combi['margin']}"
+                      f"_padding={combi['padding']}_stitching={combi['stitching']}")
+            identifier = "_" + method if config["compare"] else ""
+            start_time = datetime.datetime.now()
+            dataset, my_tiles, tiles, profile = prepare_data(cfg, combi["stride"])
+            out_profile, path_out = prepare_output(cfg, profile, identifier)
+            if rank == 0:
+                print("""    [ ] starting inference...\n""")
+            cls, conf, row0, rows = detect_zone(cfg, model, dataset, my_tiles, device, combi["stitching"])
+            H, W = dataset.raster_height, dataset.raster_width
+            if config["metrics"]:
+                n_classes = len(config["classes"]) if "classes" in config else config["n_classes"]
+                truth_dev = torch.from_numpy(np.ascontiguousarray(truth_array[row0:row0 + rows])).to(device)
+                cm = confusion_matrix_gpu(model, cls, truth_dev, n_classes)
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(cm)
+                result["confmat"] = cm.cpu().numpy()
+            if cfg["output_type"] == "argmax":
+                full_cls = _gather_strips(cls, row0, H, W, device)
+                full_conf = _gather_strips(conf, row0, H, W, device)
+                if rank == 0:
+                    _write_output(path_out, np.stack([full_cls, full_conf]), out_profile)
+            else:
+                raise NotImplementedError("output_type class_prob is not built yet (SURVEY.md section 8f rank 2)")
+            dataset.close_raster()
+            elapsed = (datetime.datetime.now() - start_time).total_seconds()
+            if rank == 0:
+                print(f"""    [X] done writing to {path_out.split('/')[-1]} raster file ({elapsed:.2f} s, {len(tiles)} tiles, """
+                      f"""{H * W / 1e6 / max(elapsed, 1e-9):.1f} Mpx/s incl. I/O).\n""")
+                result.setdefault("outputs", []).append(path_out)
+                if config["metrics"] and "classes" in config:
+                    method_metrics.append(metrics_from_confmat(result["confmat"], config, method))
+        if rank == 0 and config["metrics"] and method_metrics:
+            with open(metrics_json, "w") as f:
+                json.dump(method_metrics, f, indent=2)
+            print(f"""    [X] done writing metrics to {metrics_json.name} file.\n""")
+            result["metrics_json"] = str(metrics_json)
+            result["metrics"] = method_metrics
+    finally:
+        sys.stdout, sys.stderr = old_out, old_err
+    return result
+
+
+def main() -> None:
+    """main.py:501-515."""
+    args = argParser.parse_args()
+    config, device, use_gpu = setup(args)
+    if args.batch_mode:
+        raise NotImplementedError("batch mode (-b) is not built yet (SURVEY.md section 8f rank 4)")
+    run_pipeline(config, device, use_gpu)
+
+
+if __name__ == "__main__":
+    main()

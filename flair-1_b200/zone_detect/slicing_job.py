@@ -87,6 +87,32 @@ def tile_interiors(width: int, height: int, size: int, margin: int, stride: int 
                        for x in xs for yb in ybs], dtype=np.int64).reshape(-1, 4)
 
 
+def slice_extent(in_img, patch_size: int, margin: int, output_path, output_name: str, write_dataframe: bool, stride: int):
+    """Same call and return shape as the reference's slice_extent (slicing_job.py:19-118):
+    (tile table, profile, (res_x, res_y), [n_rows, n_cols]). The table is the int32 pixel-space array of
+    tile_table() instead of a GeoDataFrame; the profile carries what the output raster needs (size and
+    the GeoTIFF tags to copy). The reference reads the whole first band just to learn the shape (:30) and
+    names (rows, cols) "width, height"; the header is enough and the order is kept."""
+    from .. import geotiff
+    info = geotiff.read_info(in_img)
+    res = info.res
+    resolution = (abs(round(res[0], 5)), abs(round(res[1], 5)))
+    tiles = tile_table(info.width, info.height, patch_size, margin, stride)
+    profile = {"width": info.width, "height": info.height, "count": info.count, "dtype": "uint8",
+               "geo_tags": dict(info.geo_tags), "transform": info.transform}
+    if write_dataframe:
+        import os
+        path = os.path.join(str(output_path), output_name.split(".tif")[0] + "_slicing_job.csv")
+        ints = tile_interiors(info.width, info.height, patch_size, margin, stride)
+        t = info.transform or (1.0, 0.0, 0.0, 0.0, -1.0, float(info.height))
+        with open(path, "w") as f:  # the reference writes a GeoPackage through geopandas; CSV carries the same columns
+            f.write("id,left,bottom,right,top,x0_px,y0_px\n")
+            for i, ((l, b, r, tp), row) in enumerate(zip(ints, tiles)):
+                f.write(f"{i},{t[2] + l * t[0]},{t[5] + (info.height - b) * t[4]},{t[2] + r * t[0]},"
+                        f"{t[5] + (info.height - tp) * t[4]},{row[0]},{row[1]}\n")
+    return tiles, profile, resolution, [info.height, info.width]
+
+
 def split_rows_across_ranks(tiles: np.ndarray, world_size: int) -> List[np.ndarray]:
     """Shard the tile table by tile *rows* (equal y0) into `world_size` contiguous groups balanced by
     tile count; each rank then needs raster rows [min y0, max y0 + size) only. Returns index arrays

@@ -289,6 +289,28 @@ def gold_checkpoint(out: dict):
     out["checkpoint"] = res
 
 
+def gold_config(out: dict):
+    """gen_param_combination / check_list_type / setup_indiv_path of src/zone_detect/utils.py."""
+    import tempfile
+    import src.zone_detect.utils as zu
+    base = {"img_pixels_detection": 512, "margin": 128}
+    cfgs = [dict(base),
+            dict(base, overlap_strat=True, strategies={"tiling": {"enabled": True, "size_range": [256, 512, 1024], "stride_range": [0.5, 1.0]},
+                                                       "stitching": {"enabled": True, "methods": ["exact-clipping", "average"], "margin": [0.125, 0.25, 0.5]},
+                                                       "padding_overall": ["no-padding"]}),
+            dict(base, strategies={"tiling": {"enabled": False}, "stitching": {"enabled": True, "methods": ["exact-clipping"], "margin": [64.0, 0.25]}})]
+    out["gen_param_combination"] = [{"config": c, "combi": zu.gen_param_combination(c)} for c in cfgs]
+    out["check_list_type"] = [{"arg": a, "type": t.__name__, "res": zu.check_list_type(a, t)} for a, t in
+                              [(512, int), ([128, 256], int), (0.5, float), ([0.25, 0.5], float), ("max", str), (["a", "b"], str)]]
+    with tempfile.TemporaryDirectory() as d:
+        names = []
+        for _ in range(3):
+            _, p = zu.setup_indiv_path({"output_name": "zone", "local_out": d}, "_id")
+            open(p, "w").close()
+            names.append(Path(p).name)
+        out["setup_indiv_path"] = names
+
+
 def gold_metadata_forward(out: dict):
     """The reference's own FLAIR_ModelFactory.forward / MetadataMLP (flair/model.py:52-96) on top of
     the restated Unet: pins the MLP + `repeat(1,512,1,16)` broadcast + add semantics."""
@@ -324,6 +346,7 @@ def main():
     gold_metrics(out)
     gold_metadata(out)
     gold_checkpoint(out)
+    gold_config(out)
     if "--with-forward" in sys.argv:
         gold_metadata_forward(out)
     (HERE / "golden.json").write_text(json.dumps(_jsonable(out), indent=1))

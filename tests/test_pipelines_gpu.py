@@ -1,0 +1,193 @@
+"""End-to-end drop-in tests on the GPU: the `flair-detect` and `flair` entry points fed with YAML-shaped
+configs, GeoTIFF files and .pth/.ckpt checkpoints, checked against the CPU oracle."""
+import json
+import sys
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+CLASSES19 = {i + 1: [0 if i + 1 in (15, 16, 17, 19) else 1, f"class{i + 1}"] for i in range(19)}
+CLASSES15 = {i + 1: [1 if i < 12 else 0, f"class{i + 1}"] for i in range(15)}
+
+
+def _write_zone(tmp_path, W, H, seed):
+    from flair1_b200 import geotiff as gt
+    from oracle import synth
+    raster = synth.synth_raster(3, H, W, seed=seed)
+    truth = synth.synth_mask(raster, 15, 3)
+    d = tmp_path / "D001_2021" / "Z1_UU"
+    d.mkdir(parents=True)
+    tags = gt.georef_tags(800000.0, 6500000.0 + H * 0.2, 0.2, 0.2)
+    gt.write(d / "zone.tif", raster, geo_tags=tags, compress="lzw", tiled=True, blocksize=256)
+    gt.write(d / "truth.tif", truth, geo_tags=tags, compress="deflate", tiled=False, blocksize=64)
+    return raster, truth, d
+
+
+def test_flair_detect_cli_end_to_end(tmp_path, trained_3_15):
+    """flair-detect --conf x.yaml -m on a 900 x 700 GeoTIFF: 2-band uint8 LZW tiled BigTIFF with the
+    input's georeferencing, class map >= 99.9 % equal to the oracle's, metrics JSON equal to sklearn on
+    the same class map."""
+    from flair1_b200 import geotiff as gt
+    from flair1_b200.zone_detect import main as zmain
+    from flair1_b200.zone_detect.utils import read_config
+    from oracle import synth
+    from oracle.metrics_ref import class_IoU, clean_confmat, overall_accuracy, patch_confusion
+    from oracle.zone_detect_ref import GeoRaster, run_zone
+    sd, model = trained_3_15
+    W, H = 900, 700
+    raster, truth, d = _write_zone(tmp_path, W, H, seed=11)
+    torch.save({"model.seg_model." + k: v for k, v in sd.items()}, tmp_path / "weights.pth")   # prefixed layout
+    means, stds = synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3]
+    cfg = {"output_path": str(tmp_path / "out"), "output_name": "pred_zone", "input_img_path": str(d / "zone.tif"),
+           "truth_path": str(d / "truth.tif"), "channels": [1, 2, 3], "img_pixels_detection": 512, "margin": 128,
+           "output_type": "argmax", "n_classes": 15, "model_weights": str(tmp_path / "weights.pth"),
+           "model_framework": {"model_provider": "SegmentationModelsPytorch", "HuggingFace": {"org_model": None},
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}},
+           "batch_size": 4, "use_gpu": True, "num_worker": 2, "write_dataframe": True,
+           "norma_task": [{"norm_type": "custom", "norm_means": means, "norm_stds": stds}], "classes": CLASSES15}
+    conf = tmp_path / "detect.yaml"
+    conf.write_text(yaml.safe_dump(cfg))
+    args = SimpleNamespace(conf=str(conf), metrics=True, batch_mode=False, compare=False)
+    config = read_config(args)
+    res = zmain.run_pipeline(config, torch.device("cuda", 0), True)
+    out_path = Path(res["outputs"][0])
+    assert out_path.name == "pred_zone.tif" and (tmp_path / "out" / "pred_zone_slicing_job.csv").exists()
+    assert any(p.suffix == ".log" for p in (tmp_path / "out").iterdir())
+    info = gt.read_info(out_path)
+    assert (info.width, info.height, info.count, info.compression, info.tiled, info.block_w, info.bigtiff) == (W, H, 2, 5, True, 512, True)
+    assert info.geo_tags[33922] == gt.read_info(d / "zone.tif").geo_tags[33922]
+    got = gt.read(out_path)
+    ocfg = dict(cfg)
+    ref_cls, ref_conf, _ = run_zone(model, GeoRaster(raster, 800000.0, 6500000.0 + H * 0.2, 0.2), ocfg)
+    agree = (got[0] == ref_cls).mean()
+    print(f"flair-detect end-to-end agreement {agree * 100:.4f}%")
+    assert agree >= 0.999 and (got[1] == ref_conf).mean() >= 0.995
+    # metrics: bit-exact confusion matrix w.r.t. sklearn on the SAME class map, same ratios
+    cm_ref = patch_confusion(truth - 1, got[0], 15)
+    np.testing.assert_array_equal(res["confmat"], cm_ref)
+    m = json.loads(Path(res["metrics_json"]).read_text())[0]
+    (key, body), = m.items()
+    assert key.startswith("size=512_stride=256_margin=128") and Path(res["metrics_json"]).name == "metrics_per-patch_D001_2021_Z1_UU.json"
+    cleaned = clean_confmat(cm_ref, CLASSES15)
+    assert body["Avg_metrics"][0] == class_IoU(cleaned)[1] and body["Avg_metrics"][1] == overall_accuracy(cleaned)
+    # second run never overwrites
+    res2 = zmain.run_pipeline(read_config(args), torch.device("cuda", 0), True)
+    assert Path(res2["outputs"][0]).name == "pred_zone_1.tif"
+    np.testing.assert_array_equal(gt.read(res2["outputs"][0]), got)
+
+
+def test_flair_detect_rejects_what_it_cannot_do(tmp_path, trained_3_15):
+    from flair1_b200.zone_detect.model import load_model
+    sd, _ = trained_3_15
+    broken = dict(sd)
+    broken.pop("encoder.layer3.2.bn1.running_mean")
+    torch.save(broken, tmp_path / "broken.pth")
+    cfg = {"channels": [1, 2, 3], "n_classes": 15, "model_weights": str(tmp_path / "broken.pth"),
+           "model_framework": {"model_provider": "SegmentationModelsPytorch",
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}}}
+    with pytest.raises(RuntimeError, match="Missing key"):      # load_state_dict(strict=True)
+        load_model(cfg, 0)
+    cfg["model_framework"]["model_provider"] = "HuggingFace"
+    with pytest.raises(NotImplementedError):
+        load_model(cfg, 0)
+
+
+def test_flair_predict_and_metrics_end_to_end(tmp_path, trained_3_15):
+    """flair --conf x.yaml (predict + metrics) on 6 synthetic 512 x 512 patches laid out like csv_toy: PRED_*.tif
+    files with 0-based classes, metrics/confmat.npy + metrics.json equal to the oracle's on the same files."""
+    from flair1_b200 import geotiff as gt
+    from flair1_b200.flair import main as fmain
+    from oracle import synth
+    from oracle.flair_ref import norm, predict_step
+    from oracle.metrics_ref import flair_metrics, patch_confusion
+    sd, model = trained_3_15
+    means, stds = synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3]
+    data = tmp_path / "data"
+    (data / "img").mkdir(parents=True)
+    (data / "msk").mkdir()
+    rows, imgs, msks = [], [], []
+    for i in range(6):
+        img5 = synth.synth_raster(5, 512, 512, seed=100 + i)
+        msk = synth.synth_mask(img5[:3], 15, 3)
+        msk[:8] = 19                                  # labels outside 1..15 are dropped by the confusion matrix
+        ip, mp = data / "img" / f"IMG_{i:06d}.tif", data / "msk" / f"MSK_{i:06d}.tif"
+        gt.write(ip, img5, geo_tags=gt.georef_tags(900000.0 + 102.4 * i, 6400000.0, 0.2, 0.2), compress="deflate", tiled=False, blocksize=64)
+        gt.write(mp, msk, compress="lzw", tiled=False, blocksize=64)
+        rows.append(f"{ip},{mp}")
+        imgs.append(img5[:3])
+        msks.append(msk)
+    csv = tmp_path / "test.csv"
+    csv.write_text("\n".join(rows) + "\n")
+    torch.save({"state_dict": {**{"model.seg_model." + k: v for k, v in sd.items()}, "criterion.weight": torch.ones(15)}},
+               tmp_path / "model.ckpt")
+    cfg = {"paths": {"out_folder": str(tmp_path / "exp"), "out_model_name": "run1", "train_csv": None, "val_csv": None,
+                     "test_csv": str(csv), "ckpt_model_path": str(tmp_path / "model.ckpt"), "path_metadata_aerial": None},
+           "tasks": {"train": False, "train_tasks": {"init_weights_only_from_ckpt": False, "resume_training_from_ckpt": False},
+                     "predict": True, "metrics": True, "delete_preds": False},
+           "model_framework": {"model_provider": "SegmentationModelsPytorch",
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}},
+           "use_augmentation": False, "use_metadata": False, "channels": [1, 2, 3], "norm_type": "custom",
+           "norm_means": means, "norm_stds": stds, "seed": 2022, "batch_size": 4, "classes": CLASSES15,
+           "georeferencing_output": True, "cp_csv_and_conf_to_output": True, "accelerator": "gpu", "num_nodes": 1,
+           "gpus_per_node": 1, "strategy": "auto", "num_workers": 0}
+    conf = tmp_path / "flair.yaml"
+    conf.write_text(yaml.safe_dump(cfg))
+    old = sys.argv
+    sys.argv = ["flair", "--conf", str(conf)]
+    try:
+        fmain.main()
+    finally:
+        sys.argv = old
+    pred_dir = tmp_path / "exp" / "run1" / "predictions_run1"
+    assert (tmp_path / "exp" / "run1" / "flair-compute.log").exists()
+    assert (tmp_path / "exp" / "run1" / "used_csv_and_config" / "test.csv").exists()
+    agree, cms = [], []
+    for i in range(6):
+        p = pred_dir / f"PRED_IMG_{i:06d}.tif"
+        info = gt.read_info(p)
+        assert (info.count, info.compression) == (1, 5) and 33922 in info.geo_tags
+        got = gt.read(p)[0]
+        x = torch.as_tensor(norm(imgs[i], "custom", means, stds), dtype=torch.float)[None]
+        ref = predict_step(model, x)[0].numpy().astype(np.uint8)
+        agree.append((got == ref).mean())
+        cms.append(patch_confusion(msks[i] - 1, got, 15))
+    print(f"flair predict agreement {np.mean(agree) * 100:.4f}%")
+    assert np.mean(agree) >= 0.999
+    confmat = np.load(tmp_path / "exp" / "run1" / "metrics" / "confmat.npy")
+    np.testing.assert_array_equal(confmat, np.sum(cms, axis=0))
+    m = json.loads((tmp_path / "exp" / "run1" / "metrics" / "metrics.json").read_text())
+    ref_m = flair_metrics(np.sum(cms, axis=0), CLASSES15)
+    assert m["Avg_metrics"] == [float(v) for v in ref_m["Avg_metrics"]] and m["classes"] == ref_m["classes"]
+    assert m["per_class_iou"] == [float(v) for v in ref_m["per_class_iou"]]
+
+
+def test_load_checkpoint_class_count_surgery(tmp_path, trained_3_15):
+    """src/flair/main.py:106-138: a 15-class checkpoint loaded into a 13-class config gets its head
+    truncated and zeroed (so every logit is 0 and argmax is class 0 everywhere)."""
+    from flair1_b200.flair.model import FLAIR_ModelFactory, load_checkpoint
+    from oracle import synth
+    sd, _ = trained_3_15
+    torch.save({**sd, "criterion.weight": torch.ones(15)}, tmp_path / "m.pth")
+    classes13 = {i + 1: [1, f"c{i + 1}"] for i in range(13)}
+    cfg = {"paths": {"ckpt_model_path": str(tmp_path / "m.pth")}, "classes": classes13, "channels": [1, 2, 3], "use_metadata": False,
+           "model_framework": {"model_provider": "SegmentationModelsPytorch",
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}}}
+    fac = FLAIR_ModelFactory(cfg, 0)
+    load_checkpoint(cfg, fac)
+    assert fac.loaded
+    ctx = fac.seg_model
+    ctx.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+    patches = torch.from_numpy(synth.synth_raster(3, 512, 512, seed=5))[None].cuda()
+    assert int(ctx.predict_patches(patches, 512, 1).max()) == 0
+    cfg["paths"]["ckpt_model_path"] = str(tmp_path / "missing.pth")
+    fac2 = FLAIR_ModelFactory(cfg, 0)
+    load_checkpoint(cfg, fac2)                 # "Invalid checkpoint file path." and nothing loaded
+    assert not fac2.loaded
+    with pytest.raises(SystemExit):
+        load_checkpoint(cfg, fac2, exit_on_fail=True)
