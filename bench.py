@@ -275,8 +275,11 @@ def run_ours(args) -> int:
             dist.all_reduce(cm_dev)
 
     def step_e2e():
+        t = time.perf_counter()
         ctx.detect_zone_host(raster_host, [0, 1, 2], W, H, ry0, nat.FB_LAYOUT_CHW, tiles, TILE, args.batch,
                              cls_host, conf_host, W, my0, my1 - my0)
+        if rank == 0:
+            log(f"[bench] e2e step {1e3 * (time.perf_counter() - t):.1f} ms")
 
     def timed(fn, steps):
         barrier()
@@ -375,7 +378,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="tiles per forward pass")
+    ap.add_argument("--batch", type=int, default=64, help="tiles per forward pass")
     ap.add_argument("--cpu-tiles", type=int, default=160, help="tiles of the zone timed on the host cores (cpu_baseline)")
     ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the reference arm")
     args = ap.parse_args()

@@ -69,6 +69,8 @@ struct fb_ctx {
   const uint8_t* raster = nullptr;
   uint8_t* raster_own = nullptr;
   size_t raster_own_bytes = 0;
+  uint8_t* maps_own = nullptr;   // class / confidence maps of fb_detect_zone_host
+  size_t maps_own_bytes = 0;
   int bands_total = 0, rc = 0, layout = 0;
   int64_t W = 0, H = 0, row0 = 0, rows = 0;
   int* band_idx_dev = nullptr;
@@ -533,6 +535,7 @@ void fb_destroy(fb_ctx* c) {
   for (void* p : c->owned) cudaFree(p);
   if (c->lut) cudaFree(c->lut);
   if (c->raster_own) cudaFree(c->raster_own);
+  if (c->maps_own) cudaFree(c->maps_own);
   if (c->band_idx_dev) cudaFree(c->band_idx_dev);
   if (c->arena) cudaFree(c->arena);
   if (c->tile_xy_dev) cudaFree(c->tile_xy_dev);
@@ -721,11 +724,18 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
   if (!c || !host_cls || map_w <= 0 || map_rows <= 0) return FB_ERR_INVALID;
   FB_TRY(fb_upload_raster(c, host_raster, bands_total, band_idx, nc, W, H, row0, rows, layout));
   const size_t mbytes = static_cast<size_t>(map_w) * map_rows;
-  uint8_t* maps = nullptr;
-  if (cudaMalloc(&maps, mbytes * (host_conf ? 2 : 1)) != cudaSuccess) {
-    cudaGetLastError();
-    return fail(c, FB_ERR_OOM, "class map: cudaMalloc failed");
+  // context-owned, grow-only map buffer (a cudaMalloc/cudaFree pair per call would serialise the device)
+  if (mbytes * 2 > c->maps_own_bytes) {
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->maps_own) cudaFree(c->maps_own);
+    c->maps_own = nullptr; c->maps_own_bytes = 0;
+    if (cudaMalloc(&c->maps_own, mbytes * 2) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, FB_ERR_OOM, "class map: cudaMalloc failed");
+    }
+    c->maps_own_bytes = mbytes * 2;
   }
+  uint8_t* maps = c->maps_own;
   int rc = 0;
   cudaError_t e = cudaMemsetAsync(maps, 0, mbytes * (host_conf ? 2 : 1), c->stream);
   if (e != cudaSuccess) rc = cuda_fail(c, e, "cudaMemsetAsync");
@@ -736,8 +746,6 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) rc = cuda_fail(c, e, "class map download");
   }
-  cudaStreamSynchronize(c->stream);
-  cudaFree(maps);
   return rc;
 }
 
