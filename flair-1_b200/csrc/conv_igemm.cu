@@ -269,6 +269,172 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------ CTA-pair kernel
+// Same implicit GEMM with tcgen05.mma.cta_group::2: a cluster of two CTAs (one TPC) computes a 256-pixel
+// tile (two vertically adjacent 8x16 boxes) x BN channels. Each CTA stages its own box of A and HALF of
+// the weight tile, so a K=16 step costs each SM 4 KB + BN*16 B of shared-memory reads instead of
+// 4 KB + BN*32 B -- the single-CTA kernel is bound by exactly that traffic for BN >= 128.
+// The leader (cluster rank 0) owns the "full" barriers (TMA bytes of both CTAs are counted there), issues
+// the MMAs and multicasts the commits; both CTAs run their own producer thread and epilogue warps.
+template <int BN>
+struct Cfg2 {
+  static constexpr int kStages = BN >= 256 ? 6 : 8;    // 6 x 32 KB or 8 x 24 KB of operands in flight per CTA
+  static constexpr int kABytes = kBM * kBK * 2;        // 16384: this CTA's 128 pixels
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;   // this CTA's half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + 4 * kStgWarpBytes;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+  using C = Cfg2<BN>;
+  constexpr int S = C::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+  const uint32_t bars = base + S * C::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };          // used in the leader only
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };   // one per CTA, released by multicast commits
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };  // leader only: 256 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S * C::kStageBytes + (2 * S + 4) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 2 * kNumEpilogueThreads);
+      }
+      fence_mbar_init();
+      tma_prefetch_desc(&tmA);
+      if (p.C2 > 0) tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB);
+    }
+    __syncwarp();
+    tmem_alloc_2sm(smem_u32(tmem_slot), C::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive / complete_tx
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_w = p.Wout >> 4, tiles_h2 = p.Hout >> 4;   // a pair covers 16 rows x 16 columns
+  const int num_pairs = p.B * tiles_h2 * tiles_w;
+  const int num_tiles = num_pairs * p.num_n_tiles;
+  const int nk = p.num_k_iters;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp < 4) {
+    if (threadIdx.x == 0) {
+      const int c1chunks = p.C1 >> 6;
+      const int cchunks = (p.C1 + p.C2) >> 6;
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int n_tile = tile % p.num_n_tiles, pair = tile / p.num_n_tiles;
+        const int tw = pair % tiles_w, th2 = (pair / tiles_w) % tiles_h2, b = pair / (tiles_w * tiles_h2);
+        const int h0 = th2 * 16 + 8 * static_cast<int>(rank);
+        for (int kit = 0; kit < nk; ++kit, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (leader) mbar_expect_tx(full_bar(s), 2 * C::kStageBytes);
+          const int tap = kit / cchunks, cc = kit - tap * cchunks;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          const uint32_t a_dst = base + s * C::kStageBytes;
+          if (cc < c1chunks) {
+            tma_load_4d_2sm(a_dst, &tmA, full_bar(s), cc * 64, tw * 16 + kw - 1, h0 + kh - 1, b);
+          } else {
+            tma_load_4d_2sm(a_dst, &tmA2, full_bar(s), (cc - c1chunks) * 64, tw * 16 + kw - 1, h0 + kh - 1, b);
+          }
+          tma_load_2d_2sm(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK,
+                          n_tile * BN + static_cast<int>(rank) * (BN / 2));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3;
+    uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + q * kStgWarpBytes;
+    const bool f32 = p.out_f32 != nullptr;
+    const int elem = f32 ? 4 : 2;
+    const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
+    const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
+    uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2, p.Wout, p.up2_out,
+                                    [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
+    uint32_t tcount = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+      const int n_tile = tile % p.num_n_tiles, pair = tile / p.num_n_tiles;
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const int tw = pair % tiles_w, th2 = (pair / tiles_w) % tiles_h2, tb = pair / (tiles_w * tiles_h2);
+      const int h0 = th2 * 16 + 8 * static_cast<int>(rank);
+      const int oh = h0 + L.own_dh, ow = tw * 16 + L.own_dw;
+      const long long pix0 = (static_cast<long long>(tb) * p.Hout + h0) * p.Wout + tw * 16;
+      const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + 2 * h0) * (2 * p.Wout) + tw * 32;
+      uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
+      auto copy = [&](auto run, int col0, int el) {
+        warp_copy_out_fast<decltype(run)::value>(stg, lane, L, tile_dst + static_cast<size_t>(col0) * el, pixel_bytes,
+                                                 p.up2_out, up_row_bytes);
+      };
+      epilogue_tile<BN, false, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
+                                      (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
+      tc_fence_before_sync();
+      mbar_arrive_leader(tempty_bar(as));   // local arrive in the leader, remote arrive from the peer
+    }
+  } else if (leader && lane == 0) {
+    // M = 256 (both CTAs' pixels), N = BN; descriptors name the leader's smem, the peer's data sits at
+    // the same offsets of its own shared memory.
+    constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
+      const int as = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tempty_bar(as), aph ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kit = 0; kit < nk; ++kit, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after_sync();
+        const uint32_t a_addr = base + s * C::kStageBytes;
+        const uint64_t adesc = umma_desc_sw128(a_addr);
+        const uint64_t bdesc = umma_desc_sw128(a_addr + C::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)
+          umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kit | k) != 0 ? 1u : 0u);
+        umma_commit_2sm(empty_bar(s), 0b11);     // frees the stage in both CTAs
+      }
+      umma_commit_2sm(tfull_bar(as), 0b11);      // accumulator ready for both epilogues
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be read by the leader's MMAs / arrive on its barriers
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -288,6 +454,21 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap&
     configured = true;
   }
   conv_igemm_kernel<BN, TMA_A><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int BN>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvArgs& a,
+                int grid, cudaStream_t stream) {
+  using C = Cfg2<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  conv_igemm2_kernel<BN><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);  // cluster dims are static (2,1,1)
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -342,11 +523,16 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmA2, 0, sizeof(tmA2));
   memset(&tmB, 0, sizeof(tmB));
+  // CTA pairs (cta_group::2) for the wide layers: 16 x 16 pixel tiles, each CTA stages half of the weights
+  // Measured on B200 (profiles/r01_pair_vs_single.md): no faster than the single-CTA kernel on these
+  // shapes (the wide layers are not shared-memory-port bound after all), so it is opt-in: FB_PAIR=1.
+  const char* pair_env = getenv("FB_PAIR");
+  const bool use_pair = use_tma_a && BN >= 128 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1';
   {
-    // weights: [Cout][Kpad] bf16, box = 64 k x BN rows, 128-byte swizzle
+    // weights: [Cout][Kpad] bf16, box = 64 k x BN rows (BN/2 per CTA of a pair), 128-byte swizzle
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kpad), static_cast<cuuint64_t>(a.Cout)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kpad) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(BN)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(use_pair ? BN / 2 : BN)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = g_encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(weights),
                           dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -372,6 +558,15 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return -1200 - static_cast<int>(r);
     }
+  }
+
+  if (use_pair) {
+    const int num_pairs = a.B * (a.Hout / 16) * (a.Wout / 16) * a.num_n_tiles;
+    int clusters = num_sms / 2;
+    if (num_pairs < clusters) clusters = num_pairs;
+    if (clusters <= 0) return 0;
+    return BN == 256 ? launch_pair<256>(tmA, tmA2, tmB, a, 2 * clusters, stream)
+                     : launch_pair<128>(tmA, tmA2, tmB, a, 2 * clusters, stream);
   }
 
   const int num_tiles = a.num_m_tiles * a.num_n_tiles;

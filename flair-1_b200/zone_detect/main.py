@@ -173,7 +173,7 @@ def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarr
     model.set_raster(raster_dev, list(range(dataset.num_bands)), W, dataset.raster_height, row0=dataset.row0)
     cls = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
     conf = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
-    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 64)))
+    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 74)))
     stitching(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
     return cls, conf, my0, my1 - my0
 

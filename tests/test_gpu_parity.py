@@ -69,6 +69,25 @@ def test_dual_source_tma_conv(ctx):
     assert gpu_probe.conv_case(ctx, "t_dual_512p256_256", 1, 32, 32, 512, 256, 3, 1, 1, 1, C2=256), gpu_probe.RESULTS[-1]
 
 
+def test_cta_pair_kernel_matches(monkeypatch):
+    """tcgen05.mma.cta_group::2 variant (FB_PAIR=1): a cluster of two CTAs per 16 x 16 pixel tile, weights
+    split across the pair. Opt-in because it measured no faster; must give the same results."""
+    import gpu_probe
+    nat = _nat()
+    monkeypatch.setenv("FB_PAIR", "1")
+    c = nat.Context(0)
+    gpu_probe.RESULTS.clear()
+    try:
+        for case in (("p_3x3_128_res", 2, 16, 16, 128, 128, 3, 1, 1, 1, dict(res=True)),
+                     ("p_3x3_256", 3, 32, 32, 256, 256, 3, 1, 1, 1, {}),
+                     ("p_3x3_512_res_rowbias", 4, 16, 16, 512, 512, 3, 1, 1, 1, dict(res=True, rowb=True)),
+                     ("p_dual_512p256_256", 1, 32, 32, 512, 256, 3, 1, 1, 1, dict(C2=256)),
+                     ("p_many", 5, 64, 64, 128, 128, 3, 1, 1, 1, {})):
+            assert gpu_probe.conv_case(c, case[0], *case[1:10], **case[10]), gpu_probe.RESULTS[-1]
+    finally:
+        c.close()
+
+
 def test_extract_normalise_bit_exact(ctx, trained_3_15):
     """K1 against the oracle's float64 -> float32 normalisation rounded to bf16, including tiles that
     hang over every edge of the raster (boundless zero fill before normalisation)."""
