@@ -282,6 +282,8 @@ class Context:
         Hin, Win = (H1 * 2, W1 * 2) if up1 else (H1, W1)
         C2 = 0 if x2 is None else x2.shape[3]
         Cout, Kpad = weights.shape
+        if mode == 2:  # phase form: weights are [4*Cout, Kpad] (pack_phase_weight), x1 at half resolution
+            Cout //= 4
         Hout = (Hin + 2 * pad - KH) // stride + 1
         Wout = (Win + 2 * pad - KW) // stride + 1
         out = torch.empty((B, Hout, Wout, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
@@ -365,3 +367,23 @@ def lzw_decode(data: bytes, expected: int) -> np.ndarray:
     if n < 0:
         raise RuntimeError("corrupt LZW stream")
     return dst
+
+
+def pack_phase_weight(w: torch.Tensor, C1: int, C2: int) -> torch.Tensor:
+    """OIHW fp32 [Cout, C1+C2, 3, 3] -> bf16 [4*Cout, 4*C1 + 9*C2]: sub-pixel phase form of a 3x3 conv on
+    [nearest-x2-upsampled x1 (+) x2] (test helper mirroring api.cu::build_conv). Phase p = 2*(oh%2) + (ow%2);
+    columns: 4 low-res taps (di, dj) x C1 (taps of the original kernel that read the same low-res pixel are
+    summed), then the 9 original taps x C2."""
+    Cout = w.shape[0]
+    taps = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}   # (parity, low-res tap) -> original taps
+    out = torch.zeros((4, Cout, 4 * C1 + 9 * C2), dtype=torch.float32)
+    w64 = w.double()
+    for pa in range(2):
+        for pb in range(2):
+            for di in range(2):
+                for dj in range(2):
+                    s = w64[:, :C1][:, :, taps[(pa, di)]][:, :, :, taps[(pb, dj)]].sum(dim=(2, 3))
+                    out[pa * 2 + pb, :, (di * 2 + dj) * C1:(di * 2 + dj + 1) * C1] = s.float()
+            if C2:
+                out[pa * 2 + pb, :, 4 * C1:] = w[:, C1:].permute(0, 2, 3, 1).reshape(Cout, 9 * C2)
+    return out.reshape(4 * Cout, -1).to(torch.bfloat16)

@@ -26,6 +26,8 @@ std::string g_create_error;
 struct ConvLayer {
   __nv_bfloat16* w = nullptr;       // device [Cout][Kpad] (im2col order, TMA / gather producers)
   __nv_bfloat16* w_halo = nullptr;  // device, K-step order of the halo-staged kernel (or null)
+  __nv_bfloat16* w_phase = nullptr; // device [4][Cout][Kp_phase]: sub-pixel phase form of a decoder conv1 (or null)
+  int Kp_phase = 0;
   float* bias = nullptr;            // device [Cout]
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
@@ -53,6 +55,8 @@ struct fb_ctx {
   int64_t launches = 0;
   bool force_gather = false;  // FB_FORCE_GATHER=1: cp.async im2col producer everywhere (debug / A-B tests)
   bool no_halo = false;       // FB_NO_HALO=1: skip the halo-staged kernel
+  bool no_phase = false;      // FB_NO_PHASE=1: decoder conv1 on the materialised upsample instead of sub-pixel phases
+  bool dec_phase[6] = {false, false, false, false, false, false};  // per decoder block, decided by arena_plan
 
   // model
   bool loaded = false;
@@ -157,7 +161,7 @@ int64_t numel(const fb_tensor_desc* t) {
 // bf16 [CoutPad][Kpad] with k = (kh*KW + kw)*CinPad + cin, fp32 bias [CoutPad].
 int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const std::string& wkey,
                const std::string& bn, const std::string& bkey, int Cin, int Cout, int KH, int stride,
-               int pad, int C2 = 0) {
+               int pad, int C2 = 0, bool decoder_conv1 = false) {
   const fb_tensor_desc* w = find(tm, wkey);
   if (!w) return fail(c, FB_ERR_WEIGHTS, "missing tensor " + wkey);
   if (w->ndim != 4 || w->shape[0] != Cout || w->shape[1] != Cin || w->shape[2] != KH || w->shape[3] != KH)
@@ -214,6 +218,44 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
     c->owned.push_back(L.w_halo);
     FB_CUDA(c, cudaMemcpy(L.w_halo, hp.data(), n * 2, cudaMemcpyHostToDevice));
   }
+  // third packing for decoder conv1 layers: the sub-pixel phase form (conv_igemm.cuh, ConvArgs::phase_mode).
+  // x1 = the upsampled source: taps that read the same low-res pixel are summed in fp32 before the single
+  // bf16 rounding. rows(a): output-row parity a, low-res tap di -> original taps {kh}.
+  if (decoder_conv1 && KH == 3 && stride == 1 && L.C1 % 64 == 0 && L.C2 % 64 == 0 && Cin == CinPad) {
+    const int C1 = L.C1, C2 = L.C2;
+    L.Kp_phase = 4 * C1 + 9 * C2;
+    std::vector<uint16_t> pp(static_cast<size_t>(4) * CoutPad * L.Kp_phase, 0);
+    auto taps = [](int parity, int d, int* out) -> int {   // original taps feeding low-res tap d
+      if (parity == 0) { if (d == 0) { out[0] = 0; return 1; } out[0] = 1; out[1] = 2; return 2; }
+      if (d == 0) { out[0] = 0; out[1] = 1; return 2; }
+      out[0] = 2; return 1;
+    };
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb)
+        for (int o = 0; o < Cout; ++o) {
+          uint16_t* row = pp.data() + (static_cast<size_t>(pa * 2 + pb) * CoutPad + o) * L.Kp_phase;
+          for (int di = 0; di < 2; ++di)
+            for (int dj = 0; dj < 2; ++dj) {
+              int khs[2], kws[2];
+              const int nh = taps(pa, di, khs), nw = taps(pb, dj, kws);
+              for (int ci = 0; ci < C1; ++ci) {
+                double s = 0.0;
+                for (int i = 0; i < nh; ++i)
+                  for (int j = 0; j < nw; ++j)
+                    s += folded[((static_cast<size_t>(o) * Cin + ci) * 3 + khs[i]) * 3 + kws[j]];
+                row[(di * 2 + dj) * C1 + ci] = f32_to_bf16_rne(static_cast<float>(s));
+              }
+            }
+          for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw)
+              for (int ci = 0; ci < C2; ++ci)
+                row[4 * C1 + (kh * 3 + kw) * C2 + ci] =
+                    f32_to_bf16_rne(folded[((static_cast<size_t>(o) * Cin + C1 + ci) * 3 + kh) * 3 + kw]);
+        }
+    FB_CUDA(c, cudaMalloc(&L.w_phase, pp.size() * 2));
+    c->owned.push_back(L.w_phase);
+    FB_CUDA(c, cudaMemcpy(L.w_phase, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
+  }
   FB_CUDA(c, cudaMalloc(&L.w, packed.size() * 2));
   c->owned.push_back(L.w);
   FB_CUDA(c, cudaMalloc(&L.bias, bias.size() * 4));
@@ -256,6 +298,20 @@ int arena_alloc(fb_ctx* c, const std::string& name, int B, int H, int W, int C, 
 void arena_plan(fb_ctx* c, int n, int T, bool dry) {
   c->arena_used = 0;
   if (!dry) c->acts.clear();
+  // decoder block d runs its conv1 in sub-pixel phase form when the layer has the packing and the low-res
+  // grid tiles into 8 x 16 boxes; its x1 input is then kept at low resolution, otherwise the producer
+  // writes it 2x2-replicated
+  for (int d = 0; d < 5; ++d) {
+    char nm[32];
+    snprintf(nm, sizeof nm, "dec%d.conv1", d);
+    auto it = c->conv.find(nm);
+    const int S_lo = (T / 32) << d;   // low-res side of block d's x1
+    // block 3 (64+64 -> 32 at 256^2) is faster in the halo-staged kernel than as 4 x 13 narrow-N GEMM steps
+    const char* pm = getenv("FB_PHASE_MAX");
+    const int phase_max = pm ? atoi(pm) : 2;
+    c->dec_phase[d] = !c->force_gather && !c->no_phase && d <= phase_max && it != c->conv.end() && it->second.w_phase != nullptr &&
+                      S_lo % 16 == 0;
+  }
   arena_alloc(c, "x0", n, T, T, 8, 2, dry);
   arena_alloc(c, "f1", n, T / 2, T / 2, 64, 2, dry);
   arena_alloc(c, "pool", n, T / 4, T / 4, 64, 2, dry);
@@ -272,7 +328,7 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     for (int b = 0; b < kStageBlocks[st]; ++b) {
       snprintf(buf, sizeof buf, "layer%d.%d.out", st + 1, b);
       // the bottleneck feature only feeds decoder block 0, which reads it through the x2 upsample
-      arena_alloc(c, buf, n, S, S, C, 2, dry, st == 3 && b == kStageBlocks[st] - 1);
+      arena_alloc(c, buf, n, S, S, C, 2, dry, st == 3 && b == kStageBlocks[st] - 1 && !c->dec_phase[0]);
     }
     S /= 2;
   }
@@ -282,7 +338,8 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     snprintf(buf, sizeof buf, "dec%d.mid", d);
     arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry);
     snprintf(buf, sizeof buf, "dec%d", d);
-    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry, d < 4);  // dec0..3 feed the next block upsampled
+    // dec0..3 feed the next block through the x2 upsample: materialised here unless that block runs in phase form
+    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry, d < 4 && !c->dec_phase[d + 1]);
     S *= 2;
   }
   arena_alloc(c, "logits", n, T, T, 16, 4, dry);
@@ -336,13 +393,37 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 
 // ---------------------------------------------------------------------------------- graph
 int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const Act* res,
-             const float* rowbias, bool relu, const Act& out) {
+             const float* rowbias, bool relu, const Act& out, bool phase = false) {
   // `out` may be stored 2x2-replicated (Act::up2): the conv itself runs at half those dims
   const int Hout = out.up2 ? out.H / 2 : out.H, Wout = out.up2 ? out.W / 2 : out.W;
   const int C1 = x1.C, C2 = x2 ? x2->C : 0;
   if (C1 + C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
-  if (x2 && (x2->H != x1.H || x2->W != x1.W)) return fail(c, FB_ERR_INVALID, "internal: skip tensor shape mismatch");
   int rc;
+  if (phase) {
+    // decoder conv1 in sub-pixel phase form: x1 at half the output resolution, x2 (skip) at full resolution
+    if (!L.w_phase || x1.H * 2 != Hout || x1.W * 2 != Wout || (x2 && (x2->H != Hout || x2->W != Wout)) || res || rowbias)
+      return fail(c, FB_ERR_INVALID, "internal: phase-form conv shape mismatch");
+    fb::ConvArgs a;
+    memset(&a, 0, sizeof a);
+    a.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
+    a.x2 = x2 ? static_cast<const __nv_bfloat16*>(x2->ptr) : nullptr;
+    a.C1 = C1; a.C2 = C2;
+    a.B = x1.B; a.Hin = Hout; a.Win = Wout; a.Hout = Hout; a.Wout = Wout;
+    a.KH = 3; a.KW = 3; a.stride = 1; a.pad = 1;
+    a.Cout = L.Cout;
+    a.Ktot = L.Kp_phase;
+    a.bias = L.bias;
+    a.relu = relu ? 1 : 0;
+    a.out = static_cast<__nv_bfloat16*>(out.ptr);
+    a.up2_out = 0;
+    a.phase_mode = 1;
+    if (out.up2 || out.elem != 2 || !fb::conv_tma_eligible(a)) return fail(c, FB_ERR_INVALID, "internal: phase-form conv not eligible");
+    rc = fb::launch_conv(a, L.w_phase, L.Kp_phase, true, c->num_sms, c->stream);
+    if (rc != 0) return fail(c, rc, "phase conv launch failed (code " + std::to_string(rc) + ")");
+    c->launches++;
+    return 0;
+  }
+  if (x2 && (x2->H != x1.H || x2->W != x1.W)) return fail(c, FB_ERR_INVALID, "internal: skip tensor shape mismatch");
   if (!c->force_gather && !c->no_halo && L.w_halo && L.C1 == C1 && L.C2 == C2 &&
       fb::halo_supported(L.KH, L.stride, C1, C2, L.Cout, Hout, Wout)) {
     fb::HaloArgs h;
@@ -430,7 +511,8 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
     char nm[64];
     snprintf(nm, sizeof nm, "dec%d", d);
     const std::string base(nm);
-    FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid")));
+    FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid"),
+                    c->dec_phase[d]));
     FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base)));
     cur = base;
   }
@@ -524,6 +606,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->force_gather = fg && fg[0] == '1';
   const char* nh = getenv("FB_NO_HALO");
   c->no_halo = nh && nh[0] == '1';
+  const char* np = getenv("FB_NO_PHASE");
+  c->no_phase = np && np[0] == '1';
   *out = c;
   return 0;
 }
@@ -591,7 +675,7 @@ int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int
     snprintf(pre, sizeof pre, "decoder.blocks.%d", d);
     snprintf(nm, sizeof nm, "dec%d", d);
     const std::string P(pre), N(nm);
-    FB_TRY(build_conv(c, tm, N + ".conv1", P + ".conv1.0.weight", P + ".conv1.1", "", dec_in[d], kDecOut[d], 3, 1, 1, dec_skip[d]));
+    FB_TRY(build_conv(c, tm, N + ".conv1", P + ".conv1.0.weight", P + ".conv1.1", "", dec_in[d], kDecOut[d], 3, 1, 1, dec_skip[d], true));
     FB_TRY(build_conv(c, tm, N + ".conv2", P + ".conv2.0.weight", P + ".conv2.1", "", kDecOut[d], kDecOut[d], 3, 1, 1));
   }
   FB_TRY(build_conv(c, tm, "head", "segmentation_head.0.weight", "", "segmentation_head.0.bias", 16, n_classes, 3, 1, 1));
@@ -844,6 +928,16 @@ int fb_conv2d(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, int up1
   a.relu = relu;
   a.out = static_cast<__nv_bfloat16*>(out_bf16);
   a.out_f32 = out_f32;
+  if (mode == 2) {  // sub-pixel phase form: x1 is [B, Hin/2, Win/2, C1], weights are [4][Cout][Kpad]
+    a.up1 = 0;
+    a.phase_mode = 1;
+    a.Ktot = Kpad;
+    if (!fb::conv_tma_eligible(a)) return fail(c, FB_ERR_INVALID, "conv2d: shape not eligible for the phase form");
+    const int rc = fb::launch_conv(a, static_cast<const __nv_bfloat16*>(weights), Kpad, true, c->num_sms, c->stream);
+    if (rc) return fail(c, rc, "conv2d (phase) launch failed (code " + std::to_string(rc) + ")");
+    c->launches++;
+    return 0;
+  }
   const bool can_tma = fb::conv_tma_eligible(a);
   bool tma;
   if (mode == 1) {

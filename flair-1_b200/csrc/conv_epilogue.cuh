@@ -39,8 +39,10 @@ struct EpiLane {
 };
 
 // rowpos(r, dh, dw): position of tile row r. run_bytes: bytes staged per pixel (RUN).
+// scale / pitch: destination pixel offset of tile position (dh, dw) = (scale*dh)*pitch + scale*dw
+// (plain: 1, Wout; 2x2-replicated output: 2, 2*Wout; sub-pixel phase output: 2, Wout).
 template <typename RowPos>
-__device__ __forceinline__ EpiLane make_epi_lane(int warp_q, int lane, int run_bytes, int Wout, int up2, RowPos rowpos) {
+__device__ __forceinline__ EpiLane make_epi_lane(int warp_q, int lane, int run_bytes, int pitch, int scale, RowPos rowpos) {
   EpiLane L;
   rowpos(warp_q * 32 + lane, L.own_dh, L.own_dw);
   const int lpp = run_bytes / 16, ppr = 32 / lpp;
@@ -48,7 +50,7 @@ __device__ __forceinline__ EpiLane make_epi_lane(int warp_q, int lane, int run_b
   for (int rd = 0; rd < 8; ++rd) {
     int dh = 0, dw = 0;
     if (rd < lpp) rowpos(warp_q * 32 + rd * ppr + lane / lpp, dh, dw);
-    L.rnd_rel[rd] = up2 ? (2 * dh) * (2 * Wout) + 2 * dw : dh * Wout + dw;
+    L.rnd_rel[rd] = (scale * dh) * pitch + scale * dw;
   }
   return L;
 }

@@ -175,7 +175,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
     uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
     // block rows: row r is pixel (r / 8, r % 8) of the 16 x 8 block
-    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2, p.Wout, p.up2_out,
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
+                                    p.up2_out ? 2 * p.Wout : p.Wout, p.up2_out ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
@@ -222,15 +223,16 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after_sync();
         const uint32_t st16 = (stage_addr0 + s * G::STAGE) >> 4;
+        // K-step outer, block inner: consecutive MMAs hit different accumulators (block m = output columns
+        // 8m..8m+7 of the tile, 8 cells further in the stage) and share the step's filter slab
+        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+#pragma unroll 2
+        for (int k = 0; k < p.nsteps; ++k) {
+          const uint32_t a_lo = p.a_lo[k] + st16;
+          const uint32_t acc = (g | k) != 0 ? 1u : 0u;
 #pragma unroll
-        for (int m = 0; m < MB; ++m) {  // block m = output columns 8m..8m+7 of the tile: 8 cells further
-          uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
-          const uint32_t a_base = st16 + 8 * m;
-#pragma unroll 4
-          for (int k = 0; k < p.nsteps; ++k) {
-            umma_bf16_lohi(d_tmem + m * BN, p.a_lo[k] + a_base, a_hi, b_lo, b_hi, idesc, (g | k) != 0 ? 1u : 0u);
-            b_lo += 2 * BN;
-          }
+          for (int m = 0; m < MB; ++m) umma_bf16_lohi(d_tmem + m * BN, a_lo + 8 * m, a_hi, b_lo, b_hi, idesc, acc);
+          b_lo += 2 * BN;
         }
         umma_commit(empty_bar(s));
       }

@@ -85,12 +85,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================================================================== producers
     if (TMA_A) {
       if (threadIdx.x == 0) {
-        const int tiles_w = p.Wout >> 4, tiles_h = p.Hout >> 3;
-        const int c1chunks = p.C1 >> 6;
-        const int cchunks = (p.C1 + p.C2) >> 6;
+        const int tiles_w = p.tgrid_w >> 4, tiles_h = p.tgrid_h >> 3;
+        const int phases = p.phase_mode ? 4 : 1;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+          const int n_tile = tile % p.num_n_tiles;
+          const int rest = tile / p.num_n_tiles;
+          const int phase = rest % phases, m_tile = rest / phases;
+          const int pa = p.phase_mode ? (phase >> 1) : 0, pb = p.phase_mode ? (phase & 1) : 0;
           const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
           const int b = m_tile / (tiles_w * tiles_h);
           for (int kit = 0; kit < nk; ++kit, ++it) {
@@ -98,15 +100,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t ph = (it / S) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
             mbar_expect_tx(full_bar(s), C::kStageBytes);
-            const int tap = kit / cchunks, cc = kit - tap * cchunks;
-            const int kh = tap / 3, kw = tap - kh * 3;
+            const uint32_t e = p.ktab[kit];
+            const int src = e & 1, cc = (e >> 1) & 0x7F;
+            const int dx = static_cast<int>((e >> 8) & 15) - 8 + pb, dy = static_cast<int>((e >> 12) & 15) - 8 + pa;
+            const int sc = p.tm_scale[src];
             const uint32_t a_dst = base + s * C::kStageBytes;
-            if (cc < c1chunks) {
-              tma_load_4d(a_dst, &tmA, full_bar(s), cc * 64, tw * 16 + kw - 1, th * 8 + kh - 1, b);
-            } else {  // channels of the concatenated skip tensor
-              tma_load_4d(a_dst, &tmA2, full_bar(s), (cc - c1chunks) * 64, tw * 16 + kw - 1, th * 8 + kh - 1, b);
-            }
-            tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, n_tile * BN);
+            tma_load_4d(a_dst, src ? &tmA2 : &tmA, full_bar(s), cc * 64, tw * 16 * sc + dx, th * 8 * sc + dy, b);
+            tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, phase * p.Cout + n_tile * BN);
           }
         }
       }
@@ -180,7 +180,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp < 8) {
     // ===================================================================== epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access (tile rows 32q..32q+31)
-    const int tiles_w = p.Wout >> 4, tiles_h = p.Hout >> 3;
+    const int tiles_w = (TMA_A ? p.tgrid_w : p.Wout) >> 4, tiles_h = (TMA_A ? p.tgrid_h : p.Hout) >> 3;
+    const int phases = (TMA_A && p.phase_mode) ? 4 : 1;
     const int HWo = p.Hout * p.Wout;
     uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + q * kStgWarpBytes;
     const bool f32 = p.out_f32 != nullptr;
@@ -188,19 +189,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
     const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
     uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
-    // TMA tiles are 8 x 16 pixel boxes: row r of the tile is pixel (r / 16, r % 16) of the box
-    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2, p.Wout, p.up2_out,
+    // TMA tiles are 8 x 16 pixel boxes: row r of the tile is pixel (r / 16, r % 16) of the box. In phase
+    // mode the box lives on the low-res grid and pixel (dh, dw) lands at (2*dh + pa, 2*dw + pb).
+    const int osc = (p.up2_out || phases == 4) ? 2 : 1;
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
+                                    p.up2_out ? 2 * p.Wout : p.Wout, osc,
                                     [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int n_tile = tile % p.num_n_tiles, m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile % p.num_n_tiles;
+      const int rest = tile / p.num_n_tiles;
+      const int phase = rest % phases, m_tile = rest / phases;
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       if (TMA_A) {
         const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tb = m_tile / (tiles_w * tiles_h);
-        const int oh = th * 8 + L.own_dh, ow = tw * 16 + L.own_dw;
-        const long long pix0 = (static_cast<long long>(tb) * p.Hout + th * 8) * p.Wout + tw * 16;
+        const int pa = phase >> 1, pb = phase & 1;
+        const int psc = phases == 4 ? 2 : 1;   // output pixel = psc * tile-grid pixel + (pa, pb)
+        const int oh = psc * (th * 8 + L.own_dh) + pa, ow = psc * (tw * 16 + L.own_dw) + pb;
+        const long long pix0 = (static_cast<long long>(tb) * p.Hout + psc * th * 8 + pa) * p.Wout + psc * tw * 16 + pb;
         const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * 16) * (2 * p.Wout) + tw * 32;
         uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
         auto copy = [&](auto run, int col0, int el) {
@@ -375,7 +383,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
     const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
     uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
-    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2, p.Wout, p.up2_out,
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
+                                    p.up2_out ? 2 * p.Wout : p.Wout, p.up2_out ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
     uint32_t tcount = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tcount) {
@@ -494,9 +503,17 @@ int conv_pick_bn(int Cout) {
 }
 
 bool conv_tma_eligible(const ConvArgs& a) {
-  return a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.up1 == 0 && a.C1 % 64 == 0 &&
-         a.C2 % 64 == 0 && (a.C2 == 0 || a.x2 != nullptr) && a.Hout % 8 == 0 && a.Wout % 16 == 0 &&
-         a.Hin == a.Hout && a.Win == a.Wout;
+  if (a.up1 != 0 || a.C1 % 64 != 0 || a.C2 % 64 != 0 || (a.C2 > 0 && a.x2 == nullptr)) return false;
+  if (a.phase_mode) {  // x1 at half resolution, x2 at full resolution
+    return a.KH == 3 && a.KW == 3 && a.stride == 1 && a.pad == 1 && a.Hout % 16 == 0 && a.Wout % 32 == 0 &&
+           a.residual == nullptr && a.rowbias == nullptr && a.up2_out == 0 &&
+           (9 * (a.C2 / 64) + 4 * (a.C1 / 64)) <= 128;
+  }
+  const bool k3 = a.KH == 3 && a.KW == 3 && a.pad == 1, k1 = a.KH == 1 && a.KW == 1 && a.pad == 0;
+  if (!(k3 || k1) || (a.stride != 1 && a.stride != 2)) return false;
+  if (a.stride == 2 && a.C2 != 0) return false;
+  if (a.Hout % 8 != 0 || a.Wout % 16 != 0 || a.Hin != a.Hout * a.stride || a.Win != a.Wout * a.stride) return false;
+  return a.KH * a.KW * ((a.C1 + a.C2) / 64) <= 128;
 }
 
 int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bool use_tma_a,
@@ -512,8 +529,38 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   a.num_k_iters = (a.Ktot + kBK - 1) / kBK;
   if (use_tma_a) {
     if (!conv_tma_eligible(a)) return -1004;
-    a.num_m_tiles = a.B * (a.Hout / 8) * (a.Wout / 16);
+    const int c1c = a.C1 / 64, c2c = a.C2 / 64;
+    int nk = 0;
+    auto put = [&](int src, int chunk, int dx, int dy) {
+      a.ktab[nk++] = static_cast<uint32_t>(src) | (static_cast<uint32_t>(chunk) << 1) |
+                     (static_cast<uint32_t>(dx + 8) << 8) | (static_cast<uint32_t>(dy + 8) << 12);
+    };
+    if (a.phase_mode) {
+      // k order = weight column order of pack_phase_weights: 4 low-res taps x C1, then 9 taps x C2
+      a.tgrid_h = a.Hout / 2; a.tgrid_w = a.Wout / 2;
+      a.tm_scale[0] = 1; a.tm_scale[1] = 2;
+      for (int di = 0; di < 2; ++di)
+        for (int dj = 0; dj < 2; ++dj)
+          for (int c = 0; c < c1c; ++c) put(0, c, dj - 1, di - 1);   // + (pb, pa) added per phase in the kernel
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          for (int c = 0; c < c2c; ++c) put(1, c, kw - 1, kh - 1);
+      a.num_m_tiles = a.B * (a.tgrid_h / 8) * (a.tgrid_w / 16) * 4;
+    } else {
+      // k order = (kh*KW + kw)*Cin + c over the concatenated channels (pack of api.cu::build_conv)
+      a.tgrid_h = a.Hout; a.tgrid_w = a.Wout;
+      a.tm_scale[0] = a.stride; a.tm_scale[1] = 1;
+      for (int kh = 0; kh < a.KH; ++kh)
+        for (int kw = 0; kw < a.KW; ++kw) {
+          for (int c = 0; c < c1c; ++c) put(0, c, kw - a.pad, kh - a.pad);
+          for (int c = 0; c < c2c; ++c) put(1, c, kw - a.pad, kh - a.pad);
+        }
+      a.num_m_tiles = a.B * (a.tgrid_h / 8) * (a.tgrid_w / 16);
+    }
+    a.num_k_iters = nk;
+    if (nk * kBK > Kpad) return -1006;
   } else {
+    if (a.phase_mode) return -1007;
     a.num_m_tiles = (a.M_total + kBM - 1) / kBM;
   }
 
@@ -527,10 +574,12 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   // Measured on B200 (profiles/r01_pair_vs_single.md): no faster than the single-CTA kernel on these
   // shapes (the wide layers are not shared-memory-port bound after all), so it is opt-in: FB_PAIR=1.
   const char* pair_env = getenv("FB_PAIR");
-  const bool use_pair = use_tma_a && BN >= 128 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1';
+  const bool use_pair = use_tma_a && BN >= 128 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1' &&
+                        a.KH == 3 && a.stride == 1 && !a.phase_mode;
   {
-    // weights: [Cout][Kpad] bf16, box = 64 k x BN rows (BN/2 per CTA of a pair), 128-byte swizzle
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kpad), static_cast<cuuint64_t>(a.Cout)};
+    // weights: [Cout][Kpad] bf16 ([4][Cout][Kpad] in phase mode), box = 64 k x BN rows (BN/2 per CTA of a
+    // pair), 128-byte swizzle
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kpad), static_cast<cuuint64_t>(a.Cout) * (a.phase_mode ? 4 : 1)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kpad) * 2};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(use_pair ? BN / 2 : BN)};
     cuuint32_t es[2] = {1, 1};
@@ -543,15 +592,21 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   if (use_tma_a) {
     // activations: NHWC bf16 seen as (C, W, H, B); box = 64 channels x 16 x 8 pixels; out-of-range
     // coordinates are zero-filled by the TMA unit, which is exactly the conv's zero padding.
+    // A source read at stride s (stride-2 convs; the full-resolution skip tensor of phase mode) uses
+    // elementStrides = s: the box spans 16*s x 8*s pixels and every s-th one lands in shared memory.
     for (int src = 0; src < (a.C2 > 0 ? 2 : 1); ++src) {
       const int Cs = src == 0 ? a.C1 : a.C2;
       const __nv_bfloat16* base = src == 0 ? a.x1 : a.x2;
-      cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cs), static_cast<cuuint64_t>(a.Win),
-                            static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B)};
-      cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cs) * 2, static_cast<cuuint64_t>(a.Win) * Cs * 2,
-                               static_cast<cuuint64_t>(a.Hin) * a.Win * Cs * 2};
-      cuuint32_t box[4] = {64, 16, 8, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
+      const int sc = a.tm_scale[src];
+      // spatial dims of the tensor the source lives in
+      const int Ws = a.phase_mode ? (src == 0 ? a.Wout / 2 : a.Wout) : a.Win;
+      const int Hs = a.phase_mode ? (src == 0 ? a.Hout / 2 : a.Hout) : a.Hin;
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(Cs), static_cast<cuuint64_t>(Ws),
+                            static_cast<cuuint64_t>(Hs), static_cast<cuuint64_t>(a.B)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cs) * 2, static_cast<cuuint64_t>(Ws) * Cs * 2,
+                               static_cast<cuuint64_t>(Hs) * Ws * Cs * 2};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(16 * sc), static_cast<cuuint32_t>(8 * sc), 1};
+      cuuint32_t es[4] = {1, static_cast<cuuint32_t>(sc), static_cast<cuuint32_t>(sc), 1};
       CUresult r = g_encode(src == 0 ? &tmA : &tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                             const_cast<__nv_bfloat16*>(base), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

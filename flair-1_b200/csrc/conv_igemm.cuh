@@ -43,16 +43,30 @@ struct ConvArgs {
   __nv_bfloat16* out;              // [B,Hout,Wout,Cout] bf16 (null when out_f32 is used)
   float* out_f32;                  // [B,Hout,Wout,Cout] fp32 (logits) or null
   int up2_out;                     // 1: bf16 output is written 2x2-replicated into [B,2*Hout,2*Wout,Cout]
+  // Sub-pixel ("phase") form of a 3x3 conv on [nearest-x2-upsampled x1 (+) x2]: x1 is given at LOW
+  // resolution [B,Hout/2,Wout/2,C1]; the four output phases (oh%2, ow%2) are four 2x2 convs on x1 (taps
+  // that hit the same low-res pixel are pre-summed in the weights) plus the plain 3x3 taps on x2 read at
+  // stride 2. 4*C1 + 9*C2 instead of 9*(C1+C2) products per pixel and no materialised upsample.
+  // weights: [4 phases][Cout][Kpad].
+  int phase_mode;
   // tiling
   int M_total;       // B*Hout*Wout
-  int num_m_tiles;   // gather: ceil(M_total/128); TMA: B*(Hout/8)*(Wout/16)
+  int num_m_tiles;   // gather: ceil(M_total/128); TMA: B*(tile-grid H/8)*(tile-grid W/16)
   int num_n_tiles;   // Cout / BN
   int num_k_iters;   // ceil(Ktot/64)
+  // TMA producer schedule (filled by launch_conv): tiles are 8x16 boxes of a tile grid (the output, or
+  // the low-res grid in phase mode); per k-iteration one box of 64 channels is loaded from source
+  // (e&1) at chunk (e>>1)&0x7F and pixel offset (dx, dy) = (((e>>8)&15)-8, ((e>>12)&15)-8) after scaling
+  // the box origin by tm_scale[source] (2 = stride-2 convs and the skip tensor of phase mode).
+  int tgrid_h, tgrid_w;
+  int tm_scale[2];
+  uint32_t ktab[128];
 };
 
-// Launch one convolution. `use_tma_a` requires KH=KW=3, stride=1, pad=1, no input upsample,
-// C1 % 64 == 0 (and C2 % 64 == 0 when a second source is concatenated), Hout % 8 == 0,
-// Wout % 16 == 0. Returns cudaError_t as int.
+// Launch one convolution. `use_tma_a` requires conv_tma_eligible(a). Returns cudaError_t as int.
+// TMA-eligible: (3x3 pad 1 or 1x1 pad 0), stride 1 or 2 (stride 2: single source), C1 % 64 == 0,
+// C2 % 64 == 0, tile grid rows % 8 == 0 and columns % 16 == 0 (tile grid = output, or output / 2 in
+// phase mode).
 bool conv_tma_eligible(const ConvArgs& a);
 int launch_conv(const ConvArgs& a, const __nv_bfloat16* weights /*[Cout][Kpad] bf16*/, int Kpad,
                 bool use_tma_a, int num_sms, cudaStream_t stream);

@@ -48,9 +48,11 @@ def ref_conv(x1, w, bias, stride, pad, x2=None, up1=False, residual=None, rowbia
 
 
 def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=False, res=False, rowb=False,
-              relu=True, out_f32=False, seed=0, identity=False):
+              relu=True, out_f32=False, seed=0, identity=False, phase=False):
+    """phase=True: the sub-pixel phase form (mode 2) of the same conv on [upsampled x1 (+) x2]."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = ctx.device
+    up1 = up1 or phase
     h1, w1 = (H // 2, W // 2) if up1 else (H, W)
     x1 = torch.randn((B, h1, w1, C1), generator=g).to(torch.bfloat16).to(dev)
     x2 = torch.randn((B, H, W, C2), generator=g).to(torch.bfloat16).to(dev) if C2 else None
@@ -65,11 +67,11 @@ def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=Fals
     Wo = (W + 2 * pad - k) // stride + 1
     residual = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).to(dev) if res else None
     rowbias = torch.randn((B, Ho), generator=g).to(dev) if rowb else None
-    wp = nat.pack_conv_weight(w, cin_pad=Cin, cout_pad=Cout).to(dev)
+    wp = (nat.pack_phase_weight(w, C1, C2) if phase else nat.pack_conv_weight(w, cin_pad=Cin, cout_pad=Cout)).to(dev)
     t0 = time.time()
     try:
         y = ctx.conv2d(x1, wp, bias, k, k, stride, pad, x2=x2, up1=up1, residual=residual, rowbias=rowbias,
-                       relu=relu, out_f32=out_f32, mode=mode)
+                       relu=relu, out_f32=out_f32, mode=2 if phase else mode)
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         log(f"CASE {name}: EXCEPTION {e}")
@@ -80,6 +82,10 @@ def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=Fals
     err = (y.float() - yr).abs()
     scale = yr.abs().max().item() + 1e-9
     tol = 2e-5 if out_f32 else 1.0 / 128  # bf16 output: half-ulp relative 2^-9, allow 2x
+    if phase:
+        # the phase form rounds SUMS of taps to bf16 while the reference sums bf16-rounded taps: the two differ by
+        # weight-rounding noise (~2^-9 per weight), a few output ulps on small outputs; a layout error would be O(1)
+        tol *= 2.5
     rel = (err / (yr.abs() + 0.05 * scale)).max().item()
     ok = bool(rel < tol * 2 + 1e-4) and bool(torch.isfinite(y.float()).all())
     bad = (err / (yr.abs() + 0.05 * scale) > tol * 2 + 1e-4)
@@ -154,6 +160,21 @@ HALO_CASES = [
 ]
 
 
+TMA_EXTRA_CASES = [
+    # strided TMA boxes (elementStrides = 2) and the sub-pixel phase form of decoder conv1
+    ("ts_3x3s2_64_128", 2, 32, 32, 64, 128, 3, 2, 1, 1, {}),
+    ("ts_3x3s2_256_512", 3, 32, 32, 256, 512, 3, 2, 1, 1, {}),
+    ("ts_1x1s2_64_128", 2, 32, 64, 64, 128, 1, 2, 0, 1, dict(relu=False)),
+    ("ts_1x1s2_128_256", 2, 32, 32, 128, 256, 1, 2, 0, 1, dict(relu=False)),
+    ("ph_ident_64_64", 1, 16, 32, 64, 64, 3, 1, 1, 1, dict(phase=True, identity=True, relu=False)),
+    ("ph_64_64", 1, 16, 32, 64, 64, 3, 1, 1, 1, dict(phase=True)),
+    ("ph_128p64_64", 2, 32, 64, 128, 64, 3, 1, 1, 1, dict(phase=True, C2=64)),
+    ("ph_512p256_256", 2, 32, 32, 512, 256, 3, 1, 1, 1, dict(phase=True, C2=256)),
+    ("ph_256p128_128", 1, 64, 64, 256, 128, 3, 1, 1, 1, dict(phase=True, C2=128)),
+    ("ph_64p64_32", 1, 64, 64, 64, 32, 3, 1, 1, 1, dict(phase=True, C2=64)),
+]
+
+
 def main():
     want = sys.argv[1:]
     log("device:", torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
@@ -200,6 +221,9 @@ def main():
     if sel("t_dual"):
         conv_case(ctx, "t_dual_128p64_64", 2, 32, 32, 128, 64, 3, 1, 1, T, C2=64)
         conv_case(ctx, "g_dual_128p64_64", 2, 32, 32, 128, 64, 3, 1, 1, G, C2=64)
+    for c in TMA_EXTRA_CASES:
+        if sel(c[0]):
+            conv_case(ctx, c[0], *c[1:10], **c[10])
 
     if sel("confusion"):
         g = torch.Generator().manual_seed(1)

@@ -69,6 +69,16 @@ def test_dual_source_tma_conv(ctx):
     assert gpu_probe.conv_case(ctx, "t_dual_512p256_256", 1, 32, 32, 512, 256, 3, 1, 1, 1, C2=256), gpu_probe.RESULTS[-1]
 
 
+@pytest.mark.parametrize("idx", range(10))
+def test_strided_tma_and_phase_form_convs(ctx, idx):
+    """Stride-2 3x3 / 1x1 convs through strided TMA boxes, and decoder conv1 in sub-pixel phase form
+    (2x2 taps on the low-res source + 3x3 taps on the skip) against conv(upsample(x1) (+) x2)."""
+    import gpu_probe
+    case = gpu_probe.TMA_EXTRA_CASES[idx]
+    gpu_probe.RESULTS.clear()
+    assert gpu_probe.conv_case(ctx, case[0], *case[1:10], **case[10]), gpu_probe.RESULTS[-1]
+
+
 def test_cta_pair_kernel_matches(monkeypatch):
     """tcgen05.mma.cta_group::2 variant (FB_PAIR=1): a cluster of two CTAs per 16 x 16 pixel tile, weights
     split across the pair. Opt-in because it measured no faster; must give the same results."""
