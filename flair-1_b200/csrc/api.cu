@@ -28,6 +28,7 @@ struct ConvLayer {
   __nv_bfloat16* w_halo = nullptr;  // device, K-step order of the halo-staged kernel (or null)
   __nv_bfloat16* w_phase = nullptr; // device [4][Cout][Kp_phase]: sub-pixel phase form of a decoder conv1 (or null)
   int Kp_phase = 0;
+  __nv_bfloat16* w_halo_phase = nullptr;  // device, phase form for the halo-staged kernel (32 -> 16 channels) (or null)
   float* bias = nullptr;            // device [Cout]
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
@@ -256,6 +257,15 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
     c->owned.push_back(L.w_phase);
     FB_CUDA(c, cudaMemcpy(L.w_phase, pp.data(), pp.size() * 2, cudaMemcpyHostToDevice));
   }
+  // the same decomposition for the channel-poor last decoder block, in the halo kernel's step order
+  if (decoder_conv1 && KH == 3 && stride == 1 && fb::halo_phase_supported(L.C1, L.C2, CoutPad, 16, 8)) {
+    const size_t n = fb::pack_halo_weights_phase(folded.data(), Cout, CoutPad, Cin, CinPad, nullptr);
+    std::vector<uint16_t> hp(n);
+    fb::pack_halo_weights_phase(folded.data(), Cout, CoutPad, Cin, CinPad, hp.data());
+    FB_CUDA(c, cudaMalloc(&L.w_halo_phase, n * 2));
+    c->owned.push_back(L.w_halo_phase);
+    FB_CUDA(c, cudaMemcpy(L.w_halo_phase, hp.data(), n * 2, cudaMemcpyHostToDevice));
+  }
   FB_CUDA(c, cudaMalloc(&L.w, packed.size() * 2));
   c->owned.push_back(L.w);
   FB_CUDA(c, cudaMalloc(&L.bias, bias.size() * 4));
@@ -311,6 +321,11 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     const int phase_max = pm ? atoi(pm) : 2;
     c->dec_phase[d] = !c->force_gather && !c->no_phase && d <= phase_max && it != c->conv.end() && it->second.w_phase != nullptr &&
                       S_lo % 16 == 0;
+    // the last block (32 -> 16 at 512^2) has its own phase form inside the halo-staged kernel
+    const char* hp = getenv("FB_NO_HALO_PHASE");
+    if (!c->force_gather && !c->no_phase && !c->no_halo && !(hp && hp[0] == '1') && it != c->conv.end() &&
+        it->second.w_halo_phase != nullptr && fb::halo_phase_supported(it->second.C1, it->second.C2, it->second.Cout, S_lo, S_lo))
+      c->dec_phase[d] = true;
   }
   arena_alloc(c, "x0", n, T, T, 8, 2, dry);
   arena_alloc(c, "f1", n, T / 2, T / 2, 64, 2, dry);
@@ -401,8 +416,27 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
   int rc;
   if (phase) {
     // decoder conv1 in sub-pixel phase form: x1 at half the output resolution, x2 (skip) at full resolution
-    if (!L.w_phase || x1.H * 2 != Hout || x1.W * 2 != Wout || (x2 && (x2->H != Hout || x2->W != Wout)) || res || rowbias)
+    if ((!L.w_phase && !L.w_halo_phase) || x1.H * 2 != Hout || x1.W * 2 != Wout || (x2 && (x2->H != Hout || x2->W != Wout)) || res || rowbias)
       return fail(c, FB_ERR_INVALID, "internal: phase-form conv shape mismatch");
+    if (L.w_halo_phase && !x2 && fb::halo_phase_supported(C1, 0, L.Cout, x1.H, x1.W) && !out.up2 && out.elem == 2) {
+      fb::HaloArgs h;
+      memset(&h, 0, sizeof h);
+      h.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
+      h.C1 = C1;
+      h.B = x1.B; h.Hin = x1.H; h.Win = x1.W; h.Hout = Hout; h.Wout = Wout;
+      h.Cout = L.Cout;
+      h.bias = L.bias;
+      h.relu = relu ? 1 : 0;
+      h.out = static_cast<__nv_bfloat16*>(out.ptr);
+      h.wpacked = L.w_halo_phase;
+      h.phase_mode = 1;
+      fb::halo_fill_steps_phase(h);
+      rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
+      if (rc != 0) return fail(c, rc, "phase conv (halo) launch failed (code " + std::to_string(rc) + ")");
+      c->launches++;
+      return 0;
+    }
+    if (!L.w_phase) return fail(c, FB_ERR_INVALID, "internal: phase-form conv has no packing for this shape");
     fb::ConvArgs a;
     memset(&a, 0, sizeof a);
     a.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
@@ -972,6 +1006,27 @@ int fb_conv2d_halo(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, in
   h.out = static_cast<__nv_bfloat16*>(out_bf16);
   h.out_f32 = out_f32;
   h.up2_out = up2_out;
+  if (up2_out == 2) {  // sub-pixel phase form: the conv of the x2-upsampled x1, computed from the low-res x1
+    if (KH != 3 || stride != 1 || x2 || residual || out_f32 || !fb::halo_phase_supported(C1, 0, Cout, Hin, Win))
+      return fail(c, FB_ERR_INVALID, "conv2d_halo: no phase-form instantiation for this shape");
+    h.up2_out = 0;
+    h.phase_mode = 1;
+    h.Hout = 2 * Hin; h.Wout = 2 * Win;
+    const size_t n = fb::pack_halo_weights_phase(w_oihw_host, Cout, Cout, C1, C1, nullptr);
+    std::vector<uint16_t> hp(n);
+    fb::pack_halo_weights_phase(w_oihw_host, Cout, Cout, C1, C1, hp.data());
+    __nv_bfloat16* wdev = nullptr;
+    FB_CUDA(c, cudaMalloc(&wdev, n * 2));
+    cudaMemcpy(wdev, hp.data(), n * 2, cudaMemcpyHostToDevice);
+    h.wpacked = wdev;
+    fb::halo_fill_steps_phase(h);
+    const int rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(wdev);
+    if (rc) return fail(c, rc, "conv2d_halo (phase) launch failed (code " + std::to_string(rc) + ")");
+    c->launches++;
+    return 0;
+  }
   if (!fb::halo_supported(KH, stride, h.C1, h.C2, Cout, h.Hout, h.Wout))
     return fail(c, FB_ERR_INVALID, "conv2d_halo: no instantiation for this shape");
   const int Cin = h.C1 + h.C2;

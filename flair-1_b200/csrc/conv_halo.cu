@@ -43,10 +43,15 @@ struct Geo {
   static constexpr int OCC = TWO ? 2 : 1;
 };
 
-template <int KH, int STRIDE, int NCH, int BN, int MB>
-__global__ void __launch_bounds__(kThreads, Geo<KH, STRIDE, NCH, MB, BN>::OCC)
+// PH = sub-pixel phase form of a 3x3 conv on the nearest-x2-upsampled x1 (single source): the tile is a
+// 16 x 8 block of the LOW-res grid, the MB = 4 accumulators are the four output phases (oh%2, ow%2), each
+// a 2x2-tap conv on the same staged halo with phase-specific (pre-summed) weights; outputs land at
+// (2*h + pa, 2*w + pb) of the [B, 2*Hin, 2*Win, Cout] tensor.
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false>
+__global__ void __launch_bounds__(kThreads, Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
-  using G = Geo<KH, STRIDE, NCH, MB, BN>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  static_assert(!PH || (MB == 4 && KH == 3 && STRIDE == 1), "phase form: 4 accumulators on a 3x3 stride-1 halo");
   constexpr int S = G::STAGES;
   constexpr int kBarBytes = ((2 * S + 4) * 8 + 16 + 127) / 128 * 128;
   constexpr int ACC = MB * BN;  // TMEM columns of one accumulator buffer (MB blocks of 128 x BN)
@@ -54,7 +59,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int groups = p.groups1 + p.groups2;
-  const int wbytes = groups * p.nsteps * 2 * BN * 16;
+  const int wbytes = (PH ? MB : 1) * groups * p.nsteps * 2 * BN * 16;   // phase form: one filter set per phase
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t w_addr = smem_base;
   const uint32_t bias_off = ((wbytes + 127) / 128) * 128;
@@ -98,7 +103,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_w = p.Wout / G::TW, tiles_h = p.Hout / kTH;
+  const int tiles_w = (PH ? p.Win : p.Wout) / G::TW, tiles_h = (PH ? p.Hin : p.Hout) / kTH;
 
   if (warp < kMmaWarp) {
     // ===================================================================== producers (halo gather)
@@ -176,7 +181,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
     // block rows: row r is pixel (r / 8, r % 8) of the 16 x 8 block
     const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
-                                    p.up2_out ? 2 * p.Wout : p.Wout, p.up2_out ? 2 : 1,
+                                    p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
@@ -184,6 +189,22 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
+      if (PH) {
+        // accumulator m = phase (pa, pb): low-res pixel (h, w) of the block -> output (2h + pa, 2w + pb)
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          const int pa = m >> 1, pb = m & 1;
+          uint8_t* blk_dst = out_bytes + static_cast<size_t>((static_cast<long long>(tb) * p.Hout + 2 * th * kTH + pa) * p.Wout +
+                                                             2 * tw * G::TW + pb) * pixel_bytes;
+          auto copy = [&](auto run, int col0, int el) {
+            warp_copy_out_fast<decltype(run)::value>(stg, lane, L, blk_dst + static_cast<size_t>(col0) * el, pixel_bytes, 0, 0);
+          };
+          epilogue_tile<BN, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, 0, 0, copy);
+        }
+        tc_fence_before_sync();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       const int oh = th * kTH + L.own_dh;
       const long long pix0 = (static_cast<long long>(tb) * p.Hout + th * kTH) * p.Wout + tw * G::TW;
       const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * kTH * 2) * (2 * p.Wout) + tw * G::TW * 2;
@@ -226,13 +247,26 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         // K-step outer, block inner: consecutive MMAs hit different accumulators (block m = output columns
         // 8m..8m+7 of the tile, 8 cells further in the stage) and share the step's filter slab
         uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+        if (PH) {
+          // step k of phase m: a_lo[m * nsteps + k], filter slab (m * nsteps + k); k outer so that consecutive
+          // MMAs alternate between the four phase accumulators
 #pragma unroll 2
-        for (int k = 0; k < p.nsteps; ++k) {
-          const uint32_t a_lo = p.a_lo[k] + st16;
-          const uint32_t acc = (g | k) != 0 ? 1u : 0u;
+          for (int k = 0; k < p.nsteps; ++k) {
+            const uint32_t acc = k != 0 ? 1u : 0u;
 #pragma unroll
-          for (int m = 0; m < MB; ++m) umma_bf16_lohi(d_tmem + m * BN, a_lo + 8 * m, a_hi, b_lo, b_hi, idesc, acc);
-          b_lo += 2 * BN;
+            for (int m = 0; m < MB; ++m)
+              umma_bf16_lohi(d_tmem + m * BN, p.a_lo[m * p.nsteps + k] + st16, a_hi,
+                             b_lo + static_cast<uint32_t>(m * p.nsteps + k) * (2 * BN), b_hi, idesc, acc);
+          }
+        } else {
+#pragma unroll 2
+          for (int k = 0; k < p.nsteps; ++k) {
+            const uint32_t a_lo = p.a_lo[k] + st16;
+            const uint32_t acc = (g | k) != 0 ? 1u : 0u;
+#pragma unroll
+            for (int m = 0; m < MB; ++m) umma_bf16_lohi(d_tmem + m * BN, a_lo + 8 * m, a_hi, b_lo, b_hi, idesc, acc);
+            b_lo += 2 * BN;
+          }
         }
         umma_commit(empty_bar(s));
       }
@@ -248,25 +282,25 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   }
 }
 
-template <int KH, int STRIDE, int NCH, int BN, int MB>
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
-  using G = Geo<KH, STRIDE, NCH, MB, BN>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   const int groups = a.groups1 + a.groups2;
-  const int wbytes = groups * a.nsteps * 2 * BN * 16;
+  const int wbytes = (PH ? MB : 1) * groups * a.nsteps * 2 * BN * 16;
   const int smem = ((wbytes + 127) / 128) * 128 + 256 + G::STAGES * G::STAGE +
                    ((2 * G::STAGES + 4) * 8 + 16 + 127) / 128 * 128 + 4 * kStgWarpBytes;
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB>, kThreads, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH>, kThreads, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
@@ -276,7 +310,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
-  conv_halo_kernel<KH, STRIDE, NCH, BN, MB><<<grid, kThreads, smem, stream>>>(a);
+  conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH><<<grid, kThreads, smem, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -398,7 +432,73 @@ size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int Cin
   return total;
 }
 
+// ---- sub-pixel phase form (32 -> 16 channels): tile = 16 x 8 low-res pixels, halo 18 x 10 cells per chunk
+namespace {
+constexpr int kPhNch = 4, kPhPw = 10, kPhPlane16 = 18 * kPhPw;
+// original filter taps that read low-res tap d (0/1) for output parity `parity`
+int phase_taps(int parity, int d, int* out) {
+  if (parity == 0) { if (d == 0) { out[0] = 0; return 1; } out[0] = 1; out[1] = 2; return 2; }
+  if (d == 0) { out[0] = 0; out[1] = 1; return 2; }
+  out[0] = 2; return 1;
+}
+}  // namespace
+
+bool halo_phase_supported(int C1, int C2, int Cout, int Hlo, int Wlo) {
+  return C1 == 8 * kPhNch && C2 == 0 && Cout == 16 && Hlo % kTH == 0 && Wlo % 8 == 0;
+}
+
+void halo_fill_steps_phase(HaloArgs& a) {
+  a.groups1 = 1;
+  a.groups2 = 0;
+  a.nsteps = 4 * (kPhNch / 2);
+  memset(a.a_lo, 0, sizeof a.a_lo);
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb)
+      for (int di = 0; di < 2; ++di)
+        for (int dj = 0; dj < 2; ++dj)
+          for (int kk = 0; kk < kPhNch / 2; ++kk) {
+            // output (2h+pa, 2w+pb), low-res tap (di, dj) -> halo cell (h + di + pa, w + dj + pb); halo origin (-1, -1)
+            const uint32_t off = static_cast<uint32_t>((2 * kk) * kPhPlane16 + (di + pa) * kPhPw + (dj + pb));
+            a.a_lo[(pa * 2 + pb) * a.nsteps + (di * 2 + dj) * (kPhNch / 2) + kk] = off | (static_cast<uint32_t>(kPhPlane16) << 16);
+          }
+  a.num_m_tiles = a.B * (a.Hin / kTH) * (a.Win / 8);
+}
+
+size_t pack_halo_weights_phase(const float* w, int Cout, int CoutPad, int Cin, int CinPad, uint16_t* dst) {
+  const int nsteps = 4 * (CinPad / 16);
+  const size_t total = static_cast<size_t>(4) * nsteps * 2 * CoutPad * 8;
+  if (!dst) return total;
+  memset(dst, 0, total * 2);
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb)
+      for (int di = 0; di < 2; ++di)
+        for (int dj = 0; dj < 2; ++dj) {
+          int khs[2], kws[2];
+          const int nh = phase_taps(pa, di, khs), nw = phase_taps(pb, dj, kws);
+          for (int kk = 0; kk < CinPad / 16; ++kk)
+            for (int j = 0; j < 2; ++j)
+              for (int n = 0; n < Cout; ++n)
+                for (int e = 0; e < 8; ++e) {
+                  const int ci = (2 * kk + j) * 8 + e;
+                  if (ci >= Cin) continue;
+                  double s = 0.0;
+                  for (int i = 0; i < nh; ++i)
+                    for (int q = 0; q < nw; ++q) s += w[((static_cast<size_t>(n) * Cin + ci) * 3 + khs[i]) * 3 + kws[q]];
+                  const size_t step = static_cast<size_t>(pa * 2 + pb) * nsteps + (di * 2 + dj) * (CinPad / 16) + kk;
+                  dst[((step * 2 + j) * CoutPad + n) * 8 + e] = bf16_rne(static_cast<float>(s));
+                }
+        }
+  return total;
+}
+
 int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream) {
+  if (a.phase_mode) {
+    if (KH != 3 || stride != 1 || !halo_phase_supported(a.C1, a.C2, a.Cout, a.Hin, a.Win) || a.Hout != 2 * a.Hin ||
+        a.Wout != 2 * a.Win || a.residual || a.rowbias || a.up2_out || a.out_f32)
+      return -3004;
+    if (a.nsteps != 4 * (kPhNch / 2)) return -3002;
+    return launch_halo_t<3, 1, kPhNch, 16, 4, true>(a, num_sms, stream);
+  }
   const int cg = halo_group_channels(KH, a.C1, a.C2);
   const int nch = cg / 8;
   if (!halo_supported(KH, stride, a.C1, a.C2, a.Cout, a.Hout, a.Wout)) return -3001;

@@ -40,6 +40,10 @@ struct HaloArgs {
   // step's first 8-channel chunk (16-byte units, bits 0-13) | distance to its second chunk << 16 (LBO)
   uint32_t a_lo[kHaloMaxSteps];
   int num_m_tiles;
+  // 1: sub-pixel phase form. x1 is the LOW-res [B, Hin, Win, C1] input of a 3x3 conv on its nearest-x2
+  // upsample, out is [B, 2*Hin, 2*Win, Cout]; a_lo holds 4 phases x nsteps entries and wpacked one filter
+  // set per phase (pack_halo_weights_phase)
+  int phase_mode;
 };
 
 // Geometry of one instantiation, shared by host packing and the kernel.
@@ -61,6 +65,13 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride);
 // Returns the number of bf16 elements written to `dst` (dst may be null to query the size).
 size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int CinPad, int KH, int stride,
                          int C1pad, int C2pad, uint16_t* dst);
+
+// Phase form (HaloArgs::phase_mode): single source of 32 channels -> 16 output channels.
+bool halo_phase_supported(int C1, int C2, int Cout, int Hlo, int Wlo);
+void halo_fill_steps_phase(HaloArgs& a);
+// [phase = pa*2+pb][step = (di*2+dj)*(C/16) + kk][chunk 0/1][n][8]; taps of the 3x3 filter that read the same
+// low-res pixel are summed before the single bf16 rounding.
+size_t pack_halo_weights_phase(const float* w, int Cout, int CoutPad, int Cin, int CinPad, uint16_t* dst);
 
 int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream);
 

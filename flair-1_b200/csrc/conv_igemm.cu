@@ -574,7 +574,7 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   // Measured on B200 (profiles/r01_pair_vs_single.md): no faster than the single-CTA kernel on these
   // shapes (the wide layers are not shared-memory-port bound after all), so it is opt-in: FB_PAIR=1.
   const char* pair_env = getenv("FB_PAIR");
-  const bool use_pair = use_tma_a && BN >= 128 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1' &&
+  const bool use_pair = use_tma_a && BN >= 64 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1' &&
                         a.KH == 3 && a.stride == 1 && !a.phase_mode;
   {
     // weights: [Cout][Kpad] bf16 ([4][Cout][Kpad] in phase mode), box = 64 k x BN rows (BN/2 per CTA of a
@@ -621,7 +621,8 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
     if (num_pairs < clusters) clusters = num_pairs;
     if (clusters <= 0) return 0;
     return BN == 256 ? launch_pair<256>(tmA, tmA2, tmB, a, 2 * clusters, stream)
-                     : launch_pair<128>(tmA, tmA2, tmB, a, 2 * clusters, stream);
+           : BN == 128 ? launch_pair<128>(tmA, tmA2, tmB, a, 2 * clusters, stream)
+                       : launch_pair<64>(tmA, tmA2, tmB, a, 2 * clusters, stream);
   }
 
   const int num_tiles = a.num_m_tiles * a.num_n_tiles;

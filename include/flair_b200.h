@@ -140,7 +140,9 @@ int fb_conv2d(fb_ctx* ctx, const void* x1, const void* x2, int C1, int C2, int u
 /* Same convolution through the halo-staged kernel (3x3 stride 1 with <= 64 channels per source and
  * Cout in {16,32,64}, or the 7x7 stride-2 stem on 8 channels): weights are given as host fp32
  * [Cout][C1+C2][KH][KH] and packed internally. up2_out: write the bf16 result 2x2-replicated into
- * [B, 2*Hout, 2*Wout, Cout] (the decoder's nearest x2 upsample). Synchronises the stream. */
+ * [B, 2*Hout, 2*Wout, Cout] (the decoder's nearest x2 upsample). up2_out == 2 selects the sub-pixel
+ * phase form instead (32 -> 16 channels only): the result is the 3x3 conv of the x2-upsampled x1,
+ * [B, 2*Hin, 2*Win, Cout], computed from the low-res x1 as four 2x2-tap phases. Synchronises the stream. */
 int fb_conv2d_halo(fb_ctx* ctx, const void* x1, const void* x2, int C1, int C2, int B, int Hin, int Win,
                    int KH, int stride, int Cout, const float* w_oihw_host, const float* bias,
                    const void* residual, int relu, int up2_out, void* out_bf16, float* out_f32);

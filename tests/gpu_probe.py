@@ -100,8 +100,10 @@ def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=Fals
 
 
 def halo_case(ctx, name, B, H, W, C1, Cout, KH, stride, C2=0, res=False, relu=True, up2=False, out_f32=False, seed=0,
-              identity=False):
-    """Halo-staged kernel against the fp32 reference on bf16-rounded operands."""
+              identity=False, phase=False):
+    """Halo-staged kernel against the fp32 reference on bf16-rounded operands.
+
+    phase: the sub-pixel form; x1 is the LOW-res input, the reference is the conv of its nearest x2 upsample."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = ctx.device
     x1 = torch.randn((B, H, W, C1), generator=g).to(torch.bfloat16).to(dev)
@@ -118,18 +120,22 @@ def halo_case(ctx, name, B, H, W, C1, Cout, KH, stride, C2=0, res=False, relu=Tr
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KH) // stride + 1
     residual = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).to(dev) if res else None
     try:
-        y = ctx.conv2d_halo(x1, w, bias, KH, stride, x2=x2, residual=residual, relu=relu, up2_out=up2, out_f32=out_f32)
+        y = ctx.conv2d_halo(x1, w, bias, KH, stride, x2=x2, residual=residual, relu=relu, up2_out=2 if phase else up2,
+                            out_f32=out_f32)
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         log(f"CASE {name}: EXCEPTION {e}")
         RESULTS.append({"case": name, "ok": False, "error": str(e)})
         return False
-    yr = ref_conv(x1, w.to(dev), bias, stride, pad, x2=x2, residual=residual, relu=relu)
+    xin = x1.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) if phase else x1
+    yr = ref_conv(xin, w.to(dev), bias, stride, pad, x2=x2, residual=residual, relu=relu)
     if up2:
         yr = yr.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
     err = (y.float() - yr).abs()
     scale = yr.abs().max().item() + 1e-9
     tol = 2e-5 if out_f32 else 1.0 / 128
+    if phase and not identity:
+        tol *= 2.5  # collapsed taps are summed before the bf16 rounding of the weights (not after, as in the reference)
     relm = err / (yr.abs() + 0.05 * scale)
     rel = relm.max().item()
     ok = bool(rel < tol * 2 + 1e-4) and bool(torch.isfinite(y.float()).all())
@@ -157,6 +163,10 @@ HALO_CASES = [
     ("h_stem_7x7s2", 2, 64, 64, 8, 64, 7, 2, {}),
     ("h_stem_big", 3, 256, 128, 8, 64, 7, 2, {}),
     ("h_many_tiles", 4, 256, 256, 16, 16, 3, 1, {}),
+    # sub-pixel phase form (dec4.conv1): low-res input H x W -> output 2H x 2W
+    ("h_phase_ident_32_16", 1, 16, 8, 32, 16, 3, 1, dict(phase=True, identity=True, relu=False)),
+    ("h_phase_32_16", 2, 32, 24, 32, 16, 3, 1, dict(phase=True)),
+    ("h_phase_32_16_many", 3, 128, 128, 32, 16, 3, 1, dict(phase=True)),
 ]
 
 
