@@ -35,11 +35,10 @@ struct Geo {
   static constexpr int CELLS = PH * KWCELLS * NCH;
   static constexpr int CELLS_PER_THREAD = (CELLS + kProducers - 1) / kProducers;
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
-  // ring depth / cp.async groups in flight / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
+  // ring depth (= stages of loads in flight) / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
   // memory (filter bank + stages + 18 KB epilogue staging): the 16/32-channel layers run two CTAs per SM
   static constexpr bool TWO = KH == 3 && NCH <= 4;
   static constexpr int STAGES = (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
-  static constexpr int LAG = STAGES == 4 ? 2 : 1;
   static constexpr int OCC = TWO ? 2 : 1;
 };
 
@@ -78,7 +77,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.wpacked);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < wbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    if (!(p.debug_skip & 16))
+      for (int i = threadIdx.x; i < wbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
     if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
   if (warp == kMmaWarp) {
@@ -123,8 +123,27 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const uint32_t dst = static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
       cell[j] = idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
     }
+    // Optional (FB_PREFETCH=1; measured neutral, so off by default): pull the halo rows of the tile
+    // kPrefetchDist iterations ahead into L2, one bulk prefetch per halo row and source, clipped to the image.
+    constexpr int kPrefetchDist = 2;
+    const int nsrc = p.C2 > 0 ? 2 : 1;
+    auto prefetch_tile = [&](int t) {
+      if (t >= p.num_m_tiles || p.no_prefetch) return;
+      const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
+      const int iw0 = tw * G::TW * STRIDE - G::PAD;
+      const int w_lo = iw0 < 0 ? 0 : iw0, w_hi = iw0 + G::KWCELLS < p.Win ? iw0 + G::KWCELLS : p.Win;
+      for (int r = tid; r < G::PH * nsrc; r += kProducers) {
+        const int sidx = r / G::PH, ih = th * kTH * STRIDE - G::PAD + r % G::PH;
+        if (static_cast<unsigned>(ih) >= static_cast<unsigned>(p.Hin)) continue;
+        const int Cs = sidx ? p.C2 : p.C1;
+        const __nv_bfloat16* row = (sidx ? p.x2 : p.x1) + ((static_cast<long long>(b) * p.Hin + ih) * p.Win + w_lo) * Cs;
+        prefetch_l2_bulk(row, static_cast<uint32_t>((w_hi - w_lo) * Cs * 2));
+      }
+    };
+    for (int d = 0; d < kPrefetchDist; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
+      prefetch_tile(tile + kPrefetchDist * gridDim.x);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
@@ -138,7 +157,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         const __nv_bfloat16* src = (from1 ? p.x1 : p.x2) + origin * Cs + (from1 ? g : g - p.groups1) * (NCH * 8) + c8;
         const int row_elems = p.Win * Cs;  // element distance between halo rows
         const uint32_t st = stage_addr0 + s * G::STAGE;
-        if (interior) {
+        if (p.debug_skip & 1) {
+        } else if (interior) {
 #pragma unroll
           for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
             if (cell[j] != 0xFFFFFFFFu) {
@@ -158,18 +178,12 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
             }
           }
         }
-        cp_async_commit();
-        if (it >= static_cast<uint32_t>(G::LAG)) {
-          cp_async_wait<G::LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(full_bar((it - G::LAG) % S));
-        }
+        // asynchronous arrival: the stage's full barrier completes when every producer thread's copies have
+        // landed; nobody waits here, so up to S stages of loads are in flight (the consumer issues the
+        // generic -> async proxy fence after its wait)
+        cp_async_mbar_arrive_noinc(full_bar(s));
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    const uint32_t first = it >= static_cast<uint32_t>(G::LAG) ? it - G::LAG : 0u;
-    for (uint32_t j = first; j < it; ++j) mbar_arrive(full_bar(j % S));
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int q = warp & 3;
@@ -189,6 +203,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
+      if (p.debug_skip & 8) {
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after_sync();
+        tc_fence_before_sync();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       if (PH) {
         // accumulator m = phase (pa, pb): low-res pixel (h, w) of the block -> output (2h + pa, 2w + pb)
 #pragma unroll
@@ -197,6 +218,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           uint8_t* blk_dst = out_bytes + static_cast<size_t>((static_cast<long long>(tb) * p.Hout + 2 * th * kTH + pa) * p.Wout +
                                                              2 * tw * G::TW + pb) * pixel_bytes;
           auto copy = [&](auto run, int col0, int el) {
+            if (p.debug_skip & 4) return;
             warp_copy_out_fast<decltype(run)::value>(stg, lane, L, blk_dst + static_cast<size_t>(col0) * el, pixel_bytes, 0, 0);
           };
           epilogue_tile<BN, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, 0, 0, copy);
@@ -214,6 +236,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       for (int m = 0; m < MB; ++m) {  // block m = columns 8m..8m+7 of the tile
         uint8_t* blk_dst = tile_dst + static_cast<size_t>(p.up2_out ? 16 * m : 8 * m) * pixel_bytes;
         auto copy = [&](auto run, int col0, int el) {
+          if (p.debug_skip & 4) return;
           warp_copy_out_fast<decltype(run)::value>(stg, lane, L, blk_dst + static_cast<size_t>(col0) * el, pixel_bytes,
                                                    p.up2_out, up_row_bytes);
         };
@@ -223,8 +246,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // ===================================================================== MMA issuer
+    // (elect_one(), not lane == 0: each tcgen05.mma is then issued once from uniform registers instead of
+    // inside a per-lane serialisation loop, which more than halves the issue interval, tests/umma_probe.cu)
     // Only the low descriptor word (start address, LBO) changes between instructions; the high word
     // (SBO, descriptor version 1, no swizzle) is a constant per operand.
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
@@ -242,12 +267,14 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(full_bar(s), ph);
+        fence_proxy_async_smem();   // the stage was written by cp.async (generic proxy), tcgen05.mma reads it through the async proxy
         tc_fence_after_sync();
         const uint32_t st16 = (stage_addr0 + s * G::STAGE) >> 4;
         // K-step outer, block inner: consecutive MMAs hit different accumulators (block m = output columns
         // 8m..8m+7 of the tile, 8 cells further in the stage) and share the step's filter slab
         uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
-        if (PH) {
+        if (p.debug_skip & 2) {
+        } else if (PH) {
           // step k of phase m: a_lo[m * nsteps + k], filter slab (m * nsteps + k); k outer so that consecutive
           // MMAs alternate between the four phase accumulators
 #pragma unroll 2
@@ -389,6 +416,10 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride) {
       }
   }
   a.num_m_tiles = a.B * (a.Hout / kTH) * (a.Wout / (8 * g.mb));
+  const char* np = getenv("FB_PREFETCH");
+  a.no_prefetch = !(np && np[0] == '1');
+  const char* sk = getenv("FB_HALO_SKIP");
+  a.debug_skip = sk ? atoi(sk) : 0;
 }
 
 static uint16_t bf16_rne(float f) {
@@ -462,6 +493,10 @@ void halo_fill_steps_phase(HaloArgs& a) {
             a.a_lo[(pa * 2 + pb) * a.nsteps + (di * 2 + dj) * (kPhNch / 2) + kk] = off | (static_cast<uint32_t>(kPhPlane16) << 16);
           }
   a.num_m_tiles = a.B * (a.Hin / kTH) * (a.Win / 8);
+  const char* np = getenv("FB_PREFETCH");
+  a.no_prefetch = !(np && np[0] == '1');
+  const char* sk = getenv("FB_HALO_SKIP");
+  a.debug_skip = sk ? atoi(sk) : 0;
 }
 
 size_t pack_halo_weights_phase(const float* w, int Cout, int CoutPad, int Cin, int CinPad, uint16_t* dst) {

@@ -44,6 +44,10 @@ struct HaloArgs {
   // upsample, out is [B, 2*Hin, 2*Win, Cout]; a_lo holds 4 phases x nsteps entries and wpacked one filter
   // set per phase (pack_halo_weights_phase)
   int phase_mode;
+  int no_prefetch;               // 0 only with FB_PREFETCH=1: L2 prefetch of upcoming halos (measured neutral)
+  // FB_HALO_SKIP bit mask, bottleneck hunting only (results are wrong): 1 = producers copy nothing,
+  // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake
+  int debug_skip;
 };
 
 // Geometry of one instantiation, shared by host packing and the kernel.

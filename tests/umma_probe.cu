@@ -40,6 +40,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 constexpr int kOperandBytes = 96 * 1024;
 constexpr int kNoiseBytes = 32 * 1024;
 
+// ELECT: the issuing thread is chosen with elect.sync (as opposed to `tid == 0`)
+template <bool ELECT>
 __global__ void __launch_bounds__(256) probe(P p, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -62,7 +64,10 @@ __global__ void __launch_bounds__(256) probe(P p, long long* out) {
   tc_fence_after_sync();
   const uint32_t tmem = slot;
   const uint32_t base16 = smem_u32(smem) >> 4;
-  if (tid == 0) {
+  bool issuer;
+  if (ELECT) issuer = warp == 0 && elect_one();
+  else issuer = tid == 0;
+  if (issuer) {
     const long long t0 = clock64();
     int c = 0, a = 0;
     for (int i = 0; i < p.iters; ++i) {
@@ -100,6 +105,85 @@ __global__ void __launch_bounds__(256) probe(P p, long long* out) {
   }
 }
 
+// Latency probes for the barrier round trips of a warp-specialised pipeline:
+//   mode 0: tcgen05.commit -> mbarrier completion observed by the committing thread, nothing pending
+//   mode 1: the same with one M=128 N=64 MMA issued before each commit
+//   mode 2: mbarrier ping-pong between lane 0 of warp 0 and lane 0 of warp 4 (arrive -> try_wait success), per hop
+//   mode 3: commit by warp 0's elected thread observed by warp 4 (all 32 lanes waiting), which arrives back (32 arrivals)
+__global__ void __launch_bounds__(256) latency_probe(int mode, int iters, uint32_t idesc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < kOperandBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), mode == 3 ? 32 : 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = slot;
+  const uint32_t base16 = smem_u32(smem) >> 4;
+  const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]);
+  if (mode <= 1) {
+    if (warp == 0 && elect_one()) {
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        if (mode == 1)
+          umma_bf16_lohi(tmem, base16 | (1u << 16), 64u | (1u << 14) | (2u << 29), (base16 + 2048) | (1u << 16),
+                         64u | (1u << 14) | (2u << 29), idesc, 0u);
+        umma_commit(b0);
+        mbar_wait(b0, i & 1);
+      }
+      out[blockIdx.x] = clock64() - t0;
+    }
+  } else if (mode == 2) {
+    if (tid == 0) {
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        mbar_arrive(b0);
+        mbar_wait(b1, i & 1);
+      }
+      out[blockIdx.x] = (clock64() - t0) / 2;
+    } else if (tid == 128) {
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(b0, i & 1);
+        mbar_arrive(b1);
+      }
+    }
+  } else {
+    if (warp == 0 && elect_one()) {
+      const long long t0 = clock64();
+      for (int i = 0; i < iters; ++i) {
+        umma_commit(b0);
+        mbar_wait(b1, i & 1);
+        tc_fence_after_sync();
+      }
+      out[blockIdx.x] = clock64() - t0;
+    } else if (warp == 4) {
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(b0, i & 1);
+        tc_fence_after_sync();
+        tc_fence_before_sync();
+        mbar_arrive(b1);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 struct Cfg {
   const char* name;
   int M, N, layout, a_tmem, nacc, noise, per_sm;
@@ -112,9 +196,27 @@ int main() {
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
   printf("SMs %d, max clock %d MHz\n", sms, khz / 1000);
   const int smem = kOperandBytes + kNoiseBytes;
-  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long* out = nullptr;
   cudaMalloc(&out, 8 * 1024);
+  {
+    cudaFuncSetAttribute(latency_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const char* names[4] = {"commit -> own wait, nothing pending", "1 MMA (N=64) + commit -> own wait",
+                            "mbarrier arrive -> other warp's try_wait (per hop)", "commit -> warp of 32 waits -> 32 arrivals -> issuer"};
+    for (int mode = 0; mode < 4; ++mode) {
+      const int it = 2000;
+      latency_probe<<<sms, 256, smem>>>(mode, it, umma_idesc_bf16(128, 64), out);
+      cudaError_t err = cudaDeviceSynchronize();
+      if (err != cudaSuccess) { printf("latency probe %d: %s\n", mode, cudaGetErrorString(err)); return 1; }
+      std::vector<long long> h(sms);
+      cudaMemcpy(h.data(), out, sms * 8, cudaMemcpyDeviceToHost);
+      std::sort(h.begin(), h.end());
+      printf("latency: %-55s %8.1f cycles (min %.1f max %.1f)\n", names[mode], static_cast<double>(h[sms / 2]) / it,
+             static_cast<double>(h[0]) / it, static_cast<double>(h[sms - 1]) / it);
+    }
+    fflush(stdout);
+  }
   std::vector<Cfg> cfgs;
   for (int layout = 0; layout < 3; ++layout)
     for (int N : {16, 32, 64, 128, 256}) cfgs.push_back({layout == 0 ? "sw128" : layout == 1 ? "none-dense" : "none-halo", 128, N, layout, 0, 2, 0, 1});
@@ -162,12 +264,13 @@ int main() {
       if (p.b_step * 16 * p.ncyc > 64 * 1024) p.b_step = 0;
     }
     const int grid = sms * c.per_sm;
+    for (int elect = 0; elect < 2; ++elect) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    probe<<<grid, 256, smem>>>(p, out);  // warm-up
+    if (elect) probe<true><<<grid, 256, smem>>>(p, out); else probe<false><<<grid, 256, smem>>>(p, out);  // warm-up
     cudaEventRecord(e0);
-    probe<<<grid, 256, smem>>>(p, out);
+    if (elect) probe<true><<<grid, 256, smem>>>(p, out); else probe<false><<<grid, 256, smem>>>(p, out);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
@@ -181,10 +284,11 @@ int main() {
     std::sort(h.begin(), h.end());
     const double cyc = static_cast<double>(h[grid / 2]) / iters;
     const double math = 128.0 * c.N / 256.0 * (c.M / 128.0);
-    printf("%-18s M=%3d N=%3d acc=%d: %7.1f cycles/MMA (min %.1f max %.1f), kernel %.1f us -> %.1f ns/MMA; math-bound %.0f cycles; operand bytes/cycle %.1f\n",
-           c.name, c.M, c.N, p.nacc, cyc, static_cast<double>(h[0]) / iters, static_cast<double>(h[grid - 1]) / iters, ms * 1e3,
-           ms * 1e6 / iters, math, ((c.a_tmem ? 0 : c.M) + c.N) * 32.0 / cyc);
+    printf("%-18s %s M=%3d N=%3d acc=%d: %7.1f cycles/MMA (min %.1f max %.1f), kernel %.1f us -> %.1f ns/MMA; math-bound %.0f cycles; operand bytes/cycle %.1f\n",
+           c.name, elect ? "elect " : "tid==0", c.M, c.N, p.nacc, cyc, static_cast<double>(h[0]) / iters,
+           static_cast<double>(h[grid - 1]) / iters, ms * 1e3, ms * 1e6 / iters, math, ((c.a_tmem ? 0 : c.M) + c.N) * 32.0 / cyc);
     fflush(stdout);
+    }
   }
   cudaFree(out);
   return 0;
