@@ -111,7 +111,9 @@ __device__ __forceinline__ void warp_copy_out(const Args& p, const uint8_t* stg,
 // stg: this warp's staging buffer (kStgWarpBytes, 16-byte aligned).
 // own_valid / own_pix / own_rb: this lane's row: in range?, linear output pixel index, rowbias index.
 // copy(run_tag, col0, elem): cooperative copy-out of the staged column group starting at column col0.
-template <int BN, bool PREFETCH, bool BIAS_SMEM, typename Args, typename CopyFn>
+// DIRECT: no staging; copy(col0, regs) receives each finished group of 16 columns in registers
+// (const uint32_t (&)[8] = 16 packed bf16, or const float (&)[16]) and stores the lane's own pixel itself.
+template <int BN, bool PREFETCH, bool BIAS_SMEM, bool DIRECT = false, typename Args, typename CopyFn>
 __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, uint32_t taddr, uint32_t tfull_bar,
                                               uint32_t tfull_parity, int lane, int n0, uint8_t* stg, bool own_valid,
                                               long long own_pix, int own_rb, CopyFn copy) {
@@ -119,16 +121,23 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
   const float rb = (p.rowbias != nullptr && own_valid) ? p.rowbias[own_rb] : 0.f;
   const size_t obase = static_cast<size_t>(own_pix) * p.Cout + n0;
   const bool has_res = p.residual != nullptr && own_valid;
-  constexpr int NRES = PREFETCH ? BN / 8 : 1;
-  uint4 res[NRES];
+  // residual row of this lane's pixel: 32-byte (one sector) loads of 16 channels, prefetched in groups of
+  // <= 64 channels: group 0 before the accumulator wait, group g + 1 while group g is consumed
+  constexpr int CPG = PREFETCH ? (BN <= 64 ? BN / 16 : 2) : 1;   // 16-channel chunks per group (registers: 2 * CPG * 8)
+  constexpr int NG = PREFETCH ? BN / (16 * CPG) : 1;
+  uint32_t res[NG > 1 ? 2 : 1][CPG][8];
+  auto load_group = [&](int g, int buf) {
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) ld_global_nc_v8(p.residual + obase + 16 * (g * CPG + i), res[buf][i]);
+  };
   if (PREFETCH) {
 #pragma unroll
-    for (int i = 0; i < NRES; ++i) res[i] = make_uint4(0, 0, 0, 0);
-    if (has_res) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase);
+    for (int b = 0; b < (NG > 1 ? 2 : 1); ++b)
 #pragma unroll
-      for (int i = 0; i < NRES; ++i) res[i] = __ldg(rp + i);
-    }
+      for (int i = 0; i < CPG; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res[b][i][j] = 0u;
+    if (has_res) load_group(0, 0);
   }
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after_sync();
@@ -141,14 +150,14 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
   for (int c0 = 0; c0 < BN; c0 += 16) {
     uint32_t r[16];
     tmem_ld_x16(taddr + c0, r);
-    uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    uint32_t rr[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     if (PREFETCH) {
-      rr[0] = res[(c0 / 8) % NRES];
-      rr[1] = res[(c0 / 8 + 1) % NRES];
+      const int g = (c0 / 16) / CPG, i = (c0 / 16) % CPG;   // compile-time after unrolling
+      if (i == 0 && g + 1 < NG && has_res) load_group(g + 1, (g + 1) & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rr[j] = res[NG > 1 ? (g & 1) : 0][i][j];
     } else if (has_res) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-      rr[0] = __ldg(rp);
-      rr[1] = __ldg(rp + 1);
+      ld_global_nc_v8(p.residual + obase + c0, rr);
     }
     float4 bb[4];
     const float4* bp = reinterpret_cast<const float4*>(bias + n0 + c0);
@@ -165,14 +174,10 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
     }
     if (has_res) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t w[4] = {rr[h].x, rr[h].y, rr[h].z, rr[h].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-          v[8 * h + 2 * i + 0] += __low2float(b2);
-          v[8 * h + 2 * i + 1] += __high2float(b2);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+        v[2 * i + 0] += __low2float(b2);
+        v[2 * i + 1] += __high2float(b2);
       }
     }
     if (p.relu) {
@@ -182,7 +187,19 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += rb;
 
-    if (f32) {
+    if constexpr (DIRECT) {
+      if (f32) {
+        copy(n0 + c0, v);
+      } else {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        copy(n0 + c0, pk);
+      }
+    } else if (f32) {
       float4* sp = reinterpret_cast<float4*>(my_row + (c0 % GC_F32) * 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) sp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);

@@ -210,6 +210,51 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         mbar_arrive(tempty_bar(as));
         continue;
       }
+      // direct mode: every lane stores its own pixel straight from registers, 32 bytes (one sector) per
+      // instruction, instead of going through the shared-memory staging buffer
+      auto store_regs = [&](uint8_t* d, const auto& regs) {
+        if constexpr (sizeof(regs) == 32) {
+          st_global_v8(d, regs);
+        } else {
+          uint32_t lo[8], hi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            lo[i] = __float_as_uint(regs[i]);
+            hi[i] = __float_as_uint(regs[8 + i]);
+          }
+          st_global_v8(d, lo);
+          st_global_v8(d + 32, hi);
+        }
+      };
+      if (p.direct_store) {
+        const int oh = th * kTH + L.own_dh, ow = tw * G::TW + L.own_dw;
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          long long dpix, own_pix = 0;
+          if (PH) {
+            dpix = (static_cast<long long>(tb) * p.Hout + 2 * oh + (m >> 1)) * p.Wout + 2 * ow + (m & 1);
+          } else {
+            own_pix = (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow + 8 * m;
+            dpix = p.up2_out ? (static_cast<long long>(tb) * 2 * p.Hout + 2 * oh) * (2 * p.Wout) + 2 * (ow + 8 * m) : own_pix;
+          }
+          uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
+          auto direct = [&](int col0, const auto& regs) {
+            if (p.debug_skip & 4) return;
+            uint8_t* d = own_dst + static_cast<size_t>(col0) * elem;
+            store_regs(d, regs);
+            if (!PH && p.up2_out) {
+              store_regs(d + pixel_bytes, regs);
+              store_regs(d + up_row_bytes, regs);
+              store_regs(d + up_row_bytes + pixel_bytes, regs);
+            }
+          };
+          epilogue_tile<BN, true, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                              tb * p.Hout + oh, direct);
+        }
+        tc_fence_before_sync();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       if (PH) {
         // accumulator m = phase (pa, pb): low-res pixel (h, w) of the block -> output (2h + pa, 2w + pb)
 #pragma unroll
@@ -420,6 +465,9 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride) {
   a.no_prefetch = !(np && np[0] == '1');
   const char* sk = getenv("FB_HALO_SKIP");
   a.debug_skip = sk ? atoi(sk) : 0;
+  const char* ds = getenv("FB_DIRECT_STORE");
+  // 2x2-replicated outputs keep the staged copy-out (four scattered 32-byte stores per lane are slower)
+  a.direct_store = ds ? atoi(ds) : (a.up2_out ? 0 : 1);
 }
 
 static uint16_t bf16_rne(float f) {
@@ -497,6 +545,8 @@ void halo_fill_steps_phase(HaloArgs& a) {
   a.no_prefetch = !(np && np[0] == '1');
   const char* sk = getenv("FB_HALO_SKIP");
   a.debug_skip = sk ? atoi(sk) : 0;
+  const char* ds = getenv("FB_DIRECT_STORE");
+  a.direct_store = ds ? atoi(ds) : 1;
 }
 
 size_t pack_halo_weights_phase(const float* w, int Cout, int CoutPad, int Cin, int CinPad, uint16_t* dst) {

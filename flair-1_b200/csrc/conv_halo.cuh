@@ -48,6 +48,7 @@ struct HaloArgs {
   // FB_HALO_SKIP bit mask, bottleneck hunting only (results are wrong): 1 = producers copy nothing,
   // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake
   int debug_skip;
+  int direct_store;              // epilogue stores from registers (32 B per lane and instruction) instead of staging
 };
 
 // Geometry of one instantiation, shared by host packing and the kernel.

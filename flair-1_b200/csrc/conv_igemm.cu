@@ -204,11 +204,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long pix0 = (static_cast<long long>(tb) * p.Hout + psc * th * 8 + pa) * p.Wout + psc * tw * 16 + pb;
         const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * 16) * (2 * p.Wout) + tw * 32;
         uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
+        if (p.direct_store) {
+          // every lane stores its own pixel from registers, one 32-byte sector per instruction (no staging)
+          const long long own_pix = (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow;
+          const long long dpix = p.up2_out ? (static_cast<long long>(tb) * 2 * p.Hout + 2 * oh) * (2 * p.Wout) + 2 * ow : own_pix;
+          uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
+          auto store_regs = [&](uint8_t* d, const auto& regs) {
+            if constexpr (sizeof(regs) == 32) {
+              st_global_v8(d, regs);
+            } else {
+              uint32_t lo[8], hi[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                lo[i] = __float_as_uint(regs[i]);
+                hi[i] = __float_as_uint(regs[8 + i]);
+              }
+              st_global_v8(d, lo);
+              st_global_v8(d + 32, hi);
+            }
+          };
+          auto direct = [&](int col0, const auto& regs) {
+            uint8_t* d = own_dst + static_cast<size_t>(col0) * elem;
+            store_regs(d, regs);
+            if (p.up2_out) {
+              store_regs(d + pixel_bytes, regs);
+              store_regs(d + up_row_bytes, regs);
+              store_regs(d + up_row_bytes + pixel_bytes, regs);
+            }
+          };
+          epilogue_tile<BN, true, false, true>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true, own_pix,
+                                                     tb * p.Hout + oh, direct);
+          tc_fence_before_sync();
+          mbar_arrive(tempty_bar(as));
+          continue;
+        }
         auto copy = [&](auto run, int col0, int el) {
           warp_copy_out_fast<decltype(run)::value>(stg, lane, L, tile_dst + static_cast<size_t>(col0) * el, pixel_bytes,
                                                    p.up2_out, up_row_bytes);
         };
-        epilogue_tile<BN, (BN <= 64), false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
+        epilogue_tile<BN, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
                                              (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
       } else {
         // gather tiles are 128 consecutive pixels of the flattened (b, h, w) index space, possibly ragged
@@ -225,7 +259,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         };
         int b, oh, ow;
         const bool valid = rowfn(q * 32 + lane, b, oh, ow);
-        epilogue_tile<BN, (BN <= 64), false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, valid,
+        epilogue_tile<BN, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, valid,
                                              static_cast<long long>(m_tile) * kBM + q * 32 + lane, b * p.Hout + oh, copy);
       }
       tc_fence_before_sync();
@@ -398,7 +432,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         warp_copy_out_fast<decltype(run)::value>(stg, lane, L, tile_dst + static_cast<size_t>(col0) * el, pixel_bytes,
                                                  p.up2_out, up_row_bytes);
       };
-      epilogue_tile<BN, false, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
+      epilogue_tile<BN, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
                                       (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
       tc_fence_before_sync();
       mbar_arrive_leader(tempty_bar(as));   // local arrive in the leader, remote arrive from the peer
@@ -523,6 +557,10 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   a.M_total = a.B * a.Hout * a.Wout;
   a.num_n_tiles = a.Cout / BN;
   a.num_k_iters = (a.Ktot + kBK - 1) / kBK;
+  {
+    const char* ds = getenv("FB_DIRECT_STORE");
+    a.direct_store = ds ? atoi(ds) == 2 : 0;   // measured neutral-to-slower here (not shared-memory bound): opt-in with 2
+  }
   if (use_tma_a) {
     if (!conv_tma_eligible(a)) return -1004;
     const int c1c = a.C1 / 64, c2c = a.C2 / 64;

@@ -49,6 +49,10 @@ struct ConvArgs {
   // stride 2. 4*C1 + 9*C2 instead of 9*(C1+C2) products per pixel and no materialised upsample.
   // weights: [4 phases][Cout][Kpad].
   int phase_mode;
+  // TMA-producer kernel: the epilogue stores each lane's pixel from registers (32 B per instruction) instead
+  // of staging through shared memory. Set by launch_conv: off unless FB_DIRECT_STORE=2 (a win in the halo
+  // kernel, which is shared-memory-bandwidth bound; neutral to slower here).
+  int direct_store;
   // tiling
   int M_total;       // B*Hout*Wout
   int num_m_tiles;   // gather: ceil(M_total/128); TMA: B*(tile-grid H/8)*(tile-grid W/16)

@@ -100,6 +100,18 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+// 256-bit global store (sm_100+): one full 32-byte sector per lane; `ptr` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 256-bit read-only global load: one full sector per lane; `ptr` must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_nc_v8(const void* ptr, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
 // Ask L2 to fetch `bytes` (multiple of 16) starting at the 16-byte-aligned global address; no destination,
 // no completion tracking.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {

@@ -45,7 +45,9 @@ for (name, H, W, C1, C2, Cout, KH, stride, kw), B in [(s, b) for b in BATCHES fo
     res = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).cuda() if kw.get("res") else None
     up2 = 2 if kw.get("phase") else 0
     for m in MASKS:
-        os.environ["FB_HALO_SKIP"] = str(m)
+        # masks >= 1000 select the direct-store epilogue (FB_DIRECT_STORE=1) with skip mask m - 1000
+        os.environ["FB_HALO_SKIP"] = str(m % 1000)
+        os.environ["FB_DIRECT_STORE"] = "1" if m >= 1000 else "0"
         for _ in range(2):  # the second launch of each pair is the one to read
             ctx.conv2d_halo(x1, w, bias, KH, stride, x2=x2, residual=res, relu=kw.get("relu", True), up2_out=up2,
                             out_f32=kw.get("out_f32", False))
