@@ -106,6 +106,13 @@ __device__ __forceinline__ void warp_copy_out(const Args& p, const uint8_t* stg,
   }
 }
 
+// BN channels of one pixel's residual row into registers, one 32-byte sector per load (for EXT_RES).
+template <int BN>
+__device__ __forceinline__ void load_residual_row(const __nv_bfloat16* row, uint32_t (*res)[8]) {
+#pragma unroll
+  for (int i = 0; i < BN / 16; ++i) ptx::ld_global_nc_v8(row + 16 * i, res[i]);
+}
+
 // Args must provide: residual, rowbias, relu, out, out_f32, Cout, Hout, Wout, up2_out.
 // bias: fp32 [>= n0 + BN]; BIAS_SMEM selects plain (shared-memory) loads instead of the read-only path.
 // stg: this warp's staging buffer (kStgWarpBytes, 16-byte aligned).
@@ -113,14 +120,68 @@ __device__ __forceinline__ void warp_copy_out(const Args& p, const uint8_t* stg,
 // copy(run_tag, col0, elem): cooperative copy-out of the staged column group starting at column col0.
 // DIRECT: no staging; copy(col0, regs) receives each finished group of 16 columns in registers
 // (const uint32_t (&)[8] = 16 packed bf16, or const float (&)[16]) and stores the lane's own pixel itself.
-template <int BN, bool PREFETCH, bool BIAS_SMEM, bool DIRECT = false, typename Args, typename CopyFn>
+// EXT_RES: the caller has already loaded the residual row (ext_res[c][8] = channels 16c..16c+15 of this
+// lane's pixel, see load_residual_row) so that the loads of the next block overlap this block's work.
+template <int BN, bool PREFETCH, bool BIAS_SMEM, bool DIRECT = false, bool EXT_RES = false, typename Args, typename CopyFn>
 __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, uint32_t taddr, uint32_t tfull_bar,
                                               uint32_t tfull_parity, int lane, int n0, uint8_t* stg, bool own_valid,
-                                              long long own_pix, int own_rb, CopyFn copy) {
+                                              long long own_pix, int own_rb, CopyFn copy,
+                                              const uint32_t (*ext_res)[8] = nullptr) {
   using namespace ptx;
   const float rb = (p.rowbias != nullptr && own_valid) ? p.rowbias[own_rb] : 0.f;
   const size_t obase = static_cast<size_t>(own_pix) * p.Cout + n0;
   const bool has_res = p.residual != nullptr && own_valid;
+  if constexpr (EXT_RES) {
+    // same body as below with the residual taken from the caller's registers
+    mbar_wait(tfull_bar, tfull_parity);
+    tc_fence_after_sync();
+    const bool f32x = p.out_f32 != nullptr;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_x16(taddr + c0, r);
+      float4 bb[4];
+      const float4* bp = reinterpret_cast<const float4*>(bias + n0 + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bb[i] = BIAS_SMEM ? bp[i] : __ldg(bp + i);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb[i].x;
+        v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb[i].y;
+        v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb[i].z;
+        v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb[i].w;
+      }
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ext_res[c0 / 16][i]);
+          v[2 * i + 0] += __low2float(b2);
+          v[2 * i + 1] += __high2float(b2);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += rb;
+      static_assert(!EXT_RES || DIRECT, "EXT_RES is only implemented for the direct-store epilogue");
+      if (f32x) {
+        copy(n0 + c0, v);
+      } else {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        copy(n0 + c0, pk);
+      }
+    }
+    return;
+  }
   // residual row of this lane's pixel: 32-byte (one sector) loads of 16 channels, prefetched in groups of
   // <= 64 channels: group 0 before the accumulator wait, group g + 1 while group g is consumed
   constexpr int CPG = PREFETCH ? (BN <= 64 ? BN / 16 : 2) : 1;   // 16-channel chunks per group (registers: 2 * CPG * 8)
@@ -146,16 +207,27 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
   uint8_t* my_row = stg + lane * kStgPitch;
   constexpr int GC_BF16 = EpiRun<BN>::GC_BF16;
   constexpr int GC_F32 = EpiRun<BN>::GC_F32;
-#pragma unroll(PREFETCH ? BN / 16 : 2)
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  // Unrolled body = two residual groups (so that the double-buffer index is a compile-time constant) or the
+  // whole tile when it is a single group; wider tiles loop over the body to keep the code small.
+  constexpr int CHUNKS = BN / 16;
+  constexpr int UNR = PREFETCH ? (NG > 1 ? 2 * CPG : CHUNKS) : 2;
+  static_assert(CHUNKS % UNR == 0 || CHUNKS < UNR, "tile width must be a whole number of unrolled bodies");
+#pragma unroll 1
+  for (int cb = 0; cb < CHUNKS; cb += UNR) {
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    if (cb + u >= CHUNKS) break;   // only BN = 16 without prefetch (UNR = 2 > CHUNKS)
+    const int c0 = (cb + u) * 16;
     uint32_t r[16];
     tmem_ld_x16(taddr + c0, r);
     uint32_t rr[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     if (PREFETCH) {
-      const int g = (c0 / 16) / CPG, i = (c0 / 16) % CPG;   // compile-time after unrolling
-      if (i == 0 && g + 1 < NG && has_res) load_group(g + 1, (g + 1) & 1);
+      const int g = (cb + u) / CPG;
+      constexpr int kBufMask = NG > 1 ? 1 : 0;
+      const int i = u % CPG, buf = (u / CPG) & kBufMask;   // compile-time: cb is a multiple of 2 * CPG
+      if (i == 0 && g + 1 < NG && has_res) load_group(g + 1, (buf ^ 1) & kBufMask);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rr[j] = res[NG > 1 ? (g & 1) : 0][i][j];
+      for (int j = 0; j < 8; ++j) rr[j] = res[buf][i][j];
     } else if (has_res) {
       ld_global_nc_v8(p.residual + obase + c0, rr);
     }
@@ -224,6 +296,7 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
         __syncwarp();
       }
     }
+  }
   }
 }
 

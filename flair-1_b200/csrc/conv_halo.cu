@@ -228,8 +228,23 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       };
       if (p.direct_store) {
         const int oh = th * kTH + L.own_dh, ow = tw * G::TW + L.own_dw;
+        // residual rows are loaded one block ahead: block 0 before the accumulator wait, block m + 1 while
+        // block m is processed (BN <= 32: everything up front)
+        constexpr int kResBuf = PH ? 1 : (MB * BN <= 64 ? MB : 2);
+        uint32_t rbuf[kResBuf][BN / 16][8];
+        const bool has_res = !PH && p.residual != nullptr;
+        const __nv_bfloat16* res_row0 = p.residual + ((static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow) * BN;
+        if (has_res) {
+          if (kResBuf == MB) {
+#pragma unroll
+            for (int m = 0; m < MB; ++m) load_residual_row<BN>(res_row0 + 8 * m * BN, rbuf[m % kResBuf]);
+          } else {
+            load_residual_row<BN>(res_row0, rbuf[0]);
+          }
+        }
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
+          if (has_res && kResBuf != MB && m + 1 < MB) load_residual_row<BN>(res_row0 + 8 * (m + 1) * BN, rbuf[(m + 1) % kResBuf]);
           long long dpix, own_pix = 0;
           if (PH) {
             dpix = (static_cast<long long>(tb) * p.Hout + 2 * oh + (m >> 1)) * p.Wout + 2 * ow + (m & 1);
@@ -248,8 +263,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
               store_regs(d + up_row_bytes + pixel_bytes, regs);
             }
           };
-          epilogue_tile<BN, true, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
-                                              tb * p.Hout + oh, direct);
+          epilogue_tile<BN, true, true, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                                    tb * p.Hout + oh, direct, rbuf[m % kResBuf]);
         }
         tc_fence_before_sync();
         mbar_arrive(tempty_bar(as));

@@ -17,7 +17,6 @@ namespace {
 constexpr int kNumProducerThreads = 128;  // warps 0-3
 constexpr int kNumEpilogueThreads = 128;  // warps 4-7
 constexpr int kNumThreads = 288;          // + warp 8 (MMA issuer / TMEM owner)
-constexpr int kGatherLag = 2;             // cp.async groups kept in flight per producer thread
 
 template <int BN>
 struct Cfg {
