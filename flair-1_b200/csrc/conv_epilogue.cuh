@@ -133,7 +133,7 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
   const bool has_res = p.residual != nullptr && own_valid;
   if constexpr (EXT_RES) {
     // same body as below with the residual taken from the caller's registers
-    mbar_wait(tfull_bar, tfull_parity);
+    mbar_wait_relaxed(tfull_bar, tfull_parity);
     tc_fence_after_sync();
     const bool f32x = p.out_f32 != nullptr;
 #pragma unroll
@@ -200,7 +200,7 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
         for (int j = 0; j < 8; ++j) res[b][i][j] = 0u;
     if (has_res) load_group(0, 0);
   }
-  mbar_wait(tfull_bar, tfull_parity);
+  mbar_wait_relaxed(tfull_bar, tfull_parity);
   tc_fence_after_sync();
 
   const bool f32 = p.out_f32 != nullptr;

@@ -151,7 +151,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       for (int g = 0; g < groups; ++g, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_wait_relaxed(empty_bar(s), ph ^ 1);
         const bool from1 = g < p.groups1;
         const int Cs = from1 ? p.C1 : p.C2;
         const __nv_bfloat16* src = (from1 ? p.x1 : p.x2) + origin * Cs + (from1 ? g : g - p.groups1) * (NCH * 8) + c8;

@@ -60,6 +60,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same wait for whole warps whose wake-up latency does not matter (producers waiting for a free stage,
+// epilogue warps waiting for an accumulator): back off between polls so that the spinning does not eat
+// issue slots and power that the MMA-issuing thread and the busy warps could use.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+#ifdef FB_RELAXED_SLEEP_NS
+  while (!mbar_try_wait(bar, parity)) __nanosleep(FB_RELAXED_SLEEP_NS);
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
+}
 
 // ----------------------------------------------------------------------------- fences
 // generic-proxy writes (st.shared / cp.async results) -> visible to the async proxy (TMA, tcgen05.mma)
