@@ -56,6 +56,11 @@ _SIGNATURES = {
     "fb_forward_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fb_detect_strip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_int64]),
+    "fb_detect_strip_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_int64]),
+    "fb_blend_strip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "fb_blend_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "fb_detect_zone_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int64,
                                       C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
@@ -233,6 +238,37 @@ class Context:
         assert cls_map.dtype == torch.uint8 and cls_map.is_cuda
         self._check(self._lib.fb_detect_strip(self._h, t.ctypes.data, t.shape[0], tile, batch, cls_map.data_ptr(),
                                               _ptr(conf_map), map_w, map_row0))
+
+    def detect_strip_prob(self, tiles: np.ndarray, tile: int, batch: int, prob_map: torch.Tensor, map_w: int,
+                          map_row0: int = 0) -> None:
+        """output_type class_prob: prob_map uint8 [n_classes, map_rows, map_w] (device)."""
+        t = make_tiles(tiles)
+        assert prob_map.dtype == torch.uint8 and prob_map.is_cuda and prob_map.dim() == 3 and prob_map.is_contiguous()
+        self._check(self._lib.fb_detect_strip_prob(self._h, t.ctypes.data, t.shape[0], tile, batch, prob_map.data_ptr(),
+                                                   map_w, map_row0, prob_map.shape[1]))
+
+    STITCH_METHODS = {"average": 0, "average_weights": 1, "max": 2}
+
+    def blend_buffers(self, method: str, map_rows: int, map_w: int):
+        """Zeroed accumulators for blend_strip: (acc, wsum); wsum is None for 'max'."""
+        if self.STITCH_METHODS[method] == 2:
+            return torch.zeros((map_rows, map_w), dtype=torch.int64, device=self.device), None
+        return (torch.zeros((map_rows, map_w, 16), dtype=torch.float32, device=self.device),
+                torch.zeros((map_rows, map_w), dtype=torch.float32, device=self.device))
+
+    def blend_strip(self, tiles: np.ndarray, tile: int, batch: int, method: str, acc: torch.Tensor,
+                    wsum: Optional[torch.Tensor], map_w: int, map_row0: int = 0, tile_seq0: int = 0) -> None:
+        """Accumulate the whole tiles (clipped to the raster) into the blend accumulators."""
+        t = make_tiles(tiles)
+        self._check(self._lib.fb_blend_strip(self._h, t.ctypes.data, t.shape[0], tile, batch, self.STITCH_METHODS[method],
+                                             acc.data_ptr(), _ptr(wsum), map_w, map_row0, acc.shape[0], tile_seq0))
+
+    def blend_finalize(self, method: str, acc: torch.Tensor, wsum: Optional[torch.Tensor], cls_map: torch.Tensor,
+                       conf_map: Optional[torch.Tensor]) -> None:
+        npx = acc.shape[0] * acc.shape[1]
+        assert cls_map.numel() == npx and cls_map.dtype == torch.uint8
+        self._check(self._lib.fb_blend_finalize(self._h, acc.data_ptr(), _ptr(wsum), self.STITCH_METHODS[method], npx,
+                                                cls_map.data_ptr(), _ptr(conf_map)))
 
     def detect_zone_host(self, raster, band_idx: Sequence[int], W: int, H: int, row0: int, layout: int,
                          tiles: np.ndarray, tile: int, batch: int, out_cls, out_conf, map_w: int,

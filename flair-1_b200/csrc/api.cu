@@ -799,18 +799,91 @@ int fb_forward_tiles(fb_ctx* c, const int32_t* tile_xy, int n, int tile, const f
   return 0;
 }
 
-int fb_detect_strip(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, uint8_t* cls_map_dev,
-                    uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0) {
-  FB_TRY(check_ready(c, true, tile));
-  if (c->use_meta) return fail(c, FB_ERR_INVALID, "zone detection does not take metadata (zone_detect/model.py:52)");
-  if (!tiles || n < 0 || batch <= 0 || !cls_map_dev) return fail(c, FB_ERR_INVALID, "detect: bad arguments");
-  if (n == 0) return 0;
+}  // extern "C" (the sink helpers below are C++)
+
+namespace {
+// where the logits of a batch go: the class map (argmax), the probability planes, or the blend accumulators
+struct DetectSink {
+  int kind = 0;                 // 0 argmax + confidence, 1 class_prob planes, 2 blend accumulation
+  uint8_t* cls = nullptr;
+  uint8_t* conf = nullptr;
+  uint8_t* prob = nullptr;
+  float* acc = nullptr;
+  float* wsum = nullptr;
+  int method = 0;
+  int64_t map_w = 0, map_row0 = 0, map_rows = 0;
+  int seq0 = 0;
+};
+
+int check_write_rects(fb_ctx* c, const fb_tile* tiles, int n, int tile, int64_t map_w, int64_t map_row0) {
   for (int i = 0; i < n; ++i) {
     const fb_tile& t = tiles[i];
     if (t.wx1 > t.wx0 && t.wy1 > t.wy0 &&
         (t.wx0 < t.x0 || t.wy0 < t.y0 || t.wx1 > t.x0 + tile || t.wy1 > t.y0 + tile || t.wx0 < 0 || t.wx1 > map_w || t.wy0 < map_row0))
       return fail(c, FB_ERR_INVALID, "detect: write rectangle of tile " + std::to_string(i) + " is outside its tile or the map");
   }
+  return 0;
+}
+
+int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, const DetectSink& s);
+}  // namespace
+
+extern "C" {
+
+int fb_detect_strip(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, uint8_t* cls_map_dev,
+                    uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0) {
+  FB_TRY(check_ready(c, true, tile));
+  if (!tiles || n < 0 || batch <= 0 || !cls_map_dev) return fail(c, FB_ERR_INVALID, "detect: bad arguments");
+  FB_TRY(check_write_rects(c, tiles, n, tile, map_w, map_row0));
+  DetectSink s;
+  s.kind = 0; s.cls = cls_map_dev; s.conf = conf_map_dev; s.map_w = map_w; s.map_row0 = map_row0;
+  return detect_loop(c, tiles, n, tile, batch, s);
+}
+
+int fb_detect_strip_prob(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, uint8_t* prob_map_dev,
+                         int64_t map_w, int64_t map_row0, int64_t map_rows) {
+  FB_TRY(check_ready(c, true, tile));
+  if (!tiles || n < 0 || batch <= 0 || !prob_map_dev || map_rows <= 0) return fail(c, FB_ERR_INVALID, "detect (class_prob): bad arguments");
+  FB_TRY(check_write_rects(c, tiles, n, tile, map_w, map_row0));
+  for (int i = 0; i < n; ++i)
+    if (tiles[i].wy1 > tiles[i].wy0 && tiles[i].wy1 > map_row0 + map_rows)
+      return fail(c, FB_ERR_INVALID, "detect (class_prob): write rectangle below the map");
+  DetectSink s;
+  s.kind = 1; s.prob = prob_map_dev; s.map_w = map_w; s.map_row0 = map_row0; s.map_rows = map_rows;
+  return detect_loop(c, tiles, n, tile, batch, s);
+}
+
+int fb_blend_strip(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, int method, float* acc_dev,
+                   float* wsum_dev, int64_t map_w, int64_t map_row0, int64_t map_rows, int tile_seq0) {
+  FB_TRY(check_ready(c, true, tile));
+  if (!tiles || n < 0 || batch <= 0 || !acc_dev || map_rows <= 0 || map_w <= 0 || method < 0 || method > 2 ||
+      (method != 2 && !wsum_dev))
+    return fail(c, FB_ERR_INVALID, "blend: bad arguments");
+  DetectSink s;
+  s.kind = 2; s.acc = acc_dev; s.wsum = wsum_dev; s.method = method; s.map_w = map_w; s.map_row0 = map_row0;
+  s.map_rows = map_rows; s.seq0 = tile_seq0;
+  return detect_loop(c, tiles, n, tile, batch, s);
+}
+
+int fb_blend_finalize(fb_ctx* c, const float* acc_dev, const float* wsum_dev, int method, int64_t npx,
+                      uint8_t* cls_map_dev, uint8_t* conf_map_dev) {
+  if (!c) return FB_ERR_INVALID;
+  if (!c->loaded) return fail(c, FB_ERR_STATE, "blend: weights not loaded");
+  if (!acc_dev || !cls_map_dev || npx < 0 || method < 0 || method > 2 || (method != 2 && !wsum_dev))
+    return fail(c, FB_ERR_INVALID, "blend finalize: bad arguments");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  int rc = fb::launch_blend_finalize(acc_dev, wsum_dev, method, c->ncls, npx, cls_map_dev, conf_map_dev, c->num_sms, c->stream);
+  if (rc) return fail(c, rc, "blend finalize launch failed");
+  c->launches++;
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, const DetectSink& s) {
+  if (c->use_meta) return fail(c, FB_ERR_INVALID, "zone detection does not take metadata (zone_detect/model.py:52)");
+  if (n == 0) return 0;
   FB_CUDA(c, cudaSetDevice(c->device));
   if (batch > n) batch = n;
   FB_TRY(ensure_arena(c, batch, tile));
@@ -827,13 +900,24 @@ int fb_detect_strip(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch,
                        c->rows, c->tile_xy_dev + 2 * i0, nb, tile));
     FB_TRY(run_network(c, nb, tile, nullptr));
     ProfScope ps(c, 3);
-    int rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, nb, tile,
-                                      c->tiles_dev + 6 * i0, cls_map_dev, conf_map_dev, map_w, map_row0, c->stream);
-    if (rc) return fail(c, rc, "argmax/stitch launch failed");
+    const float* logits = static_cast<const float*>(c->acts["logits"].ptr);
+    int rc;
+    if (s.kind == 0)
+      rc = fb::launch_argmax_stitch(logits, c->ncls, nb, tile, c->tiles_dev + 6 * i0, s.cls, s.conf, s.map_w, s.map_row0, c->stream);
+    else if (s.kind == 1)
+      rc = fb::launch_prob_stitch(logits, c->ncls, nb, tile, c->tiles_dev + 6 * i0, s.prob, s.map_w, s.map_row0, s.map_rows,
+                                  c->stream);
+    else
+      rc = fb::launch_blend_accumulate(logits, c->ncls, nb, tile, c->tiles_dev + 6 * i0, s.method, s.acc, s.wsum, s.map_w,
+                                       s.map_row0, s.map_rows, c->W, c->H, s.seq0 + i0, c->stream);
+    if (rc) return fail(c, rc, "stitch launch failed");
     c->launches++;
   }
   return 0;
 }
+}  // namespace
+
+extern "C" {
 
 int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
                         int nc, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,

@@ -210,6 +210,148 @@ int launch_argmax_stitch(const float* logits, int ncls, int n, int T, const int*
   return static_cast<int>(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------ K6b
+// class_prob output (zone_detect/dataset.py:15-21): every class probability as uint8(p * 255), truncated.
+__device__ __forceinline__ void load_logits16(const float* p, float (&v)[16]) {
+  const float4* lp = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 f = __ldg(lp + k);
+    v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+  }
+}
+// soft-max over the first ncls entries in place (entries >= ncls become 0); returns the arg-max (first maximum)
+__device__ __forceinline__ int softmax16(float (&v)[16], int ncls, float* pmax = nullptr) {
+  float best = v[0];
+  int arg = 0;
+#pragma unroll
+  for (int k = 1; k < 16; ++k)
+    if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    v[k] = k < ncls ? __expf(v[k] - best) : 0.f;
+    den += v[k];
+  }
+  const float inv = 1.f / den;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] *= inv;
+  if (pmax) *pmax = inv;   // exp(0) / den
+  return arg;
+}
+
+__global__ void __launch_bounds__(256)
+prob_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ tiles,
+                   uint8_t* __restrict__ prob_map, long long map_w, long long map_row0, long long plane) {
+  const int t = blockIdx.y;
+  const int* tt = tiles + 6 * t;
+  const int x0 = tt[0], y0 = tt[1], wx0 = tt[2], wy0 = tt[3], wx1 = tt[4], wy1 = tt[5];
+  const int rw = wx1 - wx0, rh = wy1 - wy0;
+  if (rw <= 0 || rh <= 0) return;
+  const int total = rw * rh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ry = wy0 + i / rw, rx = wx0 + i % rw;
+    float v[16];
+    load_logits16(logits + ((static_cast<long long>(t) * T + (ry - y0)) * T + (rx - x0)) * 16, v);
+    softmax16(v, ncls);
+    const long long o = (static_cast<long long>(ry) - map_row0) * map_w + rx;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < ncls) prob_map[k * plane + o] = static_cast<uint8_t>(v[k] * 255.f);
+  }
+}
+
+int launch_prob_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* prob_map,
+                       long long map_w, long long map_row0, long long map_rows, cudaStream_t stream) {
+  if (n == 0) return 0;
+  dim3 grid((T * T + 255) / 256 > 64 ? 64 : (T * T + 255) / 256, n);
+  prob_stitch_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, prob_map, map_w, map_row0, map_rows * map_w);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ K7 / K8
+// Blended stitching: the intent of the weighted branches of zone_detect/compare.py:84-138 with the weights
+// of test/tiles.py:97-108 (mode "exp", sigma 0.5) and the per-pixel normalisation of tiles.py:111-169
+// (sum of the weights of the covering tiles) / tiles.py:54-94 (their count). The whole tile contributes,
+// clipped to the raster. Sums are accumulated with floating-point atomics (order not fixed).
+__global__ void __launch_bounds__(256)
+blend_accumulate_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ tiles, int method,
+                        float* __restrict__ acc, float* __restrict__ wsum, long long map_w, long long map_row0,
+                        long long map_rows, long long W, long long H, int seq0) {
+  const int t = blockIdx.y;
+  const int x0 = tiles[6 * t], y0 = tiles[6 * t + 1];
+  const int centre = T / 2;
+  const float inv_dmax = 1.f / static_cast<float>(centre > T - 1 - centre ? centre : T - 1 - centre);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T * T; i += gridDim.x * blockDim.x) {
+    const int ty = i / T, tx = i % T;
+    const long long ry = static_cast<long long>(y0) + ty, rx = static_cast<long long>(x0) + tx;
+    if (rx < 0 || rx >= W || ry < 0 || ry >= H || ry < map_row0 || ry >= map_row0 + map_rows || rx >= map_w) continue;
+    float v[16];
+    load_logits16(logits + ((static_cast<long long>(t) * T + ty) * T + tx) * 16, v);
+    float pmax;
+    const int arg = softmax16(v, ncls, &pmax);
+    const long long o = (ry - map_row0) * map_w + rx;
+    if (method == 2) {
+      const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pmax)) << 32) |
+                                     (static_cast<unsigned long long>((seq0 + t) & 0xFFFFFF) << 8) | static_cast<unsigned>(arg);
+      atomicMax(reinterpret_cast<unsigned long long*>(acc) + o, key);
+    } else {
+      const int dy = ty > centre ? ty - centre : centre - ty, dx = tx > centre ? tx - centre : centre - tx;
+      const float w = method == 0 ? 1.f : __expf(-0.5f * static_cast<float>(dy > dx ? dy : dx) * inv_dmax);
+      float4* a4 = reinterpret_cast<float4*>(acc + o * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (4 * k < ncls) atomicAdd(a4 + k, make_float4(v[4 * k] * w, v[4 * k + 1] * w, v[4 * k + 2] * w, v[4 * k + 3] * w));
+      atomicAdd(wsum + o, w);
+    }
+  }
+}
+
+int launch_blend_accumulate(const float* logits, int ncls, int n, int T, const int* tiles, int method, float* acc,
+                            float* wsum, long long map_w, long long map_row0, long long map_rows, long long W,
+                            long long H, int seq0, cudaStream_t stream) {
+  if (n == 0) return 0;
+  dim3 grid((T * T + 255) / 256 > 128 ? 128 : (T * T + 255) / 256, n);
+  blend_accumulate_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, method, acc, wsum, map_w, map_row0, map_rows,
+                                                     W, H, seq0);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// class = arg-max of the blended probabilities (first maximum), confidence byte = round-half-up of the
+// normalised maximum (same band-2 semantics as the exact-clipping path). Uncovered pixels stay 0.
+__global__ void __launch_bounds__(256)
+blend_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, int method, int ncls, long long npx,
+                      uint8_t* __restrict__ cls_map, uint8_t* __restrict__ conf_map) {
+  for (long long o = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; o < npx;
+       o += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int arg = 0;
+    float conf = 0.f;
+    if (method == 2) {
+      const unsigned long long key = reinterpret_cast<const unsigned long long*>(acc)[o];
+      arg = static_cast<int>(key & 0xFF);
+      conf = __uint_as_float(static_cast<unsigned>(key >> 32));
+    } else {
+      float v[16];
+      load_logits16(acc + o * 16, v);
+      float best = v[0];
+#pragma unroll
+      for (int k = 1; k < 16; ++k)
+        if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
+      const float ws = wsum[o];
+      conf = ws > 0.f ? best / ws : 0.f;
+    }
+    cls_map[o] = static_cast<uint8_t>(arg);
+    if (conf_map != nullptr) conf_map[o] = static_cast<uint8_t>(conf + 0.5f);
+  }
+}
+
+int launch_blend_finalize(const float* acc, const float* wsum, int method, int ncls, long long npx, uint8_t* cls_map,
+                          uint8_t* conf_map, int num_sms, cudaStream_t stream) {
+  if (npx == 0) return 0;
+  blend_finalize_kernel<<<num_sms * 8, 256, 0, stream>>>(acc, wsum, method, ncls, npx, cls_map, conf_map);
+  return static_cast<int>(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------ K9
 // Confusion matrix cm[truth][pred] (int64, rows = truth) over pairs with both labels < ncls; any other
 // pair is dropped, which is what sklearn.confusion_matrix(labels=range(ncls)) does. `truth_sub` is

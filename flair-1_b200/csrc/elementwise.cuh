@@ -22,6 +22,23 @@ int launch_metadata_mlp(const float* met, const float* const* wb, float* out, in
 int launch_argmax_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* cls_map,
                          uint8_t* conf_map, long long map_w, long long map_row0, cudaStream_t stream);
 
+// class_prob output: prob_map[k][y - map_row0][x] = uint8(softmax_k * 255) (truncation) for k < ncls inside
+// the write rectangles; plane stride = map_rows * map_w.
+int launch_prob_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* prob_map,
+                       long long map_w, long long map_row0, long long map_rows, cudaStream_t stream);
+
+// Blended stitching. method 0 = average (weight 1), 1 = average_weights (exp(-0.5 * chebyshev distance to the
+// tile centre / (T/2))), 2 = max (highest soft-max confidence wins, later tile on ties).
+// methods 0/1: acc = float [map_rows][map_w][16] (sum of weight * probability) and wsum = float
+// [map_rows][map_w]; method 2: acc is read as uint64 [map_rows][map_w] keys
+// (confidence bits << 32 | tile sequence number << 8 | class) and wsum is unused.
+// Every pixel of every tile that lies inside the raster [0,W)x[0,H) and inside the map rows contributes.
+int launch_blend_accumulate(const float* logits, int ncls, int n, int T, const int* tiles, int method, float* acc,
+                            float* wsum, long long map_w, long long map_row0, long long map_rows, long long W,
+                            long long H, int seq0, cudaStream_t stream);
+int launch_blend_finalize(const float* acc, const float* wsum, int method, int ncls, long long npx, uint8_t* cls_map,
+                          uint8_t* conf_map, int num_sms, cudaStream_t stream);
+
 int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, int ncls, int truth_sub,
                      long long* cm, int num_sms, cudaStream_t stream);
 

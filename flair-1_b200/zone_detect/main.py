@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from .. import geotiff
-from .compare import stitching
+from .compare import STITCH_METHODS, stitching, stitching_blend, stitching_class_prob
 from .dataset import Sliced_Dataset
 from .metrics import confusion_matrix_gpu, metrics_from_confmat
 from .model import load_model
@@ -112,6 +112,12 @@ def prepare_data(config: dict, stride: int):
     shard = split_rows_across_ranks(tiles, world)[rank]
     my_tiles = tiles[shard]
     size = config["img_pixels_detection"]
+    if len(my_tiles) and config.get("stitching", "exact-clipping") != "exact-clipping" and config["output_type"] == "argmax":
+        # blended stitching: every tile that touches the rows this rank owns contributes to them, so the
+        # neighbouring tile rows are recomputed here instead of exchanged (halo recompute, like the raster halo)
+        own0, own1 = int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())
+        my_tiles = tiles[(tiles[:, 1] < own1) & (tiles[:, 1] + size > own0)]
+        config["_own_rows"] = (own0, own1)
     row_range = (int(my_tiles[:, 1].min()), int(my_tiles[:, 1].max()) + size) if len(my_tiles) else (0, 0)
     dataset = Sliced_Dataset(dataframe=my_tiles, img_path=config["input_img_path"], resolution=resolution,
                              bands=config["channels"], patch_detection_size=size, norma_dict=config["norma_task"],
@@ -168,13 +174,21 @@ def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarr
     if len(my_tiles) == 0:
         e = torch.empty((0, W), dtype=torch.uint8, device=device)
         return e, e.clone(), 0, 0
-    my0, my1 = int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())
+    my0, my1 = config.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())))
     raster_dev = dataset.big_image.to(device, non_blocking=True)
     model.set_raster(raster_dev, list(range(dataset.num_bands)), W, dataset.raster_height, row0=dataset.row0)
+    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 74)))
+    if config["output_type"] == "class_prob":
+        # main.py:409-426 always clips exactly for this output type (compare.py:68): n_classes planes, no band 2
+        prob = torch.zeros((config["n_classes"], my1 - my0, W), dtype=torch.uint8, device=device)
+        stitching_class_prob(model, my_tiles, size, batch, prob, W, my0)
+        return prob, None, my0, my1 - my0
     cls = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
     conf = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
-    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 74)))
-    stitching(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
+    if stitch == "exact-clipping":
+        stitching(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
+    else:
+        stitching_blend(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
     return cls, conf, my0, my1 - my0
 
 
@@ -205,7 +219,9 @@ def _gather_strips(strip: torch.Tensor, row0: int, H: int, W: int, device) -> np
 
 def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
     """main.py:244-437, default branch (exact clipping, default tiling) plus `-m` whole-raster metrics;
-    with `-c` the same loop runs once per exact-clipping entry of the strategy grid."""
+    with `-c` the same loop runs once per entry of the strategy grid (tile size, stride, margin, stitching
+    method: exact-clipping / average / average_weights / max). output_type "class_prob" writes n_classes
+    probability bands instead of class + confidence."""
     rank, world = _rank_world()
     if world > 1:
         import torch.distributed as dist
@@ -225,13 +241,18 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
         truth_array, metrics_json = open_images(config, local_out, config["metrics"])
 
         if config["compare"]:
-            settings = [c for c in gen_param_combination(config) if c["stitching"] == "exact-clipping"]
-            skipped = len(gen_param_combination(config)) - len(settings)
-            if skipped and rank == 0:
-                print(f"    [x] {skipped} strategy combination(s) use a weighted stitching the reference cannot execute; skipped")
+            # the weighted stitchings (average / average_weights / max) run as stitching_blend() implements
+            # them; anything else in the grid is reported and skipped
+            grid = gen_param_combination(config)
+            settings = [c for c in grid if c["stitching"] in STITCH_METHODS]
+            if len(settings) != len(grid) and rank == 0:
+                print(f"    [x] {len(grid) - len(settings)} strategy combination(s) name an unknown stitching method; skipped")
         else:
             settings = [{"img_pixels_detection": config["img_pixels_detection"], "margin": config["margin"],
-                         "padding": "no-padding", "stitching": "exact-clipping", "stride": get_stride(config)[0]}]
+                         "padding": "no-padding", "stitching": config.get("stitching", "exact-clipping"),
+                         "stride": get_stride(config)[0]}]
+            if settings[0]["stitching"] not in STITCH_METHODS:
+                raise ValueError(f"stitching must be one of {STITCH_METHODS}")
 
         method_metrics = []
         for combi in settings:
@@ -248,7 +269,7 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                 print("""    [ ] starting inference...\n""")
             cls, conf, row0, rows = detect_zone(cfg, model, dataset, my_tiles, device, combi["stitching"])
             H, W = dataset.raster_height, dataset.raster_width
-            if config["metrics"]:
+            if config["metrics"] and cfg["output_type"] == "argmax":
                 n_classes = len(config["classes"]) if "classes" in config else config["n_classes"]
                 truth_dev = torch.from_numpy(np.ascontiguousarray(truth_array[row0:row0 + rows])).to(device)
                 cm = confusion_matrix_gpu(model, cls, truth_dev, n_classes)
@@ -262,7 +283,10 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                 if rank == 0:
                     _write_output(path_out, np.stack([full_cls, full_conf]), out_profile)
             else:
-                raise NotImplementedError("output_type class_prob is not built yet (SURVEY.md section 8f rank 2)")
+                # class_prob: `cls` holds the n_classes probability planes (band k + 1 = class k, main.py:424-426)
+                planes = [_gather_strips(cls[k], row0, H, W, device) for k in range(cls.shape[0])]
+                if rank == 0:
+                    _write_output(path_out, np.stack(planes), out_profile)
             dataset.close_raster()
             elapsed = (datetime.datetime.now() - start_time).total_seconds()
             if rank == 0:

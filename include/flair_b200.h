@@ -108,6 +108,30 @@ int fb_forward_tiles(fb_ctx* ctx, const int32_t* tile_xy, int n, int tile, const
 int fb_detect_strip(fb_ctx* ctx, const fb_tile* tiles, int n, int tile, int batch, uint8_t* cls_map_dev,
                     uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0);
 
+/* ---- the same loop with output_type "class_prob" (dataset.py:15-21 `convert`, main.py:229, 421-426):
+ *      every class probability of the margin-cropped tile as uint8(p * 255) (truncation), written to
+ *      prob_map_dev uint8 [n_classes][map_rows][map_w] (band k+1 of the reference's output = plane k). */
+int fb_detect_strip_prob(fb_ctx* ctx, const fb_tile* tiles, int n, int tile, int batch, uint8_t* prob_map_dev,
+                         int64_t map_w, int64_t map_row0, int64_t map_rows);
+
+/* ---- blended stitching: what the weighted branches of `stitching` (compare.py:84-138) intend, with the
+ *      weights of test/tiles.py:97-108 and the normalisations of tiles.py:54-94 / 111-169. The whole
+ *      tile contributes, clipped to the raster (and to the map rows). method: FB_STITCH_AVERAGE (mean
+ *      probability of the covering tiles), FB_STITCH_AVERAGE_WEIGHTS (weight exp(-0.5 * Chebyshev
+ *      distance to the tile centre / (tile/2))), FB_STITCH_MAX (class of the most confident tile, the
+ *      later tile of the write order on ties; tile i of this call has sequence number tile_seq0 + i).
+ *      acc_dev: float [map_rows][map_w][16] and wsum_dev: float [map_rows][map_w] for the two averages;
+ *      for FB_STITCH_MAX acc_dev is used as uint64 [map_rows][map_w] and wsum_dev may be NULL. The caller
+ *      zeroes the accumulators before the first call; the write rectangles of `tiles` are ignored.
+ *      fb_blend_finalize turns the accumulators of npx pixels into the class map (+ confidence band). */
+#define FB_STITCH_AVERAGE 0
+#define FB_STITCH_AVERAGE_WEIGHTS 1
+#define FB_STITCH_MAX 2
+int fb_blend_strip(fb_ctx* ctx, const fb_tile* tiles, int n, int tile, int batch, int method, float* acc_dev,
+                   float* wsum_dev, int64_t map_w, int64_t map_row0, int64_t map_rows, int tile_seq0);
+int fb_blend_finalize(fb_ctx* ctx, const float* acc_dev, const float* wsum_dev, int method, int64_t npx,
+                      uint8_t* cls_map_dev, uint8_t* conf_map_dev);
+
 /* ---- same loop, host buffers in and out (upload raster rows, detect, download class map); this is
  *      the call the end-to-end benchmark times. host_cls / host_conf: [map_rows][map_w] uint8. */
 int fb_detect_zone_host(fb_ctx* ctx, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,

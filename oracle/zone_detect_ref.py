@@ -181,3 +181,88 @@ def run_zone(model: torch.nn.Module, raster: GeoRaster, config: dict, batch_size
     if return_probs:
         return cls_map, conf_map, rows, probs_out
     return cls_map, conf_map, rows
+
+
+# --------------------------------------------------------------------------------------------- f2
+def run_zone_class_prob(model: torch.nn.Module, raster: GeoRaster, config: dict, batch_size: int = 4) -> np.ndarray:
+    """output_type "class_prob" of the default branch (main.py:229, 409-426 with dataset.py:15-21): the
+    margin-cropped soft-max of every tile as uint8(p * 255) (truncation), band k+1 = class k.
+    Returns uint8 [n_classes, H, W]."""
+    size, margin = config["img_pixels_detection"], config["margin"]
+    stride = get_stride(config)[0]
+    rows = slice_extent(raster.bounds, (raster.res, raster.res), size, margin, stride)
+    nt = config["norma_task"][0]
+    out = np.zeros((config["n_classes"], raster.height, raster.width), np.uint8)
+    model.eval()
+    for s in range(0, len(rows), batch_size):
+        idx = list(range(s, min(s + batch_size, len(rows))))
+        imgs = [torch.as_tensor(normalization(read_window_boundless(raster, config["channels"], rows[i]["geometry"], size),
+                                              nt["norm_type"], nt["norm_means"], nt["norm_stds"]), dtype=torch.float)
+                for i in idx]
+        with torch.no_grad():
+            predictions = torch.softmax(model(torch.stack(imgs)), dim=1).cpu().numpy()
+        for i, prediction in zip(idx, predictions):
+            pred = stitching_exact_clipping(prediction, margin, size, "class_prob")
+            col, row, w, h = window_of_box(raster, rows[i]["left"], rows[i]["right"], rows[i]["bottom"], rows[i]["top"])
+            out[:, row:row + h, col:col + w] = pred[:, :h, :w]
+    return out
+
+
+# --------------------------------------------------------------------------------------------- a8
+def run_zone_blend(model: torch.nn.Module, raster: GeoRaster, config: dict, method: str, batch_size: int = 4):
+    """What the weighted branches of `stitching` (compare.py:84-138) are after. They are not executable as
+    written (they accumulate ncls-channel float products through the 2-band uint8 output raster and compare
+    class indices instead of confidences), so this follows their stated intent:
+
+      average          out = sum_t p_t / count          count = patch_overlap   (tiles.py:54-94)
+      average_weights  out = sum_t p_t * w / sum_t w    w = patch_weights(size, 0.5, "exp"), sum_t w = total_weights
+                                                        (tiles.py:97-108, 111-169)
+      max              keep the class of the more confident tile; a later tile replaces an earlier one unless the
+                       earlier one is strictly more confident (compare.py:133-136)
+
+    over the whole tile clipped to the raster (compare.py:97-104), tiles in write order; then `convert` (argmax
+    + max probability). The tile squares are the ones slice_extent produces (origin -margin, clamped last
+    row / column), not the origin-0 grid test/tiles.py:get_tile_coord assumes -- one more way in which the
+    reference's branch is inconsistent with its own tiling. patch_weights is the pinned restatement in
+    oracle/tiles_ref.py. Returns (class_map uint8 [H,W], conf float32 [H,W])."""
+    from .tiles_ref import patch_weights
+    size, margin = config["img_pixels_detection"], config["margin"]
+    stride = get_stride(config)[0]
+    rows = slice_extent(raster.bounds, (raster.res, raster.res), size, margin, stride)
+    nt = config["norma_task"][0]
+    H, W, ncls = raster.height, raster.width, config["n_classes"]
+    acc = np.zeros((ncls, H, W), np.float32)
+    wsum = np.zeros((H, W), np.float32)
+    best_conf = np.full((H, W), -1.0, np.float32)
+    best_cls = np.zeros((H, W), np.uint8)
+    w_tile = {"average": np.ones((size, size), np.float32),
+              "average_weights": patch_weights(size, 0.5).astype(np.float32),
+              "max": None}[method]
+    model.eval()
+    for s in range(0, len(rows), batch_size):
+        idx = list(range(s, min(s + batch_size, len(rows))))
+        imgs = [torch.as_tensor(normalization(read_window_boundless(raster, config["channels"], rows[i]["geometry"], size),
+                                              nt["norm_type"], nt["norm_means"], nt["norm_stds"]), dtype=torch.float)
+                for i in idx]
+        with torch.no_grad():
+            predictions = torch.softmax(model(torch.stack(imgs)), dim=1).cpu().numpy()
+        for i, p in zip(idx, predictions):
+            # tile origin in raster pixels (top-left of the margin-expanded square), then clip to the raster
+            gx0, _, _, gy1 = rows[i]["geometry"]
+            x0 = int(round((gx0 - raster.min_x) / raster.res))
+            y0 = int(round((raster.max_y - gy1) / raster.res))
+            ys, ye, xs, xe = max(y0, 0), min(y0 + size, H), max(x0, 0), min(x0 + size, W)
+            pt = p[:, ys - y0:ye - y0, xs - x0:xe - x0]
+            if method == "max":
+                conf, cls = pt.max(axis=0), pt.argmax(axis=0).astype(np.uint8)
+                take = ~(best_conf[ys:ye, xs:xe] > conf)
+                best_conf[ys:ye, xs:xe] = np.where(take, conf, best_conf[ys:ye, xs:xe])
+                best_cls[ys:ye, xs:xe] = np.where(take, cls, best_cls[ys:ye, xs:xe])
+            else:
+                wt = w_tile[ys - y0:ye - y0, xs - x0:xe - x0]
+                acc[:, ys:ye, xs:xe] += pt * wt
+                wsum[ys:ye, xs:xe] += wt
+    if method == "max":
+        return best_cls, best_conf
+    norm = acc / np.maximum(wsum, 1e-30)
+    return norm.argmax(axis=0).astype(np.uint8), norm.max(axis=0)

@@ -89,6 +89,52 @@ def test_get_stride_and_weights(golden):
         assert sorted(tiles_ref.get_tile_coord(*g["args"])) == g["coords"]
 
 
+def test_blend_oracle_properties():
+    """a8: the blend restatement on a position-only toy model (probabilities depend on the tile-local pixel
+    position, so overlapping tiles disagree): `average` equals the mean over the covering tiles, the weighted
+    mean lies between the per-tile extremes, `max` picks the most confident tile, and class_prob is the
+    exact-clipping map of uint8(p * 255)."""
+    import torch
+
+    class Toy(torch.nn.Module):
+        def forward(self, x):                       # logits from the tile-local coordinates only
+            n, _, h, w = x.shape
+            yy = torch.linspace(-2, 2, h).view(1, 1, h, 1).expand(n, 1, h, w)
+            xx = torch.linspace(-2, 2, w).view(1, 1, 1, w).expand(n, 1, h, w)
+            return torch.cat([yy, xx, -yy - xx], dim=1)
+
+    H, W, T, m = 96, 80, 32, 8
+    raster = zref.GeoRaster(np.zeros((3, H, W), np.uint8), 10.0, 50.0, 0.5)
+    config = {"img_pixels_detection": T, "margin": m, "channels": [1, 2, 3], "n_classes": 3,
+              "norma_task": [{"norm_type": "scaling", "norm_means": [], "norm_stds": []}]}
+    rows = zref.slice_extent(raster.bounds, (0.5, 0.5), T, m, T - 2 * m)
+    probs = torch.softmax(Toy()(torch.zeros(1, 3, T, T)), dim=1)[0].numpy()
+    cover = np.zeros((H, W), np.int32)
+    psum = np.zeros((3, H, W), np.float64)
+    pbest = np.zeros((H, W), np.float64)
+    for r in rows:
+        x0 = int(round((r["geometry"][0] - raster.min_x) / 0.5)); y0 = int(round((raster.max_y - r["geometry"][3]) / 0.5))
+        ys, ye, xs, xe = max(y0, 0), min(y0 + T, H), max(x0, 0), min(x0 + T, W)
+        cover[ys:ye, xs:xe] += 1
+        psum[:, ys:ye, xs:xe] += probs[:, ys - y0:ye - y0, xs - x0:xe - x0]
+        pbest[ys:ye, xs:xe] = np.maximum(pbest[ys:ye, xs:xe], probs[:, ys - y0:ye - y0, xs - x0:xe - x0].max(axis=0))
+    assert cover.min() >= 1 and cover.max() >= 4
+    cls_avg, conf_avg = zref.run_zone_blend(Toy(), raster, config, "average")
+    np.testing.assert_allclose(conf_avg, (psum / cover).max(axis=0), rtol=1e-5)
+    top2 = np.sort(psum / cover, axis=0)
+    clear = top2[-1] - top2[-2] > 1e-5              # the toy model is symmetric: exact ties exist
+    np.testing.assert_array_equal(cls_avg[clear], (psum / cover).argmax(axis=0)[clear])
+    cls_w, conf_w = zref.run_zone_blend(Toy(), raster, config, "average_weights")
+    assert conf_w.min() > 1 / 3 - 1e-6 and (conf_w <= pbest + 1e-6).all()
+    cls_max, conf_max = zref.run_zone_blend(Toy(), raster, config, "max")
+    np.testing.assert_allclose(conf_max, pbest, rtol=1e-6)
+    cp = zref.run_zone_class_prob(Toy(), raster, config)
+    assert cp.shape == (3, H, W) and (cp.sum(axis=0) >= 253).all() and (cp.sum(axis=0) <= 255).all()
+    cls_clip, _, _ = zref.run_zone(Toy(), raster, config)
+    np.testing.assert_array_equal(cp.astype(np.int32).argmax(axis=0)[cp.max(axis=0) > cp.min(axis=0) + 2],
+                                  cls_clip[cp.max(axis=0) > cp.min(axis=0) + 2])
+
+
 def test_convert_and_normalisation():
     z = np.load(GOLDEN / "convert_norm.npz")
     np.testing.assert_array_equal(zref.convert(z["probs"], "argmax"), z["argmax"])

@@ -82,6 +82,55 @@ def test_flair_detect_cli_end_to_end(tmp_path, trained_3_15):
     np.testing.assert_array_equal(gt.read(res2["outputs"][0]), got)
 
 
+def test_flair_detect_class_prob_and_compare_grid(tmp_path, trained_3_15):
+    """output_type class_prob -> n_classes uint8 bands; `-c` with strategies.stitching -> one output per
+    stitching method (exact-clipping, average, average_weights, max), each >= 99.9 % equal to its oracle."""
+    from flair1_b200 import geotiff as gt
+    from flair1_b200.zone_detect import main as zmain
+    from flair1_b200.zone_detect.utils import read_config
+    from oracle import synth
+    from oracle.zone_detect_ref import GeoRaster, run_zone, run_zone_blend, run_zone_class_prob
+    sd, model = trained_3_15
+    W, H = 800, 600
+    raster, truth, d = _write_zone(tmp_path, W, H, seed=23)
+    torch.save(sd, tmp_path / "weights.pth")
+    means, stds = synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3]
+    cfg = {"output_path": str(tmp_path / "out"), "output_name": "pz", "input_img_path": str(d / "zone.tif"),
+           "truth_path": str(d / "truth.tif"), "channels": [1, 2, 3], "img_pixels_detection": 512, "margin": 128,
+           "output_type": "class_prob", "n_classes": 15, "model_weights": str(tmp_path / "weights.pth"),
+           "model_framework": {"model_provider": "SegmentationModelsPytorch", "HuggingFace": {"org_model": None},
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}},
+           "batch_size": 4, "use_gpu": True, "num_worker": 2, "write_dataframe": False,
+           "norma_task": [{"norm_type": "custom", "norm_means": means, "norm_stds": stds}], "classes": CLASSES15}
+    georaster = GeoRaster(raster, 800000.0, 6500000.0 + H * 0.2, 0.2)
+    conf = tmp_path / "prob.yaml"
+    conf.write_text(yaml.safe_dump(cfg))
+    res = zmain.run_pipeline(read_config(SimpleNamespace(conf=str(conf), metrics=False, batch_mode=False, compare=False)),
+                             torch.device("cuda", 0), True)
+    got = gt.read(res["outputs"][0]).astype(np.int32)
+    ref = run_zone_class_prob(model, georaster, cfg).astype(np.int32)
+    assert got.shape == (15, H, W) and gt.read_info(res["outputs"][0]).count == 15
+    assert (np.abs(got - ref) <= 4).mean() >= 0.999
+
+    cfg.update({"output_type": "argmax", "output_name": "cmp", "overlap_strat": False,
+                "strategies": {"tiling": {"enabled": False, "size_range": [], "stride_range": []},
+                               "stitching": {"enabled": True, "methods": ["exact-clipping", "average", "average_weights", "max"],
+                                             "margin": [0.25]},      # a fraction of the tile size (utils.py:87-92)
+                               "padding_overall": None}})
+    conf2 = tmp_path / "cmp.yaml"
+    conf2.write_text(yaml.safe_dump(cfg))
+    res = zmain.run_pipeline(read_config(SimpleNamespace(conf=str(conf2), metrics=True, batch_mode=False, compare=True)),
+                             torch.device("cuda", 0), True)
+    assert len(res["outputs"]) == 4 and len(res["metrics"]) == 4
+    for path in res["outputs"]:
+        method = Path(path).stem.split("stitching=")[1]
+        cls = gt.read(path)[0]
+        ref_cls = run_zone(model, georaster, cfg)[0] if method == "exact-clipping" else run_zone_blend(model, georaster, cfg, method)[0]
+        agree = (cls == ref_cls).mean()
+        print(f"compare grid, stitching={method}: agreement {agree * 100:.4f}%")
+        assert agree >= 0.999
+
+
 def test_flair_detect_rejects_what_it_cannot_do(tmp_path, trained_3_15):
     from flair1_b200.zone_detect.model import load_model
     sd, _ = trained_3_15
