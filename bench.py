@@ -299,11 +299,12 @@ def run_ours(args) -> int:
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = ctx.launch_count
+    launches0, flops0 = ctx.launch_count, ctx.flop_count
     ctx.profile_begin()
     ms_total, t0, t1 = timed(step_resident, args.steps)
     prof = ctx.profile_end()
     launches = ctx.launch_count - launches0
+    flops = ctx.flop_count - flops0   # algorithmic FLOPs of the conv outputs this rank actually computed
     clocks = sampler.stop(t0, t1) if sampler else None
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -311,9 +312,13 @@ def run_ours(args) -> int:
 
     lt = torch.tensor([launches, raster_host.numel(), cls_host.numel() + conf_host.numel()], dtype=torch.int64, device=dev)
     conv_ms = torch.tensor([prof["conv_ms"]], dtype=torch.float64, device=dev)
+    # per-GPU conv rate of this rank (executed FLOPs / its summed conv time); the line reports the slowest rank
+    rate = torch.tensor([flops / (prof["conv_ms"] / 1e3) / 1e12, -flops / max(len(tiles), 1) / args.steps / 1e9],
+                        dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(lt)
         dist.all_reduce(conv_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rate, op=dist.ReduceOp.MIN)
     mpx = W * H / 1e6
     value = mpx * args.steps / (ms_total / 1e3)
     e2e_value = mpx * args.steps / (ms_e2e / 1e3)
@@ -327,7 +332,9 @@ def run_ours(args) -> int:
             if "bf16_tflops_sustained" in peaks else (1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)")
         # conv kernels of the slowest rank: its tiles * 63.569 GFLOP per step over its summed conv time
         max_tiles = max(len(s) for s in split_rows_across_ranks(tiles_all, world))
-        conv_tflops = max_tiles * GFLOP_PER_TILE * args.steps / (float(conv_ms.item()) / 1e3) / 1e3
+        conv_tflops = float(rate[0].item())
+        gflop_per_tile = -float(rate[1].item())
+        full_tile_tflops = max_tiles * GFLOP_PER_TILE * args.steps / (float(conv_ms.item()) / 1e3) / 1e3
         # CPU baseline + agreement on a bounded sample of rank 0's tiles
         torch.set_num_threads(os.cpu_count() or 1)
         ny = len(np.unique(tiles[:, 1]))
@@ -355,7 +362,12 @@ def run_ours(args) -> int:
             "gpu_launches": int(lt[0].item()),
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": conv_tflops / peak_tf, "traffic": None, "peak_source": peak_src,
-                         "kernel": "conv_igemm_kernel (47 launches per batch; algorithmic 63.569 GFLOP per tile / summed conv time)",
+                         "kernel": "conv_igemm_kernel + conv_halo_kernel (47 launches per batch); achieved = algorithmic FLOPs "
+                                   "(2*MAC of the direct conv) of the outputs actually computed / summed conv time",
+                         "gflop_per_tile_computed": gflop_per_tile, "gflop_per_tile_full": GFLOP_PER_TILE,
+                         "note": "the decoder skips outputs that can only reach the cropped margin (bit-identical class map, "
+                                 "csrc/tile_need.cuh); full_tile_equivalent_tflops counts 63.569 GFLOP per tile instead",
+                         "full_tile_equivalent_tflops": full_tile_tflops,
                          "conv_share_of_step": float(conv_ms.item()) / ms_total},
             "cpu_baseline": {"value": cpu_px / cpu_s / 1e6, "unit": "Mpixels/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{len(idx)} of rank 0's {len(tiles)} tiles (batch 4, fp32 torch CPU oracle), linear in tiles"},

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "fb_profile_begin": (C.c_int, [C.c_void_p]),
     "fb_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fb_launch_count": (C.c_int64, [C.c_void_p]),
+    "fb_flop_count": (C.c_double, [C.c_void_p]),
     "fb_lzw_bound": (C.c_int64, [C.c_int64]),
     "fb_lzw_encode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "fb_lzw_decode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
@@ -166,6 +167,11 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self._lib.fb_launch_count(self._h))
+
+    @property
+    def flop_count(self) -> float:
+        """Algorithmic conv FLOPs of the outputs computed so far (fb_flop_count)."""
+        return float(self._lib.fb_flop_count(self._h))
 
     # ------------------------------------------------------------------ model
     def load_weights(self, state_dict: Mapping[str, torch.Tensor], in_channels: int, n_classes: int,

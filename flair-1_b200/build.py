@@ -19,7 +19,7 @@ LIB_PATH = PKG_DIR / "libflairb200.so"
 STAMP = PKG_DIR / ".libflairb200.stamp"
 
 SOURCES = ["conv_igemm.cu", "conv_halo.cu", "elementwise.cu", "api.cu", "host_codec.cu"]
-HEADERS = ["ptx.cuh", "conv_igemm.cuh", "conv_halo.cuh", "conv_epilogue.cuh", "elementwise.cuh"]
+HEADERS = ["ptx.cuh", "conv_igemm.cuh", "conv_halo.cuh", "conv_epilogue.cuh", "elementwise.cuh", "tile_need.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,6 +18,7 @@
 #include "conv_halo.cuh"
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
+#include "tile_need.cuh"
 
 namespace {
 
@@ -32,6 +33,7 @@ struct ConvLayer {
   float* bias = nullptr;            // device [Cout]
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
+  double flops_px = 0;              // algorithmic FLOPs per output pixel: 2 * Cout * Cin * KH * KW, unpadded channels
 };
 
 struct Act {  // a named NHWC bf16 (or fp32) activation in the arena
@@ -39,6 +41,20 @@ struct Act {  // a named NHWC bf16 (or fp32) activation in the arena
   int B = 0, H = 0, W = 0, C = 0;   // stored dims (already doubled when up2)
   int elem = 2;
   bool up2 = false;                 // producer writes it 2x2-replicated (decoder nearest x2 upsample)
+};
+
+// The tiles of the batch a network pass works on, for dead-output elimination (tile_need.cuh) and the fused
+// class-map sink of the head: device and host copies of the same [n][6] table.
+struct NeedCtx {
+  const int* tiles_dev = nullptr;
+  const int* tiles_host = nullptr;
+  int n = 0, T = 0;
+  bool restrict_tiles = false;   // false: the table only serves the head's sink, every kernel tile is computed
+};
+struct HeadSink {
+  uint8_t* cls = nullptr;
+  uint8_t* conf = nullptr;
+  int64_t map_w = 0, map_row0 = 0;
 };
 
 struct ProfRec {
@@ -58,6 +74,11 @@ struct fb_ctx {
   bool no_halo = false;       // FB_NO_HALO=1: skip the halo-staged kernel
   bool no_phase = false;      // FB_NO_PHASE=1: decoder conv1 on the materialised upsample instead of sub-pixel phases
   bool dec_phase[6] = {false, false, false, false, false, false};  // per decoder block, decided by arena_plan
+  bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
+  bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
+  double flops = 0;           // algorithmic FLOPs of the conv outputs actually computed since creation
+  int* list_dev = nullptr;    // active-tile list of the current conv launch
+  size_t list_cap = 0;        // in ints
 
   // model
   bool loaded = false;
@@ -196,6 +217,7 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
   L.Kpad = (L.Ktot + 63) / 64 * 64;
   L.C2 = C2;
   L.C1 = CinPad - C2;
+  L.flops_px = 2.0 * Cout * Cin * KH * KH;
   std::vector<uint16_t> packed(static_cast<size_t>(CoutPad) * L.Kpad, 0);
   std::vector<float> bias(CoutPad, 0.f);
   std::vector<float> folded(static_cast<size_t>(Cout) * Cin * KH * KH);
@@ -407,12 +429,44 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 }
 
 // ---------------------------------------------------------------------------------- graph
+// Active-tile list of one conv launch (tile_need.cuh): kernel tiles of th x tw pixels on the tile grid
+// (output grid / scale), gh x gw of them per image. *list stays null when every tile is active.
+int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, int th, int tw, int gh, int gw,
+                   const int** list, long long* active) {
+  *list = nullptr;
+  const long long full = static_cast<long long>(B) * gh * gw;
+  *active = full;
+  if (!need || !need->restrict_tiles || layer < 0 || need->n != B) return 0;
+  const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, th, tw);
+  if (cnt >= full) return 0;
+  if (static_cast<size_t>(full) > c->list_cap) {
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->list_dev) cudaFree(c->list_dev);
+    c->list_dev = nullptr; c->list_cap = 0;
+    FB_CUDA(c, cudaMalloc(&c->list_dev, static_cast<size_t>(full) * sizeof(int)));
+    c->list_cap = static_cast<size_t>(full);
+  }
+  const int rc = fb::launch_build_tile_list(need->tiles_dev, B, need->T, layer, scale, th, tw, gh, gw, c->list_dev, c->stream);
+  if (rc) return fail(c, rc, "tile list launch failed (code " + std::to_string(rc) + ")");
+  c->launches++;
+  *list = c->list_dev;
+  *active = cnt;
+  return 0;
+}
+
+// need / layer: restrict the launch to the kernel tiles the write rectangles of the batch need (decoder layers of
+// the exact-clipping zone loop). sink: the head writes class / confidence bytes instead of logits (*sunk says
+// whether the kernel that ran could do it).
 int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const Act* res,
-             const float* rowbias, bool relu, const Act& out, bool phase = false) {
+             const float* rowbias, bool relu, const Act& out, bool phase = false, const NeedCtx* need = nullptr,
+             int layer = -1, const HeadSink* sink = nullptr, bool* sunk = nullptr) {
   // `out` may be stored 2x2-replicated (Act::up2): the conv itself runs at half those dims
   const int Hout = out.up2 ? out.H / 2 : out.H, Wout = out.up2 ? out.W / 2 : out.W;
   const int C1 = x1.C, C2 = x2 ? x2->C : 0;
   if (C1 + C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
+  if (sunk) *sunk = false;
+  const int* list = nullptr;
+  long long active = 0;
   int rc;
   if (phase) {
     // decoder conv1 in sub-pixel phase form: x1 at half the output resolution, x2 (skip) at full resolution
@@ -431,6 +485,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
       h.wpacked = L.w_halo_phase;
       h.phase_mode = 1;
       fb::halo_fill_steps_phase(h);
+      FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 8, x1.H / 16, x1.W / 8, &list, &active));
+      if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
+      c->flops += static_cast<double>(active) * (16 * 8 * 4) * L.flops_px;
       rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
       if (rc != 0) return fail(c, rc, "phase conv (halo) launch failed (code " + std::to_string(rc) + ")");
       c->launches++;
@@ -452,6 +509,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     a.up2_out = 0;
     a.phase_mode = 1;
     if (out.up2 || out.elem != 2 || !fb::conv_tma_eligible(a)) return fail(c, FB_ERR_INVALID, "internal: phase-form conv not eligible");
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 8, 16, Hout / 16, Wout / 32, &list, &active));
+    if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }
+    c->flops += static_cast<double>(active) * (8 * 16 * 4) * L.flops_px;
     rc = fb::launch_conv(a, L.w_phase, L.Kp_phase, true, c->num_sms, c->stream);
     if (rc != 0) return fail(c, rc, "phase conv launch failed (code " + std::to_string(rc) + ")");
     c->launches++;
@@ -475,6 +535,19 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     h.up2_out = out.up2 ? 1 : 0;
     h.wpacked = L.w_halo;
     fb::halo_fill_steps(h, L.KH, L.stride);
+    const int tw = 8 * fb::halo_blocks(L.KH, fb::halo_group_channels(L.KH, C1, C2) / 8, L.Cout);
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active));
+    if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
+    c->flops += static_cast<double>(active) * (16 * tw) * L.flops_px;
+    if (sink && need && out.elem == 4 && L.Cout == 16 && h.direct_store && !out.up2) {
+      h.sink_tiles = need->tiles_dev;
+      h.sink_cls = sink->cls;
+      h.sink_conf = sink->conf;
+      h.sink_map_w = sink->map_w;
+      h.sink_map_row0 = sink->map_row0;
+      h.sink_ncls = c->ncls;
+      if (sunk) *sunk = true;
+    }
     rc = fb::launch_conv_halo(h, L.KH, L.stride, c->num_sms, c->stream);
   } else {
     fb::ConvArgs a;
@@ -495,6 +568,14 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     if (out.elem == 4) a.out_f32 = static_cast<float*>(out.ptr); else a.out = static_cast<__nv_bfloat16*>(out.ptr);
     a.up2_out = out.up2 ? 1 : 0;
     const bool tma = !c->force_gather && fb::conv_tma_eligible(a);
+    const char* pair_env = getenv("FB_PAIR");
+    if (tma && !(pair_env && pair_env[0] == '1')) {
+      FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active));
+      if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }
+      c->flops += static_cast<double>(active) * (8 * 16) * L.flops_px;
+    } else {
+      c->flops += static_cast<double>(x1.B) * Hout * Wout * L.flops_px;
+    }
     rc = fb::launch_conv(a, L.w, L.Kpad, tma, c->num_sms, c->stream);
   }
   if (rc != 0) return fail(c, rc, "conv launch failed (code " + std::to_string(rc) + ")");
@@ -503,7 +584,8 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
 }
 
 // x0 (normalised tiles) must already be in the arena; enqueues encoder + decoder + head.
-int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
+int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* need = nullptr,
+                const HeadSink* sink = nullptr, bool* sunk = nullptr) {
   auto A = [&](const std::string& k) -> Act& { return c->acts[k]; };
   auto L = [&](const std::string& k) -> const ConvLayer& { return c->conv[k]; };
   {
@@ -546,11 +628,11 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev) {
     snprintf(nm, sizeof nm, "dec%d", d);
     const std::string base(nm);
     FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid"),
-                    c->dec_phase[d]));
-    FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base)));
+                    c->dec_phase[d], need, 2 * d));
+    FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base), false, need, 2 * d + 1));
     cur = base;
   }
-  FB_TRY(run_conv(c, L("head"), A(cur), nullptr, nullptr, nullptr, false, A("logits")));
+  FB_TRY(run_conv(c, L("head"), A(cur), nullptr, nullptr, nullptr, false, A("logits"), false, need, 10, sink, sunk));
   return 0;
 }
 
@@ -642,6 +724,10 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_halo = nh && nh[0] == '1';
   const char* np = getenv("FB_NO_PHASE");
   c->no_phase = np && np[0] == '1';
+  const char* ft = getenv("FB_FULL_TILES");
+  c->full_tiles = ft && ft[0] == '1';
+  const char* nf = getenv("FB_NO_FUSED_SINK");
+  c->no_fused_sink = nf && nf[0] == '1';
   *out = c;
   return 0;
 }
@@ -660,6 +746,7 @@ void fb_destroy(fb_ctx* c) {
   if (c->tiles_dev) cudaFree(c->tiles_dev);
   if (c->meta_dev) cudaFree(c->meta_dev);
   if (c->menc_dev) cudaFree(c->menc_dev);
+  if (c->list_dev) cudaFree(c->list_dev);
   delete c;
 }
 
@@ -670,6 +757,8 @@ int fb_synchronize(fb_ctx* c) {
 }
 
 int64_t fb_launch_count(const fb_ctx* c) { return c ? c->launches : 0; }
+
+double fb_flop_count(const fb_ctx* c) { return c ? c->flops : 0.0; }
 
 int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int in_channels,
                     int n_classes, int use_metadata) {
@@ -898,7 +987,18 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
     if (nb != c->arena_n) FB_TRY(ensure_arena(c, nb, tile));  // ragged last batch: re-plan inside the same block
     FB_TRY(run_extract(c, c->raster, c->layout, c->bands_total, c->band_idx_dev, c->rc, c->W, c->H, c->row0,
                        c->rows, c->tile_xy_dev + 2 * i0, nb, tile));
-    FB_TRY(run_network(c, nb, tile, nullptr));
+    // exact clipping (kinds 0 and 1) only ever reads the logits inside the write rectangles: the decoder computes
+    // nothing else (tile_need.cuh), and for the class map the head's epilogue writes the bytes itself
+    NeedCtx need;
+    need.tiles_dev = c->tiles_dev + 6 * i0;
+    need.tiles_host = &tiles[i0].x0;
+    need.n = nb; need.T = tile;
+    need.restrict_tiles = s.kind != 2 && !c->full_tiles;
+    HeadSink hs;
+    hs.cls = s.cls; hs.conf = s.conf; hs.map_w = s.map_w; hs.map_row0 = s.map_row0;
+    bool sunk = false;
+    FB_TRY(run_network(c, nb, tile, nullptr, &need, (s.kind == 0 && !c->no_fused_sink) ? &hs : nullptr, &sunk));
+    if (sunk) continue;
     ProfScope ps(c, 3);
     const float* logits = static_cast<const float*>(c->acts["logits"].ptr);
     int rc;
@@ -995,8 +1095,16 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
       if (rc) rc = fail(c, rc, "extract launch failed");
       c->launches++;
     }
-    if (!rc) rc = run_network(c, nb, tile, menc);
-    if (!rc) {
+    NeedCtx need;
+    need.tiles_dev = c->tiles_dev;
+    need.tiles_host = rect.data();
+    need.n = nb; need.T = tile;
+    HeadSink hs;
+    hs.cls = cls_out_dev + static_cast<size_t>(i0) * tile * tile;
+    hs.map_w = tile;
+    bool sunk = false;
+    if (!rc) rc = run_network(c, nb, tile, menc, &need, c->no_fused_sink ? nullptr : &hs, &sunk);
+    if (!rc && !sunk) {
       ProfScope ps(c, 3);
       rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, nb, tile, c->tiles_dev,
                                     cls_out_dev + static_cast<size_t>(i0) * tile * tile, nullptr, tile, 0, c->stream);

@@ -104,6 +104,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int tiles_w = (PH ? p.Win : p.Wout) / G::TW, tiles_h = (PH ? p.Hin : p.Hout) / kTH;
+  // position i of this launch's schedule -> tile of the full grid (identity unless an active-tile list is given)
+  auto tile_of = [&](int i) { return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i; };
 
   if (warp < kMmaWarp) {
     // ===================================================================== producers (halo gather)
@@ -129,6 +131,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     const int nsrc = p.C2 > 0 ? 2 : 1;
     auto prefetch_tile = [&](int t) {
       if (t >= p.num_m_tiles || p.no_prefetch) return;
+      t = tile_of(t);
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
       const int iw0 = tw * G::TW * STRIDE - G::PAD;
       const int w_lo = iw0 < 0 ? 0 : iw0, w_hi = iw0 + G::KWCELLS < p.Win ? iw0 + G::KWCELLS : p.Win;
@@ -142,8 +145,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     };
     for (int d = 0; d < kPrefetchDist; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x) {
-      prefetch_tile(tile + kPrefetchDist * gridDim.x);
+    for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x) {
+      prefetch_tile(ti + kPrefetchDist * gridDim.x);
+      const int tile = tile_of(ti);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
@@ -198,7 +202,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                                     p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
+    for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x, ++tcount) {
+      const int tile = tile_of(ti);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
@@ -228,6 +233,12 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       };
       if (p.direct_store) {
         const int oh = th * kTH + L.own_dh, ow = tw * G::TW + L.own_dw;
+        int sink_x0 = 0, sink_y0 = 0, sink_wx0 = 0, sink_wy0 = 0, sink_wx1 = 0, sink_wy1 = 0;
+        if (!PH && BN == 16 && p.sink_cls != nullptr) {
+          const int* st = p.sink_tiles + 6 * tb;
+          sink_x0 = __ldg(st); sink_y0 = __ldg(st + 1); sink_wx0 = __ldg(st + 2); sink_wy0 = __ldg(st + 3);
+          sink_wx1 = __ldg(st + 4); sink_wy1 = __ldg(st + 5);
+        }
         // residual rows are loaded one block ahead: block 0 before the accumulator wait, block m + 1 while
         // block m is processed (BN <= 32: everything up front)
         constexpr int kResBuf = PH ? 1 : (MB * BN <= 64 ? MB : 2);
@@ -255,6 +266,27 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
           auto direct = [&](int col0, const auto& regs) {
             if (p.debug_skip & 4) return;
+            if constexpr (!PH && BN == 16 && sizeof(regs) == 64) {
+              if (p.sink_cls != nullptr) {
+                // fused K6: regs = the 16 fp32 logits of pixel (oh, ow + 8m) of image tb
+                const int rx = sink_x0 + ow + 8 * m, ry = sink_y0 + oh;
+                if (rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1) {
+                  float best = regs[0];
+                  int arg = 0;
+#pragma unroll
+                  for (int k = 1; k < 16; ++k)
+                    if (k < p.sink_ncls && regs[k] > best) { best = regs[k]; arg = k; }
+                  float den = 0.f;
+#pragma unroll
+                  for (int k = 0; k < 16; ++k)
+                    if (k < p.sink_ncls) den += __expf(regs[k] - best);
+                  const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
+                  p.sink_cls[o] = static_cast<uint8_t>(arg);
+                  if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);
+                }
+                return;
+              }
+            }
             uint8_t* d = own_dst + static_cast<size_t>(col0) * elem;
             store_regs(d, regs);
             if (!PH && p.up2_out) {

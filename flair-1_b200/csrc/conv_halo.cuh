@@ -49,6 +49,20 @@ struct HaloArgs {
   // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake
   int debug_skip;
   int direct_store;              // epilogue stores from registers (32 B per lane and instruction) instead of staging
+  // Active-tile list (tile_need.cuh): when non-null the kernel walks tile_list[0 .. num_m_tiles) instead of the
+  // full tile grid; every entry is a linear (image, tile row, tile column) index of the full grid.
+  const int* tile_list;
+  // Fused class-map sink of the segmentation head (Cout == 16, out_f32 set but never written): instead of storing
+  // the 16 fp32 logits of its pixel, a lane takes their soft-max maximum / arg-max (first maximum, numpy
+  // semantics; confidence byte = round-half-up of the max probability) and, when the pixel lies inside the write
+  // rectangle of its image, writes the two bytes straight into the class / confidence maps
+  // (zone_detect/compare.py:35,66-82 + dataset.py:11-34 + the window write of main.py:421-423).
+  // sink_tiles: int32 [B][6] = x0, y0, wx0, wy0, wx1, wy1 of the images of this launch.
+  const int* sink_tiles;
+  uint8_t* sink_cls;
+  uint8_t* sink_conf;            // may be null
+  long long sink_map_w, sink_map_row0;
+  int sink_ncls;
 };
 
 // Geometry of one instantiation, shared by host packing and the kernel.

@@ -90,7 +90,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.num_n_tiles;
           const int rest = tile / p.num_n_tiles;
-          const int phase = rest % phases, m_tile = rest / phases;
+          const int phase = rest % phases;
+          const int m_tile = p.tile_list != nullptr ? __ldg(p.tile_list + rest / phases) : rest / phases;
           const int pa = p.phase_mode ? (phase >> 1) : 0, pb = p.phase_mode ? (phase & 1) : 0;
           const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
           const int b = m_tile / (tiles_w * tiles_h);
@@ -191,7 +192,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int n_tile = tile % p.num_n_tiles;
       const int rest = tile / p.num_n_tiles;
-      const int phase = rest % phases, m_tile = rest / phases;
+      const int phase = rest % phases;
+      const int m_tile = (TMA_A && p.tile_list != nullptr) ? __ldg(p.tile_list + rest / phases) : rest / phases;
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -590,10 +592,12 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
         }
       a.num_m_tiles = a.B * (a.tgrid_h / 8) * (a.tgrid_w / 16);
     }
+    if (a.tile_list != nullptr) a.num_m_tiles = a.tile_list_len * (a.phase_mode ? 4 : 1);
     a.num_k_iters = nk;
     if (nk * kBK > Kpad) return -1006;
   } else {
     if (a.phase_mode) return -1007;
+    if (a.tile_list != nullptr) return -1008;
     a.num_m_tiles = (a.M_total + kBM - 1) / kBM;
   }
 
@@ -608,7 +612,7 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   // shapes (the wide layers are not shared-memory-port bound after all), so it is opt-in: FB_PAIR=1.
   const char* pair_env = getenv("FB_PAIR");
   const bool use_pair = use_tma_a && BN >= 64 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1' &&
-                        a.KH == 3 && a.stride == 1 && !a.phase_mode;
+                        a.KH == 3 && a.stride == 1 && !a.phase_mode && a.tile_list == nullptr;
   {
     // weights: [Cout][Kpad] bf16 ([4][Cout][Kpad] in phase mode), box = 64 k x BN rows (BN/2 per CTA of a
     // pair), 128-byte swizzle

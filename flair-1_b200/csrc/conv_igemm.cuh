@@ -65,6 +65,10 @@ struct ConvArgs {
   int tgrid_h, tgrid_w;
   int tm_scale[2];
   uint32_t ktab[128];
+  // Active-tile list (tile_need.cuh), TMA producer only: when non-null the kernel walks the tile_list_len 8x16
+  // boxes tile_list[i] = (b * tgrid_h/8 + th) * tgrid_w/16 + tw instead of the full tile grid.
+  const int* tile_list;
+  int tile_list_len;
 };
 
 // Launch one convolution. `use_tma_a` requires conv_tma_eligible(a). Returns cudaError_t as int.

@@ -5,6 +5,7 @@
 //   K6  softmax-max / argmax / margin clip / stitch (src/zone_detect/compare.py:35,66-82, dataset.py:11-34)
 //   K9  confusion-matrix histogram                  (src/flair/metrics.py:60-74, src/zone_detect/test/metrics.py:146-163)
 #include "elementwise.cuh"
+#include "tile_need.cuh"
 
 #include <cuda_bf16.h>
 
@@ -425,6 +426,62 @@ int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, i
   confusion_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       pred, truth, npx, ncls, truth_sub, reinterpret_cast<unsigned long long*>(cm));
   return static_cast<int>(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ active tiles
+// Expands the per-image needed regions (tile_need.cuh) into the list of kernel tiles one conv launch walks.
+// One block: per-image counts, a serial scan (n is a batch, <= a few hundred), then warps write the entries.
+constexpr int kListMaxImages = 1024;
+
+__global__ void __launch_bounds__(256)
+build_tile_list_kernel(const int* __restrict__ tiles, int n, int T, int layer, int scale, int th, int tw, int gh,
+                       int gw, int* __restrict__ list) {
+  __shared__ int off[kListMaxImages + 1];
+  __shared__ NeedRect rng[kListMaxImages];
+  for (int b = threadIdx.x; b < n; b += blockDim.x) {
+    const int* t = tiles + 6 * b;
+    const NeedRect r = need_rect(T, layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
+    NeedRect k = need_tile_range(r, scale, th, tw);
+    if (k.x1 > gw) k.x1 = gw;
+    if (k.y1 > gh) k.y1 = gh;
+    rng[b] = k;
+    off[b + 1] = (k.x1 - k.x0) * (k.y1 - k.y0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    off[0] = 0;
+    for (int b = 0; b < n; ++b) off[b + 1] += off[b];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < n; b += blockDim.x >> 5) {
+    const NeedRect k = rng[b];
+    const int nx = k.x1 - k.x0, cnt = off[b + 1] - off[b];
+    for (int i = lane; i < cnt; i += 32) list[off[b] + i] = (b * gh + k.y0 + i / nx) * gw + k.x0 + i % nx;
+  }
+}
+
+int launch_build_tile_list(const int* tiles_dev, int n, int T, int layer, int scale, int th, int tw, int gh, int gw,
+                           int* list_dev, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n > kListMaxImages) return -2101;
+  build_tile_list_kernel<<<1, 256, 0, stream>>>(tiles_dev, n, T, layer, scale, th, tw, gh, gw, list_dev);
+  return static_cast<int>(cudaGetLastError());
+}
+
+long long count_active_tiles(const int* tiles, int n, int T, int layer, int scale, int th, int tw) {
+  const int S = layer >= 10 ? T : (T / 16) << (layer / 2);
+  const int gh = (S / scale) / th, gw = (S / scale) / tw;
+  long long total = 0;
+  for (int b = 0; b < n; ++b) {
+    const int* t = tiles + 6 * b;
+    const NeedRect r = need_rect(T, layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
+    NeedRect k = need_tile_range(r, scale, th, tw);
+    if (k.x1 > gw) k.x1 = gw;
+    if (k.y1 > gh) k.y1 = gh;
+    total += static_cast<long long>(k.x1 - k.x0) * (k.y1 - k.y0);
+  }
+  return total;
 }
 
 }  // namespace fb

@@ -185,6 +185,11 @@ int fb_profile_begin(fb_ctx* ctx);
 int fb_profile_end(fb_ctx* ctx, float* ms4);
 /* Number of kernels this library has launched on the context since creation. */
 int64_t fb_launch_count(const fb_ctx* ctx);
+/* Algorithmic FLOPs (2 * MAC of the direct convolution, unpadded channels) of the conv outputs this context
+ * has computed since creation. A full 512^2 tile, 3 bands / 15 classes, is 63.569 GFLOP;
+ * the exact-clipping zone loop computes less per tile because the decoder skips outputs that can only reach
+ * the cropped margin (compare.py:66-82; FB_FULL_TILES=1 in the environment turns that off). */
+double fb_flop_count(const fb_ctx* ctx);
 
 /* ---- host-side TIFF LZW codec (compression 5, libtiff/GDAL-compatible) used by the GeoTIFF
  *      reader/writer that stands in for rasterio (main.py:218-232, 421-426; writer.py:38-50).

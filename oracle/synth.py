@@ -65,10 +65,13 @@ def synth_mask(raster: np.ndarray, n_classes: int, bands_used: int, seed: int = 
 
 
 def train_synthetic_checkpoint(in_channels: int = 3, n_classes: int = 15, steps: int = 240, seed: int = 2022,
-                               use_metadata: bool = False, verbose: bool = False) -> dict:
-    """Adam lr 2e-3, `steps` steps of 8 x 128^2 crops, BN in train mode (Appendix E recipe)."""
+                               use_metadata: bool = False, verbose: bool = False, device: str = "cpu") -> dict:
+    """Adam lr 2e-3, `steps` steps of 8 x 128^2 crops, BN in train mode (Appendix E recipe). The batches are
+    drawn on the CPU from seeded generators; `device` only says where torch runs the training steps (a GPU box
+    trains in seconds what takes the host cores minutes; the weights are synthetic either way)."""
     torch.manual_seed(seed)
     model = FlairModel(in_channels, n_classes, use_metadata) if use_metadata else Unet(in_channels, n_classes)
+    model.to(device)
     model.train()
     opt = torch.optim.Adam(model.parameters(), lr=2e-3)
     P = class_projection(n_classes, in_channels)
@@ -82,12 +85,12 @@ def train_synthetic_checkpoint(in_channels: int = 3, n_classes: int = 15, steps:
         img = F.interpolate(low, size=(size, size), mode="bicubic", align_corners=False) * 50 + 110
         img = (img + torch.randn(img.shape, generator=g) * 10).clamp(0, 255).round()
         x = (img - m) / s
-        y = _labels_from(x, P)
+        y = _labels_from(x, P).to(device)
         if use_metadata:
             met = torch.rand((bs, 45), generator=g)
-            logits = model(x, met)
+            logits = model(x.to(device), met.to(device))
         else:
-            logits = model(x)
+            logits = model(x.to(device))
         loss = F.cross_entropy(logits, y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -95,7 +98,7 @@ def train_synthetic_checkpoint(in_channels: int = 3, n_classes: int = 15, steps:
         if verbose and it % 40 == 0:
             print(f"  synth-train step {it} loss {loss.item():.3f}", flush=True)
     model.eval()
-    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
 
 
 def cached_checkpoint(in_channels: int = 3, n_classes: int = 15, use_metadata: bool = False, steps: int = 240) -> dict:
@@ -105,10 +108,20 @@ def cached_checkpoint(in_channels: int = 3, n_classes: int = 15, use_metadata: b
     path = CACHE_DIR / f"synth_c{in_channels}_n{n_classes}_m{int(use_metadata)}_s{steps}.pth"
     if path.exists():
         return torch.load(path, map_location="cpu")
+    if int(os.environ.get("RANK", "0")) != 0:
+        # one process per GPU (torchrun): rank 0 trains and writes the cache, the others wait for the file
+        import time
+        deadline = time.time() + 1800
+        while not path.exists():
+            if time.time() > deadline:
+                raise RuntimeError(f"{path} did not appear: rank 0 failed to build the synthetic checkpoint")
+            time.sleep(0.5)
+        return torch.load(path, map_location="cpu")
     nthreads = torch.get_num_threads()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    device = f"cuda:{os.environ.get('LOCAL_RANK', '0')}" if torch.cuda.is_available() else "cpu"
     try:
-        sd = train_synthetic_checkpoint(in_channels, n_classes, steps=steps, use_metadata=use_metadata)
+        sd = train_synthetic_checkpoint(in_channels, n_classes, steps=steps, use_metadata=use_metadata, device=device)
     finally:
         torch.set_num_threads(nthreads)
     tmp = path.with_suffix(".tmp")

@@ -301,6 +301,51 @@ def test_zone_detect_vs_oracle(ctx, trained_3_15, W, H, T, margin):
     np.testing.assert_array_equal(out_cls, cls_h)
 
 
+@pytest.mark.parametrize("W,H,T,margin", [(1500, 1300, 512, 128), (700, 520, 256, 32), (640, 512, 512, 0)])
+def test_dead_output_elimination_and_fused_sink_are_bit_exact(trained_3_15, monkeypatch, W, H, T, margin):
+    """The exact-clipping loop only computes the decoder outputs inside the receptive field of each write
+    rectangle (csrc/tile_need.cuh) and lets the head's epilogue write the class / confidence bytes. Both
+    must leave the maps bit-identical to the plain path (every tile in full, fp32 logits, separate K6
+    kernel), for class map, confidence band and class_prob planes; the FLOP counter shows the saving and is
+    63.569 GFLOP per 512^2 tile on the plain path."""
+    from oracle import synth
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    nat = _nat()
+    sd, _ = trained_3_15
+    raster = torch.from_numpy(synth.synth_raster(3, H, W, seed=W * 3 + H)).cuda()
+    tiles = tile_table(W, H, T, margin)
+    res = {}
+    for mode in ("plain", "fast"):
+        monkeypatch.setenv("FB_FULL_TILES", "1" if mode == "plain" else "0")
+        monkeypatch.setenv("FB_NO_FUSED_SINK", "1" if mode == "plain" else "0")
+        c = nat.Context(0)
+        c.load_weights(sd, 3, 15)
+        c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+        c.set_raster(raster, [0, 1, 2], W, H)
+        cls = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        conf = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        f0 = c.flop_count
+        c.detect_strip(tiles, T, 7, cls, conf, W, 0)
+        torch.cuda.synchronize()
+        flops = c.flop_count - f0
+        prob = torch.zeros((15, H, W), dtype=torch.uint8, device="cuda")
+        c.detect_strip_prob(tiles, T, 7, prob, W, 0)
+        res[mode] = (cls.cpu().numpy(), conf.cpu().numpy(), prob.cpu().numpy(), flops)
+        c.close()
+    np.testing.assert_array_equal(res["fast"][0], res["plain"][0])
+    np.testing.assert_array_equal(res["fast"][1], res["plain"][1])
+    np.testing.assert_array_equal(res["fast"][2], res["plain"][2])
+    assert (res["fast"][0] < 15).all()
+    per_tile = res["plain"][3] / len(tiles) / 1e9
+    print(f"zone {W}x{H} T={T} m={margin}: {len(tiles)} tiles, {per_tile:.3f} GFLOP per tile in full, "
+          f"{res['fast'][3] / len(tiles) / 1e9:.3f} with dead-output elimination")
+    if T == 512:
+        assert abs(per_tile - 63.569) < 0.01
+    assert res["fast"][3] <= res["plain"][3]
+    if margin >= 128:   # small tiles / thin margins save little: the regions grow by one pixel per 3x3 conv
+        assert res["fast"][3] < 0.9 * res["plain"][3]
+
+
 def _zone_setup(ctx, trained_3_15, W, H, T, margin, seed):
     from oracle import synth
     from oracle.zone_detect_ref import GeoRaster
