@@ -56,6 +56,8 @@ _SIGNATURES = {
     "fb_forward_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fb_detect_strip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int64, C.c_int64]),
+    "fb_detect_strip_metrics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
     "fb_detect_strip_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_int64]),
     "fb_blend_strip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -244,6 +246,22 @@ class Context:
         assert cls_map.dtype == torch.uint8 and cls_map.is_cuda
         self._check(self._lib.fb_detect_strip(self._h, t.ctypes.data, t.shape[0], tile, batch, cls_map.data_ptr(),
                                               _ptr(conf_map), map_w, map_row0))
+
+    def detect_strip_metrics(self, tiles: np.ndarray, windows: np.ndarray, tile: int, batch: int, cls_map: torch.Tensor,
+                             conf_map: Optional[torch.Tensor], map_w: int, map_row0: int, truth: torch.Tensor,
+                             truth_sub: int = 0) -> torch.Tensor:
+        """detect_strip plus the per-patch confusion matrices of the compare loop (fb_detect_strip_metrics):
+        returns int64 [n, n_classes, n_classes] (device), tile i's own prediction over windows[i] against `truth`
+        (uint8, same geometry as cls_map)."""
+        t, w = make_tiles(tiles), make_tiles(windows)
+        assert t.shape == w.shape
+        assert cls_map.dtype == torch.uint8 and cls_map.is_cuda and truth.dtype == torch.uint8 and truth.is_cuda
+        assert truth.is_contiguous() and truth.shape == cls_map.shape
+        cm = torch.zeros((t.shape[0], self.n_classes, self.n_classes), dtype=torch.int64, device=self.device)
+        self._check(self._lib.fb_detect_strip_metrics(self._h, t.ctypes.data, w.ctypes.data, t.shape[0], tile, batch,
+                                                      cls_map.data_ptr(), _ptr(conf_map), map_w, map_row0,
+                                                      truth.data_ptr(), truth_sub, cm.data_ptr()))
+        return cm
 
     def detect_strip_prob(self, tiles: np.ndarray, tile: int, batch: int, prob_map: torch.Tensor, map_w: int,
                           map_row0: int = 0) -> None:

@@ -109,6 +109,8 @@ struct fb_ctx {
   int* tile_xy_dev = nullptr;  // [cap][2]
   int* tiles_dev = nullptr;    // [cap][6]
   int tile_cap = 0;
+  int* win_dev = nullptr;      // [cap][6] metric windows of fb_detect_strip_metrics
+  int win_cap = 0;
   float* meta_dev = nullptr;   // [n][45]
   float* menc_dev = nullptr;   // [n][16]
   int meta_cap = 0;
@@ -747,6 +749,7 @@ void fb_destroy(fb_ctx* c) {
   if (c->meta_dev) cudaFree(c->meta_dev);
   if (c->menc_dev) cudaFree(c->menc_dev);
   if (c->list_dev) cudaFree(c->list_dev);
+  if (c->win_dev) cudaFree(c->win_dev);
   delete c;
 }
 
@@ -902,6 +905,11 @@ struct DetectSink {
   int method = 0;
   int64_t map_w = 0, map_row0 = 0, map_rows = 0;
   int seq0 = 0;
+  // kind 0 only: per-tile confusion matrices of each tile's own prediction over its metric window
+  const fb_tile* windows = nullptr;
+  const uint8_t* truth = nullptr;
+  int truth_sub = 0;
+  int64_t* tile_cm = nullptr;
 };
 
 int check_write_rects(fb_ctx* c, const fb_tile* tiles, int n, int tile, int64_t map_w, int64_t map_row0) {
@@ -926,6 +934,23 @@ int fb_detect_strip(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch,
   FB_TRY(check_write_rects(c, tiles, n, tile, map_w, map_row0));
   DetectSink s;
   s.kind = 0; s.cls = cls_map_dev; s.conf = conf_map_dev; s.map_w = map_w; s.map_row0 = map_row0;
+  return detect_loop(c, tiles, n, tile, batch, s);
+}
+
+int fb_detect_strip_metrics(fb_ctx* c, const fb_tile* tiles, const fb_tile* windows, int n, int tile, int batch,
+                            uint8_t* cls_map_dev, uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0,
+                            const uint8_t* truth_dev, int truth_sub, int64_t* cm_tiles_dev) {
+  FB_TRY(check_ready(c, true, tile));
+  if (!tiles || !windows || n < 0 || batch <= 0 || !cls_map_dev || !truth_dev || !cm_tiles_dev)
+    return fail(c, FB_ERR_INVALID, "detect (metrics): bad arguments");
+  FB_TRY(check_write_rects(c, tiles, n, tile, map_w, map_row0));
+  FB_TRY(check_write_rects(c, windows, n, tile, map_w, map_row0));
+  for (int i = 0; i < n; ++i)
+    if (windows[i].x0 != tiles[i].x0 || windows[i].y0 != tiles[i].y0)
+      return fail(c, FB_ERR_INVALID, "detect (metrics): window " + std::to_string(i) + " belongs to another tile origin");
+  DetectSink s;
+  s.kind = 0; s.cls = cls_map_dev; s.conf = conf_map_dev; s.map_w = map_w; s.map_row0 = map_row0;
+  s.windows = windows; s.truth = truth_dev; s.truth_sub = truth_sub; s.tile_cm = cm_tiles_dev;
   return detect_loop(c, tiles, n, tile, batch, s);
 }
 
@@ -981,6 +1006,17 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
   for (int i = 0; i < n; ++i) { xy[2 * i] = tiles[i].x0; xy[2 * i + 1] = tiles[i].y0; }
   FB_CUDA(c, cudaMemcpyAsync(c->tile_xy_dev, xy.data(), xy.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   FB_CUDA(c, cudaMemcpyAsync(c->tiles_dev, tiles, static_cast<size_t>(n) * sizeof(fb_tile), cudaMemcpyHostToDevice, c->stream));
+  if (s.tile_cm) {
+    // the metric windows may reach outside the write rectangles (clamped last row / column): whole tiles, fp32 logits
+    if (n > c->win_cap) {
+      FB_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (c->win_dev) cudaFree(c->win_dev);
+      c->win_dev = nullptr; c->win_cap = 0;
+      FB_CUDA(c, cudaMalloc(&c->win_dev, static_cast<size_t>(n) * sizeof(fb_tile)));
+      c->win_cap = n;
+    }
+    FB_CUDA(c, cudaMemcpyAsync(c->win_dev, s.windows, static_cast<size_t>(n) * sizeof(fb_tile), cudaMemcpyHostToDevice, c->stream));
+  }
   FB_CUDA(c, cudaStreamSynchronize(c->stream));  // xy is a local
   for (int i0 = 0; i0 < n; i0 += batch) {
     const int nb = (n - i0 < batch) ? n - i0 : batch;
@@ -993,11 +1029,11 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
     need.tiles_dev = c->tiles_dev + 6 * i0;
     need.tiles_host = &tiles[i0].x0;
     need.n = nb; need.T = tile;
-    need.restrict_tiles = s.kind != 2 && !c->full_tiles;
+    need.restrict_tiles = s.kind != 2 && !c->full_tiles && !s.tile_cm;
     HeadSink hs;
     hs.cls = s.cls; hs.conf = s.conf; hs.map_w = s.map_w; hs.map_row0 = s.map_row0;
     bool sunk = false;
-    FB_TRY(run_network(c, nb, tile, nullptr, &need, (s.kind == 0 && !c->no_fused_sink) ? &hs : nullptr, &sunk));
+    FB_TRY(run_network(c, nb, tile, nullptr, &need, (s.kind == 0 && !c->no_fused_sink && !s.tile_cm) ? &hs : nullptr, &sunk));
     if (sunk) continue;
     ProfScope ps(c, 3);
     const float* logits = static_cast<const float*>(c->acts["logits"].ptr);
@@ -1012,6 +1048,12 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
                                        s.map_row0, s.map_rows, c->W, c->H, s.seq0 + i0, c->stream);
     if (rc) return fail(c, rc, "stitch launch failed");
     c->launches++;
+    if (s.tile_cm) {
+      rc = fb::launch_tile_confusion(logits, c->ncls, nb, tile, c->win_dev + 6 * i0, s.truth, s.truth_sub, s.map_w, s.map_row0,
+                                     reinterpret_cast<long long*>(s.tile_cm) + static_cast<long long>(i0) * c->ncls * c->ncls, c->stream);
+      if (rc) return fail(c, rc, "tile confusion launch failed");
+      c->launches++;
+    }
   }
   return 0;
 }

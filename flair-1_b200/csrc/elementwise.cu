@@ -428,6 +428,54 @@ int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, i
   return static_cast<int>(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------ K9b
+// Per-tile confusion matrices of the compare loop (zone_detect/main.py:349-366 -> test/metrics.py:124-163,
+// compute_metrics_patch): tile t's OWN arg-max prediction over its metric window against the truth raster, as
+// sklearn.confusion_matrix(labels=range(ncls)) counts them. windows: int32 [n][6] = x0, y0 (tile origin),
+// then the half-open window in raster pixels. truth: uint8 map with the class map's geometry; `truth_sub` is
+// subtracted with uint8 wrap-around first. cm: u64 [n][ncls][ncls], accumulated.
+__global__ void __launch_bounds__(256)
+tile_confusion_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ windows,
+                      const uint8_t* __restrict__ truth, int truth_sub, long long map_w, long long map_row0,
+                      unsigned long long* __restrict__ cm) {
+  __shared__ unsigned int bins[kMaxCls * kMaxCls];
+  const int nb = ncls * ncls;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  const int t = blockIdx.y;
+  const int* tt = windows + 6 * t;
+  const int x0 = tt[0], y0 = tt[1], wx0 = tt[2], wy0 = tt[3], wx1 = tt[4], wy1 = tt[5];
+  const int rw = wx1 - wx0, rh = wy1 - wy0;
+  if (rw <= 0 || rh <= 0) return;
+  const int total = rw * rh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ry = wy0 + i / rw, rx = wx0 + i % rw;
+    float v[16];
+    load_logits16(logits + ((static_cast<long long>(t) * T + (ry - y0)) * T + (rx - x0)) * 16, v);
+    float best = v[0];
+    unsigned arg = 0;
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+      if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
+    const unsigned tb = (static_cast<unsigned>(truth[(static_cast<long long>(ry) - map_row0) * map_w + rx]) - truth_sub) & 0xFF;
+    if (tb < static_cast<unsigned>(ncls)) atomicAdd(&bins[tb * ncls + arg], 1u);
+  }
+  __syncthreads();
+  unsigned long long* out = cm + static_cast<long long>(t) * nb;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (bins[i] != 0) atomicAdd(&out[i], static_cast<unsigned long long>(bins[i]));
+}
+
+int launch_tile_confusion(const float* logits, int ncls, int n, int T, const int* windows, const uint8_t* truth,
+                          int truth_sub, long long map_w, long long map_row0, long long* cm, cudaStream_t stream) {
+  if (ncls <= 0 || ncls > 16) return -2002;
+  if (n == 0) return 0;
+  dim3 grid(16, n);
+  tile_confusion_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, windows, truth, truth_sub & 0xFF, map_w, map_row0,
+                                                  reinterpret_cast<unsigned long long*>(cm));
+  return static_cast<int>(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------ active tiles
 // Expands the per-image needed regions (tile_need.cuh) into the list of kernel tiles one conv launch walks.
 // One block: per-image counts, a serial scan (n is a batch, <= a few hundred), then warps write the entries.

@@ -16,7 +16,8 @@ from .. import geotiff
 
 
 def overall_accuracy(npcm):
-    return 100 * np.trace(npcm) / npcm.sum()
+    oa = np.trace(npcm) / npcm.sum()   # the ratio first, then the percentage: the order fixes the last ulp
+    return 100 * oa
 
 
 def class_IoU(npcm, n_class=None):

@@ -26,9 +26,9 @@ import torch
 from .. import geotiff
 from .compare import STITCH_METHODS, stitching, stitching_blend, stitching_class_prob
 from .dataset import Sliced_Dataset
-from .metrics import confusion_matrix_gpu, metrics_from_confmat
+from .metrics import batch_metrics, confusion_matrix_gpu, metrics_from_confmat
 from .model import load_model
-from .slicing_job import slice_extent, split_rows_across_ranks
+from .slicing_job import slice_extent, split_rows_across_ranks, tile_windows
 from .tiles import get_stride
 from .utils import gen_param_combination, open_images, setup, setup_device, setup_indiv_path, setup_out_path
 
@@ -112,6 +112,10 @@ def prepare_data(config: dict, stride: int):
     shard = split_rows_across_ranks(tiles, world)[rank]
     my_tiles = tiles[shard]
     size = config["img_pixels_detection"]
+    # the margin-cropped window of every tile of this rank (per-patch metrics of the compare loop) and its
+    # position in the write order
+    config["_my_windows"] = tile_windows(profile["width"], profile["height"], size, config["margin"], stride)[shard]
+    config["_my_index"] = shard
     if len(my_tiles) and config.get("stitching", "exact-clipping") != "exact-clipping" and config["output_type"] == "argmax":
         # blended stitching: every tile that touches the rows this rank owns contributes to them, so the
         # neighbouring tile rows are recomputed here instead of exchanged (halo recompute, like the raster halo)
@@ -166,9 +170,12 @@ def run_from_config(config: dict) -> None:
 
 
 def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarray, device: torch.device,
-                stitch: str = "exact-clipping"):
+                stitch: str = "exact-clipping", truth_dev: torch.Tensor | None = None):
     """One rank's share of the hot loop. Returns (class strip, confidence strip, first row, rows) with the
-    strips on the device."""
+    strips on the device. With `truth_dev` (the truth rows of this rank's strip, already minus 1) and exact
+    clipping, config["_patch_cm"] receives the per-tile confusion matrices of compute_metrics_patch
+    (main.py:349-366): each tile's own prediction over its margin-cropped window."""
+    config["_patch_cm"] = None
     size = config["img_pixels_detection"]
     W = dataset.raster_width
     if len(my_tiles) == 0:
@@ -185,7 +192,13 @@ def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarr
         return prob, None, my0, my1 - my0
     cls = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
     conf = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
-    if stitch == "exact-clipping":
+    if stitch == "exact-clipping" and truth_dev is not None:
+        # a window may reach above / below the rows this rank owns (clamped last row): score what lies inside
+        win = np.array(config["_my_windows"], dtype=np.int32)
+        win[:, 3] = np.clip(win[:, 3], my0, my1)
+        win[:, 5] = np.clip(win[:, 5], my0, my1)
+        config["_patch_cm"] = model.detect_strip_metrics(my_tiles, win, size, batch, cls, conf, W, my0, truth_dev)
+    elif stitch == "exact-clipping":
         stitching(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
     else:
         stitching_blend(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
@@ -215,6 +228,57 @@ def _gather_strips(strip: torch.Tensor, row0: int, H: int, W: int, device) -> np
         r0, n = int(m[0].item()), int(m[1].item())
         out[r0:r0 + n] = b[:n].cpu().numpy()
     return out
+
+
+def _gather_patch_metrics(cfg: dict, method: str) -> list | None:
+    """Per-patch metric dictionaries (test/metrics.py:165-192) of every tile in write order; rank 0 receives the
+    other ranks' confusion matrices (they are tiny: n_tiles x n_classes^2 int64)."""
+    rank, world = _rank_world()
+    cm = cfg.get("_patch_cm")
+    mine = (np.asarray(cfg["_my_index"]), np.asarray(cfg["_my_windows"]),
+            cm.cpu().numpy() if cm is not None else np.zeros((0, cfg["n_classes"], cfg["n_classes"]), np.int64))
+    parts = [mine]
+    if world > 1:
+        import torch.distributed as dist
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    rows = []
+    for idx, win, cms in parts:
+        for i, w, c in zip(idx, win, cms):
+            rows.append((int(i), metrics_from_confmat(c, cfg, f"{method}_{int(w[2])}_{int(w[3])}")))
+    return [m for _, m in sorted(rows, key=lambda r: r[0])]
+
+
+def batch_metrics_pipeline(config: dict, truth_dpt: Path, device: torch.device, use_gpu: bool) -> str | None:
+    """main.py:440-497: every zone directory of the department that holds a `*<data_type>.tif` image and has a
+    ground-truth raster is run through run_pipeline (with `-c` the predictions land in time-stamped folders, which
+    is what batch_metrics collects), then the per-method metrics over all zones are written to metrics_out."""
+    out_json = Path(config["metrics_out"])
+    file_pattern = f"*{config['data_type']}.tif"
+    assert out_json, "Please provide an output path for the metrics"
+    inputs_dpt = Path(config["input_path"])
+    for full_zone in sorted(p for p in inputs_dpt.iterdir() if p.is_dir()):
+        irc_path = next(full_zone.glob(file_pattern), None)
+        if irc_path is None:
+            continue
+        zone = irc_path.parts[-2]
+        truth_path = next(Path(truth_dpt / zone).glob("*.tif"), None)
+        if truth_path is None:
+            print(f"No ground truth found for zone: {zone}")
+            continue
+        config.update({"input_img_path": str(irc_path), "truth_path": str(truth_path),
+                       "output_name": f"{irc_path.stem}-ARGMAX-S"})
+        run_pipeline(config, device, use_gpu)
+    out = out_json.with_suffix(".json")
+    if _rank_world()[0] != 0:
+        return None
+    metrics_file = batch_metrics(config, truth_dpt)
+    with open(out, "w") as f:
+        json.dump(metrics_file, f)
+    print(f"Metrics saved to {out}")
+    return str(out)
 
 
 def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
@@ -255,6 +319,8 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                 raise ValueError(f"stitching must be one of {STITCH_METHODS}")
 
         method_metrics = []
+        method_times = {}
+        patch_metrics = {}
         for combi in settings:
             cfg = dict(config)
             cfg.update({"img_pixels_detection": combi["img_pixels_detection"], "margin": combi["margin"],
@@ -267,11 +333,19 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
             out_profile, path_out = prepare_output(cfg, profile, identifier)
             if rank == 0:
                 print("""    [ ] starting inference...\n""")
-            cls, conf, row0, rows = detect_zone(cfg, model, dataset, my_tiles, device, combi["stitching"])
             H, W = dataset.raster_height, dataset.raster_width
-            if config["metrics"] and cfg["output_type"] == "argmax":
+            want_metrics = config["metrics"] and cfg["output_type"] == "argmax"
+            truth_dev = None
+            if want_metrics and len(my_tiles):
+                r0, r1 = cfg.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())))
+                truth_dev = torch.from_numpy(np.ascontiguousarray(truth_array[r0:r1])).to(device)
+            per_patch = want_metrics and config["compare"] and "classes" in config and len(config["classes"]) == config["n_classes"]
+            cls, conf, row0, rows = detect_zone(cfg, model, dataset, my_tiles, device, combi["stitching"],
+                                                truth_dev if per_patch else None)
+            if want_metrics:
                 n_classes = len(config["classes"]) if "classes" in config else config["n_classes"]
-                truth_dev = torch.from_numpy(np.ascontiguousarray(truth_array[row0:row0 + rows])).to(device)
+                if truth_dev is None:
+                    truth_dev = torch.empty((0, W), dtype=torch.uint8, device=device)
                 cm = confusion_matrix_gpu(model, cls, truth_dev, n_classes)
                 if world > 1:
                     import torch.distributed as dist
@@ -289,15 +363,32 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                     _write_output(path_out, np.stack(planes), out_profile)
             dataset.close_raster()
             elapsed = (datetime.datetime.now() - start_time).total_seconds()
+            method_times.setdefault(method, []).append(elapsed * 1000)   # main.py:352-358 (per zone here, not per patch)
+            if per_patch and combi["stitching"] == "exact-clipping":
+                got = _gather_patch_metrics(cfg, method)
+                if rank == 0:
+                    patch_metrics[method] = got
             if rank == 0:
                 print(f"""    [X] done writing to {path_out.split('/')[-1]} raster file ({elapsed:.2f} s, {len(tiles)} tiles, """
                       f"""{H * W / 1e6 / max(elapsed, 1e-9):.1f} Mpx/s incl. I/O).\n""")
                 result.setdefault("outputs", []).append(path_out)
                 if config["metrics"] and "classes" in config:
                     method_metrics.append(metrics_from_confmat(result["confmat"], config, method))
+        config["times"] = method_times   # main.py:378, read by batch_metrics
         if rank == 0 and config["metrics"] and method_metrics:
-            with open(metrics_json, "w") as f:
-                json.dump(method_metrics, f, indent=2)
+            if patch_metrics:
+                # the reference dumps the per-patch list of every method to the same file, the last one stays
+                # (main.py:379-384); the whole-raster figures per method go to a file of their own
+                with open(metrics_json, "w") as f:
+                    json.dump(list(patch_metrics.values())[-1], f, indent=2)
+                per_method = metrics_json.with_name(metrics_json.name.replace("metrics_per-patch", "metrics_per-method"))
+                with open(per_method, "w") as f:
+                    json.dump(method_metrics, f, indent=2)
+                result["patch_metrics"] = patch_metrics
+                result["metrics_per_method_json"] = str(per_method)
+            else:
+                with open(metrics_json, "w") as f:
+                    json.dump(method_metrics, f, indent=2)
             print(f"""    [X] done writing metrics to {metrics_json.name} file.\n""")
             result["metrics_json"] = str(metrics_json)
             result["metrics"] = method_metrics
@@ -311,8 +402,11 @@ def main() -> None:
     args = argParser.parse_args()
     config, device, use_gpu = setup(args)
     if args.batch_mode:
-        raise NotImplementedError("batch mode (-b) is not built yet (SURVEY.md section 8f rank 4)")
-    run_pipeline(config, device, use_gpu)
+        gt_dir = Path(config["truth_root"])
+        gt_dpt = gt_dir / Path(config["truth_path"]).parts[-3]
+        batch_metrics_pipeline(config, gt_dpt, device, use_gpu)
+    else:
+        run_pipeline(config, device, use_gpu)
 
 
 if __name__ == "__main__":

@@ -87,6 +87,23 @@ def tile_interiors(width: int, height: int, size: int, margin: int, stride: int 
                        for x in xs for yb in ybs], dtype=np.int64).reshape(-1, 4)
 
 
+def tile_windows(width: int, height: int, size: int, margin: int, stride: int = 0) -> np.ndarray:
+    """int32 [n, 6] rows (x0, y0, cx0, cy0, cx1, cy1), same order as tile_table: the margin-cropped window each
+    tile's prediction is written to and scored on (compare.py:66-82 -> `window`; test/metrics.py:146-149), in
+    pixel coordinates with y growing downwards. Unlike the write rectangles these overlap where a clamped last
+    row / column re-covers pixels."""
+    if stride <= 0:
+        stride = size - 2 * margin
+    t = tile_table(width, height, size, margin, stride)
+    ints = tile_interiors(width, height, size, margin, stride)
+    out = t.copy()
+    out[:, 2] = ints[:, 0]
+    out[:, 3] = height - ints[:, 3]
+    out[:, 4] = ints[:, 2]
+    out[:, 5] = height - ints[:, 1]
+    return out
+
+
 def slice_extent(in_img, patch_size: int, margin: int, output_path, output_name: str, write_dataframe: bool, stride: int):
     """Same call and return shape as the reference's slice_extent (slicing_job.py:19-118):
     (tile table, profile, (res_x, res_y), [n_rows, n_cols]). The table is the int32 pixel-space array of

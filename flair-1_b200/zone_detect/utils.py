@@ -112,6 +112,45 @@ def gen_param_combination(config: dict) -> list:
     return combi
 
 
+def extract_method(method: str, info: dict | None = None) -> dict:
+    """src/zone_detect/utils.py:170-188: "size=512_stride=256_..." -> parameters. Values cannot contain "_"
+    ("stitching=average_weights" raises IndexError there as well)."""
+    info = {} if info is None else info
+    for param in method.split("_"):
+        if param.startswith("size="):
+            info["patch_size"] = int(param.split("=")[1])
+        elif param.startswith("stride="):
+            info["stride"] = int(param.split("=")[1])
+        elif param.startswith("margin="):
+            info["margin"] = int(param.split("=")[1])
+        elif param.startswith("padding="):
+            info["padding"] = param.split("=")[1]
+        elif param.startswith("stitching="):
+            info["stitching"] = param.split("=")[1]
+        else:
+            kv = param.split("=")
+            info[kv[0]] = kv[1]
+    return info
+
+
+def info_extract(file: Path) -> dict:
+    """src/zone_detect/utils.py:191-217: "<dpt>_<year>_<zone...>_<type>-ARGMAX-S_<method>.tif" -> dpt, zone and
+    the method parameters. As in the reference, "dpt" is only set when the name does not already start with "D"."""
+    filename = str(file)
+    if not filename.endswith(".tif"):
+        raise ValueError("Filename should end with .tif what are you doing ?")
+    name = filename.split("/")[-1].split(".")[0]
+    info = {}
+    region_type, method = name.split("-ARGMAX-S_")
+    region_type = region_type.split("_")
+    dpt, zone = region_type[:2], region_type[2:-1]
+    if not dpt[0].startswith("D"):
+        info["dpt"] = "D" + "_".join(dpt)
+    info["zone"] = "_".join(zone)
+    info["method"] = method
+    return extract_method(method, info)
+
+
 #### SETUP ####
 def setup_out_path(config: dict) -> dict:
     """src/zone_detect/utils.py:221-236."""

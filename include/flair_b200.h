@@ -108,6 +108,17 @@ int fb_forward_tiles(fb_ctx* ctx, const int32_t* tile_xy, int n, int tile, const
 int fb_detect_strip(fb_ctx* ctx, const fb_tile* tiles, int n, int tile, int batch, uint8_t* cls_map_dev,
                     uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0);
 
+/* ---- the same loop with the per-patch metrics of the compare loop (main.py:349-366 -> test/metrics.py:124-163,
+ *      compute_metrics_patch): besides writing the maps, tile i's OWN arg-max prediction over windows[i]
+ *      (x0, y0 = the tile's origin, [wx0,wx1) x [wy0,wy1) = its margin-cropped window, which for a clamped
+ *      last row / column overlaps what other tiles own) is counted against the truth raster:
+ *      cm_tiles_dev[i][t][p] += #{ px in window : (uint8)(truth - truth_sub) == t, pred == p, t < n_classes }.
+ *      truth_dev: uint8 with the class map's geometry; cm_tiles_dev: int64 [n][n_classes][n_classes], zeroed
+ *      by the caller. Whole tiles are computed (no dead-output elimination). */
+int fb_detect_strip_metrics(fb_ctx* ctx, const fb_tile* tiles, const fb_tile* windows, int n, int tile, int batch,
+                            uint8_t* cls_map_dev, uint8_t* conf_map_dev, int64_t map_w, int64_t map_row0,
+                            const uint8_t* truth_dev, int truth_sub, int64_t* cm_tiles_dev);
+
 /* ---- the same loop with output_type "class_prob" (dataset.py:15-21 `convert`, main.py:229, 421-426):
  *      every class probability of the margin-cropped tile as uint8(p * 255) (truncation), written to
  *      prob_map_dev uint8 [n_classes][map_rows][map_w] (band k+1 of the reference's output = plane k). */

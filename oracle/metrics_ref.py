@@ -34,7 +34,8 @@ def clean_confmat(confmat: np.ndarray, classes: dict) -> np.ndarray:
 
 
 def overall_accuracy(npcm):  # flair/metrics.py:10-12
-    return 100 * np.trace(npcm) / npcm.sum()
+    oa = np.trace(npcm) / npcm.sum()   # the ratio first, then the percentage: the order fixes the last ulp
+    return 100 * oa
 
 
 def class_IoU(npcm):  # flair/metrics.py:15-22

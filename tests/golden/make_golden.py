@@ -93,6 +93,21 @@ class _FakeRaster:
 
 
 _RASTERS = {}
+_ARRAYS = {}   # path -> uint8 [H, W] band 1 of a stubbed raster (batch_metrics reads predictions and truths)
+
+
+class _ArrayRaster:
+    def __init__(self, arr):
+        self.arr = arr
+
+    def read(self, band):
+        return self.arr.copy()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def install_stubs():
@@ -105,7 +120,8 @@ def install_stubs():
         if n.split(".")[0] in ("scipy",):
             continue
         _stub(n)
-    sys.modules["rasterio"].open = lambda path, *a, **k: _FakeRaster(_RASTERS[str(path)])
+    sys.modules["rasterio"].open = lambda path, *a, **k: (_ArrayRaster(_ARRAYS[str(path)]) if str(path) in _ARRAYS
+                                                          else _FakeRaster(_RASTERS[str(path)]))
     sys.modules["geopandas"].GeoDataFrame = _Frame
     sys.modules["shapely.geometry"].box = _Box
     sys.modules["shapely"].Polygon = _Box
@@ -311,6 +327,69 @@ def gold_config(out: dict):
         out["setup_indiv_path"] = names
 
 
+def gold_batch(out: dict):
+    """Batch mode (-b): filename grammar (utils.py:170-217), prediction/truth collection and the per-method
+    metrics of test/metrics.py:48-84, 195-287 executed on a small synthetic department: 2 zones x 2 methods,
+    64 x 48 rasters. Only rasterio.open(...).read(1) is stubbed (arrays registered per path)."""
+    import tempfile
+    import src.zone_detect.utils as zu
+    import src.zone_detect.test.metrics as zm
+    names = ["032_2019_UA-zone_1_RGBI-ARGMAX-S_size=512_stride=256_margin=128_padding=no-padding_stitching=exact-clipping.tif",
+             "077_2021_UN_S-12_3_IRC-ARGMAX-S_size=1024_stride=512_margin=256_padding=no-padding_stitching=average.tif",
+             "D032_2019_UA-zone_1_RGBI-ARGMAX-S_size=256_stride=192_margin=32_padding=some-padding_stitching=max_extra=7.tif"]
+    res = {"info_extract": [{"file": "/a/b/" + n, "info": zu.info_extract(Path("/a/b/" + n))} for n in names],
+           "extract_method": [{"method": m, "info": zu.extract_method(m, {})} for m in
+                              ["size=512_stride=256_margin=128_padding=no-padding_stitching=exact-clipping",
+                               "size=128_stride=96_margin=16_padding=reflect_stitching=average_foo=bar"]]}
+    # the "_" separated grammar cannot carry a value with an underscore: "stitching=average_weights" raises
+    try:
+        zu.extract_method("size=512_stride=256_margin=128_padding=no-padding_stitching=average_weights", {})
+        res["extract_method_underscore_value"] = None
+    except IndexError as e:
+        res["extract_method_underscore_value"] = "IndexError"
+    try:
+        zu.info_extract(Path("/a/b/zone.png"))
+        res["info_extract_bad_suffix"] = None
+    except ValueError as e:
+        res["info_extract_bad_suffix"] = str(e)
+    rng = np.random.default_rng(23)
+    classes = {i + 1: [0 if i + 1 in (13, 14, 15) else 1, f"class{i + 1}"] for i in range(15)}
+    methods = ["size=512_stride=256_margin=128_padding=no-padding_stitching=exact-clipping",
+               "size=256_stride=192_margin=32_padding=no-padding_stitching=max"]
+    zones = ["UA-zone_1", "UN_S-12_3"]
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        out_dir, truth_dir = d / "out", d / "truth" / "032_2019"
+        files = {}
+        for zi, zone in enumerate(zones):
+            ts = out_dir / f"20250101_00000{zi}"
+            ts.mkdir(parents=True)
+            (truth_dir / zone).mkdir(parents=True)
+            tpath = truth_dir / zone / f"032_2019_{zone}_MSK.tif"
+            tpath.touch()
+            truth = rng.integers(0, 17, size=(48, 64), dtype=np.uint8)   # 0 wraps to 255 after -1; 16 is out of range
+            _ARRAYS[str(tpath)] = truth
+            files[f"truth/{zone}"] = truth.tolist()
+            for method in methods:
+                ppath = ts / f"032_2019_{zone}_RGBI-ARGMAX-S_{method}.tif"
+                ppath.touch()
+                pred = rng.integers(0, 15, size=(48, 64), dtype=np.uint8)
+                _ARRAYS[str(ppath)] = pred
+                files[f"pred/{zone}/{method}"] = pred.tolist()
+        config = {"output_path": str(out_dir), "classes": classes, "model_name": "resnet34-unet",
+                  "times": {methods[0]: [10.0, 30.0]}}
+        df = zm.collect_paths_truth(config, truth_dir)
+        res["collect_paths_truth"] = sorted([[Path(r.pred_path).name, Path(r.truth_path).name, r.method] for r in df.itertuples()])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            metrics = zm.batch_metrics(config, truth_dir)
+        res["batch_metrics"] = metrics
+        res["files"] = files
+        res["zones"] = zones
+        res["methods"] = methods
+        res["classes"] = {str(k): v for k, v in classes.items()}
+    out["batch"] = res
+
+
 def gold_metadata_forward(out: dict):
     """The reference's own FLAIR_ModelFactory.forward / MetadataMLP (flair/model.py:52-96) on top of
     the restated Unet: pins the MLP + `repeat(1,512,1,16)` broadcast + add semantics."""
@@ -347,6 +426,7 @@ def main():
     gold_metadata(out)
     gold_checkpoint(out)
     gold_config(out)
+    gold_batch(out)
     if "--with-forward" in sys.argv:
         gold_metadata_forward(out)
     (HERE / "golden.json").write_text(json.dumps(_jsonable(out), indent=1))

@@ -1,6 +1,7 @@
 """The oracle against vectors produced by the reference's own code (tests/golden/make_golden.py),
 and the product's integer tile grid against the same vectors. CPU only."""
 import json
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -221,3 +222,69 @@ def test_unet_restatement_pins():
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 65, 64))
     assert Unet(5, 19).state_dict()["encoder.conv1.weight"].shape == (64, 5, 7, 7)
+
+
+def test_batch_mode_filename_grammar_and_metrics(tmp_path, monkeypatch):
+    """Batch mode `-b` host logic against the reference's own code (golden["batch"], produced by executing
+    utils.info_extract / extract_method and test/metrics.collect_paths_truth / batch_metrics of /root/reference):
+    file-name grammar, prediction <-> truth pairing, per-method grouping and every metric value. The one GPU
+    call (confusion matrix of two rasters) is replaced by the oracle's numpy count here; the GPU suite runs
+    the real thing."""
+    import json as _json
+    from oracle.metrics_ref import confusion_numpy
+    import flair1_b200.zone_detect.metrics as zmet
+    from flair1_b200.zone_detect.utils import extract_method, info_extract
+    g = _json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())["batch"]
+    for case in g["info_extract"]:
+        assert info_extract(Path(case["file"])) == case["info"]
+    for case in g["extract_method"]:
+        assert extract_method(case["method"]) == case["info"]
+    assert g["extract_method_underscore_value"] == "IndexError"
+    with pytest.raises(IndexError):
+        extract_method("size=512_stride=256_margin=128_padding=no-padding_stitching=average_weights")
+    with pytest.raises(ValueError, match=g["info_extract_bad_suffix"][:20]):
+        info_extract(Path("/a/b/zone.png"))
+
+    out_dir, truth_dir = tmp_path / "out", tmp_path / "truth" / "032_2019"
+    arrays = {}
+    for zi, zone in enumerate(g["zones"]):
+        ts = out_dir / f"20250101_00000{zi}"
+        ts.mkdir(parents=True)
+        (truth_dir / zone).mkdir(parents=True)
+        tpath = truth_dir / zone / f"032_2019_{zone}_MSK.tif"
+        tpath.touch()
+        arrays[str(tpath)] = np.array(g["files"][f"truth/{zone}"], np.uint8)
+        for method in g["methods"]:
+            ppath = ts / f"032_2019_{zone}_RGBI-ARGMAX-S_{method}.tif"
+            ppath.touch()
+            arrays[str(ppath)] = np.array(g["files"][f"pred/{zone}/{method}"], np.uint8)
+    classes = {int(k): v for k, v in g["classes"].items()}
+    config = {"output_path": str(out_dir), "classes": classes, "model_name": "resnet34-unet",
+              "times": {g["methods"][0]: [10.0, 30.0]}}
+    df = zmet.collect_paths_truth(config, truth_dir)
+    got = sorted([[Path(r.pred_path).name, Path(r.truth_path).name, r.method] for r in df.itertuples()])
+    assert got == g["collect_paths_truth"]
+    monkeypatch.setattr(zmet, "confmat_of_rasters",
+                        lambda model, pp, tp, n: confusion_numpy(arrays[tp], arrays[pp], n, 1))
+    res = zmet.batch_metrics(config, truth_dir, model=object())
+    assert _json.loads(_json.dumps(res)) == g["batch_metrics"]
+
+
+def test_tile_windows_are_the_interiors():
+    """tile_windows = the reference's left/bottom/right/top interior boxes (already pinned by the slice_extent
+    golden cases through tile_interiors) flipped to top-left pixel coordinates; every write rectangle lies in
+    its window and the windows cover the raster."""
+    from flair1_b200.zone_detect.slicing_job import tile_interiors, tile_table, tile_windows
+    for W, H, T, m in [(1000, 700, 512, 128), (513, 513, 512, 0), (10000, 10000, 512, 128), (300, 280, 256, 32)]:
+        t, w, ints = tile_table(W, H, T, m), tile_windows(W, H, T, m), tile_interiors(W, H, T, m)
+        assert (w[:, :2] == t[:, :2]).all()
+        assert (w[:, 2] == ints[:, 0]).all() and (w[:, 4] == ints[:, 2]).all()
+        assert (w[:, 3] == H - ints[:, 3]).all() and (w[:, 5] == H - ints[:, 1]).all()
+        own = (t[:, 4] > t[:, 2]) & (t[:, 5] > t[:, 3])
+        assert (t[own, 2] >= w[own, 2]).all() and (t[own, 4] <= w[own, 4]).all()
+        assert (t[own, 3] >= w[own, 3]).all() and (t[own, 5] <= w[own, 5]).all()
+        assert (w[:, 2] >= t[:, 0]).all() and (w[:, 4] <= t[:, 0] + T).all() and (w[:, 3] >= t[:, 1]).all() and (w[:, 5] <= t[:, 1] + T).all()
+        cover = np.zeros((H, W), bool)
+        for x0, y0, a, b, c, d in w:
+            cover[b:d, a:c] = True
+        assert cover.all()

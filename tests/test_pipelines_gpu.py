@@ -240,3 +240,106 @@ def test_load_checkpoint_class_count_surgery(tmp_path, trained_3_15):
     assert not fac2.loaded
     with pytest.raises(SystemExit):
         load_checkpoint(cfg, fac2, exit_on_fail=True)
+
+
+def test_per_patch_confusion_is_bit_exact(ctx, trained_3_15):
+    """fb_detect_strip_metrics (compute_metrics_patch of the compare loop, test/metrics.py:124-163): tile i's own
+    arg-max over its margin-cropped window against truth - 1, bit-exact w.r.t. numpy on the same logits, incl. the
+    clamped last row / column whose windows overlap other tiles; the maps equal the plain detect_strip."""
+    from flair1_b200.zone_detect.slicing_job import tile_table, tile_windows
+    from oracle import synth
+    from oracle.metrics_ref import patch_confusion
+    sd, _ = trained_3_15
+    W, H, T, margin = 900, 700, 512, 128
+    raster = synth.synth_raster(3, H, W, seed=5)
+    truth = synth.synth_mask(raster, 15, 3)
+    truth[::7, ::5] = 0          # wraps to 255 after - 1: dropped
+    truth[3::11, 2::9] = 17      # 16 after - 1: out of range, dropped
+    ctx.load_weights(sd, 3, 15)
+    ctx.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+    ctx.set_raster(torch.from_numpy(raster).cuda(), [0, 1, 2], W, H)
+    tiles, wins = tile_table(W, H, T, margin), tile_windows(W, H, T, margin)
+    cls = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    conf = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    cm = ctx.detect_strip_metrics(tiles, wins, T, 5, cls, conf, W, 0, torch.from_numpy(truth).cuda(), truth_sub=1).cpu().numpy()
+    cls2 = torch.zeros_like(cls)
+    conf2 = torch.zeros_like(conf)
+    ctx.detect_strip(tiles, T, 5, cls2, conf2, W, 0)
+    assert torch.equal(cls, cls2) and torch.equal(conf, conf2)
+    logits = ctx.forward_tiles(np.ascontiguousarray(tiles[:, :2]), T).cpu().numpy()[..., :15]
+    overlap = 0
+    for i, (x0, y0, a, b, c, d) in enumerate(wins):
+        pred = logits[i].argmax(-1)[b - y0:d - y0, a - x0:c - x0].astype(np.uint8)
+        ref = patch_confusion(truth[b:d, a:c] - np.uint8(1), pred, 15)
+        np.testing.assert_array_equal(cm[i], ref)
+        overlap += (d - b) * (c - a)
+    assert overlap > W * H     # the clamped windows really do overlap
+
+
+def test_flair_detect_batch_mode(tmp_path, trained_3_15):
+    """flair-detect -c -m -b over a department directory (main.py:440-497): two zones (one directory without
+    imagery and one without ground truth are skipped), two stitching methods; metrics.json holds one entry per
+    method with the metrics of the confusion matrices summed over the zones, computed from the prediction rasters
+    the run wrote; per-patch metrics of the compare loop land in metrics_per-patch_<dpt>_<zone>.json."""
+    from flair1_b200 import geotiff as gt
+    from flair1_b200.zone_detect import main as zmain
+    from flair1_b200.zone_detect.utils import read_config
+    from oracle import synth
+    from oracle.metrics_ref import class_IoU, clean_confmat, overall_accuracy, patch_confusion
+    sd, _ = trained_3_15
+    torch.save(sd, tmp_path / "weights.pth")
+    dpt_in, dpt_gt = tmp_path / "images" / "032_2019", tmp_path / "labels" / "032_2019"
+    truths = {}
+    for zi, (zone, (W, H)) in enumerate({"UA-zone_1": (700, 600), "UN_S-12_3": (640, 520)}.items()):
+        raster = synth.synth_raster(3, H, W, seed=40 + zi)
+        truths[zone] = synth.synth_mask(raster, 15, 3)
+        (dpt_in / zone).mkdir(parents=True)
+        (dpt_gt / zone).mkdir(parents=True)
+        tags = gt.georef_tags(800000.0, 6500000.0 + H * 0.2, 0.2, 0.2)
+        gt.write(dpt_in / zone / f"032_2019_{zone}_RGB.tif", raster, geo_tags=tags, compress="lzw", tiled=True, blocksize=256)
+        gt.write(dpt_gt / zone / f"032_2019_{zone}_MSK.tif", truths[zone], geo_tags=tags, compress="deflate", tiled=False, blocksize=64)
+    (dpt_in / "no_imagery").mkdir()
+    (dpt_in / "no_truth").mkdir()
+    gt.write(dpt_in / "no_truth" / "032_2019_no_truth_RGB.tif", synth.synth_raster(3, 64, 64, seed=1), compress="lzw", tiled=False, blocksize=64)
+    first = dpt_in / "UA-zone_1" / "032_2019_UA-zone_1_RGB.tif"
+    cfg = {"output_path": str(tmp_path / "out"), "output_name": "unused", "input_img_path": str(first), "input_path": str(dpt_in),
+           "truth_path": str(dpt_gt / "UA-zone_1" / "032_2019_UA-zone_1_MSK.tif"), "truth_root": str(tmp_path / "labels"),
+           "data_type": "RGB", "model_name": "resnet34-unet",
+           "channels": [1, 2, 3], "img_pixels_detection": 256, "margin": 32, "output_type": "argmax", "n_classes": 15,
+           "model_weights": str(tmp_path / "weights.pth"),
+           "model_framework": {"model_provider": "SegmentationModelsPytorch", "HuggingFace": {"org_model": None},
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}},
+           "batch_size": 4, "use_gpu": True, "num_worker": 2, "write_dataframe": False,
+           "norma_task": [{"norm_type": "custom", "norm_means": synth.FLAIR_MEANS[:3], "norm_stds": synth.FLAIR_STDS[:3]}],
+           "classes": CLASSES15, "overlap_strat": False,
+           "strategies": {"tiling": {"enabled": False, "size_range": [], "stride_range": []},
+                          "stitching": {"enabled": True, "methods": ["exact-clipping", "max"], "margin": [0.125]},
+                          "padding_overall": None}}
+    conf = tmp_path / "batch.yaml"
+    conf.write_text(yaml.safe_dump(cfg))
+    config = read_config(SimpleNamespace(conf=str(conf), metrics=True, batch_mode=True, compare=True))
+    gt_dpt = Path(config["truth_root"]) / Path(config["truth_path"]).parts[-3]
+    assert gt_dpt == dpt_gt
+    out = zmain.batch_metrics_pipeline(config, gt_dpt, torch.device("cuda", 0), True)
+    metrics = json.loads(Path(out).read_text())
+    assert Path(out).name == "metrics.json" and len(metrics) == 2
+    preds = sorted((tmp_path / "out").rglob("*.tif"))
+    assert len(preds) == 4 and all("-ARGMAX-S_size=256_stride=192_margin=32_padding=no-padding_stitching=" in p.name for p in preds)
+    for entry in metrics:
+        stitch = entry["Parameters values"][5]
+        assert entry["Parameters values"][:5] == ["resnet34-unet", 256, 192, 32, "no-padding"] and stitch in ("exact-clipping", "max")
+        cm = np.zeros((15, 15))
+        for zone, truth in truths.items():
+            (pp,) = [p for p in preds if f"_{zone}_RGB" in p.name and p.name.endswith(f"stitching={stitch}.tif")]
+            cm += patch_confusion(truth - np.uint8(1), gt.read(pp)[0], 15)
+        cleaned = clean_confmat(cm, CLASSES15)
+        assert entry["Avg_metrics"][0] == class_IoU(cleaned)[1] and entry["Avg_metrics"][1] == overall_accuracy(cleaned)
+        assert entry["Avg_metrics"][3] > 0 and len(entry["per_class_iou"]) == 12
+    per_patch = sorted((tmp_path / "out").rglob("metrics_per-patch_032_2019_*.json"))
+    assert len(per_patch) == 2
+    body = json.loads(per_patch[0].read_text())
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    assert len(body) == len(tile_table(700, 600, 256, 32))
+    (key, val), = body[0].items()
+    # first tile of the write order = bottom-left corner: window rows [600 - 192, 600)
+    assert key == "size=256_stride=192_margin=32_padding=no-padding_stitching=exact-clipping_0_408" and len(val["Avg_metrics"]) == 3
