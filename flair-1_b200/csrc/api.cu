@@ -77,8 +77,11 @@ struct fb_ctx {
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   double flops = 0;           // algorithmic FLOPs of the conv outputs actually computed since creation
-  int* list_dev = nullptr;    // active-tile list of the current conv launch
+  int* list_dev = nullptr;    // active-tile lists of the current network pass
   size_t list_cap = 0;        // in ints
+  fb::TileListPlan list_plan; // tiling of every decoder launch of the pass (make_tile_list)
+  size_t list_plan_ints = 0;
+  int plan_mode = 0;          // 1: planning walk (run_conv launches nothing), 2: real walk with planned lists
 
   // model
   bool loaded = false;
@@ -431,28 +434,48 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 }
 
 // ---------------------------------------------------------------------------------- graph
-// Active-tile list of one conv launch (tile_need.cuh): kernel tiles of th x tw pixels on the tile grid
-// (output grid / scale), gh x gw of them per image. *list stays null when every tile is active.
+// Active-tile lists (tile_need.cuh). The decoder of one network pass is walked twice: a planning walk in which
+// run_conv only reports the tiling of the kernel it would launch (kernel tiles of th x tw pixels on the tile grid
+// = output grid / scale, gh x gw of them per image) so that ONE build_tile_lists launch can expand the needed
+// regions of all eleven layers, then the real walk, in which every launch picks up its list.
+// *list stays null when every tile is active.
 int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, int th, int tw, int gh, int gw,
                    const int** list, long long* active) {
   *list = nullptr;
   const long long full = static_cast<long long>(B) * gh * gw;
   *active = full;
-  if (!need || !need->restrict_tiles || layer < 0 || need->n != B) return 0;
-  const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, th, tw);
-  if (cnt >= full) return 0;
-  if (static_cast<size_t>(full) > c->list_cap) {
+  if (!need || !need->restrict_tiles || layer < 0 || layer >= fb::kNeedLayers || need->n != B) return 0;
+  fb::TileListSpec& sp = c->list_plan.spec[layer];
+  if (c->plan_mode == 1) {
+    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, th, tw);
+    sp.layer = layer; sp.scale = scale; sp.th = th; sp.tw = tw; sp.gh = gh; sp.gw = gw;
+    sp.count = static_cast<int>(cnt);
+    sp.offset = static_cast<int>(c->list_plan_ints);
+    sp.use = cnt < full ? 1 : 0;
+    if (sp.use) c->list_plan_ints += static_cast<size_t>(cnt);
+    return 0;
+  }
+  if (sp.scale != scale || sp.th != th || sp.tw != tw || sp.gh != gh || sp.gw != gw)
+    return fail(c, FB_ERR_INVALID, "internal: tile list planned for another kernel tiling");
+  *active = sp.count;
+  if (sp.use) *list = c->list_dev + sp.offset;
+  return 0;
+}
+
+// After the planning walk: one launch builds every planned list of this pass.
+int build_planned_lists(fb_ctx* c, const NeedCtx* need) {
+  if (c->list_plan_ints == 0) return 0;
+  if (c->list_plan_ints > c->list_cap) {
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->list_dev) cudaFree(c->list_dev);
     c->list_dev = nullptr; c->list_cap = 0;
-    FB_CUDA(c, cudaMalloc(&c->list_dev, static_cast<size_t>(full) * sizeof(int)));
-    c->list_cap = static_cast<size_t>(full);
+    const size_t want = c->list_plan_ints + c->list_plan_ints / 4;
+    FB_CUDA(c, cudaMalloc(&c->list_dev, want * sizeof(int)));
+    c->list_cap = want;
   }
-  const int rc = fb::launch_build_tile_list(need->tiles_dev, B, need->T, layer, scale, th, tw, gh, gw, c->list_dev, c->stream);
+  const int rc = fb::launch_build_tile_lists(need->tiles_dev, need->n, need->T, c->list_plan, c->list_dev, c->stream);
   if (rc) return fail(c, rc, "tile list launch failed (code " + std::to_string(rc) + ")");
   c->launches++;
-  *list = c->list_dev;
-  *active = cnt;
   return 0;
 }
 
@@ -488,6 +511,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
       h.phase_mode = 1;
       fb::halo_fill_steps_phase(h);
       FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 8, x1.H / 16, x1.W / 8, &list, &active));
+      if (c->plan_mode == 1) return 0;
       if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
       c->flops += static_cast<double>(active) * (16 * 8 * 4) * L.flops_px;
       rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
@@ -512,6 +536,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     a.phase_mode = 1;
     if (out.up2 || out.elem != 2 || !fb::conv_tma_eligible(a)) return fail(c, FB_ERR_INVALID, "internal: phase-form conv not eligible");
     FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 8, 16, Hout / 16, Wout / 32, &list, &active));
+    if (c->plan_mode == 1) return 0;
     if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }
     c->flops += static_cast<double>(active) * (8 * 16 * 4) * L.flops_px;
     rc = fb::launch_conv(a, L.w_phase, L.Kp_phase, true, c->num_sms, c->stream);
@@ -539,6 +564,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     fb::halo_fill_steps(h, L.KH, L.stride);
     const int tw = 8 * fb::halo_blocks(L.KH, fb::halo_group_channels(L.KH, C1, C2) / 8, L.Cout);
     FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active));
+    if (c->plan_mode == 1) return 0;
     if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
     c->flops += static_cast<double>(active) * (16 * tw) * L.flops_px;
     if (sink && need && out.elem == 4 && L.Cout == 16 && h.direct_store && !out.up2) {
@@ -573,9 +599,11 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     const char* pair_env = getenv("FB_PAIR");
     if (tma && !(pair_env && pair_env[0] == '1')) {
       FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active));
+      if (c->plan_mode == 1) return 0;
       if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }
       c->flops += static_cast<double>(active) * (8 * 16) * L.flops_px;
     } else {
+      if (c->plan_mode == 1) return 0;
       c->flops += static_cast<double>(x1.B) * Hout * Wout * L.flops_px;
     }
     rc = fb::launch_conv(a, L.w, L.Kpad, tma, c->num_sms, c->stream);
@@ -625,17 +653,34 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
     }
   }
   const char* skips[5] = {"layer3.5.out", "layer2.3.out", "layer1.2.out", "f1", nullptr};
-  for (int d = 0; d < 5; ++d) {
-    char nm[64];
-    snprintf(nm, sizeof nm, "dec%d", d);
-    const std::string base(nm);
-    FB_TRY(run_conv(c, L(base + ".conv1"), A(cur), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid"),
-                    c->dec_phase[d], need, 2 * d));
-    FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base), false, need, 2 * d + 1));
-    cur = base;
+  const std::string enc_out = cur;
+  auto decoder = [&]() -> int {
+    std::string x = enc_out;
+    for (int d = 0; d < 5; ++d) {
+      char nm[64];
+      snprintf(nm, sizeof nm, "dec%d", d);
+      const std::string base(nm);
+      FB_TRY(run_conv(c, L(base + ".conv1"), A(x), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid"),
+                      c->dec_phase[d], need, 2 * d));
+      FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base), false, need, 2 * d + 1));
+      x = base;
+    }
+    return run_conv(c, L("head"), A(x), nullptr, nullptr, nullptr, false, A("logits"), false, need, 10, sink, sunk);
+  };
+  if (need && need->restrict_tiles) {
+    memset(&c->list_plan, 0, sizeof c->list_plan);
+    c->list_plan_ints = 0;
+    c->plan_mode = 1;
+    const int rc = decoder();
+    c->plan_mode = 0;
+    if (rc) return rc;
+    FB_TRY(build_planned_lists(c, need));
+    c->plan_mode = 2;
+    const int rc2 = decoder();
+    c->plan_mode = 0;
+    return rc2;
   }
-  FB_TRY(run_conv(c, L("head"), A(cur), nullptr, nullptr, nullptr, false, A("logits"), false, need, 10, sink, sunk));
-  return 0;
+  return decoder();
 }
 
 int run_extract(fb_ctx* c, const uint8_t* raster, int layout, int bands_total, const int* band_idx_dev,

@@ -46,10 +46,16 @@ struct Geo {
 // 16 x 8 block of the LOW-res grid, the MB = 4 accumulators are the four output phases (oh%2, ow%2), each
 // a 2x2-tap conv on the same staged halo with phase-specific (pre-summed) weights; outputs land at
 // (2*h + pa, 2*w + pb) of the [B, 2*Hin, 2*Win, Cout] tensor.
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false>
-__global__ void __launch_bounds__(kThreads, Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
+// EPI = epilogue warp groups (1 or 2). With 2, warps 8-11 drain the odd 128-pixel blocks of every tile while warps
+// 4-7 drain the even ones (direct-store mode only; a warp may only touch the TMEM lanes of its quarter, warp % 4,
+// so a group is always four warps). Used for the one-CTA-per-SM configurations, whose drain (64 accumulator
+// columns + residual per block) otherwise outlasts the MMAs of the next tile.
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1>
+__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  static_assert(EPI == 1 || (G::OCC == 1 && !PH && MB % 2 == 0), "two epilogue groups: one CTA per SM, even block count");
+  constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   static_assert(!PH || (MB == 4 && KH == 3 && STRIDE == 1), "phase form: 4 accumulators on a 3x3 stride-1 halo");
   constexpr int S = G::STAGES;
   constexpr int kBarBytes = ((2 * S + 4) * 8 + 16 + 127) / 128 * 128;
@@ -78,7 +84,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     const uint4* src = reinterpret_cast<const uint4*>(p.wpacked);
     uint4* dst = reinterpret_cast<uint4*>(smem);
     if (!(p.debug_skip & 16))
-      for (int i = threadIdx.x; i < wbytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+      for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + i);
     if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
   if (warp == kMmaWarp) {
@@ -89,7 +95,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 128);
+        mbar_init(tempty_bar(a), 128 * EPI);
       }
       fence_mbar_init();
     }
@@ -191,6 +197,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     const int q = warp & 3;
+    const int grp = warp >= 8 ? 1 : 0;   // second epilogue group (EPI == 2): odd blocks, direct stores only
     uint8_t* stg = smem + (bars - smem_base) + kBarBytes + q * kStgWarpBytes;
     const bool f32 = p.out_f32 != nullptr;
     const int elem = f32 ? 4 : 2;
@@ -245,7 +252,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         uint32_t rbuf[kResBuf][BN / 16][8];
         const bool has_res = !PH && p.residual != nullptr;
         const __nv_bfloat16* res_row0 = p.residual + ((static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow) * BN;
-        if (has_res) {
+        if (EPI == 2) {
+          // this group's blocks: m = grp, grp + 2, ...; residual rows one block (of the group) ahead
+          if (has_res) load_residual_row<BN>(res_row0 + 8 * grp * BN, rbuf[0]);
+        } else if (has_res) {
           if (kResBuf == MB) {
 #pragma unroll
             for (int m = 0; m < MB; ++m) load_residual_row<BN>(res_row0 + 8 * m * BN, rbuf[m % kResBuf]);
@@ -254,8 +264,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           }
         }
 #pragma unroll
-        for (int m = 0; m < MB; ++m) {
-          if (has_res && kResBuf != MB && m + 1 < MB) load_residual_row<BN>(res_row0 + 8 * (m + 1) * BN, rbuf[(m + 1) % kResBuf]);
+        for (int mi = 0; mi < MB / EPI; ++mi) {
+          const int m = EPI == 2 ? 2 * mi + grp : mi;
+          if (EPI == 2) {
+            if (has_res && mi + 1 < MB / EPI) load_residual_row<BN>(res_row0 + 8 * (m + 2) * BN, rbuf[(mi + 1) % kResBuf]);
+          } else if (has_res && kResBuf != MB && m + 1 < MB) {
+            load_residual_row<BN>(res_row0 + 8 * (m + 1) * BN, rbuf[(m + 1) % kResBuf]);
+          }
           long long dpix, own_pix = 0;
           if (PH) {
             dpix = (static_cast<long long>(tb) * p.Hout + 2 * oh + (m >> 1)) * p.Wout + 2 * ow + (m & 1);
@@ -296,8 +311,16 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
             }
           };
           epilogue_tile<BN, true, true, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
-                                                    tb * p.Hout + oh, direct, rbuf[m % kResBuf]);
+                                                    tb * p.Hout + oh, direct, rbuf[(EPI == 2 ? mi : m) % kResBuf]);
         }
+        tc_fence_before_sync();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
+      if (EPI == 2 && grp == 1) {
+        // staged copy-out (2x2-replicated outputs) is done by the first group alone
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after_sync();
         tc_fence_before_sync();
         mbar_arrive(tempty_bar(as));
         continue;
@@ -401,8 +424,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   }
 }
 
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false>
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
+  constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   const int groups = a.groups1 + a.groups2;
   const int wbytes = (PH ? MB : 1) * groups * a.nsteps * 2 * BN * 16;
@@ -411,15 +435,15 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH>, kThreads, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>, kThreadsK, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
@@ -429,7 +453,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
-  conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH><<<grid, kThreads, smem, stream>>>(a);
+  conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI><<<grid, kThreadsK, smem, stream>>>(a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -635,6 +659,14 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   const int nch = cg / 8;
   if (!halo_supported(KH, stride, a.C1, a.C2, a.Cout, a.Hout, a.Wout)) return -3001;
   if (a.nsteps <= 0 || a.nsteps > kHaloMaxSteps) return -3002;
+  // two epilogue groups for the one-CTA-per-SM configurations (FB_EPI2=0: one group, for A/B runs)
+  const char* e2 = getenv("FB_EPI2");
+  const bool epi2 = !(e2 && e2[0] == '0') && a.direct_store;
+  if (epi2) {
+    if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2, false, 2>(a, num_sms, stream);
+    if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32, 2, false, 2>(a, num_sms, stream);
+    if (nch == 8 && a.Cout == 64) return launch_halo_t<3, 1, 8, 64, 2, false, 2>(a, num_sms, stream);
+  }
   if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2>(a, num_sms, stream);
   if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4>(a, num_sms, stream);
   if (nch == 4 && a.Cout == 16) return launch_halo_t<3, 1, 4, 16, 2>(a, num_sms, stream);

@@ -18,22 +18,29 @@ constexpr int kNumProducerThreads = 128;  // warps 0-3
 constexpr int kNumEpilogueThreads = 128;  // warps 4-7
 constexpr int kNumThreads = 288;          // + warp 8 (MMA issuer / TMEM owner)
 
-template <int BN>
+// EPI = epilogue warp groups. With 2, warps 9-12 form a second group of four and every accumulator tile is
+// drained by both: group g takes columns [g*BN/2, (g+1)*BN/2) (a warp may only touch the 32 TMEM lanes of its
+// own quarter, warp % 4, so a group always needs one warp per quarter). For BN <= 128 the drain of a tile
+// otherwise takes longer than the MMAs of the next one and the tensor pipe idles on "accumulator empty".
+template <int BN, int EPI = 1>
 struct Cfg {
-  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kThreads = EPI == 2 ? 416 : kNumThreads;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 && EPI == 2) ? 5 : 6;
   static constexpr int kABytes = kBM * kBK * 2;  // 16384
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + 4 * kStgWarpBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + 4 * EPI * kStgWarpBytes;
 };
 
-template <int BN, bool TMA_A>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <int BN, bool TMA_A, int EPI = 1>
+__global__ void __launch_bounds__((Cfg<BN, EPI>::kThreads), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
+  static_assert(EPI == 1 || (TMA_A && BN % 32 == 0), "two epilogue groups: TMA producer, BN/2 a multiple of 16");
+  constexpr int BNE = BN / EPI;   // accumulator columns drained by one epilogue group
   constexpr int S = C::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -59,7 +66,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), kNumEpilogueThreads);
+        mbar_init(tempty_bar(a), kNumEpilogueThreads * EPI);
       }
       fence_mbar_init();
       if (TMA_A) {
@@ -170,13 +177,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp != 8) {
     // ===================================================================== epilogue
     const int q = warp & 3;            // TMEM lane quarter this warp may access (tile rows 32q..32q+31)
+    const int grp = warp > 8 ? 1 : 0;  // second group (EPI == 2): the upper half of the accumulator columns
     const int tiles_w = (TMA_A ? p.tgrid_w : p.Wout) >> 4, tiles_h = (TMA_A ? p.tgrid_h : p.Hout) >> 3;
     const int phases = (TMA_A && p.phase_mode) ? 4 : 1;
     const int HWo = p.Hout * p.Wout;
-    uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + q * kStgWarpBytes;
+    uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + (grp * 4 + q) * kStgWarpBytes;
     const bool f32 = p.out_f32 != nullptr;
     const int elem = f32 ? 4 : 2;
     const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
@@ -185,7 +193,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // TMA tiles are 8 x 16 pixel boxes: row r of the tile is pixel (r / 16, r % 16) of the box. In phase
     // mode the box lives on the low-res grid and pixel (dh, dw) lands at (2*dh + pa, 2*dw + pb).
     const int osc = (p.up2_out || phases == 4) ? 2 : 1;
-    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BNE>::GC_F32 * 4 : EpiRun<BNE>::GC_BF16 * 2,
                                     p.up2_out ? 2 * p.Wout : p.Wout, osc,
                                     [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
     uint32_t tcount = 0;
@@ -196,7 +204,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m_tile = (TMA_A && p.tile_list != nullptr) ? __ldg(p.tile_list + rest / phases) : rest / phases;
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + grp * BNE;
+      const int n0 = n_tile * BN + grp * BNE;   // first output channel this warp drains
       if (TMA_A) {
         const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tb = m_tile / (tiles_w * tiles_h);
         const int pa = phase >> 1, pb = phase & 1;
@@ -233,8 +242,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               store_regs(d + up_row_bytes + pixel_bytes, regs);
             }
           };
-          epilogue_tile<BN, true, false, true>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true, own_pix,
-                                                     tb * p.Hout + oh, direct);
+          epilogue_tile<BNE, true, false, true>(p, p.bias, taddr, tfull_bar(as), aph, lane, n0, stg, true, own_pix,
+                                                      tb * p.Hout + oh, direct);
           tc_fence_before_sync();
           mbar_arrive(tempty_bar(as));
           continue;
@@ -243,8 +252,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           warp_copy_out_fast<decltype(run)::value>(stg, lane, L, tile_dst + static_cast<size_t>(col0) * el, pixel_bytes,
                                                    p.up2_out, up_row_bytes);
         };
-        epilogue_tile<BN, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
-                                             (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
+        epilogue_tile<BNE, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n0, stg, true,
+                                              (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
       } else {
         // gather tiles are 128 consecutive pixels of the flattened (b, h, w) index space, possibly ragged
         auto rowfn = [&](int r, int& b, int& oh, int& ow) -> bool {
@@ -260,8 +269,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         };
         int b, oh, ow;
         const bool valid = rowfn(q * 32 + lane, b, oh, ow);
-        epilogue_tile<BN, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, valid,
-                                             static_cast<long long>(m_tile) * kBM + q * 32 + lane, b * p.Hout + oh, copy);
+        epilogue_tile<BNE, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n0, stg, valid,
+                                              static_cast<long long>(m_tile) * kBM + q * 32 + lane, b * p.Hout + oh, copy);
       }
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(as));
@@ -482,18 +491,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
-template <int BN, bool TMA_A>
+template <int BN, bool TMA_A, int EPI = 1>
 int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvArgs& a,
              int grid, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, TMA_A>,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, TMA_A, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_igemm_kernel<BN, TMA_A><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
+  conv_igemm_kernel<BN, TMA_A, EPI><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -665,6 +674,14 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   const int num_tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (grid <= 0) return 0;
+
+  // two epilogue warp groups where the drain of a tile is longer than the next tile's MMAs (FB_EPI2=0: one group)
+  {
+    const char* e2 = getenv("FB_EPI2");
+    const bool epi2 = use_tma_a && !(e2 && e2[0] == '0');
+    if (epi2 && BN == 128) return launch_t<128, true, 2>(tmA, tmA2, tmB, a, grid, stream);
+    if (epi2 && BN == 64) return launch_t<64, true, 2>(tmA, tmA2, tmB, a, grid, stream);
+  }
 
 #define FB_DISPATCH(BN_)                                                               \
   case BN_:                                                                            \

@@ -12,9 +12,10 @@
 namespace fb {
 
 // ------------------------------------------------------------------------------------------ K1
-// One thread per output pixel: gathers `c` band bytes (coalesced along x for the planar layout),
+// One thread per four consecutive output pixels of a tile row (blockIdx.y = tile): gathers their `c` band bytes
+// (all loads of the four pixels are issued before the first use, coalesced along x for the planar layout),
 // maps each through a 256-entry bf16 table (the host builds it in float64 -> float32 -> bf16 so the
-// result is bit-identical to rounding the reference's float32 tensor), writes 8 bf16 (16 bytes).
+// result is bit-identical to rounding the reference's float32 tensor), writes 4 x 8 bf16 (64 contiguous bytes).
 // Pixels outside the raster read raw 0 *before* normalisation (rasterio boundless=True semantics).
 __global__ void __launch_bounds__(256)
 extract_normalise_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int bands_total,
@@ -26,31 +27,34 @@ extract_normalise_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int
   for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_lut[i] = lut[i];
   if (threadIdx.x < 8) s_band[threadIdx.x] = threadIdx.x < c ? band_idx[threadIdx.x] : 0;
   __syncthreads();
-  const long long total = static_cast<long long>(n) * T * T;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int t = static_cast<int>(idx / (static_cast<long long>(T) * T));
-    const int rem = static_cast<int>(idx - static_cast<long long>(t) * T * T);
-    const int y = rem / T, x = rem - y * T;
-    const long long rx = tile_xy[2 * t] + static_cast<long long>(x);
-    const long long ry = tile_xy[2 * t + 1] + static_cast<long long>(y);
-    const bool inside = rx >= 0 && rx < W && ry >= 0 && ry < H && ry >= row0 && ry < row0 + rows;
-    __align__(16) __nv_bfloat16 v[8];
+  const int t = blockIdx.y;
+  const int TQ = T >> 2;
+  const int quads = T * TQ;
+  const long long tx0 = tile_xy[2 * t], ty0 = tile_xy[2 * t + 1];
+  __nv_bfloat16* tile_out = out + static_cast<long long>(t) * T * T * 8;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+    const int y = q / TQ, x = (q - y * TQ) << 2;
+    const long long ry = ty0 + y, rx = tx0 + x;
+    const bool row_ok = ry >= 0 && ry < H && ry >= row0 && ry < row0 + rows;
+    const long long ly = ry - row0;
+    unsigned raw[8][4];
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
-      if (ch < c) {
-        unsigned raw = 0;
-        if (inside) {
-          const long long ly = ry - row0;
-          raw = layout_hwc ? raster[(ly * W + rx) * bands_total + s_band[ch]]
-                           : raster[(static_cast<long long>(s_band[ch]) * rows + ly) * W + rx];
-        }
-        v[ch] = s_lut[ch * 256 + raw];
-      } else {
-        v[ch] = __float2bfloat16(0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        raw[ch][j] = 0;
+        if (ch < c && row_ok && rx + j >= 0 && rx + j < W)
+          raw[ch][j] = layout_hwc ? raster[(ly * W + rx + j) * bands_total + s_band[ch]]
+                                  : raster[(static_cast<long long>(s_band[ch]) * rows + ly) * W + rx + j];
       }
     }
-    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) v[ch] = ch < c ? s_lut[ch * 256 + raw[ch][j]] : __float2bfloat16(0.f);
+      *reinterpret_cast<uint4*>(tile_out + (static_cast<long long>(y) * T + x + j) * 8) = *reinterpret_cast<const uint4*>(v);
+    }
   }
 }
 
@@ -58,12 +62,15 @@ int launch_extract_normalise(const uint8_t* raster, int layout_hwc, int bands_to
                              int c, long long W, long long H, long long row0, long long rows,
                              const int* tile_xy, int n, int T, const __nv_bfloat16* lut,
                              __nv_bfloat16* out, int num_sms, cudaStream_t stream) {
-  const long long total = static_cast<long long>(n) * T * T;
-  if (total == 0) return 0;
-  long long blocks = (total + 255) / 256;
-  const long long cap = static_cast<long long>(num_sms) * 8;
-  if (blocks > cap) blocks = cap;
-  extract_normalise_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+  if (n <= 0 || T <= 0) return 0;
+  if (T % 4 != 0) return -2003;
+  // ~8 resident blocks per SM over the whole batch, at least one block per tile
+  int bx = (num_sms * 8 + n - 1) / n;
+  const int need = (T * (T / 4) + 255) / 256;
+  if (bx > need) bx = need;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  extract_normalise_kernel<<<grid, 256, 0, stream>>>(
       raster, layout_hwc, bands_total, band_idx, c, W, H, row0, rows, tile_xy, n, T, lut, out);
   return static_cast<int>(cudaGetLastError());
 }
@@ -482,16 +489,19 @@ int launch_tile_confusion(const float* logits, int ncls, int n, int T, const int
 constexpr int kListMaxImages = 1024;
 
 __global__ void __launch_bounds__(256)
-build_tile_list_kernel(const int* __restrict__ tiles, int n, int T, int layer, int scale, int th, int tw, int gh,
-                       int gw, int* __restrict__ list) {
+build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __grid_constant__ TileListPlan plan,
+                        int* __restrict__ list_base) {
   __shared__ int off[kListMaxImages + 1];
   __shared__ NeedRect rng[kListMaxImages];
+  const TileListSpec& sp = plan.spec[blockIdx.x];
+  if (!sp.use) return;
+  int* list = list_base + sp.offset;
   for (int b = threadIdx.x; b < n; b += blockDim.x) {
     const int* t = tiles + 6 * b;
-    const NeedRect r = need_rect(T, layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
-    NeedRect k = need_tile_range(r, scale, th, tw);
-    if (k.x1 > gw) k.x1 = gw;
-    if (k.y1 > gh) k.y1 = gh;
+    const NeedRect r = need_rect(T, sp.layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
+    NeedRect k = need_tile_range(r, sp.scale, sp.th, sp.tw);
+    if (k.x1 > sp.gw) k.x1 = sp.gw;
+    if (k.y1 > sp.gh) k.y1 = sp.gh;
     rng[b] = k;
     off[b + 1] = (k.x1 - k.x0) * (k.y1 - k.y0);
   }
@@ -505,15 +515,15 @@ build_tile_list_kernel(const int* __restrict__ tiles, int n, int T, int layer, i
   for (int b = warp; b < n; b += blockDim.x >> 5) {
     const NeedRect k = rng[b];
     const int nx = k.x1 - k.x0, cnt = off[b + 1] - off[b];
-    for (int i = lane; i < cnt; i += 32) list[off[b] + i] = (b * gh + k.y0 + i / nx) * gw + k.x0 + i % nx;
+    for (int i = lane; i < cnt; i += 32) list[off[b] + i] = (b * sp.gh + k.y0 + i / nx) * sp.gw + k.x0 + i % nx;
   }
 }
 
-int launch_build_tile_list(const int* tiles_dev, int n, int T, int layer, int scale, int th, int tw, int gh, int gw,
-                           int* list_dev, cudaStream_t stream) {
+int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPlan& plan, int* list_dev,
+                            cudaStream_t stream) {
   if (n <= 0) return 0;
   if (n > kListMaxImages) return -2101;
-  build_tile_list_kernel<<<1, 256, 0, stream>>>(tiles_dev, n, T, layer, scale, th, tw, gh, gw, list_dev);
+  build_tile_lists_kernel<<<kNeedLayers, 256, 0, stream>>>(tiles_dev, n, T, plan, list_dev);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -65,11 +65,22 @@ __host__ __device__ inline NeedRect need_tile_range(NeedRect r, int scale, int t
   return t;
 }
 
-// tiles: int32 [n][6] = x0, y0, wx0, wy0, wx1, wy1 (fb_tile). list[i] = (b * gh + ty) * gw + tx of the i-th active
-// kernel tile, images in order. gh x gw = kernel tiles per image. Returns cudaError_t as int.
-int launch_build_tile_list(const int* tiles_dev, int n, int T, int layer, int scale, int th, int tw, int gh, int gw,
-                           int* list_dev, cudaStream_t stream);
-// The same count on the host (tiles = host copy of the same table).
+// One conv launch's kernel tiling: tiles of th x tw pixels on the tile grid (= output grid / scale), gh x gw of them
+// per image; its active tiles go to list[offset .. offset + count), entries (b * gh + ty) * gw + tx, images in order.
+struct TileListSpec {
+  int layer, scale, th, tw, gh, gw;
+  int offset, count;
+  int use;   // 0: every tile is active, no list is built
+};
+struct TileListPlan {
+  TileListSpec spec[kNeedLayers];
+};
+
+// tiles: int32 [n][6] = x0, y0, wx0, wy0, wx1, wy1 (fb_tile). Builds every list of the plan in one launch (one
+// block per layer). Returns cudaError_t as int.
+int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPlan& plan, int* list_dev,
+                            cudaStream_t stream);
+// The count of one list on the host (tiles = host copy of the same table).
 long long count_active_tiles(const int* tiles_host, int n, int T, int layer, int scale, int th, int tw);
 
 }  // namespace fb
