@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <functional>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -100,6 +102,8 @@ struct fb_ctx {
   size_t raster_own_bytes = 0;
   uint8_t* maps_own = nullptr;   // class / confidence maps of fb_detect_zone_host
   size_t maps_own_bytes = 0;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of fb_detect_zone_host (non-blocking)
+  std::vector<cudaEvent_t> copy_events;                     // grow-only pool, timing disabled
   int bands_total = 0, rc = 0, layout = 0;
   int64_t W = 0, H = 0, row0 = 0, rows = 0;
   int* band_idx_dev = nullptr;
@@ -787,6 +791,9 @@ void fb_destroy(fb_ctx* c) {
   if (c->lut) cudaFree(c->lut);
   if (c->raster_own) cudaFree(c->raster_own);
   if (c->maps_own) cudaFree(c->maps_own);
+  for (cudaEvent_t e : c->copy_events) cudaEventDestroy(e);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->band_idx_dev) cudaFree(c->band_idx_dev);
   if (c->arena) cudaFree(c->arena);
   if (c->tile_xy_dev) cudaFree(c->tile_xy_dev);
@@ -955,6 +962,9 @@ struct DetectSink {
   const uint8_t* truth = nullptr;
   int truth_sub = 0;
   int64_t* tile_cm = nullptr;
+  // called on the host right before the first launch / right after the last launch of the batch of tiles
+  // [i0, i0 + nb) (fb_detect_zone_host hangs its copy-stream dependencies here)
+  std::function<int(int, int)> before_batch, after_batch;
 };
 
 int check_write_rects(fb_ctx* c, const fb_tile* tiles, int n, int tile, int64_t map_w, int64_t map_row0) {
@@ -1066,6 +1076,7 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
   for (int i0 = 0; i0 < n; i0 += batch) {
     const int nb = (n - i0 < batch) ? n - i0 : batch;
     if (nb != c->arena_n) FB_TRY(ensure_arena(c, nb, tile));  // ragged last batch: re-plan inside the same block
+    if (s.before_batch) FB_TRY(s.before_batch(i0, nb));
     FB_TRY(run_extract(c, c->raster, c->layout, c->bands_total, c->band_idx_dev, c->rc, c->W, c->H, c->row0,
                        c->rows, c->tile_xy_dev + 2 * i0, nb, tile));
     // exact clipping (kinds 0 and 1) only ever reads the logits inside the write rectangles: the decoder computes
@@ -1079,7 +1090,10 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
     hs.cls = s.cls; hs.conf = s.conf; hs.map_w = s.map_w; hs.map_row0 = s.map_row0;
     bool sunk = false;
     FB_TRY(run_network(c, nb, tile, nullptr, &need, (s.kind == 0 && !c->no_fused_sink && !s.tile_cm) ? &hs : nullptr, &sunk));
-    if (sunk) continue;
+    if (sunk) {
+      if (s.after_batch) FB_TRY(s.after_batch(i0, nb));
+      continue;
+    }
     ProfScope ps(c, 3);
     const float* logits = static_cast<const float*>(c->acts["logits"].ptr);
     int rc;
@@ -1099,6 +1113,7 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
       if (rc) return fail(c, rc, "tile confusion launch failed");
       c->launches++;
     }
+    if (s.after_batch) FB_TRY(s.after_batch(i0, nb));
   }
   return 0;
 }
@@ -1106,14 +1121,37 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
 
 extern "C" {
 
+// Host buffers in, host buffers out, software-pipelined: the raster goes up in row chunks on a copy stream while
+// the compute stream already works on the tile rows whose pixels have landed, and every class-map row is sent
+// back on a second copy stream as soon as no remaining tile can write it. The tiles are processed by rows
+// (sorted by y0) for that; their write rectangles are disjoint by contract (fb_tile), so the order in which
+// they run does not change a byte of the result.
 int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
                         int nc, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
                         const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
                         uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows) {
-  if (!c || !host_cls || map_w <= 0 || map_rows <= 0) return FB_ERR_INVALID;
-  FB_TRY(fb_upload_raster(c, host_raster, bands_total, band_idx, nc, W, H, row0, rows, layout));
+  if (!c || !host_cls || !host_raster || !band_idx || map_w <= 0 || map_rows <= 0 || (n > 0 && !tiles) || n < 0 || batch <= 0)
+    return FB_ERR_INVALID;
+  FB_TRY(check_ready(c, false, tile));
+  FB_TRY(set_raster_common(c, bands_total, band_idx, nc, W, H, row0, rows, layout));
+  FB_TRY(check_write_rects(c, tiles, n, tile, map_w, map_row0));
+  for (int i = 0; i < n; ++i)
+    if (tiles[i].wy1 > tiles[i].wy0 && tiles[i].wy1 > map_row0 + map_rows)
+      return fail(c, FB_ERR_INVALID, "detect: write rectangle below the map");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  const size_t rbytes = static_cast<size_t>(bands_total) * rows * W;
   const size_t mbytes = static_cast<size_t>(map_w) * map_rows;
-  // context-owned, grow-only map buffer (a cudaMalloc/cudaFree pair per call would serialise the device)
+  // context-owned, grow-only buffers (a cudaMalloc/cudaFree pair per call would serialise the device)
+  if (rbytes > c->raster_own_bytes) {
+    FB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->raster_own) cudaFree(c->raster_own);
+    c->raster_own = nullptr; c->raster_own_bytes = 0;
+    if (cudaMalloc(&c->raster_own, rbytes) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(c, FB_ERR_OOM, "raster upload: cudaMalloc failed");
+    }
+    c->raster_own_bytes = rbytes;
+  }
   if (mbytes * 2 > c->maps_own_bytes) {
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->maps_own) cudaFree(c->maps_own);
@@ -1124,17 +1162,94 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
     }
     c->maps_own_bytes = mbytes * 2;
   }
+  if (!c->h2d_stream) FB_CUDA(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  if (!c->d2h_stream) FB_CUDA(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  c->raster = c->raster_own;
   uint8_t* maps = c->maps_own;
-  int rc = 0;
-  cudaError_t e = cudaMemsetAsync(maps, 0, mbytes * (host_conf ? 2 : 1), c->stream);
-  if (e != cudaSuccess) rc = cuda_fail(c, e, "cudaMemsetAsync");
-  if (!rc) rc = fb_detect_strip(c, tiles, n, tile, batch, maps, host_conf ? maps + mbytes : nullptr, map_w, map_row0);
-  if (!rc) {
-    e = cudaMemcpyAsync(host_cls, maps, mbytes, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && host_conf) e = cudaMemcpyAsync(host_conf, maps + mbytes, mbytes, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) rc = cuda_fail(c, e, "class map download");
+  uint8_t* conf_dev = host_conf ? maps + mbytes : nullptr;
+
+  // tiles by rows
+  std::vector<fb_tile> sorted(tiles, tiles + n);
+  std::stable_sort(sorted.begin(), sorted.end(), [](const fb_tile& a, const fb_tile& b) { return a.y0 < b.y0; });
+  // suffix minimum of the first written row: after tile i, map rows below low_after[i + 1] are final
+  std::vector<int64_t> low_after(static_cast<size_t>(n) + 1, map_row0 + map_rows);
+  for (int i = n - 1; i >= 0; --i) {
+    const bool writes = sorted[i].wx1 > sorted[i].wx0 && sorted[i].wy1 > sorted[i].wy0;
+    low_after[i] = writes ? std::min<int64_t>(low_after[i + 1], sorted[i].wy0) : low_after[i + 1];
   }
+
+  // upload: chunks of raster rows, one event per chunk. Work already queued on the compute stream (an earlier
+  // call still reading the raster buffer) must finish before the first byte is overwritten.
+  const int64_t chunk_rows = 512;
+  const int nchunks = static_cast<int>((rows + chunk_rows - 1) / chunk_rows);
+  const size_t nbatches = static_cast<size_t>((n + batch - 1) / batch);
+  while (c->copy_events.size() < static_cast<size_t>(nchunks) + nbatches + 1) {
+    cudaEvent_t ev;
+    FB_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->copy_events.push_back(ev);
+  }
+  cudaEvent_t* ev_up = c->copy_events.data();
+  cudaEvent_t* ev_batch = c->copy_events.data() + nchunks;
+  cudaEvent_t ev_start = c->copy_events[static_cast<size_t>(nchunks) + nbatches];
+  FB_CUDA(c, cudaMemsetAsync(maps, 0, mbytes * (host_conf ? 2 : 1), c->stream));
+  FB_CUDA(c, cudaEventRecord(ev_start, c->stream));
+  FB_CUDA(c, cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
+  FB_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
+  for (int k = 0; k < nchunks; ++k) {
+    const int64_t r0 = k * chunk_rows, nr = std::min<int64_t>(chunk_rows, rows - r0);
+    if (layout == FB_LAYOUT_HWC) {
+      const size_t off = static_cast<size_t>(r0) * W * bands_total;
+      FB_CUDA(c, cudaMemcpyAsync(c->raster_own + off, host_raster + off, static_cast<size_t>(nr) * W * bands_total,
+                                 cudaMemcpyHostToDevice, c->h2d_stream));
+    } else {
+      for (int b = 0; b < bands_total; ++b) {
+        const size_t off = (static_cast<size_t>(b) * rows + r0) * W;
+        FB_CUDA(c, cudaMemcpyAsync(c->raster_own + off, host_raster + off, static_cast<size_t>(nr) * W,
+                                   cudaMemcpyHostToDevice, c->h2d_stream));
+      }
+    }
+    FB_CUDA(c, cudaEventRecord(ev_up[k], c->h2d_stream));
+  }
+
+  int64_t sent = map_row0;   // map rows [map_row0, sent) are already on their way to the host
+  auto send_rows = [&](int64_t upto) -> int {
+    if (upto <= sent) return 0;
+    const size_t off = static_cast<size_t>(sent - map_row0) * map_w, len = static_cast<size_t>(upto - sent) * map_w;
+    FB_CUDA(c, cudaMemcpyAsync(host_cls + off, maps + off, len, cudaMemcpyDeviceToHost, c->d2h_stream));
+    if (host_conf) FB_CUDA(c, cudaMemcpyAsync(host_conf + off, conf_dev + off, len, cudaMemcpyDeviceToHost, c->d2h_stream));
+    sent = upto;
+    return 0;
+  };
+  DetectSink s;
+  s.kind = 0; s.cls = maps; s.conf = conf_dev; s.map_w = map_w; s.map_row0 = map_row0;
+  s.before_batch = [&](int i0, int nb) -> int {
+    // the batch reads raster rows up to its lowest tile's bottom edge (the table is sorted by y0)
+    int64_t last = static_cast<int64_t>(sorted[i0 + nb - 1].y0) + tile - 1 - row0;
+    if (last < 0) return 0;
+    if (last > rows - 1) last = rows - 1;
+    FB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_up[last / chunk_rows], 0));
+    return 0;
+  };
+  s.after_batch = [&](int i0, int nb) -> int {
+    const size_t bi = static_cast<size_t>(i0 / batch);
+    FB_CUDA(c, cudaEventRecord(ev_batch[bi], c->stream));
+    FB_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, ev_batch[bi], 0));
+    return send_rows(low_after[i0 + nb]);
+  };
+  int rc = detect_loop(c, sorted.data(), n, tile, batch, s);
+  if (!rc) {
+    // whatever no tile wrote (or an empty table): the zeroed rows still go back
+    cudaError_t e = cudaEventRecord(ev_start, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->d2h_stream, ev_start, 0);
+    if (e != cudaSuccess) rc = cuda_fail(c, e, "class map download");
+    if (!rc) rc = send_rows(map_row0 + map_rows);
+  }
+  // every stream is drained before the host buffers are handed back, also on failure
+  cudaError_t e1 = cudaStreamSynchronize(c->h2d_stream);
+  cudaError_t e2 = cudaStreamSynchronize(c->d2h_stream);
+  cudaError_t e3 = cudaStreamSynchronize(c->stream);
+  if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+    rc = cuda_fail(c, e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3, "class map download");
   return rc;
 }
 
