@@ -378,6 +378,20 @@ class Context:
         self._check(self._lib.fb_debug_activation(self._h, name.encode(), out.data_ptr(), C.byref(cnt), dims))
         return out
 
+    def debug_input_tiles(self) -> torch.Tensor:
+        """The normalised tiles of the last forward pass as bf16 [n, T, T, in_channels], whichever way the library
+        stored them: [n, T, T, 8] (channel-padded) or, for <= 4 bands, the 2x2 space-to-depth form
+        [n, T/2, T/2, 16] with channel (py*2 + px)*in_channels + band (csrc/conv_halo.cuh). Padding lanes must be 0."""
+        x0 = self.debug_activation("x0")
+        c = self.in_channels
+        if x0.shape[-1] == 8:
+            assert bool((x0[..., c:] == 0).all())
+            return x0[..., :c].contiguous()
+        n, t2 = x0.shape[0], x0.shape[1]
+        assert x0.shape[-1] == 16 and bool((x0[..., 4 * c:] == 0).all())
+        g = x0[..., :4 * c].reshape(n, t2, t2, 2, 2, c)            # Y, X, py, px, band
+        return g.permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * t2, 2 * t2, c).contiguous()
+
     def profile_begin(self) -> None:
         self._check(self._lib.fb_profile_begin(self._h))
 

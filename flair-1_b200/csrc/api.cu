@@ -32,6 +32,7 @@ struct ConvLayer {
   __nv_bfloat16* w_phase = nullptr; // device [4][Cout][Kp_phase]: sub-pixel phase form of a decoder conv1 (or null)
   int Kp_phase = 0;
   __nv_bfloat16* w_halo_phase = nullptr;  // device, phase form for the halo-staged kernel (32 -> 16 channels) (or null)
+  __nv_bfloat16* w_s2d = nullptr;         // device, the stem as a 4x4 filter on the 2x2 space-to-depth image (<= 4 bands)
   float* bias = nullptr;            // device [Cout]
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
@@ -76,6 +77,8 @@ struct fb_ctx {
   bool no_halo = false;       // FB_NO_HALO=1: skip the halo-staged kernel
   bool no_phase = false;      // FB_NO_PHASE=1: decoder conv1 on the materialised upsample instead of sub-pixel phases
   bool dec_phase[6] = {false, false, false, false, false, false};  // per decoder block, decided by arena_plan
+  bool no_s2d = false;        // FB_NO_S2D=1: 7x7 stride-2 stem on the 8-channel-padded tile also for <= 4 bands
+  bool stem_s2d = false;      // decided by arena_plan: x0 is stored in space-to-depth form
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   double flops = 0;           // algorithmic FLOPs of the conv outputs actually computed since creation
@@ -250,6 +253,27 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
     c->owned.push_back(L.w_halo);
     FB_CUDA(c, cudaMemcpy(L.w_halo, hp.data(), n * 2, cudaMemcpyHostToDevice));
   }
+  // the stem on the 2x2 space-to-depth image (conv_halo.cuh): w2[o][(py*2+px)*Cin + c][a][b] = w[o][c][2a+py-1][2b+px-1]
+  if (name == "stem" && KH == 7 && stride == 2 && Cin <= 4 && Cout == 64) {
+    std::vector<float> w2(static_cast<size_t>(Cout) * 16 * 4 * 4, 0.f);
+    for (int o = 0; o < Cout; ++o)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b)
+            for (int py = 0; py < 2; ++py)
+              for (int px = 0; px < 2; ++px) {
+                const int kh = 2 * a + py - 1, kw = 2 * b + px - 1;
+                if (kh < 0 || kw < 0 || kh > 6 || kw > 6) continue;
+                w2[((static_cast<size_t>(o) * 16 + (py * 2 + px) * Cin + ci) * 4 + a) * 4 + b] =
+                    folded[((static_cast<size_t>(o) * Cin + ci) * 7 + kh) * 7 + kw];
+              }
+    const size_t n = fb::pack_halo_weights(w2.data(), Cout, CoutPad, 16, 16, 4, 1, 16, 0, nullptr);
+    std::vector<uint16_t> hp(n);
+    fb::pack_halo_weights(w2.data(), Cout, CoutPad, 16, 16, 4, 1, 16, 0, hp.data());
+    FB_CUDA(c, cudaMalloc(&L.w_s2d, n * 2));
+    c->owned.push_back(L.w_s2d);
+    FB_CUDA(c, cudaMemcpy(L.w_s2d, hp.data(), n * 2, cudaMemcpyHostToDevice));
+  }
   // third packing for decoder conv1 layers: the sub-pixel phase form (conv_igemm.cuh, ConvArgs::phase_mode).
   // x1 = the upsampled source: taps that read the same low-res pixel are summed in fp32 before the single
   // bf16 rounding. rows(a): output-row parity a, low-res tap di -> original taps {kh}.
@@ -358,7 +382,13 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
         it->second.w_halo_phase != nullptr && fb::halo_phase_supported(it->second.C1, it->second.C2, it->second.Cout, S_lo, S_lo))
       c->dec_phase[d] = true;
   }
-  arena_alloc(c, "x0", n, T, T, 8, 2, dry);
+  {
+    auto it = c->conv.find("stem");
+    c->stem_s2d = !c->no_s2d && !c->force_gather && !c->no_halo && it != c->conv.end() && it->second.w_s2d != nullptr &&
+                  c->in_ch <= 4 && fb::halo_supported(4, 1, 16, 0, 64, T / 2, T / 2);
+  }
+  if (c->stem_s2d) arena_alloc(c, "x0", n, T / 2, T / 2, 16, 2, dry);
+  else arena_alloc(c, "x0", n, T, T, 8, 2, dry);
   arena_alloc(c, "f1", n, T / 2, T / 2, 64, 2, dry);
   arena_alloc(c, "pool", n, T / 4, T / 4, 64, 2, dry);
   int S = T / 4;
@@ -624,7 +654,28 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
   auto L = [&](const std::string& k) -> const ConvLayer& { return c->conv[k]; };
   {
     ProfScope ps(c, 1);
-    FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, nullptr, nullptr, true, A("f1")));
+    if (c->stem_s2d) {
+      const ConvLayer& S = L("stem");
+      const Act& x0 = A("x0");
+      const Act& f1 = A("f1");
+      fb::HaloArgs h;
+      memset(&h, 0, sizeof h);
+      h.x1 = static_cast<const __nv_bfloat16*>(x0.ptr);
+      h.C1 = 16;
+      h.B = x0.B; h.Hin = x0.H; h.Win = x0.W; h.Hout = f1.H; h.Wout = f1.W;
+      h.Cout = S.Cout;
+      h.bias = S.bias;
+      h.relu = 1;
+      h.out = static_cast<__nv_bfloat16*>(f1.ptr);
+      h.wpacked = S.w_s2d;
+      fb::halo_fill_steps(h, 4, 1);
+      c->flops += static_cast<double>(f1.B) * f1.H * f1.W * S.flops_px;
+      const int rc = fb::launch_conv_halo(h, 4, 1, c->num_sms, c->stream);
+      if (rc != 0) return fail(c, rc, "stem (space-to-depth) launch failed (code " + std::to_string(rc) + ")");
+      c->launches++;
+    } else {
+      FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, nullptr, nullptr, true, A("f1")));
+    }
   }
   {
     ProfScope ps(c, 2);
@@ -690,9 +741,11 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
 int run_extract(fb_ctx* c, const uint8_t* raster, int layout, int bands_total, const int* band_idx_dev,
                 int rc_, int64_t W, int64_t H, int64_t row0, int64_t rows, const int* xy_dev, int n, int T) {
   ProfScope ps(c, 0);
-  int rc = fb::launch_extract_normalise(raster, layout, bands_total, band_idx_dev, rc_, W, H, row0, rows,
-                                        xy_dev, n, T, c->lut,
-                                        static_cast<__nv_bfloat16*>(c->acts["x0"].ptr), c->num_sms, c->stream);
+  int rc = c->stem_s2d
+               ? fb::launch_extract_normalise_s2d(raster, layout, bands_total, band_idx_dev, rc_, W, H, row0, rows, xy_dev, n, T,
+                                                  c->lut, static_cast<__nv_bfloat16*>(c->acts["x0"].ptr), c->num_sms, c->stream)
+               : fb::launch_extract_normalise(raster, layout, bands_total, band_idx_dev, rc_, W, H, row0, rows, xy_dev, n, T,
+                                              c->lut, static_cast<__nv_bfloat16*>(c->acts["x0"].ptr), c->num_sms, c->stream);
   if (rc) return fail(c, rc, "extract launch failed");
   c->launches++;
   return 0;
@@ -775,6 +828,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_halo = nh && nh[0] == '1';
   const char* np = getenv("FB_NO_PHASE");
   c->no_phase = np && np[0] == '1';
+  const char* ns = getenv("FB_NO_S2D");
+  c->no_s2d = ns && ns[0] == '1';
   const char* ft = getenv("FB_FULL_TILES");
   c->full_tiles = ft && ft[0] == '1';
   const char* nf = getenv("FB_NO_FUSED_SINK");
@@ -828,6 +883,7 @@ int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int
   c->owned.clear();
   c->conv.clear();
   c->loaded = false;
+  c->arena_n = 0;   // the arena plan depends on the model (input layout of the stem): re-plan on the next pass
 
   FB_TRY(build_conv(c, tm, "stem", "encoder.conv1.weight", "encoder.bn1", "", in_channels, 64, 7, 2, 3));
   int cin = 64;
@@ -1290,10 +1346,13 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
     for (int j = 0; j < nb && !rc; ++j) {
       const uint8_t* patch = dev_patches + static_cast<size_t>(i0 + j) * c->in_ch * tile * tile;
       ProfScope ps(c, 0);
-      rc = fb::launch_extract_normalise(patch, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
-                                        c->tile_xy_dev /* (0,0) */, 1, tile, c->lut,
-                                        static_cast<__nv_bfloat16*>(c->acts["x0"].ptr) + static_cast<size_t>(j) * tile * tile * 8,
-                                        c->num_sms, c->stream);
+      // (x0 holds 8 * tile * tile bf16 per patch in the plain layout, 16 * (tile/2)^2 in the space-to-depth one)
+      __nv_bfloat16* x0j = static_cast<__nv_bfloat16*>(c->acts["x0"].ptr) +
+                           static_cast<size_t>(j) * tile * tile * (c->stem_s2d ? 4 : 8);
+      rc = c->stem_s2d ? fb::launch_extract_normalise_s2d(patch, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
+                                                          c->tile_xy_dev /* (0,0) */, 1, tile, c->lut, x0j, c->num_sms, c->stream)
+                       : fb::launch_extract_normalise(patch, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
+                                                      c->tile_xy_dev /* (0,0) */, 1, tile, c->lut, x0j, c->num_sms, c->stream);
       if (rc) rc = fail(c, rc, "extract launch failed");
       c->launches++;
     }

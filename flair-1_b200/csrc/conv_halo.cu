@@ -460,7 +460,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 int halo_blocks(int KH, int nch, int bn) {
-  if (KH == 7) return 2;
+  if (KH == 7 || KH == 4) return 2;
   if (nch == 2) return 4;               // 16 -> 16 @ 512^2: 16 x 32 pixel tiles
   if (nch == 4 && bn == 16) return 2;   // 32 -> 16 @ 512^2 (two CTAs per SM)
   return 2;
@@ -492,6 +492,8 @@ int halo_group_channels(int KH, int C1, int C2) {
 bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int Wout) {
   if (Hout % kTH != 0) return false;
   if (KH == 7) return stride == 2 && C1 == 8 && C2 == 0 && Cout == 64 && Wout % (8 * halo_blocks(7, 1, 64)) == 0;
+  // the stem in space-to-depth form: 4x4 stride 1 on 16 channels (taps at rows oh-2 .. oh+1)
+  if (KH == 4) return stride == 1 && C1 == 16 && C2 == 0 && Cout == 64 && Wout % (8 * halo_blocks(4, 2, 64)) == 0;
   if (KH != 3 || stride != 1) return false;
   const int cg = halo_group_channels(KH, C1, C2);
   if (cg < 16 || C1 % cg != 0 || C2 % cg != 0) return false;
@@ -662,6 +664,8 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // two epilogue groups for the one-CTA-per-SM configurations (FB_EPI2=0: one group, for A/B runs)
   const char* e2 = getenv("FB_EPI2");
   const bool epi2 = !(e2 && e2[0] == '0') && a.direct_store;
+  if (KH == 4) return epi2 ? launch_halo_t<4, 1, 2, 64, 2, false, 2>(a, num_sms, stream)
+                           : launch_halo_t<4, 1, 2, 64, 2>(a, num_sms, stream);
   if (epi2) {
     if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2, false, 2>(a, num_sms, stream);
     if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32, 2, false, 2>(a, num_sms, stream);

@@ -2,6 +2,11 @@
 // channel-poor: the stem (7x7 stride 2 on the 8-channel-padded image), layer1 / dec2.conv2 (64 ch at
 // 128^2), dec3 (64+64 / 32 ch at 256^2), dec4 and the segmentation head (32 / 16 ch at 512^2).
 //
+// For models with <= 4 bands the stem runs in 2x2 space-to-depth form instead: the 7x7 stride-2 filter, padded with a
+// zero row and column in front, is a 4x4 stride-1 filter over [T/2][T/2][4*bands <= 16] (pixel (2Y+py, 2X+px), band c
+// -> channel (py*2+px)*bands + c; filter tap (kh, kw) -> tap ((kh+1)/2, (kw+1)/2) of phase ((kh+1)%2, (kw+1)%2)),
+// reading rows oh-2 .. oh+1: 16 K=16 steps instead of 28 and half the input bytes (KH = 4 instantiation).
+//
 // An im2col operand re-reads every input pixel KH*KW times. Here each CTA copies the (16*s+KH-s) x
 // (8*s+KW-s) input halo of its 16 x 8 output tile into shared memory ONCE, as planes of 16-byte cells
 // [channel-chunk][w-parity][h][w] (no swizzle), and every filter tap is just a different start address

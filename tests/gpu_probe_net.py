@@ -61,7 +61,7 @@ def main():
         imgs.append(torch.as_tensor(img, dtype=torch.float))
     x = torch.stack(imgs)
     acts = layer_activations(model, x)
-    x0 = ctx.debug_activation("x0").float().cpu()[..., :3].permute(0, 3, 1, 2)
+    x0 = ctx.debug_input_tiles().float().cpu().permute(0, 3, 1, 2)
     log(f"LAYER {'x0':14s} maxabs={(x0 - x).abs().max().item():.4e} (vs fp32 normalised input; bf16 rounding expected) "
         f"exact_vs_bf16={(x0 == x.to(torch.bfloat16).float()).all().item()}")
     names = ["f1", "pool"] + [f"layer{l}.{b}.out" for l, n in ((1, 3), (2, 4), (3, 6), (4, 3)) for b in range(n)] + \

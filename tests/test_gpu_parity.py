@@ -113,23 +113,51 @@ def test_extract_normalise_bit_exact(ctx, trained_3_15):
         ctx.set_raster(torch.from_numpy(raster).cuda(), [3, 0, 2], W, H)
         xy = np.array([[-30, -20], [W - 40, H - 30], [100, 50], [-64, 10], [W, H]], np.int32)
         ctx.forward_tiles(xy, T)
-        got = ctx.debug_activation("x0").float().cpu().numpy()
-        assert (got[..., 3:] == 0).all()
+        got = ctx.debug_input_tiles().float().cpu().numpy()      # [n, T, T, 3], padding lanes checked to be 0
+        assert got.shape == (len(xy), T, T, 3)
         for i, (x0, y0) in enumerate(xy):
             patch = np.zeros((3, T, T), np.uint8)
             r0, r1, c0, c1 = max(y0, 0), min(y0 + T, H), max(x0, 0), min(x0 + T, W)
             if r1 > r0 and c1 > c0:
                 patch[:, r0 - y0:r1 - y0, c0 - x0:c1 - x0] = raster[[3, 0, 2], r0:r1, c0:c1]
             ref = torch.as_tensor(normalization(patch, norm_type, means, stds), dtype=torch.float).to(torch.bfloat16).float().numpy()
-            np.testing.assert_array_equal(got[i, ..., :3].transpose(2, 0, 1), ref)
+            np.testing.assert_array_equal(got[i].transpose(2, 0, 1), ref)
     # HWC layout gives the same tiles
     ctx.set_norm("custom", means, stds)
     ctx.set_raster(torch.from_numpy(np.ascontiguousarray(raster.transpose(1, 2, 0))).cuda(), [3, 0, 2], W, H, layout=1)
     ctx.forward_tiles(xy, T)
-    got_hwc = ctx.debug_activation("x0").float().cpu().numpy()
+    got_hwc = ctx.debug_input_tiles().float().cpu().numpy()
     ctx.set_raster(torch.from_numpy(raster).cuda(), [3, 0, 2], W, H)
     ctx.forward_tiles(xy, T)
-    np.testing.assert_array_equal(got_hwc, ctx.debug_activation("x0").float().cpu().numpy())
+    np.testing.assert_array_equal(got_hwc, ctx.debug_input_tiles().float().cpu().numpy())
+
+
+def test_space_to_depth_stem_matches_plain_stem(trained_3_15, monkeypatch):
+    """<= 4 bands: the stem runs as a 4x4 stride-1 conv on the 2x2 space-to-depth tile (16 instead of 28 MMA steps,
+    half the input bytes). Same bf16 products as the 7x7 stride-2 form, other summation order: the stem output may
+    differ by a bf16 rounding, the input tiles are bit-identical, and the logits stay within the tolerance."""
+    from oracle import synth
+    nat = _nat()
+    sd, _ = trained_3_15
+    raster = torch.from_numpy(synth.synth_raster(3, 600, 700, seed=9)).cuda()
+    xy = np.array([[0, 0], [-100, 37], [300, 200], [700 - 256, 600 - 256]], np.int32)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FB_NO_S2D", mode)
+        c = nat.Context(0)
+        c.load_weights(sd, 3, 15)
+        c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+        c.set_raster(raster, [0, 1, 2], 700, 600)
+        logits = c.forward_tiles(xy, 512).cpu()
+        res[mode] = (c.debug_input_tiles().cpu(), c.debug_activation("f1").float().cpu(), logits, tuple(c.debug_activation("x0").shape))
+        c.close()
+    assert res["1"][3] == (4, 512, 512, 8) and res["0"][3] == (4, 256, 256, 16)
+    assert torch.equal(res["0"][0], res["1"][0])
+    f_rel = (res["0"][1] - res["1"][1]).abs().max().item() / res["1"][1].abs().max().item()
+    l_rel = (res["0"][2] - res["1"][2]).abs().max().item() / res["1"][2].abs().max().item()
+    print(f"space-to-depth stem vs 7x7 stem: f1 rel diff {f_rel:.3e}, logits rel diff {l_rel:.3e}")
+    assert f_rel < 1e-2 and l_rel < 1e-2
+    assert (res["0"][2][..., :15].argmax(-1) == res["1"][2][..., :15].argmax(-1)).float().mean().item() > 0.999
 
 
 def test_confusion_bit_exact_vs_sklearn(ctx):
