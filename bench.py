@@ -390,7 +390,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=74, help="tiles per forward pass (74 = 148 SMs / 2: whole waves on every layer)")
+    ap.add_argument("--batch", type=int, default=148, help="tiles per forward pass (148 = one per SM; 74 / 111 / 148 measured 906 / 907 / 922 Mpx/s)")
     ap.add_argument("--cpu-tiles", type=int, default=160, help="tiles of the zone timed on the host cores (cpu_baseline)")
     ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the reference arm")
     args = ap.parse_args()

@@ -184,7 +184,7 @@ def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarr
     my0, my1 = config.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())))
     raster_dev = dataset.big_image.to(device, non_blocking=True)
     model.set_raster(raster_dev, list(range(dataset.num_bands)), W, dataset.raster_height, row0=dataset.row0)
-    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 74)))
+    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 148)))
     if config["output_type"] == "class_prob":
         # main.py:409-426 always clips exactly for this output type (compare.py:68): n_classes planes, no band 2
         prob = torch.zeros((config["n_classes"], my1 - my0, W), dtype=torch.uint8, device=device)
