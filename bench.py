@@ -361,7 +361,13 @@ def run_ours(args) -> int:
                     "d2h_bytes_per_step": int(lt[2].item())},
             "gpu_launches": int(lt[0].item()),
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": conv_tflops / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "frac": conv_tflops / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the family's top kernel
+                         # (conv_igemm_kernel<256>, a layer3 3x3 conv on 74 tiles: 38.8 MB in, 38.8 MB out, 1.2 MB
+                         # of weights; the output mostly stays in the 126 MB L2 for the next layer), from the
+                         # `ncu --set full` capture summarised in profiles/r01_ncu_full_igemm256_v13.csv
+                         "traffic": 42.77e6, "traffic_unit": "bytes per launch (conv_igemm_kernel<256>, 74 tiles)",
+                         "peak_source": peak_src,
                          "kernel": "conv_igemm_kernel + conv_halo_kernel (47 launches per batch); achieved = algorithmic FLOPs "
                                    "(2*MAC of the direct conv) of the outputs actually computed / summed conv time",
                          "gflop_per_tile_computed": gflop_per_tile, "gflop_per_tile_full": GFLOP_PER_TILE,

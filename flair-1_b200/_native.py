@@ -79,6 +79,7 @@ _SIGNATURES = {
     "fb_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "fb_launch_count": (C.c_int64, [C.c_void_p]),
     "fb_flop_count": (C.c_double, [C.c_void_p]),
+    "fb_logit_stride": (C.c_int, [C.c_void_p]),
     "fb_lzw_bound": (C.c_int64, [C.c_int64]),
     "fb_lzw_encode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "fb_lzw_decode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
@@ -171,6 +172,11 @@ class Context:
         return int(self._lib.fb_launch_count(self._h))
 
     @property
+    def logit_stride(self) -> int:
+        """Floats per pixel of logits / blend accumulators for the loaded model (16, or 32 above 16 classes)."""
+        return int(self._lib.fb_logit_stride(self._h))
+
+    @property
     def flop_count(self) -> float:
         """Algorithmic conv FLOPs of the outputs computed so far (fb_flop_count)."""
         return float(self._lib.fb_flop_count(self._h))
@@ -232,11 +238,11 @@ class Context:
 
     # ------------------------------------------------------------------ compute
     def forward_tiles(self, tile_xy: np.ndarray, tile: int, metadata: Optional[np.ndarray] = None) -> torch.Tensor:
-        """logits [n, tile, tile, 16] fp32 (device) for tiles at (x0, y0) of the current raster."""
+        """logits [n, tile, tile, logit_stride] fp32 (device) for tiles at (x0, y0) of the current raster."""
         xy = np.ascontiguousarray(tile_xy, dtype=np.int32).reshape(-1, 2)
         n = xy.shape[0]
         md = None if metadata is None else np.ascontiguousarray(metadata, dtype=np.float32).reshape(n, METADATA_DIM)
-        out = torch.empty((n, tile, tile, LOGIT_STRIDE), dtype=torch.float32, device=self.device)
+        out = torch.empty((n, tile, tile, self.logit_stride), dtype=torch.float32, device=self.device)
         self._check(self._lib.fb_forward_tiles(self._h, xy.ctypes.data, n, tile, _np_ptr(md), out.data_ptr()))
         return out
 
@@ -277,7 +283,7 @@ class Context:
         """Zeroed accumulators for blend_strip: (acc, wsum); wsum is None for 'max'."""
         if self.STITCH_METHODS[method] == 2:
             return torch.zeros((map_rows, map_w), dtype=torch.int64, device=self.device), None
-        return (torch.zeros((map_rows, map_w, 16), dtype=torch.float32, device=self.device),
+        return (torch.zeros((map_rows, map_w, self.logit_stride), dtype=torch.float32, device=self.device),
                 torch.zeros((map_rows, map_w), dtype=torch.float32, device=self.device))
 
     def blend_strip(self, tiles: np.ndarray, tile: int, batch: int, method: str, acc: torch.Tensor,

@@ -91,6 +91,7 @@ struct fb_ctx {
   // model
   bool loaded = false;
   int in_ch = 0, ncls = 0, use_meta = 0;
+  int ls = 16;                // floats per pixel of the logits: 16 for <= 16 classes, 32 above
   std::map<std::string, ConvLayer> conv;
   float* mlp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> owned;  // device allocations freed at destroy
@@ -418,7 +419,7 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry, d < 4 && !c->dec_phase[d + 1]);
     S *= 2;
   }
-  arena_alloc(c, "logits", n, T, T, 16, 4, dry);
+  arena_alloc(c, "logits", n, T, T, c->ls, 4, dry);
 }
 
 int ensure_arena(fb_ctx* c, int n, int T) {
@@ -870,11 +871,13 @@ int64_t fb_launch_count(const fb_ctx* c) { return c ? c->launches : 0; }
 
 double fb_flop_count(const fb_ctx* c) { return c ? c->flops : 0.0; }
 
+int fb_logit_stride(const fb_ctx* c) { return c ? c->ls : 0; }
+
 int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int in_channels,
                     int n_classes, int use_metadata) {
   if (!c || !tensors || n_tensors <= 0) return FB_ERR_INVALID;
   if (in_channels < 1 || in_channels > 8) return fail(c, FB_ERR_INVALID, "in_channels must be in 1..8");
-  if (n_classes < 1 || n_classes > 16) return fail(c, FB_ERR_INVALID, "n_classes must be in 1..16");
+  if (n_classes < 1 || n_classes > 32) return fail(c, FB_ERR_INVALID, "n_classes must be in 1..32");
   FB_CUDA(c, cudaSetDevice(c->device));
   TensorMap tm;
   for (int i = 0; i < n_tensors; ++i)
@@ -923,6 +926,7 @@ int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int
   }
   c->in_ch = in_channels;
   c->ncls = n_classes;
+  c->ls = n_classes <= 16 ? 16 : 32;
   c->use_meta = use_metadata ? 1 : 0;
   c->loaded = true;
   return 0;
@@ -994,7 +998,7 @@ int fb_forward_tiles(fb_ctx* c, const int32_t* tile_xy, int n, int tile, const f
                      c->rows, c->tile_xy_dev, n, tile));
   FB_TRY(run_network(c, n, tile, menc));
   if (logits_dev)
-    FB_CUDA(c, cudaMemcpyAsync(logits_dev, c->acts["logits"].ptr, static_cast<size_t>(n) * tile * tile * 16 * 4,
+    FB_CUDA(c, cudaMemcpyAsync(logits_dev, c->acts["logits"].ptr, static_cast<size_t>(n) * tile * tile * c->ls * 4,
                                cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
@@ -1097,7 +1101,7 @@ int fb_blend_finalize(fb_ctx* c, const float* acc_dev, const float* wsum_dev, in
   if (!acc_dev || !cls_map_dev || npx < 0 || method < 0 || method > 2 || (method != 2 && !wsum_dev))
     return fail(c, FB_ERR_INVALID, "blend finalize: bad arguments");
   FB_CUDA(c, cudaSetDevice(c->device));
-  int rc = fb::launch_blend_finalize(acc_dev, wsum_dev, method, c->ncls, npx, cls_map_dev, conf_map_dev, c->num_sms, c->stream);
+  int rc = fb::launch_blend_finalize(acc_dev, wsum_dev, method, c->ncls, c->ls, npx, cls_map_dev, conf_map_dev, c->num_sms, c->stream);
   if (rc) return fail(c, rc, "blend finalize launch failed");
   c->launches++;
   return 0;
@@ -1154,17 +1158,17 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
     const float* logits = static_cast<const float*>(c->acts["logits"].ptr);
     int rc;
     if (s.kind == 0)
-      rc = fb::launch_argmax_stitch(logits, c->ncls, nb, tile, c->tiles_dev + 6 * i0, s.cls, s.conf, s.map_w, s.map_row0, c->stream);
+      rc = fb::launch_argmax_stitch(logits, c->ncls, c->ls, nb, tile, c->tiles_dev + 6 * i0, s.cls, s.conf, s.map_w, s.map_row0, c->stream);
     else if (s.kind == 1)
-      rc = fb::launch_prob_stitch(logits, c->ncls, nb, tile, c->tiles_dev + 6 * i0, s.prob, s.map_w, s.map_row0, s.map_rows,
+      rc = fb::launch_prob_stitch(logits, c->ncls, c->ls, nb, tile, c->tiles_dev + 6 * i0, s.prob, s.map_w, s.map_row0, s.map_rows,
                                   c->stream);
     else
-      rc = fb::launch_blend_accumulate(logits, c->ncls, nb, tile, c->tiles_dev + 6 * i0, s.method, s.acc, s.wsum, s.map_w,
+      rc = fb::launch_blend_accumulate(logits, c->ncls, c->ls, nb, tile, c->tiles_dev + 6 * i0, s.method, s.acc, s.wsum, s.map_w,
                                        s.map_row0, s.map_rows, c->W, c->H, s.seq0 + i0, c->stream);
     if (rc) return fail(c, rc, "stitch launch failed");
     c->launches++;
     if (s.tile_cm) {
-      rc = fb::launch_tile_confusion(logits, c->ncls, nb, tile, c->win_dev + 6 * i0, s.truth, s.truth_sub, s.map_w, s.map_row0,
+      rc = fb::launch_tile_confusion(logits, c->ncls, c->ls, nb, tile, c->win_dev + 6 * i0, s.truth, s.truth_sub, s.map_w, s.map_row0,
                                      reinterpret_cast<long long*>(s.tile_cm) + static_cast<long long>(i0) * c->ncls * c->ncls, c->stream);
       if (rc) return fail(c, rc, "tile confusion launch failed");
       c->launches++;
@@ -1367,7 +1371,7 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
     if (!rc) rc = run_network(c, nb, tile, menc, &need, c->no_fused_sink ? nullptr : &hs, &sunk);
     if (!rc && !sunk) {
       ProfScope ps(c, 3);
-      rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, nb, tile, c->tiles_dev,
+      rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, c->ls, nb, tile, c->tiles_dev,
                                     cls_out_dev + static_cast<size_t>(i0) * tile * tile, nullptr, tile, 0, c->stream);
       if (rc) rc = fail(c, rc, "argmax launch failed");
       c->launches++;
@@ -1573,7 +1577,7 @@ int fb_profile_forward(fb_ctx* c, int n, int tile, int iters, float* ms5) {
     if (!rc) rc = run_network(c, n, tile, menc);
     if (!rc) {
       ProfScope ps(c, 3);
-      rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, n, tile, c->tiles_dev,
+      rc = fb::launch_argmax_stitch(static_cast<const float*>(c->acts["logits"].ptr), c->ncls, c->ls, n, tile, c->tiles_dev,
                                     scratch, nullptr, c->W, c->row0, c->stream);
       c->launches++;
     }

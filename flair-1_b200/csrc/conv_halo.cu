@@ -108,6 +108,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above touched only this CTA's shared memory / TMEM and the static
+  // filter bank; from here on the kernel reads what its predecessor in the stream wrote
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_w = (PH ? p.Win : p.Wout) / G::TW, tiles_h = (PH ? p.Hin : p.Hout) / kTH;
   // position i of this launch's schedule -> tile of the full grid (identity unless an active-tile list is given)
@@ -453,8 +457,10 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
-  conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI><<<grid, kThreadsK, smem, stream>>>(a);
-  return static_cast<int>(cudaGetLastError());
+  static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
+  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>, dim3(grid), dim3(kThreadsK),
+                                           static_cast<size_t>(smem), stream, pdl, a);
+  return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 }  // namespace
@@ -500,7 +506,7 @@ bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int 
   const int nch = cg / 8;
   if ((C1 + C2) / cg > 2) return false;
   if (Wout % (8 * halo_blocks(KH, nch, Cout)) != 0) return false;
-  return (nch == 2 && Cout == 16) || (nch == 4 && (Cout == 16 || Cout == 32)) ||
+  return (nch == 2 && (Cout == 16 || Cout == 32)) || (nch == 4 && (Cout == 16 || Cout == 32)) ||
          (nch == 8 && (Cout == 32 || Cout == 64));
 }
 
@@ -673,6 +679,7 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   }
   if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2>(a, num_sms, stream);
   if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4>(a, num_sms, stream);
+  if (nch == 2 && a.Cout == 32) return launch_halo_t<3, 1, 2, 32, 4>(a, num_sms, stream);   // head of a 17..32-class model
   if (nch == 4 && a.Cout == 16) return launch_halo_t<3, 1, 4, 16, 2>(a, num_sms, stream);
   if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32, 2>(a, num_sms, stream);
   if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32, 2>(a, num_sms, stream);

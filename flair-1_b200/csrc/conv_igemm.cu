@@ -3,6 +3,7 @@
 #include "conv_igemm.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "conv_epilogue.cuh"
@@ -83,6 +84,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch (ptx.cuh): barriers, TMEM and descriptor prefetch are set up while the
+  // predecessor drains; its outputs (and the tile list) are only touched after this point
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int nk = p.num_k_iters;
@@ -502,8 +507,10 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap&
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_igemm_kernel<BN, TMA_A, EPI><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
-  return static_cast<int>(cudaGetLastError());
+  static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
+  const cudaError_t le = launch_kernel_pdl(conv_igemm_kernel<BN, TMA_A, EPI>, dim3(grid), dim3(C::kThreads),
+                                           static_cast<size_t>(C::kSmemBytes), stream, pdl, tmA, tmA2, tmB, a);
+  return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 template <int BN>

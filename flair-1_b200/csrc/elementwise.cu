@@ -257,9 +257,48 @@ int launch_metadata_mlp(const float* met, const float* const* wb, float* out, in
   return static_cast<int>(cudaGetLastError());
 }
 
+// Logits (and blend accumulators) are stored LS = 16 floats per pixel for models with <= 16 classes, 32 above
+// (the 19-class nomenclature): the kernels below are instantiated for both.
+template <int LS>
+__device__ __forceinline__ void load_logits(const float* p, float (&v)[LS]) {
+  const float4* lp = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int k = 0; k < LS / 4; ++k) {
+    const float4 f = __ldg(lp + k);
+    v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
+  }
+}
+// soft-max over the first ncls entries in place (entries >= ncls become 0); returns the arg-max (first maximum)
+template <int LS>
+__device__ __forceinline__ int softmax_ls(float (&v)[LS], int ncls, float* pmax = nullptr) {
+  float best = v[0];
+  int arg = 0;
+#pragma unroll
+  for (int k = 1; k < LS; ++k)
+    if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < LS; ++k) {
+    v[k] = k < ncls ? __expf(v[k] - best) : 0.f;
+    den += v[k];
+  }
+  const float inv = 1.f / den;
+#pragma unroll
+  for (int k = 0; k < LS; ++k) v[k] *= inv;
+  if (pmax) *pmax = inv;   // exp(0) / den
+  return arg;
+}
+#define FB_LS_DISPATCH(ls_, ...)                      \
+  do {                                                \
+    if ((ls_) == 16) { constexpr int LS = 16; __VA_ARGS__; } \
+    else if ((ls_) == 32) { constexpr int LS = 32; __VA_ARGS__; } \
+    else return -2006;                                \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------ K6
 // One thread per written pixel. argmax = first maximum (numpy semantics); confidence byte =
 // round-half-up of the max soft-max probability (what a float32 -> uint8 raster write produces).
+template <int LS>
 __global__ void __launch_bounds__(256)
 argmax_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ tiles,
                      uint8_t* __restrict__ cls_map, uint8_t* __restrict__ conf_map, long long map_w,
@@ -273,22 +312,16 @@ argmax_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const in
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ry = wy0 + i / rw, rx = wx0 + i % rw;
     const int ty = ry - y0, tx = rx - x0;
-    const float4* lp = reinterpret_cast<const float4*>(
-        logits + ((static_cast<long long>(t) * T + ty) * T + tx) * 16);
-    float v[16];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 f = __ldg(lp + k);
-      v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
-    }
+    float v[LS];
+    load_logits<LS>(logits + ((static_cast<long long>(t) * T + ty) * T + tx) * LS, v);
     float best = v[0];
     int arg = 0;
 #pragma unroll
-    for (int k = 1; k < 16; ++k)
+    for (int k = 1; k < LS; ++k)
       if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
     float den = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
+    for (int k = 0; k < LS; ++k)
       if (k < ncls) den += __expf(v[k] - best);
     const float pmax = 1.f / den;
     const long long o = (static_cast<long long>(ry) - map_row0) * map_w + rx;
@@ -297,45 +330,17 @@ argmax_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const in
   }
 }
 
-int launch_argmax_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* cls_map,
+int launch_argmax_stitch(const float* logits, int ncls, int ls, int n, int T, const int* tiles, uint8_t* cls_map,
                          uint8_t* conf_map, long long map_w, long long map_row0, cudaStream_t stream) {
   if (n == 0) return 0;
   dim3 grid((T * T + 255) / 256 > 64 ? 64 : (T * T + 255) / 256, n);
-  argmax_stitch_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, cls_map, conf_map, map_w,
-                                                 map_row0);
+  FB_LS_DISPATCH(ls, argmax_stitch_kernel<LS><<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, cls_map, conf_map, map_w, map_row0));
   return static_cast<int>(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------ K6b
 // class_prob output (zone_detect/dataset.py:15-21): every class probability as uint8(p * 255), truncated.
-__device__ __forceinline__ void load_logits16(const float* p, float (&v)[16]) {
-  const float4* lp = reinterpret_cast<const float4*>(p);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4 f = __ldg(lp + k);
-    v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
-  }
-}
-// soft-max over the first ncls entries in place (entries >= ncls become 0); returns the arg-max (first maximum)
-__device__ __forceinline__ int softmax16(float (&v)[16], int ncls, float* pmax = nullptr) {
-  float best = v[0];
-  int arg = 0;
-#pragma unroll
-  for (int k = 1; k < 16; ++k)
-    if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
-  float den = 0.f;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    v[k] = k < ncls ? __expf(v[k] - best) : 0.f;
-    den += v[k];
-  }
-  const float inv = 1.f / den;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] *= inv;
-  if (pmax) *pmax = inv;   // exp(0) / den
-  return arg;
-}
-
+template <int LS>
 __global__ void __launch_bounds__(256)
 prob_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ tiles,
                    uint8_t* __restrict__ prob_map, long long map_w, long long map_row0, long long plane) {
@@ -347,21 +352,21 @@ prob_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const int*
   const int total = rw * rh;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ry = wy0 + i / rw, rx = wx0 + i % rw;
-    float v[16];
-    load_logits16(logits + ((static_cast<long long>(t) * T + (ry - y0)) * T + (rx - x0)) * 16, v);
-    softmax16(v, ncls);
+    float v[LS];
+    load_logits<LS>(logits + ((static_cast<long long>(t) * T + (ry - y0)) * T + (rx - x0)) * LS, v);
+    softmax_ls<LS>(v, ncls);
     const long long o = (static_cast<long long>(ry) - map_row0) * map_w + rx;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
+    for (int k = 0; k < LS; ++k)
       if (k < ncls) prob_map[k * plane + o] = static_cast<uint8_t>(v[k] * 255.f);
   }
 }
 
-int launch_prob_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* prob_map,
+int launch_prob_stitch(const float* logits, int ncls, int ls, int n, int T, const int* tiles, uint8_t* prob_map,
                        long long map_w, long long map_row0, long long map_rows, cudaStream_t stream) {
   if (n == 0) return 0;
   dim3 grid((T * T + 255) / 256 > 64 ? 64 : (T * T + 255) / 256, n);
-  prob_stitch_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, prob_map, map_w, map_row0, map_rows * map_w);
+  FB_LS_DISPATCH(ls, prob_stitch_kernel<LS><<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, prob_map, map_w, map_row0, map_rows * map_w));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -370,6 +375,7 @@ int launch_prob_stitch(const float* logits, int ncls, int n, int T, const int* t
 // of test/tiles.py:97-108 (mode "exp", sigma 0.5) and the per-pixel normalisation of tiles.py:111-169
 // (sum of the weights of the covering tiles) / tiles.py:54-94 (their count). The whole tile contributes,
 // clipped to the raster. Sums are accumulated with floating-point atomics (order not fixed).
+template <int LS>
 __global__ void __launch_bounds__(256)
 blend_accumulate_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ tiles, int method,
                         float* __restrict__ acc, float* __restrict__ wsum, long long map_w, long long map_row0,
@@ -382,10 +388,10 @@ blend_accumulate_kernel(const float* __restrict__ logits, int ncls, int T, const
     const int ty = i / T, tx = i % T;
     const long long ry = static_cast<long long>(y0) + ty, rx = static_cast<long long>(x0) + tx;
     if (rx < 0 || rx >= W || ry < 0 || ry >= H || ry < map_row0 || ry >= map_row0 + map_rows || rx >= map_w) continue;
-    float v[16];
-    load_logits16(logits + ((static_cast<long long>(t) * T + ty) * T + tx) * 16, v);
+    float v[LS];
+    load_logits<LS>(logits + ((static_cast<long long>(t) * T + ty) * T + tx) * LS, v);
     float pmax;
-    const int arg = softmax16(v, ncls, &pmax);
+    const int arg = softmax_ls<LS>(v, ncls, &pmax);
     const long long o = (ry - map_row0) * map_w + rx;
     if (method == 2) {
       const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pmax)) << 32) |
@@ -394,27 +400,28 @@ blend_accumulate_kernel(const float* __restrict__ logits, int ncls, int T, const
     } else {
       const int dy = ty > centre ? ty - centre : centre - ty, dx = tx > centre ? tx - centre : centre - tx;
       const float w = method == 0 ? 1.f : __expf(-0.5f * static_cast<float>(dy > dx ? dy : dx) * inv_dmax);
-      float4* a4 = reinterpret_cast<float4*>(acc + o * 16);
+      float4* a4 = reinterpret_cast<float4*>(acc + o * LS);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < LS / 4; ++k)
         if (4 * k < ncls) atomicAdd(a4 + k, make_float4(v[4 * k] * w, v[4 * k + 1] * w, v[4 * k + 2] * w, v[4 * k + 3] * w));
       atomicAdd(wsum + o, w);
     }
   }
 }
 
-int launch_blend_accumulate(const float* logits, int ncls, int n, int T, const int* tiles, int method, float* acc,
+int launch_blend_accumulate(const float* logits, int ncls, int ls, int n, int T, const int* tiles, int method, float* acc,
                             float* wsum, long long map_w, long long map_row0, long long map_rows, long long W,
                             long long H, int seq0, cudaStream_t stream) {
   if (n == 0) return 0;
   dim3 grid((T * T + 255) / 256 > 128 ? 128 : (T * T + 255) / 256, n);
-  blend_accumulate_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, method, acc, wsum, map_w, map_row0, map_rows,
-                                                     W, H, seq0);
+  FB_LS_DISPATCH(ls, blend_accumulate_kernel<LS><<<grid, 256, 0, stream>>>(logits, ncls, T, tiles, method, acc, wsum, map_w, map_row0,
+                                                                              map_rows, W, H, seq0));
   return static_cast<int>(cudaGetLastError());
 }
 
 // class = arg-max of the blended probabilities (first maximum), confidence byte = round-half-up of the
 // normalised maximum (same band-2 semantics as the exact-clipping path). Uncovered pixels stay 0.
+template <int LS>
 __global__ void __launch_bounds__(256)
 blend_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, int method, int ncls, long long npx,
                       uint8_t* __restrict__ cls_map, uint8_t* __restrict__ conf_map) {
@@ -427,11 +434,11 @@ blend_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ w
       arg = static_cast<int>(key & 0xFF);
       conf = __uint_as_float(static_cast<unsigned>(key >> 32));
     } else {
-      float v[16];
-      load_logits16(acc + o * 16, v);
+      float v[LS];
+      load_logits<LS>(acc + o * LS, v);
       float best = v[0];
 #pragma unroll
-      for (int k = 1; k < 16; ++k)
+      for (int k = 1; k < LS; ++k)
         if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
       const float ws = wsum[o];
       conf = ws > 0.f ? best / ws : 0.f;
@@ -441,10 +448,10 @@ blend_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ w
   }
 }
 
-int launch_blend_finalize(const float* acc, const float* wsum, int method, int ncls, long long npx, uint8_t* cls_map,
+int launch_blend_finalize(const float* acc, const float* wsum, int method, int ncls, int ls, long long npx, uint8_t* cls_map,
                           uint8_t* conf_map, int num_sms, cudaStream_t stream) {
   if (npx == 0) return 0;
-  blend_finalize_kernel<<<num_sms * 8, 256, 0, stream>>>(acc, wsum, method, ncls, npx, cls_map, conf_map);
+  FB_LS_DISPATCH(ls, blend_finalize_kernel<LS><<<num_sms * 8, 256, 0, stream>>>(acc, wsum, method, ncls, npx, cls_map, conf_map));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -529,6 +536,7 @@ int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, i
 // sklearn.confusion_matrix(labels=range(ncls)) counts them. windows: int32 [n][6] = x0, y0 (tile origin),
 // then the half-open window in raster pixels. truth: uint8 map with the class map's geometry; `truth_sub` is
 // subtracted with uint8 wrap-around first. cm: u64 [n][ncls][ncls], accumulated.
+template <int LS>
 __global__ void __launch_bounds__(256)
 tile_confusion_kernel(const float* __restrict__ logits, int ncls, int T, const int* __restrict__ windows,
                       const uint8_t* __restrict__ truth, int truth_sub, long long map_w, long long map_row0,
@@ -545,12 +553,12 @@ tile_confusion_kernel(const float* __restrict__ logits, int ncls, int T, const i
   const int total = rw * rh;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int ry = wy0 + i / rw, rx = wx0 + i % rw;
-    float v[16];
-    load_logits16(logits + ((static_cast<long long>(t) * T + (ry - y0)) * T + (rx - x0)) * 16, v);
+    float v[LS];
+    load_logits<LS>(logits + ((static_cast<long long>(t) * T + (ry - y0)) * T + (rx - x0)) * LS, v);
     float best = v[0];
     unsigned arg = 0;
 #pragma unroll
-    for (int k = 1; k < 16; ++k)
+    for (int k = 1; k < LS; ++k)
       if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
     const unsigned tb = (static_cast<unsigned>(truth[(static_cast<long long>(ry) - map_row0) * map_w + rx]) - truth_sub) & 0xFF;
     if (tb < static_cast<unsigned>(ncls)) atomicAdd(&bins[tb * ncls + arg], 1u);
@@ -561,13 +569,13 @@ tile_confusion_kernel(const float* __restrict__ logits, int ncls, int T, const i
     if (bins[i] != 0) atomicAdd(&out[i], static_cast<unsigned long long>(bins[i]));
 }
 
-int launch_tile_confusion(const float* logits, int ncls, int n, int T, const int* windows, const uint8_t* truth,
+int launch_tile_confusion(const float* logits, int ncls, int ls, int n, int T, const int* windows, const uint8_t* truth,
                           int truth_sub, long long map_w, long long map_row0, long long* cm, cudaStream_t stream) {
-  if (ncls <= 0 || ncls > 16) return -2002;
+  if (ncls <= 0 || ncls > ls) return -2002;
   if (n == 0) return 0;
   dim3 grid(16, n);
-  tile_confusion_kernel<<<grid, 256, 0, stream>>>(logits, ncls, T, windows, truth, truth_sub & 0xFF, map_w, map_row0,
-                                                  reinterpret_cast<unsigned long long*>(cm));
+  FB_LS_DISPATCH(ls, tile_confusion_kernel<LS><<<grid, 256, 0, stream>>>(logits, ncls, T, windows, truth, truth_sub & 0xFF, map_w, map_row0,
+                                                                         reinterpret_cast<unsigned long long*>(cm)));
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -24,13 +24,14 @@ int launch_maxpool3x3s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int 
 // wb = {w0[64x45], b0[64], w1[32x64], b1[32], w2[16x32], b2[16]} (device fp32)
 int launch_metadata_mlp(const float* met, const float* const* wb, float* out, int n, cudaStream_t stream);
 
+// ls = floats per pixel of the logits / blend accumulators: 16 for <= 16 classes, 32 above.
 // tiles: int32 [n][6] = x0, y0 (tile origin in raster px), wx0, wy0, wx1, wy1 (half-open write rect)
-int launch_argmax_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* cls_map,
+int launch_argmax_stitch(const float* logits, int ncls, int ls, int n, int T, const int* tiles, uint8_t* cls_map,
                          uint8_t* conf_map, long long map_w, long long map_row0, cudaStream_t stream);
 
 // class_prob output: prob_map[k][y - map_row0][x] = uint8(softmax_k * 255) (truncation) for k < ncls inside
 // the write rectangles; plane stride = map_rows * map_w.
-int launch_prob_stitch(const float* logits, int ncls, int n, int T, const int* tiles, uint8_t* prob_map,
+int launch_prob_stitch(const float* logits, int ncls, int ls, int n, int T, const int* tiles, uint8_t* prob_map,
                        long long map_w, long long map_row0, long long map_rows, cudaStream_t stream);
 
 // Blended stitching. method 0 = average (weight 1), 1 = average_weights (exp(-0.5 * chebyshev distance to the
@@ -39,10 +40,10 @@ int launch_prob_stitch(const float* logits, int ncls, int n, int T, const int* t
 // [map_rows][map_w]; method 2: acc is read as uint64 [map_rows][map_w] keys
 // (confidence bits << 32 | tile sequence number << 8 | class) and wsum is unused.
 // Every pixel of every tile that lies inside the raster [0,W)x[0,H) and inside the map rows contributes.
-int launch_blend_accumulate(const float* logits, int ncls, int n, int T, const int* tiles, int method, float* acc,
+int launch_blend_accumulate(const float* logits, int ncls, int ls, int n, int T, const int* tiles, int method, float* acc,
                             float* wsum, long long map_w, long long map_row0, long long map_rows, long long W,
                             long long H, int seq0, cudaStream_t stream);
-int launch_blend_finalize(const float* acc, const float* wsum, int method, int ncls, long long npx, uint8_t* cls_map,
+int launch_blend_finalize(const float* acc, const float* wsum, int method, int ncls, int ls, long long npx, uint8_t* cls_map,
                           uint8_t* conf_map, int num_sms, cudaStream_t stream);
 
 int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, int ncls, int truth_sub,
@@ -50,7 +51,7 @@ int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, i
 
 // Per-tile confusion matrices from each tile's own arg-max over its metric window (compute_metrics_patch of the
 // compare loop). windows: int32 [n][6] = x0, y0, then the half-open window; cm: int64 [n][ncls][ncls], accumulated.
-int launch_tile_confusion(const float* logits, int ncls, int n, int T, const int* windows, const uint8_t* truth,
+int launch_tile_confusion(const float* logits, int ncls, int ls, int n, int T, const int* windows, const uint8_t* truth,
                           int truth_sub, long long map_w, long long map_row0, long long* cm, cudaStream_t stream);
 
 }  // namespace fb

@@ -77,6 +77,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: its CTAs take the SMs the predecessor's CTAs leave, run their prologue (barrier init,
+// TMEM allocation, filter bank -> shared memory: nothing the predecessor writes) and then block in pdl_wait() until
+// the predecessor grid has completed and its writes are visible. pdl_launch_dependents() lets the successor in.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -285,4 +293,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 }
 
 }  // namespace ptx
+
+// Launch `kernel` on `stream`, optionally as a programmatic dependent of the work before it (see ptx::pdl_wait).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace fb

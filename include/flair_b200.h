@@ -40,7 +40,8 @@ extern "C" {
 #define FB_LAYOUT_CHW 0 /* band-planar, what rasterio's read() returns */
 #define FB_LAYOUT_HWC 1 /* pixel-interleaved */
 
-#define FB_LOGIT_STRIDE 16 /* logits are written as [n, T, T, 16] fp32; classes >= n_classes are 0 */
+#define FB_LOGIT_STRIDE 16 /* logits are written as [n, T, T, S] fp32 with S = fb_logit_stride(ctx): 16 for models
+                             with <= 16 classes, 32 above (the 19-class nomenclature); entries >= n_classes are 0 */
 #define FB_METADATA_DIM 45 /* src/flair/tasks_utils.py:158-213 */
 
 typedef struct fb_ctx fb_ctx;
@@ -76,9 +77,12 @@ int fb_synchronize(fb_ctx* ctx);
 /* ---- model: replaces smp.create_model + load_state_dict(strict=True)
  *      (src/zone_detect/model.py:30-39,79-88; src/flair/model.py:20-50, src/flair/main.py:77-146).
  *      Folds eval-mode BatchNorm into the conv weights in float64, rounds once to bf16, repacks to
- *      [Cout][kh][kw][Cin] and uploads. in_channels in 1..8, n_classes in 1..16. */
+ *      [Cout][kh][kw][Cin] and uploads. in_channels in 1..8, n_classes in 1..32. */
 int fb_load_weights(fb_ctx* ctx, const fb_tensor_desc* tensors, int n_tensors, int in_channels,
                     int n_classes, int use_metadata);
+/* Floats per pixel of the logits (fb_forward_tiles) and of the blend accumulators (fb_blend_strip) for the loaded
+ * model: 16 for <= 16 classes, 32 above. */
+int fb_logit_stride(const fb_ctx* ctx);
 
 /* ---- input normalisation: Sliced_Dataset.normalization (dataset.py:68-88) / norm()
  *      (data_loader.py:9-30). mean/std are per selected band (ignored unless FB_NORM_CUSTOM). */
@@ -97,7 +101,7 @@ int fb_upload_raster(fb_ctx* ctx, const uint8_t* host_raster, int bands_total, c
 
 /* ---- logits = model(imgs [, met]) (compare.py:27-33; task_module.py:206-210; flair/model.py:52-70)
  *      for n tiles of tile x tile pixels cut from the current raster at host tile_xy[n][2] = (x0, y0).
- *      metadata: host [n][45] or NULL. logits_dev: device [n][tile][tile][16] fp32. */
+ *      metadata: host [n][45] or NULL. logits_dev: device [n][tile][tile][fb_logit_stride] fp32. */
 int fb_forward_tiles(fb_ctx* ctx, const int32_t* tile_xy, int n, int tile, const float* metadata,
                      float* logits_dev);
 
@@ -131,7 +135,7 @@ int fb_detect_strip_prob(fb_ctx* ctx, const fb_tile* tiles, int n, int tile, int
  *      probability of the covering tiles), FB_STITCH_AVERAGE_WEIGHTS (weight exp(-0.5 * Chebyshev
  *      distance to the tile centre / (tile/2))), FB_STITCH_MAX (class of the most confident tile, the
  *      later tile of the write order on ties; tile i of this call has sequence number tile_seq0 + i).
- *      acc_dev: float [map_rows][map_w][16] and wsum_dev: float [map_rows][map_w] for the two averages;
+ *      acc_dev: float [map_rows][map_w][fb_logit_stride] and wsum_dev: float [map_rows][map_w] for the two averages;
  *      for FB_STITCH_MAX acc_dev is used as uint64 [map_rows][map_w] and wsum_dev may be NULL. The caller
  *      zeroes the accumulators before the first call; the write rectangles of `tiles` are ignored.
  *      fb_blend_finalize turns the accumulators of npx pixels into the class map (+ confidence band). */

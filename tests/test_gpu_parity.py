@@ -292,6 +292,76 @@ def test_five_band_metadata_model_logits(ctx):
         ctx.forward_tiles(xy, T)      # metadata model without metadata must fail loudly
 
 
+def test_nineteen_class_model(ctx):
+    """Configs 1/5 of BASELINE.json name the 19-class nomenclature: n_classes > 16 switches logits and blend
+    accumulators to 32 floats per pixel (fb_logit_stride) and the head to a 32-column accumulator. Random-init
+    5-band / 19-class model (torch defaults, manual_seed(5)): logits tolerance; patch predict = arg-max of the same
+    logits; and, on a briefly trained 3-band / 19-class checkpoint, the zone loop (exact clipping, class_prob and
+    the three blended stitchings) against the oracle."""
+    from oracle import synth
+    from oracle.flair_ref import norm
+    from oracle.unet_smp033 import Unet
+    from oracle.zone_detect_ref import GeoRaster, run_zone, run_zone_blend, run_zone_class_prob
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    torch.manual_seed(5)
+    model = Unet(5, 19).eval()
+    g = torch.Generator().manual_seed(5)
+    B, T = 2, 512
+    patches = torch.randint(0, 256, (B, 5, T, T), generator=g, dtype=torch.uint8)
+    ctx.load_weights(model.state_dict(), 5, 19)
+    assert ctx.logit_stride == 32
+    ctx.set_norm("custom", synth.FLAIR_MEANS, synth.FLAIR_STDS)
+    x = torch.stack([torch.as_tensor(norm(p.numpy(), "custom", synth.FLAIR_MEANS, synth.FLAIR_STDS), dtype=torch.float) for p in patches])
+    with torch.no_grad():
+        ref = model(x)
+    raster = patches.permute(1, 0, 2, 3).reshape(5, B * T, T).contiguous().cuda()
+    ctx.set_raster(raster, [0, 1, 2, 3, 4], T, B * T)
+    xy = np.array([[0, i * T] for i in range(B)], np.int32)
+    full = ctx.forward_tiles(xy, T).cpu()
+    assert full.shape == (B, T, T, 32) and (full[..., 19:] == 0).all()
+    got = full.permute(0, 3, 1, 2)[:, :19]
+    rel = (got - ref).abs().max().item() / ref.abs().max().item()
+    print(f"5-band/19-class: logits rel err {rel:.4e}; agreement {(got.argmax(1) == ref.argmax(1)).float().mean().item() * 100:.3f}% (not asserted)")
+    assert rel <= LOGIT_TOL
+    cls = ctx.predict_patches(patches.cuda(), T, 2).cpu()
+    assert torch.equal(cls.long(), got.argmax(1))
+
+    # zone loop on a trained 19-class checkpoint
+    sd = synth.cached_checkpoint(3, 19)
+    m = Unet(3, 19)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    W, H, T, margin = 700, 560, 256, 32
+    raster = synth.synth_raster(3, H, W, seed=19)
+    means, stds = synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3]
+    ctx.load_weights(sd, 3, 19)
+    ctx.set_norm("custom", means, stds)
+    ctx.set_raster(torch.from_numpy(raster).cuda(), [0, 1, 2], W, H)
+    tiles = tile_table(W, H, T, margin)
+    config = {"img_pixels_detection": T, "margin": margin, "channels": [1, 2, 3], "n_classes": 19,
+              "norma_task": [{"norm_type": "custom", "norm_means": means, "norm_stds": stds}]}
+    geo = GeoRaster(raster, 800000.0, 6500000.0 + H * 0.2, 0.2)
+    cls = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+    conf = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+    ctx.detect_strip(tiles, T, 5, cls, conf, W, 0)
+    ref_cls, ref_conf, _ = run_zone(m, geo, config)
+    agree = (cls.cpu().numpy() == ref_cls).mean()
+    print(f"19-class zone {W}x{H}: agreement {agree * 100:.4f}%, classes present {np.unique(ref_cls).size}")
+    assert agree >= AGREE_MIN and (cls.cpu().numpy() < 19).all()
+    prob = torch.zeros((19, H, W), dtype=torch.uint8, device="cuda")
+    ctx.detect_strip_prob(tiles, T, 4, prob, W, 0)
+    diff = np.abs(prob.cpu().numpy().astype(np.int32) - run_zone_class_prob(m, geo, config).astype(np.int32))
+    assert (diff <= 4).mean() >= 0.999
+    for method in ("average", "average_weights", "max"):
+        acc, wsum = ctx.blend_buffers(method, H, W)
+        ctx.blend_strip(tiles, T, 4, method, acc, wsum, W, 0)
+        bc = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+        ctx.blend_finalize(method, acc, wsum, bc, None)
+        a = (bc.cpu().numpy() == run_zone_blend(m, geo, config, method)[0]).mean()
+        print(f"19-class blend {method}: agreement {a * 100:.4f}%")
+        assert a >= AGREE_MIN
+
+
 def nat_error():
     return _nat().NativeError
 
