@@ -1115,6 +1115,7 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
   if (n == 0) return 0;
   FB_CUDA(c, cudaSetDevice(c->device));
   if (batch > n) batch = n;
+  if (batch > 1024) batch = 1024;   // images per launch the tile-list builder handles (elementwise.cu)
   FB_TRY(ensure_arena(c, batch, tile));
   FB_TRY(ensure_tile_buffers(c, n));
   std::vector<int> xy(static_cast<size_t>(n) * 2);
@@ -1343,20 +1344,17 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
     if (nb != c->arena_n) rc = ensure_arena(c, nb, tile);
     const float* menc = nullptr;
     if (!rc) rc = run_metadata(c, metadata ? metadata + static_cast<size_t>(i0) * FB_METADATA_DIM : nullptr, nb, &menc);
-    // the batch is seen as one planar raster of width `tile` and height nb*tile per band... but patches are
-    // stored patch-major ([n][c][T][T]), so extract patch by patch view: band stride = T*T inside a patch.
-    // launch_extract_normalise's planar addressing is (band*rows + y)*W + x with rows = raster rows; using
-    // rows = tile and one launch per patch keeps the addressing exact.
-    for (int j = 0; j < nb && !rc; ++j) {
-      const uint8_t* patch = dev_patches + static_cast<size_t>(i0 + j) * c->in_ch * tile * tile;
+    // patches are stored patch-major ([n][c][T][T]): every patch is its own band-planar raster of T rows, cut at
+    // (0, 0); one launch for the batch (tile_stride = bytes per patch)
+    if (!rc) {
+      const uint8_t* first = dev_patches + static_cast<size_t>(i0) * c->in_ch * tile * tile;
+      const long long stride = static_cast<long long>(c->in_ch) * tile * tile;
+      __nv_bfloat16* x0 = static_cast<__nv_bfloat16*>(c->acts["x0"].ptr);
       ProfScope ps(c, 0);
-      // (x0 holds 8 * tile * tile bf16 per patch in the plain layout, 16 * (tile/2)^2 in the space-to-depth one)
-      __nv_bfloat16* x0j = static_cast<__nv_bfloat16*>(c->acts["x0"].ptr) +
-                           static_cast<size_t>(j) * tile * tile * (c->stem_s2d ? 4 : 8);
-      rc = c->stem_s2d ? fb::launch_extract_normalise_s2d(patch, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
-                                                          c->tile_xy_dev /* (0,0) */, 1, tile, c->lut, x0j, c->num_sms, c->stream)
-                       : fb::launch_extract_normalise(patch, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
-                                                      c->tile_xy_dev /* (0,0) */, 1, tile, c->lut, x0j, c->num_sms, c->stream);
+      rc = c->stem_s2d ? fb::launch_extract_normalise_s2d(first, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
+                                                          c->tile_xy_dev /* (0,0) */, nb, tile, c->lut, x0, c->num_sms, c->stream, stride)
+                       : fb::launch_extract_normalise(first, FB_LAYOUT_CHW, c->in_ch, ident_dev, c->in_ch, tile, tile, 0, tile,
+                                                      c->tile_xy_dev /* (0,0) */, nb, tile, c->lut, x0, c->num_sms, c->stream, stride);
       if (rc) rc = fail(c, rc, "extract launch failed");
       c->launches++;
     }

@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(256)
 extract_normalise_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int bands_total,
                          const int* __restrict__ band_idx, int c, long long W, long long H,
                          long long row0, long long rows, const int* __restrict__ tile_xy, int n,
-                         int T, const __nv_bfloat16* __restrict__ lut, __nv_bfloat16* __restrict__ out) {
+                         int T, const __nv_bfloat16* __restrict__ lut, __nv_bfloat16* __restrict__ out,
+                         long long tile_stride) {
   __shared__ __nv_bfloat16 s_lut[8 * 256];
   __shared__ int s_band[8];
   for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_lut[i] = lut[i];
@@ -30,7 +31,9 @@ extract_normalise_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int
   const int t = blockIdx.y;
   const int TQ = T >> 2;
   const int quads = T * TQ;
-  const long long tx0 = tile_xy[2 * t], ty0 = tile_xy[2 * t + 1];
+  // tile_stride != 0: every tile is cut from its own little raster (patch predict), all at tile_xy[0..1]
+  raster += static_cast<long long>(t) * tile_stride;
+  const long long tx0 = tile_xy[tile_stride ? 0 : 2 * t], ty0 = tile_xy[tile_stride ? 1 : 2 * t + 1];
   __nv_bfloat16* tile_out = out + static_cast<long long>(t) * T * T * 8;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
     const int y = q / TQ, x = (q - y * TQ) << 2;
@@ -61,7 +64,7 @@ extract_normalise_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int
 int launch_extract_normalise(const uint8_t* raster, int layout_hwc, int bands_total, const int* band_idx,
                              int c, long long W, long long H, long long row0, long long rows,
                              const int* tile_xy, int n, int T, const __nv_bfloat16* lut,
-                             __nv_bfloat16* out, int num_sms, cudaStream_t stream) {
+                             __nv_bfloat16* out, int num_sms, cudaStream_t stream, long long tile_stride) {
   if (n <= 0 || T <= 0) return 0;
   if (T % 4 != 0) return -2003;
   // ~8 resident blocks per SM over the whole batch, at least one block per tile
@@ -71,7 +74,7 @@ int launch_extract_normalise(const uint8_t* raster, int layout_hwc, int bands_to
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
   extract_normalise_kernel<<<grid, 256, 0, stream>>>(
-      raster, layout_hwc, bands_total, band_idx, c, W, H, row0, rows, tile_xy, n, T, lut, out);
+      raster, layout_hwc, bands_total, band_idx, c, W, H, row0, rows, tile_xy, n, T, lut, out, tile_stride);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(256)
 extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc, int bands_total,
                              const int* __restrict__ band_idx, long long W, long long H,
                              long long row0, long long rows, const int* __restrict__ tile_xy, int n,
-                             int T, const __nv_bfloat16* __restrict__ lut, __nv_bfloat16* __restrict__ out) {
+                             int T, const __nv_bfloat16* __restrict__ lut, __nv_bfloat16* __restrict__ out,
+                             long long tile_stride) {
   __shared__ __nv_bfloat16 s_lut[4 * 256];
   __shared__ int s_band[4];
   for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) s_lut[i] = lut[i];
@@ -94,7 +98,8 @@ extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc,
   const int t = blockIdx.y;
   const int T2 = T >> 1, TQ = T >> 2;
   const int items = T2 * TQ;
-  const long long tx0 = tile_xy[2 * t], ty0 = tile_xy[2 * t + 1];
+  raster += static_cast<long long>(t) * tile_stride;
+  const long long tx0 = tile_xy[tile_stride ? 0 : 2 * t], ty0 = tile_xy[tile_stride ? 1 : 2 * t + 1];
   __nv_bfloat16* tile_out = out + static_cast<long long>(t) * T2 * T2 * 16;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < items; q += gridDim.x * blockDim.x) {
     const int Y = q / TQ, X = (q - Y * TQ) << 1;        // space-to-depth pixels (Y, X) and (Y, X + 1)
@@ -138,7 +143,7 @@ extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc,
 int launch_extract_normalise_s2d(const uint8_t* raster, int layout_hwc, int bands_total, const int* band_idx,
                                  int c, long long W, long long H, long long row0, long long rows,
                                  const int* tile_xy, int n, int T, const __nv_bfloat16* lut,
-                                 __nv_bfloat16* out, int num_sms, cudaStream_t stream) {
+                                 __nv_bfloat16* out, int num_sms, cudaStream_t stream, long long tile_stride) {
   if (n <= 0 || T <= 0) return 0;
   if (T % 4 != 0 || c < 1 || c > 4) return -2004;
   int bx = (num_sms * 8 + n - 1) / n;
@@ -149,7 +154,7 @@ int launch_extract_normalise_s2d(const uint8_t* raster, int layout_hwc, int band
 #define FB_S2D(C_)                                                                                             \
   case C_:                                                                                                     \
     extract_normalise_s2d_kernel<C_><<<grid, 256, 0, stream>>>(raster, layout_hwc, bands_total, band_idx, W, H, \
-                                                               row0, rows, tile_xy, n, T, lut, out);          \
+                                                               row0, rows, tile_xy, n, T, lut, out, tile_stride); \
     break;
   switch (c) {
     FB_S2D(1)

@@ -7,16 +7,17 @@
 
 namespace fb {
 
+// tile_stride != 0 (patch predict): tile t is cut at tile_xy[0..1] from its own raster at raster + t * tile_stride.
 int launch_extract_normalise(const uint8_t* raster, int layout_hwc, int bands_total, const int* band_idx,
                              int c, long long W, long long H, long long row0, long long rows,
                              const int* tile_xy, int n, int T, const __nv_bfloat16* lut,
-                             __nv_bfloat16* out, int num_sms, cudaStream_t stream);
+                             __nv_bfloat16* out, int num_sms, cudaStream_t stream, long long tile_stride = 0);
 
 // <= 4 bands: the tile in 2x2 space-to-depth form, out = [n][T/2][T/2][16] bf16, channel (py*2 + px)*c + band.
 int launch_extract_normalise_s2d(const uint8_t* raster, int layout_hwc, int bands_total, const int* band_idx,
                                  int c, long long W, long long H, long long row0, long long rows,
                                  const int* tile_xy, int n, int T, const __nv_bfloat16* lut,
-                                 __nv_bfloat16* out, int num_sms, cudaStream_t stream);
+                                 __nv_bfloat16* out, int num_sms, cudaStream_t stream, long long tile_stride = 0);
 
 int launch_maxpool3x3s2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C,
                         int num_sms, cudaStream_t stream);

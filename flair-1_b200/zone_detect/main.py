@@ -184,7 +184,10 @@ def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarr
     my0, my1 = config.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())))
     raster_dev = dataset.big_image.to(device, non_blocking=True)
     model.set_raster(raster_dev, list(range(dataset.num_bands)), W, dataset.raster_height, row0=dataset.row0)
-    batch = max(int(config.get("batch_size", 4)), int(config.get("tiles_per_launch", 148)))
+    # tiles per forward pass: one 512^2 tile per SM by default, scaled with the tile area so that the activation
+    # arena (~70 MB per 512^2 tile) stays near 10 GB for the 128 .. 2048 px tiles of the compare grid
+    per_launch = int(config.get("tiles_per_launch", max(1, min(1024, round(148 * (512 / size) ** 2)))))
+    batch = min(1024, max(int(config.get("batch_size", 4)), per_launch))
     if config["output_type"] == "class_prob":
         # main.py:409-426 always clips exactly for this output type (compare.py:68): n_classes planes, no band 2
         prob = torch.zeros((config["n_classes"], my1 - my0, W), dtype=torch.uint8, device=device)
