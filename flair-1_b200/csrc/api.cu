@@ -602,7 +602,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     if (c->plan_mode == 1) return 0;
     if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
     c->flops += static_cast<double>(active) * (16 * tw) * L.flops_px;
-    if (sink && need && out.elem == 4 && L.Cout == 16 && h.direct_store && !out.up2) {
+    if (sink && need && out.elem == 4 && (L.Cout == 16 || L.Cout == 32) && h.direct_store && !out.up2) {
       h.sink_tiles = need->tiles_dev;
       h.sink_cls = sink->cls;
       h.sink_conf = sink->conf;

@@ -245,7 +245,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       if (p.direct_store) {
         const int oh = th * kTH + L.own_dh, ow = tw * G::TW + L.own_dw;
         int sink_x0 = 0, sink_y0 = 0, sink_wx0 = 0, sink_wy0 = 0, sink_wx1 = 0, sink_wy1 = 0;
-        if (!PH && BN == 16 && p.sink_cls != nullptr) {
+        float sink_best = 0.f, sink_den = 0.f;
+        int sink_arg = 0;
+        if (!PH && (BN == 16 || BN == 32) && p.sink_cls != nullptr) {
           const int* st = p.sink_tiles + 6 * tb;
           sink_x0 = __ldg(st); sink_y0 = __ldg(st + 1); sink_wx0 = __ldg(st + 2); sink_wy0 = __ldg(st + 3);
           sink_wx1 = __ldg(st + 4); sink_wy1 = __ldg(st + 5);
@@ -285,20 +287,34 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
           auto direct = [&](int col0, const auto& regs) {
             if (p.debug_skip & 4) return;
-            if constexpr (!PH && BN == 16 && sizeof(regs) == 64) {
+            if constexpr (!PH && (BN == 16 || BN == 32) && sizeof(regs) == 64) {
               if (p.sink_cls != nullptr) {
-                // fused K6: regs = the 16 fp32 logits of pixel (oh, ow + 8m) of image tb
+                // fused K6: the fp32 logits of pixel (oh, ow + 8m) of image tb arrive 16 at a time. Arg-max = first
+                // maximum; max probability = 1 / sum(exp(v - max)). With 32 columns (17..32 classes) the first half
+                // leaves its maximum, arg-max and exponent sum behind and the second half rescales that sum.
+                float best = regs[0];
+                int arg = col0;
+#pragma unroll
+                for (int k = 1; k < 16; ++k)
+                  if (col0 + k < p.sink_ncls && regs[k] > best) { best = regs[k]; arg = col0 + k; }
+                float den = 0.f;
+                if (BN == 32 && col0 != 0) {
+                  if (col0 >= p.sink_ncls || !(best > sink_best)) {   // the earlier (lower) class wins ties
+                    if (col0 >= p.sink_ncls) best = sink_best;
+                    else best = fmaxf(best, sink_best);
+                    arg = sink_arg;
+                  }
+                  den = sink_den * __expf(sink_best - best);
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (col0 + k < p.sink_ncls) den += __expf(regs[k] - best);
+                if (BN == 32 && col0 == 0) {
+                  sink_best = best; sink_arg = arg; sink_den = den;
+                  return;
+                }
                 const int rx = sink_x0 + ow + 8 * m, ry = sink_y0 + oh;
                 if (rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1) {
-                  float best = regs[0];
-                  int arg = 0;
-#pragma unroll
-                  for (int k = 1; k < 16; ++k)
-                    if (k < p.sink_ncls && regs[k] > best) { best = regs[k]; arg = k; }
-                  float den = 0.f;
-#pragma unroll
-                  for (int k = 0; k < 16; ++k)
-                    if (k < p.sink_ncls) den += __expf(regs[k] - best);
                   const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
                   p.sink_cls[o] = static_cast<uint8_t>(arg);
                   if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);

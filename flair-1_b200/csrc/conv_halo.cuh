@@ -57,8 +57,8 @@ struct HaloArgs {
   // Active-tile list (tile_need.cuh): when non-null the kernel walks tile_list[0 .. num_m_tiles) instead of the
   // full tile grid; every entry is a linear (image, tile row, tile column) index of the full grid.
   const int* tile_list;
-  // Fused class-map sink of the segmentation head (Cout == 16, out_f32 set but never written): instead of storing
-  // the 16 fp32 logits of its pixel, a lane takes their soft-max maximum / arg-max (first maximum, numpy
+  // Fused class-map sink of the segmentation head (Cout == 16 or 32, out_f32 set but never written): instead of
+  // storing the fp32 logits of its pixel, a lane takes their soft-max maximum / arg-max (first maximum, numpy
   // semantics; confidence byte = round-half-up of the max probability) and, when the pixel lies inside the write
   // rectangle of its image, writes the two bytes straight into the class / confidence maps
   // (zone_detect/compare.py:35,66-82 + dataset.py:11-34 + the window write of main.py:421-423).
