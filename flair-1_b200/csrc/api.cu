@@ -873,6 +873,13 @@ double fb_flop_count(const fb_ctx* c) { return c ? c->flops : 0.0; }
 
 int fb_logit_stride(const fb_ctx* c) { return c ? c->ls : 0; }
 
+int fb_debug_need_rect(int tile, int layer, int ax0, int ay0, int ax1, int ay1, int32_t* rect4) {
+  if (!rect4 || tile <= 0 || tile % 32 != 0 || layer < 0 || layer >= fb::kNeedLayers) return FB_ERR_INVALID;
+  const fb::NeedRect r = fb::need_rect(tile, layer, ax0, ay0, ax1, ay1);
+  rect4[0] = r.x0; rect4[1] = r.y0; rect4[2] = r.x1; rect4[3] = r.y1;
+  return 0;
+}
+
 int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int in_channels,
                     int n_classes, int use_metadata) {
   if (!c || !tensors || n_tensors <= 0) return FB_ERR_INVALID;

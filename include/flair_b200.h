@@ -206,6 +206,11 @@ int64_t fb_launch_count(const fb_ctx* ctx);
  * the cropped margin (compare.py:66-82; FB_FULL_TILES=1 in the environment turns that off). */
 double fb_flop_count(const fb_ctx* ctx);
 
+/* Host-only (no device needed): the output region of decoder layer `layer` (2*d = dec<d>.conv1, 2*d + 1 =
+ * dec<d>.conv2, 10 = segmentation head) that a tile x tile input needs when only [ax0,ax1) x [ay0,ay1) of its
+ * logits is used (csrc/tile_need.cuh, dead-output elimination). rect4 = x0, y0, x1, y1 in that layer's output grid. */
+int fb_debug_need_rect(int tile, int layer, int ax0, int ay0, int ax1, int ay1, int32_t* rect4);
+
 /* ---- host-side TIFF LZW codec (compression 5, libtiff/GDAL-compatible) used by the GeoTIFF
  *      reader/writer that stands in for rasterio (main.py:218-232, 421-426; writer.py:38-50).
  *      encode/decode return the number of bytes produced, or -1 (buffer too small / corrupt). */

@@ -325,3 +325,52 @@ def test_two_rank_confusion_allreduce_and_strip_gather_gloo(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_dead_output_regions_cover_the_receptive_field():
+    """csrc/tile_need.cuh (host half, no GPU): for random write rectangles the region need_rect() reports for every
+    decoder layer equals the exact dependency set obtained by pushing a pixel mask backwards through the decoder
+    (3x3 conv = dilation by one pixel clipped to the grid, nearest x2 upsample = pixel (y, x) reads (y//2, x//2)),
+    which is what makes the elimination bit-exact: nothing outside is read, nothing inside is missing."""
+    import ctypes as C
+    import flair1_b200._native as nat
+    lib = nat.load_library(build_if_missing=False)
+    rng = np.random.default_rng(7)
+
+    def dilate(m):
+        p = np.pad(m, 1)
+        out = np.zeros_like(m)
+        for dy in range(3):
+            for dx in range(3):
+                out |= p[dy:dy + m.shape[0], dx:dx + m.shape[1]]
+        return out
+
+    def bbox(m):
+        ys, xs = np.nonzero(m)
+        return [int(xs.min()), int(ys.min()), int(xs.max()) + 1, int(ys.max()) + 1] if ys.size else [0, 0, 0, 0]
+
+    cases = [(512, 128, 128, 384, 384), (512, 0, 0, 256, 384), (512, 128, 0, 512, 512), (256, 32, 32, 224, 224), (64, 0, 0, 64, 64)]
+    for _ in range(12):
+        T = int(rng.choice([64, 128, 256, 512]))
+        x0, y0 = int(rng.integers(0, T - 1)), int(rng.integers(0, T - 1))
+        cases.append((T, x0, y0, int(rng.integers(x0 + 1, T + 1)), int(rng.integers(y0 + 1, T + 1))))
+    for T, ax0, ay0, ax1, ay1 in cases:
+        mask = np.zeros((T, T), bool)
+        mask[ay0:ay1, ax0:ax1] = True
+        want = {10: mask}
+        cur = dilate(mask)                       # the head's 3x3 window -> dec4.conv2 output
+        for d in range(4, -1, -1):
+            want[2 * d + 1] = cur
+            cur = dilate(cur)                    # conv2's window -> conv1 output
+            want[2 * d] = cur
+            cur = dilate(cur)                    # conv1's window on the upsampled grid
+            S = cur.shape[0] // 2
+            cur = cur.reshape(S, 2, S, 2).any(axis=(1, 3))   # -> pixels of the low-res producer that are read
+        for layer, m in want.items():
+            r = (C.c_int32 * 4)()
+            assert lib.fb_debug_need_rect(T, layer, ax0, ay0, ax1, ay1, r) == 0
+            bb = bbox(m)
+            assert list(r) == bb, (T, layer, (ax0, ay0, ax1, ay1), list(r), bb)
+            assert m[bb[1]:bb[3], bb[0]:bb[2]].all()          # the dependency set is exactly that rectangle
+    r = (C.c_int32 * 4)()
+    assert lib.fb_debug_need_rect(512, 3, 10, 10, 10, 40, r) == 0 and list(r) == [0, 0, 0, 0]   # empty write rectangle
