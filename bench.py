@@ -200,7 +200,7 @@ def run_reference(args) -> int:
         "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -382,7 +382,7 @@ def run_ours(args) -> int:
         }
         if world > 1:
             line["cpu_baseline"] = None  # reported at N=1 only (torchrun pins OMP threads; see the N=1 line)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -390,7 +390,20 @@ def run_ours(args) -> int:
     return 0
 
 
+def emit(line: dict) -> None:
+    """The one JSON line of this run, on the process's ORIGINAL stdout (see main())."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main() -> int:
+    # Libraries may chat on stdout (NCCL prints its version line there): everything but the JSON line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
