@@ -77,6 +77,7 @@ struct fb_ctx {
   bool no_halo = false;       // FB_NO_HALO=1: skip the halo-staged kernel
   bool no_phase = false;      // FB_NO_PHASE=1: decoder conv1 on the materialised upsample instead of sub-pixel phases
   bool dec_phase[6] = {false, false, false, false, false, false};  // per decoder block, decided by arena_plan
+  int front_chunk = 0;        // FB_FRONT_CHUNK: tiles per stem + max-pool chunk (0 = the whole batch)
   bool no_s2d = false;        // FB_NO_S2D=1: 7x7 stride-2 stem on the 8-channel-padded tile also for <= 4 bands
   bool stem_s2d = false;      // decided by arena_plan: x0 is stored in space-to-depth form
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
@@ -653,39 +654,50 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
                 const HeadSink* sink = nullptr, bool* sunk = nullptr) {
   auto A = [&](const std::string& k) -> Act& { return c->acts[k]; };
   auto L = [&](const std::string& k) -> const ConvLayer& { return c->conv[k]; };
+  // Stem + max-pool in chunks of front_chunk tiles: the stem's output (8.4 MB per 512^2 tile) is read straight back by
+  // the bandwidth-bound pool kernel, and a chunk that fits the 126 MB L2 is read from there instead of from HBM.
   {
-    ProfScope ps(c, 1);
-    if (c->stem_s2d) {
-      const ConvLayer& S = L("stem");
-      const Act& x0 = A("x0");
-      const Act& f1 = A("f1");
-      fb::HaloArgs h;
-      memset(&h, 0, sizeof h);
-      h.x1 = static_cast<const __nv_bfloat16*>(x0.ptr);
-      h.C1 = 16;
-      h.B = x0.B; h.Hin = x0.H; h.Win = x0.W; h.Hout = f1.H; h.Wout = f1.W;
-      h.Cout = S.Cout;
-      h.bias = S.bias;
-      h.relu = 1;
-      h.out = static_cast<__nv_bfloat16*>(f1.ptr);
-      h.wpacked = S.w_s2d;
-      fb::halo_fill_steps(h, 4, 1);
-      c->flops += static_cast<double>(f1.B) * f1.H * f1.W * S.flops_px;
-      const int rc = fb::launch_conv_halo(h, 4, 1, c->num_sms, c->stream);
-      if (rc != 0) return fail(c, rc, "stem (space-to-depth) launch failed (code " + std::to_string(rc) + ")");
-      c->launches++;
-    } else {
-      FB_TRY(run_conv(c, L("stem"), A("x0"), nullptr, nullptr, nullptr, true, A("f1")));
+    const Act x0 = A("x0"), f1 = A("f1"), pool = A("pool");
+    const size_t x0_px = static_cast<size_t>(x0.H) * x0.W * x0.C, f1_px = static_cast<size_t>(f1.H) * f1.W * f1.C,
+                 pool_px = static_cast<size_t>(pool.H) * pool.W * pool.C;
+    const int chunk = c->front_chunk > 0 ? c->front_chunk : n;
+    for (int b0 = 0; b0 < n; b0 += chunk) {
+      const int nb = n - b0 < chunk ? n - b0 : chunk;
+      Act x0c = x0, f1c = f1;
+      x0c.B = nb; x0c.ptr = static_cast<__nv_bfloat16*>(x0.ptr) + b0 * x0_px;
+      f1c.B = nb; f1c.ptr = static_cast<__nv_bfloat16*>(f1.ptr) + b0 * f1_px;
+      {
+        ProfScope ps(c, 1);
+        if (c->stem_s2d) {
+          const ConvLayer& S = L("stem");
+          fb::HaloArgs h;
+          memset(&h, 0, sizeof h);
+          h.x1 = static_cast<const __nv_bfloat16*>(x0c.ptr);
+          h.C1 = 16;
+          h.B = nb; h.Hin = x0.H; h.Win = x0.W; h.Hout = f1.H; h.Wout = f1.W;
+          h.Cout = S.Cout;
+          h.bias = S.bias;
+          h.relu = 1;
+          h.out = static_cast<__nv_bfloat16*>(f1c.ptr);
+          h.wpacked = S.w_s2d;
+          fb::halo_fill_steps(h, 4, 1);
+          c->flops += static_cast<double>(nb) * f1.H * f1.W * S.flops_px;
+          const int rc = fb::launch_conv_halo(h, 4, 1, c->num_sms, c->stream);
+          if (rc != 0) return fail(c, rc, "stem (space-to-depth) launch failed (code " + std::to_string(rc) + ")");
+          c->launches++;
+        } else {
+          FB_TRY(run_conv(c, L("stem"), x0c, nullptr, nullptr, nullptr, true, f1c));
+        }
+      }
+      {
+        ProfScope ps(c, 2);
+        int rc = fb::launch_maxpool3x3s2(static_cast<const __nv_bfloat16*>(f1c.ptr),
+                                         static_cast<__nv_bfloat16*>(pool.ptr) + b0 * pool_px, nb, f1.H, f1.W, 64,
+                                         c->num_sms, c->stream);
+        if (rc) return fail(c, rc, "maxpool launch failed");
+        c->launches++;
+      }
     }
-  }
-  {
-    ProfScope ps(c, 2);
-    Act& f1 = A("f1");
-    int rc = fb::launch_maxpool3x3s2(static_cast<const __nv_bfloat16*>(f1.ptr),
-                                     static_cast<__nv_bfloat16*>(A("pool").ptr), n, f1.H, f1.W, 64,
-                                     c->num_sms, c->stream);
-    if (rc) return fail(c, rc, "maxpool launch failed");
-    c->launches++;
   }
   ProfScope ps_convs(c, 1);  // every launch from here to the end of the function is a conv
   std::string cur = "pool";
@@ -829,6 +841,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_halo = nh && nh[0] == '1';
   const char* np = getenv("FB_NO_PHASE");
   c->no_phase = np && np[0] == '1';
+  const char* fc = getenv("FB_FRONT_CHUNK");
+  c->front_chunk = fc ? atoi(fc) : 0;
   const char* ns = getenv("FB_NO_S2D");
   c->no_s2d = ns && ns[0] == '1';
   const char* ft = getenv("FB_FULL_TILES");
