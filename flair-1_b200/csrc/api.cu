@@ -633,7 +633,11 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     a.up2_out = out.up2 ? 1 : 0;
     const bool tma = !c->force_gather && fb::conv_tma_eligible(a);
     const char* pair_env = getenv("FB_PAIR");
-    if (tma && !(pair_env && pair_env[0] == '1')) {
+    // (the CTA-pair kernel does not take tile lists: it serves the N = 256 encoder layers, which run in full anyway)
+    const int pair_sel = pair_env ? atoi(pair_env) : 256;
+    const bool pair_layer = (pair_sel == 1 || pair_sel == fb::conv_pick_bn(L.Cout)) && L.KH == 3 && L.stride == 1 && Hout % 16 == 0 &&
+                            fb::conv_pick_bn(L.Cout) >= 64;
+    if (tma && !pair_layer) {
       FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active));
       if (c->plan_mode == 1) return 0;
       if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }

@@ -623,11 +623,14 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
   memset(&tmA, 0, sizeof(tmA));
   memset(&tmA2, 0, sizeof(tmA2));
   memset(&tmB, 0, sizeof(tmB));
-  // CTA pairs (cta_group::2) for the wide layers: 16 x 16 pixel tiles, each CTA stages half of the weights
-  // Measured on B200 (profiles/r01_pair_vs_single.md): no faster than the single-CTA kernel on these
-  // shapes (the wide layers are not shared-memory-port bound after all), so it is opt-in: FB_PAIR=1.
+  // CTA pairs (cta_group::2) for the wide layers: 16 x 16 pixel tiles, each CTA stages half of the weights, so a
+  // K = 16 step costs each SM 4 KB + BN*16 B of shared-memory operand reads instead of 4 KB + BN*32 B.
   const char* pair_env = getenv("FB_PAIR");
-  const bool use_pair = use_tma_a && BN >= 64 && a.Hout % 16 == 0 && pair_env != nullptr && pair_env[0] == '1' &&
+  // Default: the N = 256 layers (measured +2.4 % on the zone at 148 tiles per pass, profiles/r01_v19_summary.md; N = 128
+  // neutral). FB_PAIR=0: never; FB_PAIR=1: every eligible layer; FB_PAIR=<BN>: the layers of that width only.
+  const int pair_sel = pair_env != nullptr ? atoi(pair_env) : 256;
+  const bool pair_on = pair_sel == 1 || pair_sel == BN;
+  const bool use_pair = use_tma_a && BN >= 64 && a.Hout % 16 == 0 && pair_on &&
                         a.KH == 3 && a.stride == 1 && !a.phase_mode && a.tile_list == nullptr;
   {
     // weights: [Cout][Kpad] bf16 ([4][Cout][Kpad] in phase mode), box = 64 k x BN rows (BN/2 per CTA of a

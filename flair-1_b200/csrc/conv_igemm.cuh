@@ -76,6 +76,7 @@ struct ConvArgs {
 // C2 % 64 == 0, tile grid rows % 8 == 0 and columns % 16 == 0 (tile grid = output, or output / 2 in
 // phase mode).
 bool conv_tma_eligible(const ConvArgs& a);
+int conv_pick_bn(int Cout);   // accumulator width the kernel uses for this Cout (256, 128, 64, 32 or 16)
 int launch_conv(const ConvArgs& a, const __nv_bfloat16* weights /*[Cout][Kpad] bf16*/, int Kpad,
                 bool use_tma_a, int num_sms, cudaStream_t stream);
 
