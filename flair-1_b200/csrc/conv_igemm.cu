@@ -329,23 +329,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // 4 KB + BN*32 B -- the single-CTA kernel is bound by exactly that traffic for BN >= 128.
 // The leader (cluster rank 0) owns the "full" barriers (TMA bytes of both CTAs are counted there), issues
 // the MMAs and multicasts the commits; both CTAs run their own producer thread and epilogue warps.
-template <int BN>
+template <int BN, int EPI = 1>
 struct Cfg2 {
-  static constexpr int kStages = BN >= 256 ? 6 : 8;    // 6 x 32 KB or 8 x 24 KB of operands in flight per CTA
+  static constexpr int kThreads = EPI == 2 ? 416 : kNumThreads;
+  // 6 x 32 KB or 8 x 24 KB of operands in flight per CTA (7 when the second epilogue group needs its staging buffers)
+  static constexpr int kStages = BN >= 256 ? 6 : (EPI == 2 ? 7 : 8);
   static constexpr int kABytes = kBM * kBK * 2;        // 16384: this CTA's 128 pixels
   static constexpr int kBBytes = (BN / 2) * kBK * 2;   // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + 4 * kStgWarpBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kBarBytes + 4 * EPI * kStgWarpBytes;
 };
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+// EPI = 2: a second group of four epilogue warps (9-12) in each CTA drains the upper half of the accumulator
+// columns, as in the single-CTA kernel.
+template <int BN, int EPI = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg2<BN, EPI>::kThreads), 1)
 conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                    const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, EPI>;
   constexpr int S = C::kStages;
+  constexpr int BNE = BN / EPI;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -370,7 +375,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 2 * kNumEpilogueThreads);
+        mbar_init(tempty_bar(a), 2 * kNumEpilogueThreads * EPI);
       }
       fence_mbar_init();
       tma_prefetch_desc(&tmA);
@@ -420,15 +425,16 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp != 8) {
     const int q = warp & 3;
-    uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + q * kStgWarpBytes;
+    const int grp = warp > 8 ? 1 : 0;
+    uint8_t* stg = smem + S * C::kStageBytes + C::kBarBytes + (grp * 4 + q) * kStgWarpBytes;
     const bool f32 = p.out_f32 != nullptr;
     const int elem = f32 ? 4 : 2;
     const size_t pixel_bytes = static_cast<size_t>(p.Cout) * elem;
     const size_t up_row_bytes = static_cast<size_t>(2 * p.Wout) * pixel_bytes;
     uint8_t* out_bytes = f32 ? reinterpret_cast<uint8_t*>(p.out_f32) : reinterpret_cast<uint8_t*>(p.out);
-    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
+    const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BNE>::GC_F32 * 4 : EpiRun<BNE>::GC_BF16 * 2,
                                     p.up2_out ? 2 * p.Wout : p.Wout, p.up2_out ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
     uint32_t tcount = 0;
@@ -436,7 +442,7 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int n_tile = tile % p.num_n_tiles, pair = tile / p.num_n_tiles;
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + grp * BNE;
       const int tw = pair % tiles_w, th2 = (pair / tiles_w) % tiles_h2, tb = pair / (tiles_w * tiles_h2);
       const int h0 = th2 * 16 + 8 * static_cast<int>(rank);
       const int oh = h0 + L.own_dh, ow = tw * 16 + L.own_dw;
@@ -447,8 +453,8 @@ conv_igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         warp_copy_out_fast<decltype(run)::value>(stg, lane, L, tile_dst + static_cast<size_t>(col0) * el, pixel_bytes,
                                                  p.up2_out, up_row_bytes);
       };
-      epilogue_tile<BN, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN, stg, true,
-                                      (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
+      epilogue_tile<BNE, true, false>(p, p.bias, taddr, tfull_bar(as), aph, lane, n_tile * BN + grp * BNE, stg, true,
+                                       (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow, tb * p.Hout + oh, copy);
       tc_fence_before_sync();
       mbar_arrive_leader(tempty_bar(as));   // local arrive in the leader, remote arrive from the peer
     }
@@ -513,18 +519,18 @@ int launch_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap&
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
 
-template <int BN>
+template <int BN, int EPI = 1>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvArgs& a,
                 int grid, cudaStream_t stream) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  conv_igemm2_kernel<BN><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);  // cluster dims are static (2,1,1)
+  conv_igemm2_kernel<BN, EPI><<<grid, C::kThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);  // cluster dims are static (2,1,1)
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -676,8 +682,11 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
     int clusters = num_sms / 2;
     if (num_pairs < clusters) clusters = num_pairs;
     if (clusters <= 0) return 0;
+    const char* e2 = getenv("FB_EPI2");
+    const bool epi2 = !(e2 && e2[0] == '0');
     return BN == 256 ? launch_pair<256>(tmA, tmA2, tmB, a, 2 * clusters, stream)
-           : BN == 128 ? launch_pair<128>(tmA, tmA2, tmB, a, 2 * clusters, stream)
+           : BN == 128 ? (epi2 ? launch_pair<128, 2>(tmA, tmA2, tmB, a, 2 * clusters, stream)
+                               : launch_pair<128>(tmA, tmA2, tmB, a, 2 * clusters, stream))
                        : launch_pair<64>(tmA, tmA2, tmB, a, 2 * clusters, stream);
   }
 
