@@ -363,12 +363,12 @@ def run_ours(args) -> int:
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": conv_tflops / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the family's top kernel
-                         # (conv_igemm_kernel<256>, a layer3 3x3 conv on 74 tiles: 38.8 MB in, 38.8 MB out, 1.2 MB
-                         # of weights; the output mostly stays in the 126 MB L2 for the next layer), from the
-                         # `ncu --set full` capture summarised in profiles/r01_ncu_full_igemm256_v13.csv
-                         "traffic": 42.77e6, "traffic_unit": "bytes per launch (conv_igemm_kernel<256>, 74 tiles)",
+                         # (conv_igemm2_kernel<256>, a layer3 3x3 conv on 148 tiles: 77.6 MB in, 77.6 MB out, 1.2 MB of
+                         # weights; part of the output stays in the 126 MB L2 for the next layer; 114.2 us, tensor pipe
+                         # 88 % active), from the `ncu --set full` capture in profiles/r01_ncu_full_igemm2_256_v21.csv
+                         "traffic": 114.74e6, "traffic_unit": "bytes per launch (conv_igemm2_kernel<256>, 148 tiles)",
                          "peak_source": peak_src,
-                         "kernel": "conv_igemm_kernel + conv_halo_kernel (47 launches per batch); achieved = algorithmic FLOPs "
+                         "kernel": "conv_igemm2_kernel / conv_igemm_kernel / conv_halo_kernel (47 launches per batch); achieved = algorithmic FLOPs "
                                    "(2*MAC of the direct conv) of the outputs actually computed / summed conv time",
                          "gflop_per_tile_computed": gflop_per_tile, "gflop_per_tile_full": GFLOP_PER_TILE,
                          "note": "the decoder skips outputs that can only reach the cropped margin (bit-identical class map, "

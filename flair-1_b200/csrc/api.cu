@@ -112,6 +112,7 @@ struct fb_ctx {
   int bands_total = 0, rc = 0, layout = 0;
   int64_t W = 0, H = 0, row0 = 0, rows = 0;
   int* band_idx_dev = nullptr;
+  int* ident_dev = nullptr;      // 0..7: band selection of fb_predict_patches (patches hold the selected bands only)
 
   // activation arena
   uint8_t* arena = nullptr;
@@ -869,6 +870,7 @@ void fb_destroy(fb_ctx* c) {
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->band_idx_dev) cudaFree(c->band_idx_dev);
+  if (c->ident_dev) cudaFree(c->ident_dev);
   if (c->arena) cudaFree(c->arena);
   if (c->tile_xy_dev) cudaFree(c->tile_xy_dev);
   if (c->tiles_dev) cudaFree(c->tiles_dev);
@@ -1350,10 +1352,12 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
   FB_TRY(ensure_tile_buffers(c, batch));
   if (!c->band_idx_dev) FB_CUDA(c, cudaMalloc(&c->band_idx_dev, 8 * sizeof(int)));
   // every patch is its own little band-planar raster of c bands; the write rectangle is the whole tile
-  int ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-  int* ident_dev = nullptr;
-  FB_CUDA(c, cudaMalloc(&ident_dev, sizeof ident));
-  FB_CUDA(c, cudaMemcpyAsync(ident_dev, ident, sizeof ident, cudaMemcpyHostToDevice, c->stream));
+  if (!c->ident_dev) {
+    const int ident[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    FB_CUDA(c, cudaMalloc(&c->ident_dev, sizeof ident));
+    FB_CUDA(c, cudaMemcpy(c->ident_dev, ident, sizeof ident, cudaMemcpyHostToDevice));
+  }
+  int* ident_dev = c->ident_dev;
   std::vector<int> xy(static_cast<size_t>(batch) * 2), rect(static_cast<size_t>(batch) * 6);
   for (int i = 0; i < batch; ++i) {
     xy[2 * i] = 0; xy[2 * i + 1] = i * tile;
@@ -1400,8 +1404,7 @@ int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metad
       c->launches++;
     }
   }
-  cudaStreamSynchronize(c->stream);
-  cudaFree(ident_dev);
+  cudaStreamSynchronize(c->stream);   // rect / xy are locals, and the caller reads cls_out next
   return rc;
 }
 
