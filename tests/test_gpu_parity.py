@@ -292,6 +292,39 @@ def test_five_band_metadata_model_logits(ctx):
         ctx.forward_tiles(xy, T)      # metadata model without metadata must fail loudly
 
 
+@pytest.mark.parametrize("bands,ncls", [(1, 7), (2, 15), (4, 16), (6, 13), (8, 19)])
+def test_other_band_counts_logits(ctx, bands, ncls):
+    """1, 2 and 4 bands take the space-to-depth stem (one extract instantiation each), 6 and 8 the 7x7 stride-2 stem on
+    the 8-channel tile; class counts at the 16 / 17 boundary. Random-init models, tiles hanging over the raster edge:
+    logits within the tolerance of the fp32 oracle."""
+    from oracle.unet_smp033 import Unet
+    from oracle.zone_detect_ref import normalization
+    torch.manual_seed(100 + bands)
+    model = Unet(bands, ncls).eval()
+    g = torch.Generator().manual_seed(bands)
+    W, H, T = 400, 300, 256
+    raster = torch.randint(0, 256, (bands, H, W), generator=g, dtype=torch.uint8)
+    means = [100.0 + 3 * i for i in range(bands)]
+    stds = [40.0 + 2 * i for i in range(bands)]
+    ctx.load_weights(model.state_dict(), bands, ncls)
+    ctx.set_norm("custom", means, stds)
+    ctx.set_raster(raster.cuda(), list(range(bands)), W, H)
+    xy = np.array([[-40, -30], [W - 200, H - 180], [72, 20]], np.int32)
+    got = ctx.forward_tiles(xy, T).cpu()
+    assert got.shape[-1] == (16 if ncls <= 16 else 32) and (got[..., ncls:] == 0).all()
+    patches = []
+    for x0, y0 in xy:
+        patch = np.zeros((bands, T, T), np.uint8)
+        r0, r1, c0, c1 = max(y0, 0), min(y0 + T, H), max(x0, 0), min(x0 + T, W)
+        patch[:, r0 - y0:r1 - y0, c0 - x0:c1 - x0] = raster.numpy()[:, r0:r1, c0:c1]
+        patches.append(torch.as_tensor(normalization(patch, "custom", means, stds), dtype=torch.float))
+    with torch.no_grad():
+        ref = model(torch.stack(patches))
+    rel = (got.permute(0, 3, 1, 2)[:, :ncls] - ref).abs().max().item() / ref.abs().max().item()
+    print(f"{bands} bands / {ncls} classes: logits rel err {rel:.4e}")
+    assert rel <= LOGIT_TOL
+
+
 def test_nineteen_class_model(ctx):
     """Configs 1/5 of BASELINE.json name the 19-class nomenclature: n_classes > 16 switches logits and blend
     accumulators to 32 floats per pixel (fb_logit_stride) and the head to a 32-column accumulator. Random-init
