@@ -153,6 +153,16 @@ def read_info(path) -> TiffInfo:
                     geo_tags={t: tags[t] for t in GEO_TAGS if t in tags})
 
 
+def _default_threads() -> int:
+    """Block codec threads: the host cores this process may use (torchrun pins OMP threads, not these), at most 32."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(1, min(32, n))
+
+
 def _packbits_decode(data: bytes, expected: int) -> np.ndarray:
     out = bytearray()
     i, n = 0, len(data)
@@ -230,7 +240,7 @@ def read(path, bands: Optional[Sequence[int]] = None, window: Optional[Tuple[int
             blk = np.cumsum(blk, axis=1, dtype=np.uint8)
         return job, blk
 
-    with ThreadPoolExecutor(max_workers=8) as ex:
+    with ThreadPoolExecutor(max_workers=_default_threads()) as ex:   # the codecs release the GIL
         for (by, bx, pl), blk in ex.map(decode, jobs):
             y0, x0 = by * bh, bx * bw
             ys, ye = max(y0, r0), min(y0 + blk.shape[0], r0 + h)
@@ -261,7 +271,7 @@ def _encode_block(blk: np.ndarray, compress: str) -> bytes:
 
 
 def write(path, data: np.ndarray, geo_tags: Optional[Dict[int, Tuple[int, tuple]]] = None, compress: str = "lzw",
-          tiled: bool = True, blocksize: int = 512, bigtiff: Optional[bool] = None, threads: int = 8) -> None:
+          tiled: bool = True, blocksize: int = 512, bigtiff: Optional[bool] = None, threads: int = 0) -> None:
     """Write uint8 [bands, H, W] (or [H, W]) as a chunky (pixel-interleaved) TIFF.
 
     compress in {"lzw", "deflate", "none"}; tiled blocks are blocksize x blocksize (the reference uses
@@ -289,7 +299,7 @@ def write(path, data: np.ndarray, geo_tags: Optional[Dict[int, Tuple[int, tuple]
         return _encode_block(blk, compress)
 
     jobs = [(by, bx) for by in range(nby) for bx in range(nbx)]
-    with ThreadPoolExecutor(max_workers=threads) as ex:
+    with ThreadPoolExecutor(max_workers=threads if threads > 0 else _default_threads()) as ex:
         blocks = list(ex.map(make, jobs))
 
     comp_code = {"none": 1, "lzw": 5, "deflate": 8}[compress]
