@@ -77,6 +77,8 @@ struct fb_ctx {
   bool no_halo = false;       // FB_NO_HALO=1: skip the halo-staged kernel
   bool no_phase = false;      // FB_NO_PHASE=1: decoder conv1 on the materialised upsample instead of sub-pixel phases
   bool dec_phase[6] = {false, false, false, false, false, false};  // per decoder block, decided by arena_plan
+  bool dec_up1[6] = {false, false, false, false, false, false};    // block reads its low-res x1 through the halo kernel's x2 upsample
+  bool no_up1 = false;        // FB_NO_UP1=1: such blocks read a 2x2-replicated x1 written by the producer instead
   int front_chunk = 0;        // FB_FRONT_CHUNK: tiles per stem + max-pool chunk (0 = the whole batch)
   bool no_s2d = false;        // FB_NO_S2D=1: 7x7 stride-2 stem on the 8-channel-padded tile also for <= 4 bands
   bool stem_s2d = false;      // decided by arena_plan: x0 is stored in space-to-depth form
@@ -384,6 +386,13 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     if (!c->force_gather && !c->no_phase && !c->no_halo && !(hp && hp[0] == '1') && it != c->conv.end() &&
         it->second.w_halo_phase != nullptr && fb::halo_phase_supported(it->second.C1, it->second.C2, it->second.Cout, S_lo, S_lo))
       c->dec_phase[d] = true;
+    // no phase form: the halo kernel can still read the low-res x1 itself (upsample in its gather) when the block
+    // is one of its shapes; otherwise the producer materialises the 2x2 replication
+    c->dec_up1[d] = false;
+    if (!c->dec_phase[d] && d >= 1 && !c->no_up1 && !c->force_gather && !c->no_halo && it != c->conv.end() &&
+        it->second.w_halo != nullptr &&
+        fb::halo_supported(3, 1, it->second.C1, it->second.C2, it->second.Cout, 2 * S_lo, 2 * S_lo))
+      c->dec_up1[d] = true;
   }
   {
     auto it = c->conv.find("stem");
@@ -418,7 +427,7 @@ void arena_plan(fb_ctx* c, int n, int T, bool dry) {
     arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry);
     snprintf(buf, sizeof buf, "dec%d", d);
     // dec0..3 feed the next block through the x2 upsample: materialised here unless that block runs in phase form
-    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry, d < 4 && !c->dec_phase[d + 1]);
+    arena_alloc(c, buf, n, S, S, kDecOut[d], 2, dry, d < 4 && !c->dec_phase[d + 1] && !c->dec_up1[d + 1]);
     S *= 2;
   }
   arena_alloc(c, "logits", n, T, T, c->ls, 4, dry);
@@ -521,7 +530,7 @@ int build_planned_lists(fb_ctx* c, const NeedCtx* need) {
 // whether the kernel that ran could do it).
 int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const Act* res,
              const float* rowbias, bool relu, const Act& out, bool phase = false, const NeedCtx* need = nullptr,
-             int layer = -1, const HeadSink* sink = nullptr, bool* sunk = nullptr) {
+             int layer = -1, const HeadSink* sink = nullptr, bool* sunk = nullptr, bool up1 = false) {
   // `out` may be stored 2x2-replicated (Act::up2): the conv itself runs at half those dims
   const int Hout = out.up2 ? out.H / 2 : out.H, Wout = out.up2 ? out.W / 2 : out.W;
   const int C1 = x1.C, C2 = x2 ? x2->C : 0;
@@ -581,15 +590,22 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     c->launches++;
     return 0;
   }
-  if (x2 && (x2->H != x1.H || x2->W != x1.W)) return fail(c, FB_ERR_INVALID, "internal: skip tensor shape mismatch");
-  if (!c->force_gather && !c->no_halo && L.w_halo && L.C1 == C1 && L.C2 == C2 &&
-      fb::halo_supported(L.KH, L.stride, C1, C2, L.Cout, Hout, Wout)) {
+  if (up1) {
+    if (x1.up2 || x1.H * 2 != Hout || x1.W * 2 != Wout || (x2 && (x2->H != Hout || x2->W != Wout)) || L.KH != 3 || L.stride != 1 ||
+        !L.w_halo || !fb::halo_supported(3, 1, C1, C2, L.Cout, Hout, Wout))
+      return fail(c, FB_ERR_INVALID, "internal: upsampling halo conv shape mismatch");
+  } else if (x2 && (x2->H != x1.H || x2->W != x1.W)) {
+    return fail(c, FB_ERR_INVALID, "internal: skip tensor shape mismatch");
+  }
+  if (up1 || (!c->force_gather && !c->no_halo && L.w_halo && L.C1 == C1 && L.C2 == C2 &&
+              fb::halo_supported(L.KH, L.stride, C1, C2, L.Cout, Hout, Wout))) {
     fb::HaloArgs h;
     memset(&h, 0, sizeof h);
     h.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
     h.x2 = x2 ? static_cast<const __nv_bfloat16*>(x2->ptr) : nullptr;
     h.C1 = C1; h.C2 = C2;
-    h.B = x1.B; h.Hin = x1.H; h.Win = x1.W; h.Hout = Hout; h.Wout = Wout;
+    h.up1 = up1 ? 1 : 0;
+    h.B = x1.B; h.Hin = up1 ? Hout : x1.H; h.Win = up1 ? Wout : x1.W; h.Hout = Hout; h.Wout = Wout;
     h.Cout = L.Cout;
     h.bias = L.bias;
     h.residual = res ? static_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
@@ -734,7 +750,7 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
       snprintf(nm, sizeof nm, "dec%d", d);
       const std::string base(nm);
       FB_TRY(run_conv(c, L(base + ".conv1"), A(x), skips[d] ? &A(skips[d]) : nullptr, nullptr, nullptr, true, A(base + ".mid"),
-                      c->dec_phase[d], need, 2 * d));
+                      c->dec_phase[d], need, 2 * d, nullptr, nullptr, c->dec_up1[d]));
       FB_TRY(run_conv(c, L(base + ".conv2"), A(base + ".mid"), nullptr, nullptr, nullptr, true, A(base), false, need, 2 * d + 1));
       x = base;
     }
@@ -846,6 +862,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_halo = nh && nh[0] == '1';
   const char* np = getenv("FB_NO_PHASE");
   c->no_phase = np && np[0] == '1';
+  const char* nu = getenv("FB_NO_UP1");
+  c->no_up1 = nu && nu[0] == '1';
   const char* fc = getenv("FB_FRONT_CHUNK");
   c->front_chunk = fc ? atoi(fc) : 0;
   const char* ns = getenv("FB_NO_S2D");

@@ -140,7 +140,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     constexpr int kPrefetchDist = 2;
     const int nsrc = p.C2 > 0 ? 2 : 1;
     auto prefetch_tile = [&](int t) {
-      if (t >= p.num_m_tiles || p.no_prefetch) return;
+      if (t >= p.num_m_tiles || p.no_prefetch || p.up1) return;
       t = tile_of(t);
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
       const int iw0 = tw * G::TW * STRIDE - G::PAD;
@@ -172,6 +172,21 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         const int row_elems = p.Win * Cs;  // element distance between halo rows
         const uint32_t st = stage_addr0 + s * G::STAGE;
         if (p.debug_skip & 1) {
+        } else if (p.up1 && from1) {
+          // x1 is read through a nearest x2 upsample: halo pixel (ih, iw) of the conv's input grid is pixel
+          // (ih >> 1, iw >> 1) of the low-res tensor [B, Hin/2, Win/2, C1] (decoder block without a phase form)
+          const int Hlo = p.Hin >> 1, Wlo = p.Win >> 1;
+          const __nv_bfloat16* lo = p.x1 + static_cast<long long>(b) * Hlo * Wlo * Cs + g * (NCH * 8) + c8;
+#pragma unroll
+          for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+            if (cell[j] != 0xFFFFFFFFu) {
+              const int ih = ih0 + static_cast<int>((cell[j] >> 16) & 0xFF), iw = iw0 + static_cast<int>(cell[j] >> 24);
+              const bool ok = static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hin) &&
+                              static_cast<unsigned>(iw) < static_cast<unsigned>(p.Win);
+              const __nv_bfloat16* gp = ok ? lo + (static_cast<long long>(ih >> 1) * Wlo + (iw >> 1)) * Cs : p.x1;
+              cp_async_16(st + (cell[j] & 0xFFFFu), gp, ok ? 16u : 0u);
+            }
+          }
         } else if (interior) {
 #pragma unroll
           for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {

@@ -27,6 +27,7 @@ struct HaloArgs {
   const __nv_bfloat16* x1;
   const __nv_bfloat16* x2;       // optional second source concatenated after x1's channels
   int C1, C2;
+  int up1;                       // 1: x1 is [B, Hin/2, Win/2, C1] and is read through a nearest x2 upsample (3x3 stride 1 only)
   int B, Hin, Win, Hout, Wout;
   int Cout;                      // == BN of the instantiation
   // epilogue (same meaning as ConvArgs)
