@@ -60,6 +60,8 @@ struct HeadSink {
   int64_t map_w = 0, map_row0 = 0;
 };
 
+static_assert(sizeof(fb_tile) == 6 * sizeof(int32_t), "fb_tile is handed to the kernels as int32 [n][6]");
+
 struct ProfRec {
   int cat;
   cudaEvent_t a, b;

@@ -221,10 +221,6 @@ def read(path, bands: Optional[Sequence[int]] = None, window: Optional[Tuple[int
                     continue
                 jobs.append((by, bx, pl))
     with open(path, "rb") as f:
-        def load(job):
-            by, bx, pl = job
-            idx = (pl * nby + by) * nbx + bx
-            return job, idx
         raws = {}
         for job in jobs:
             by, bx, pl = job
