@@ -558,3 +558,51 @@ def test_zone_confusion_matches_oracle_given_same_predictions(ctx, trained_3_15)
     ref = patch_confusion(truth.numpy() - 1, pred.numpy(), 15)
     np.testing.assert_array_equal(cm, ref)
     assert class_IoU(cm)[1] == class_IoU(ref)[1] and overall_accuracy(cm) == overall_accuracy(ref)
+
+
+def test_full_size_zone_properties(ctx, trained_3_15):
+    """BASELINE configs[1] at full size (10000 x 10000, 1600 tiles of 512 / margin 128), through properties that do not
+    need the oracle: every pixel written with a valid class, the run is idempotent, sharding the tile rows the way the
+    multi-GPU path does (4 strips, each with its own raster rows and map band) gives the same bytes as the whole table,
+    the host entry point (row-sorted, pipelined copies) gives the same bytes, and the confusion matrix of the whole
+    map is the sum over the strips and counts every pixel whose truth is in range."""
+    import bench
+    from oracle import synth
+    from flair1_b200.zone_detect.slicing_job import split_rows_across_ranks, tile_table
+    sd, _ = trained_3_15
+    W = H = 10000
+    T, M = 512, 128
+    dev = torch.device("cuda", 0)
+    raster = bench.synth_rows_gpu(W, H, 0, H, 1, dev)
+    ctx.load_weights(sd, 3, 15)
+    ctx.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+    ctx.set_raster(raster, [0, 1, 2], W, H)
+    tiles = tile_table(W, H, T, M)
+    assert len(tiles) == 1600
+    cls = torch.full((H, W), 255, dtype=torch.uint8, device=dev)
+    conf = torch.full((H, W), 255, dtype=torch.uint8, device=dev)
+    ctx.detect_strip(tiles, T, 148, cls, conf, W, 0)
+    assert int(cls.max()) < 15 and int(conf.max()) <= 1                     # every pixel written
+    cls2 = torch.full_like(cls, 255)
+    ctx.detect_strip(tiles, T, 74, cls2, None, W, 0)                          # another batch size, no confidence band
+    assert torch.equal(cls, cls2)
+    truth = torch.randint(0, 21, (H, W), dtype=torch.uint8, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    cm = ctx.confusion(cls, truth, 15, truth_sub=1)
+    assert int(cm.sum()) == int(((truth >= 1) & (truth <= 15)).sum())
+    # the multi-GPU sharding, emulated on one device: 4 strips, own raster rows, own map band
+    cm_sum = torch.zeros_like(cm)
+    for shard in split_rows_across_ranks(tiles, 4):
+        mine = tiles[shard]
+        ry0, ry1 = max(int(mine[:, 1].min()), 0), min(int(mine[:, 1].max()) + T, H)
+        my0, my1 = int(mine[:, 3].min()), int(mine[:, 5].max())
+        ctx.set_raster(raster[:, ry0:ry1].contiguous(), [0, 1, 2], W, H, row0=ry0)
+        band = torch.full((my1 - my0, W), 255, dtype=torch.uint8, device=dev)
+        ctx.detect_strip(mine, T, 148, band, None, W, my0)
+        assert torch.equal(band, cls[my0:my1])
+        cm_sum += ctx.confusion(band, truth[my0:my1].contiguous(), 15, truth_sub=1)
+    assert torch.equal(cm_sum, cm)
+    # host in / host out
+    host_r = raster.cpu().numpy()
+    out_cls, out_conf = np.zeros((H, W), np.uint8), np.zeros((H, W), np.uint8)
+    ctx.detect_zone_host(host_r, [0, 1, 2], W, H, 0, 0, tiles, T, 148, out_cls, out_conf, W, 0, H)
+    assert np.array_equal(out_cls, cls.cpu().numpy()) and np.array_equal(out_conf, conf.cpu().numpy())
