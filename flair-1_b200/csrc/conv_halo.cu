@@ -155,9 +155,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     };
     for (int d = 0; d < kPrefetchDist; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);
     uint32_t it = 0;
+    // the tile id of the NEXT iteration is loaded now, so that the list lookup (a global load) never sits on the
+    // path between two tiles
+    int tile_next = blockIdx.x < p.num_m_tiles ? tile_of(blockIdx.x) : 0;
     for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x) {
       prefetch_tile(ti + kPrefetchDist * gridDim.x);
-      const int tile = tile_of(ti);
+      const int tile = tile_next;
+      if (ti + static_cast<int>(gridDim.x) < p.num_m_tiles) tile_next = tile_of(ti + gridDim.x);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
@@ -228,8 +232,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                                     p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     uint32_t tcount = 0;
+    int tile_next = blockIdx.x < p.num_m_tiles ? tile_of(blockIdx.x) : 0;
     for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x, ++tcount) {
-      const int tile = tile_of(ti);
+      const int tile = tile_next;
+      if (ti + static_cast<int>(gridDim.x) < p.num_m_tiles) tile_next = tile_of(ti + gridDim.x);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;

@@ -99,11 +99,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tiles_w = p.tgrid_w >> 4, tiles_h = p.tgrid_h >> 3;
         const int phases = p.phase_mode ? 4 : 1;
         uint32_t it = 0;
+        // list lookups run one iteration ahead (a global load must not sit between two tiles)
+        auto m_tile_of = [&](int t) {
+          const int idx = (t / p.num_n_tiles) / phases;
+          return p.tile_list != nullptr ? __ldg(p.tile_list + idx) : idx;
+        };
+        int m_next = blockIdx.x < num_tiles ? m_tile_of(blockIdx.x) : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.num_n_tiles;
           const int rest = tile / p.num_n_tiles;
           const int phase = rest % phases;
-          const int m_tile = p.tile_list != nullptr ? __ldg(p.tile_list + rest / phases) : rest / phases;
+          const int m_tile = m_next;
+          if (tile + static_cast<int>(gridDim.x) < num_tiles) m_next = m_tile_of(tile + gridDim.x);
           const int pa = p.phase_mode ? (phase >> 1) : 0, pb = p.phase_mode ? (phase & 1) : 0;
           const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
           const int b = m_tile / (tiles_w * tiles_h);
@@ -202,11 +209,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                     p.up2_out ? 2 * p.Wout : p.Wout, osc,
                                     [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
     uint32_t tcount = 0;
+    auto m_tile_of = [&](int t) {
+      const int idx = (t / p.num_n_tiles) / phases;
+      return (TMA_A && p.tile_list != nullptr) ? __ldg(p.tile_list + idx) : idx;
+    };
+    int m_next = blockIdx.x < num_tiles ? m_tile_of(blockIdx.x) : 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int n_tile = tile % p.num_n_tiles;
       const int rest = tile / p.num_n_tiles;
       const int phase = rest % phases;
-      const int m_tile = (TMA_A && p.tile_list != nullptr) ? __ldg(p.tile_list + rest / phases) : rest / phases;
+      const int m_tile = m_next;
+      if (tile + static_cast<int>(gridDim.x) < num_tiles) m_next = m_tile_of(tile + gridDim.x);
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + grp * BNE;
