@@ -313,6 +313,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                 // fused K6: the fp32 logits of pixel (oh, ow + 8m) of image tb arrive 16 at a time. Arg-max = first
                 // maximum; max probability = 1 / sum(exp(v - max)). With 32 columns (17..32 classes) the first half
                 // leaves its maximum, arg-max and exponent sum behind and the second half rescales that sum.
+                // pixels of an active kernel tile that lie outside the write rectangle are not worth the exponentials
+                const int rx = sink_x0 + ow + 8 * m, ry = sink_y0 + oh;
+                if (!(rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1)) return;
                 float best = regs[0];
                 int arg = col0;
 #pragma unroll
@@ -334,12 +337,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                   sink_best = best; sink_arg = arg; sink_den = den;
                   return;
                 }
-                const int rx = sink_x0 + ow + 8 * m, ry = sink_y0 + oh;
-                if (rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1) {
-                  const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
-                  p.sink_cls[o] = static_cast<uint8_t>(arg);
-                  if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);
-                }
+                const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
+                p.sink_cls[o] = static_cast<uint8_t>(arg);
+                if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);
                 return;
               }
             }
