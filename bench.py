@@ -296,9 +296,11 @@ def run_ours(args) -> int:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), t0, t1
 
+    # nvidia-smi needs a few hundred ms to deliver its first sample: start it before the warm-up, keep the samples that
+    # fall inside the timed region
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0, flops0 = ctx.launch_count, ctx.flop_count
     ctx.profile_begin()
     ms_total, t0, t1 = timed(step_resident, args.steps)
