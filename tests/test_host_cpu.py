@@ -374,3 +374,20 @@ def test_dead_output_regions_cover_the_receptive_field():
             assert m[bb[1]:bb[3], bb[0]:bb[2]].all()          # the dependency set is exactly that rectangle
     r = (C.c_int32 * 4)()
     assert lib.fb_debug_need_rect(512, 3, 10, 10, 10, 40, r) == 0 and list(r) == [0, 0, 0, 0]   # empty write rectangle
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU path: the oracle port on the host cores) on a two-tile sample: exactly one
+    line on stdout, carrying the keys of the measurement contract."""
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-tiles", "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "zone_detect Mpixels/s" and d["unit"] == "Mpixels/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "10000x10000" in d["config"]["workload"] and d["config"]["tiles"] == 1600
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
