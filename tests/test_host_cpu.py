@@ -391,3 +391,53 @@ def test_bench_reference_arm_prints_one_json_line():
     assert "10000x10000" in d["config"]["workload"] and d["config"]["tiles"] == 1600
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+_WORKER_MAIN = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from flair1_b200.zone_detect import main as zmain
+from flair1_b200.zone_detect.metrics import metrics_from_confmat
+from flair1_b200.zone_detect.slicing_job import split_rows_across_ranks, tile_table, tile_windows
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+W, H, T, M, NC = 1500, 1100, 512, 128, 15
+rng = np.random.default_rng(11)
+full = rng.integers(0, NC, (H, W), dtype=np.uint8)
+tiles, wins = tile_table(W, H, T, M), tile_windows(W, H, T, M)
+shard = split_rows_across_ranks(tiles, world)[rank]
+mine = tiles[shard]
+r0, r1 = int(mine[:, 3].min()), int(mine[:, 5].max())
+# the product's own strip gather (NCCL on the GPU box, gloo here)
+got = zmain._gather_strips(torch.from_numpy(full[r0:r1].copy()), r0, H, W, torch.device("cpu"))
+assert (got is None) == (rank != 0)
+if rank == 0:
+    assert np.array_equal(got, full)
+# the product's own per-patch metric gather: every rank contributes the confusion matrices of its tiles
+classes = {{i + 1: [1 if i < 12 else 0, "class%d" % (i + 1)] for i in range(NC)}}
+all_cm = rng.integers(0, 1000, (len(tiles), NC, NC)).astype(np.int64)
+cfg = {{"classes": classes, "n_classes": NC, "_my_index": shard, "_my_windows": wins[shard], "_patch_cm": torch.from_numpy(all_cm[shard])}}
+res = zmain._gather_patch_metrics(cfg, "m")
+if rank == 0:
+    ref = [metrics_from_confmat(all_cm[i], cfg, "m_%d_%d" % (wins[i][2], wins[i][3])) for i in range(len(tiles))]
+    assert res == ref and len(res) == len(tiles)
+else:
+    assert res is None
+dist.destroy_process_group()
+sys.stdout.write("rank %d ok\n" % rank)
+sys.stdout.flush()
+"""
+
+
+def test_two_rank_strip_and_patch_metric_gather_of_the_pipeline_gloo(tmp_path):
+    """zone_detect.main._gather_strips / _gather_patch_metrics (the multi-GPU tail of run_pipeline) under gloo with two
+    ranks: rank 0 ends up with the whole class map and with every tile's metrics in write order."""
+    script = tmp_path / "worker_main.py"
+    script.write_text(_WORKER_MAIN.format(root=str(ROOT)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
