@@ -441,3 +441,12 @@ def test_two_rank_strip_and_patch_metric_gather_of_the_pipeline_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/flair_b200.h is the drop-in boundary: it must compile as C99 (plain pointers and sizes, no C++ / torch types)."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "flair_b200.h"\nint main(void) { fb_tile t = {0, 0, 0, 0, 0, 0}; return t.x0 + (FB_API_VERSION != 1); }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(ROOT / "include"), str(src)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
