@@ -66,8 +66,22 @@ _SIGNATURES = {
     "fb_detect_zone_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int64,
                                       C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
+    "fb_detect_zone_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int64,
+                                       C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                       C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "fb_predict_patches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fb_confusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "fb_confusion_rect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                    C.c_int, C.c_void_p]),
+    "fb_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fb_host_unregister": (C.c_int, [C.c_void_p]),
+    "fb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "fb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "fb_allreduce_confusion": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "fb_gather_bytes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                  C.c_int]),
     "fb_conv2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
@@ -322,6 +336,36 @@ class Context:
                                                   layout, t.ctypes.data, t.shape[0], tile, batch, hp(out_cls)[0],
                                                   hp(out_conf)[0], map_w, map_row0, map_rows))
 
+    def detect_zone_shard(self, raster, band_idx: Sequence[int], W: int, H: int, row0: int, layout: int,
+                          tiles: np.ndarray, tile: int, batch: int, out_cls, out_conf, map_w: int, map_row0: int,
+                          map_rows: int, truth=None, truth_row0: int = 0, truth_sub: int = 0,
+                          cm: Optional[torch.Tensor] = None) -> None:
+        """One shard of a zone (fb_detect_zone_shard): host raster rows in, ONLY this shard's write rectangles out
+        into the (possibly shared) host maps out_cls / out_conf [map_rows, map_w]. With `truth` (host uint8 rows
+        starting at truth_row0, pitch map_w) the shard's confusion matrix is added to `cm` (device int64
+        [ncls, ncls])."""
+        def hp(x):
+            if x is None:
+                return None, None
+            if torch.is_tensor(x):
+                assert not x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()
+                return x.data_ptr(), tuple(x.shape)
+            assert x.dtype == np.uint8 and x.flags["C_CONTIGUOUS"]
+            return x.ctypes.data, x.shape
+        rptr, rshape = hp(raster)
+        bands_total = rshape[0] if layout == FB_LAYOUT_CHW else rshape[2]
+        rows = rshape[1] if layout == FB_LAYOUT_CHW else rshape[0]
+        bi = (C.c_int32 * len(band_idx))(*band_idx)
+        t = make_tiles(tiles)
+        ncls = 0
+        if truth is not None:
+            assert cm is not None and cm.dtype == torch.int64 and cm.is_cuda and cm.is_contiguous() and cm.shape[0] == cm.shape[1]
+            ncls = int(cm.shape[0])
+        self._check(self._lib.fb_detect_zone_shard(self._h, rptr, bands_total, bi, len(band_idx), W, H, row0, rows, layout,
+                                                   t.ctypes.data, t.shape[0], tile, batch, hp(out_cls)[0], hp(out_conf)[0],
+                                                   map_w, map_row0, map_rows, hp(truth)[0], truth_row0, truth_sub, ncls,
+                                                   _ptr(cm)))
+
     def predict_patches(self, patches: torch.Tensor, tile: int, batch: int, metadata: Optional[np.ndarray] = None) -> torch.Tensor:
         """patches: uint8 device [n, c, tile, tile]; returns uint8 device [n, tile, tile] class ids."""
         assert patches.dtype == torch.uint8 and patches.is_cuda and patches.is_contiguous()
@@ -340,6 +384,60 @@ class Context:
             out = torch.zeros((ncls, ncls), dtype=torch.int64, device=self.device)
         self._check(self._lib.fb_confusion(self._h, pred.data_ptr(), truth.data_ptr(), pred.numel(), ncls, truth_sub, out.data_ptr()))
         return out
+
+    def confusion_rect(self, pred: torch.Tensor, truth: torch.Tensor, ncls: int, truth_sub: int = 0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """confusion() over two 2-D uint8 device views of the same shape whose rows may be strided (a rectangle
+        cut out of a wider map): fb_confusion_rect."""
+        assert pred.dtype == torch.uint8 and truth.dtype == torch.uint8 and pred.is_cuda and truth.is_cuda
+        assert pred.dim() == 2 and pred.shape == truth.shape and pred.stride(1) == 1 and truth.stride(1) == 1
+        if out is None:
+            out = torch.zeros((ncls, ncls), dtype=torch.int64, device=self.device)
+        if pred.numel():
+            self._check(self._lib.fb_confusion_rect(self._h, pred.data_ptr(), truth.data_ptr(), pred.shape[0], pred.shape[1],
+                                                    pred.stride(0) if pred.shape[0] > 1 else pred.shape[1],
+                                                    truth.stride(0) if truth.shape[0] > 1 else truth.shape[1],
+                                                    ncls, truth_sub, out.data_ptr()))
+        return out
+
+    # ------------------------------------------------------------------ multi-GPU (NCCL through the C ABI)
+    def comm_init(self, rank: int, world: int, exchange) -> None:
+        """Join the library's own NCCL communicator. `exchange(bytes_or_None) -> bytes` hands rank 0's 128-byte id
+        to every rank (e.g. a torch.distributed broadcast_object_list wrapper)."""
+        ident = None
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            rc = self._lib.fb_comm_unique_id(buf)
+            if rc != 0:
+                msg = self._lib.fb_last_error(None)
+                raise NativeError(rc, msg.decode() if msg else "fb_comm_unique_id failed")
+            ident = bytes(buf)
+        ident = exchange(ident)
+        assert isinstance(ident, (bytes, bytearray)) and len(ident) == 128
+        arr = (C.c_uint8 * 128).from_buffer_copy(bytes(ident))
+        self._check(self._lib.fb_comm_init(self._h, arr, rank, world))
+        self._comm_rank = rank
+
+    def comm_destroy(self) -> None:
+        self._check(self._lib.fb_comm_destroy(self._h))
+
+    def allreduce_confusion(self, cm: torch.Tensor) -> torch.Tensor:
+        """In-place sum over ranks of the int64 [ncls, ncls] device matrix (fb_allreduce_confusion)."""
+        assert cm.dtype == torch.int64 and cm.is_cuda and cm.is_contiguous() and cm.dim() == 2 and cm.shape[0] == cm.shape[1]
+        self._check(self._lib.fb_allreduce_confusion(self._h, cm.data_ptr(), cm.shape[0]))
+        return cm
+
+    def gather_bytes(self, send: torch.Tensor, counts: Sequence[int], root: int = 0) -> Optional[torch.Tensor]:
+        """Every rank's uint8 device tensor `send` (counts[rank] bytes) concatenated in rank order on `root`
+        (fb_gather_bytes); returns the uint8 device buffer on root, None elsewhere."""
+        assert send.dtype == torch.uint8 and send.is_cuda and send.is_contiguous()
+        world = len(counts)
+        cnt = (C.c_int64 * world)(*[int(x) for x in counts])
+        offs = (C.c_int64 * world)(*np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64).tolist())
+        rank_is_root = self._comm_rank == root if hasattr(self, "_comm_rank") else None
+        recv = torch.empty(int(sum(counts)), dtype=torch.uint8, device=self.device) if rank_is_root in (True, None) else None
+        self._check(self._lib.fb_gather_bytes(self._h, send.data_ptr(), send.numel(), _ptr(recv), offs, cnt, root))
+        return recv if rank_is_root in (True, None) else None
 
     def conv2d(self, x1: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, KH: int, KW: int, stride: int,
                pad: int, x2: Optional[torch.Tensor] = None, up1: bool = False, residual: Optional[torch.Tensor] = None,

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <climits>
 #include <functional>
 #include <map>
 #include <string>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../include/flair_b200.h"
+#include "comm.cuh"
 #include "conv_halo.cuh"
 #include "conv_igemm.cuh"
 #include "elementwise.cuh"
@@ -109,8 +111,9 @@ struct fb_ctx {
   const uint8_t* raster = nullptr;
   uint8_t* raster_own = nullptr;
   size_t raster_own_bytes = 0;
-  uint8_t* maps_own = nullptr;   // class / confidence maps of fb_detect_zone_host
+  uint8_t* maps_own = nullptr;   // class / confidence (/ truth) maps of fb_detect_zone_host / fb_detect_zone_shard
   size_t maps_own_bytes = 0;
+  fb::Comm* comm = nullptr;      // fb_comm_init
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // copy streams of fb_detect_zone_host (non-blocking)
   std::vector<cudaEvent_t> copy_events;                     // grow-only pool, timing disabled
   int bands_total = 0, rc = 0, layout = 0;
@@ -882,6 +885,7 @@ void fb_destroy(fb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->comm) fb::comm_destroy(c->comm);
   for (void* p : c->owned) cudaFree(p);
   if (c->lut) cudaFree(c->lut);
   if (c->raster_own) cudaFree(c->raster_own);
@@ -929,10 +933,16 @@ int fb_load_weights(fb_ctx* c, const fb_tensor_desc* tensors, int n_tensors, int
   TensorMap tm;
   for (int i = 0; i < n_tensors; ++i)
     if (tensors[i].name && tensors[i].data) tm[tensors[i].name] = &tensors[i];
+  // a reload on a live context: nothing queued may still read the old weights when they are freed
+  FB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->h2d_stream) FB_CUDA(c, cudaStreamSynchronize(c->h2d_stream));
+  if (c->d2h_stream) FB_CUDA(c, cudaStreamSynchronize(c->d2h_stream));
   for (void* p : c->owned) cudaFree(p);
   c->owned.clear();
   c->conv.clear();
+  for (float*& m : c->mlp) m = nullptr;
   c->loaded = false;
+  c->use_meta = 0;
   c->arena_n = 0;   // the arena plan depends on the model (input layout of the stem): re-plan on the next pass
 
   FB_TRY(build_conv(c, tm, "stem", "encoder.conv1.weight", "encoder.bn1", "", in_channels, 64, 7, 2, 3));
@@ -1225,19 +1235,32 @@ int detect_loop(fb_ctx* c, const fb_tile* tiles, int n, int tile, int batch, con
   }
   return 0;
 }
-}  // namespace
 
-extern "C" {
+// What fb_detect_zone_shard adds to fb_detect_zone_host.
+struct ZoneHostOpts {
+  bool owned_only = false;              // D2H only the write rectangles of `tiles` (the host maps may be shared between ranks)
+  const uint8_t* host_truth = nullptr;  // optional: truth rows [truth_row0, ...) with pitch map_w -> fused confusion matrix
+  int64_t truth_row0 = 0;
+  int truth_sub = 0, ncls_cm = 0;
+  int64_t* cm_dev = nullptr;
+};
+
+// One maximal run of tiles of the y-sorted table that share their written rows and own adjacent columns: the unit
+// in which a shard's part of the class map goes back to the host (and is scored against the truth).
+struct RowRect {
+  int64_t y0, y1, x0, x1;
+  int last;   // index (in the sorted table) of the last tile that writes into it
+};
 
 // Host buffers in, host buffers out, software-pipelined: the raster goes up in row chunks on a copy stream while
-// the compute stream already works on the tile rows whose pixels have landed, and every class-map row is sent
-// back on a second copy stream as soon as no remaining tile can write it. The tiles are processed by rows
-// (sorted by y0) for that; their write rectangles are disjoint by contract (fb_tile), so the order in which
-// they run does not change a byte of the result.
-int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
-                        int nc, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
-                        const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
-                        uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows) {
+// the compute stream already works on the tile rows whose pixels have landed, and every finished piece of the
+// class map is sent back on a second copy stream as soon as no remaining tile can write it. The tiles are
+// processed by rows (sorted by y0) for that; their write rectangles are disjoint by contract (fb_tile), so the
+// order in which they run does not change a byte of the result.
+int zone_host_impl(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx, int nc, int64_t W,
+                   int64_t H, int64_t row0, int64_t rows, int layout, const fb_tile* tiles, int n, int tile, int batch,
+                   uint8_t* host_cls, uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows,
+                   const ZoneHostOpts& o) {
   if (!c || !host_cls || !host_raster || !band_idx || map_w <= 0 || map_rows <= 0 || (n > 0 && !tiles) || n < 0 || batch <= 0)
     return FB_ERR_INVALID;
   FB_TRY(check_ready(c, false, tile));
@@ -1246,9 +1269,42 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
   for (int i = 0; i < n; ++i)
     if (tiles[i].wy1 > tiles[i].wy0 && tiles[i].wy1 > map_row0 + map_rows)
       return fail(c, FB_ERR_INVALID, "detect: write rectangle below the map");
+  const bool score = o.host_truth != nullptr;
+  if (score && (!o.owned_only || !o.cm_dev || o.ncls_cm < 1 || o.ncls_cm > 32 || o.truth_row0 < 0))
+    return fail(c, FB_ERR_INVALID, "detect (shard): bad truth / confusion-matrix arguments");
   FB_CUDA(c, cudaSetDevice(c->device));
+
+  // tiles by rows (stable: the columns of one tile row keep their write order, i.e. ascending x)
+  std::vector<fb_tile> sorted(tiles, tiles + n);
+  std::stable_sort(sorted.begin(), sorted.end(), [](const fb_tile& a, const fb_tile& b) { return a.y0 < b.y0; });
+
+  // device maps: the rows of the host maps (whole-map mode) or just the rows this shard writes (owned-only mode)
+  int64_t dev_row0 = map_row0, dev_rows = map_rows;
+  std::vector<RowRect> rects;
+  if (o.owned_only) {
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int i = 0; i < n; ++i) {
+      const fb_tile& t = sorted[i];
+      if (t.wx1 <= t.wx0 || t.wy1 <= t.wy0) continue;
+      lo = std::min<int64_t>(lo, t.wy0);
+      hi = std::max<int64_t>(hi, t.wy1);
+      if (!rects.empty() && rects.back().y0 == t.wy0 && rects.back().y1 == t.wy1 && rects.back().x1 == t.wx0) {
+        rects.back().x1 = t.wx1;
+        rects.back().last = i;
+      } else {
+        rects.push_back(RowRect{t.wy0, t.wy1, t.wx0, t.wx1, i});
+      }
+    }
+    if (rects.empty()) return 0;   // this shard writes nothing
+    dev_row0 = lo;
+    dev_rows = hi - lo;
+    if (score)
+      for (const RowRect& r : rects)
+        if (r.y0 < o.truth_row0) return fail(c, FB_ERR_INVALID, "detect (shard): truth rows start below a write rectangle");
+  }
   const size_t rbytes = static_cast<size_t>(bands_total) * rows * W;
-  const size_t mbytes = static_cast<size_t>(map_w) * map_rows;
+  const size_t mbytes = static_cast<size_t>(map_w) * dev_rows;
+  const size_t nmaps = 2 + (score ? 1 : 0);
   // context-owned, grow-only buffers (a cudaMalloc/cudaFree pair per call would serialise the device)
   if (rbytes > c->raster_own_bytes) {
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1260,30 +1316,31 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
     }
     c->raster_own_bytes = rbytes;
   }
-  if (mbytes * 2 > c->maps_own_bytes) {
+  if (mbytes * nmaps > c->maps_own_bytes) {
     FB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->maps_own) cudaFree(c->maps_own);
     c->maps_own = nullptr; c->maps_own_bytes = 0;
-    if (cudaMalloc(&c->maps_own, mbytes * 2) != cudaSuccess) {
+    if (cudaMalloc(&c->maps_own, mbytes * nmaps) != cudaSuccess) {
       cudaGetLastError();
       return fail(c, FB_ERR_OOM, "class map: cudaMalloc failed");
     }
-    c->maps_own_bytes = mbytes * 2;
+    c->maps_own_bytes = mbytes * nmaps;
   }
   if (!c->h2d_stream) FB_CUDA(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
   if (!c->d2h_stream) FB_CUDA(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   c->raster = c->raster_own;
   uint8_t* maps = c->maps_own;
   uint8_t* conf_dev = host_conf ? maps + mbytes : nullptr;
+  uint8_t* truth_dev = score ? maps + 2 * mbytes : nullptr;
 
-  // tiles by rows
-  std::vector<fb_tile> sorted(tiles, tiles + n);
-  std::stable_sort(sorted.begin(), sorted.end(), [](const fb_tile& a, const fb_tile& b) { return a.y0 < b.y0; });
-  // suffix minimum of the first written row: after tile i, map rows below low_after[i + 1] are final
-  std::vector<int64_t> low_after(static_cast<size_t>(n) + 1, map_row0 + map_rows);
-  for (int i = n - 1; i >= 0; --i) {
-    const bool writes = sorted[i].wx1 > sorted[i].wx0 && sorted[i].wy1 > sorted[i].wy0;
-    low_after[i] = writes ? std::min<int64_t>(low_after[i + 1], sorted[i].wy0) : low_after[i + 1];
+  // whole-map mode: suffix minimum of the first written row -- after tile i, map rows below low_after[i + 1] are final
+  std::vector<int64_t> low_after;
+  if (!o.owned_only) {
+    low_after.assign(static_cast<size_t>(n) + 1, map_row0 + map_rows);
+    for (int i = n - 1; i >= 0; --i) {
+      const bool writes = sorted[i].wx1 > sorted[i].wx0 && sorted[i].wy1 > sorted[i].wy0;
+      low_after[i] = writes ? std::min<int64_t>(low_after[i + 1], sorted[i].wy0) : low_after[i + 1];
+    }
   }
 
   // upload: chunks of raster rows, one event per chunk. Work already queued on the compute stream (an earlier
@@ -1291,7 +1348,8 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
   const int64_t chunk_rows = 512;
   const int nchunks = static_cast<int>((rows + chunk_rows - 1) / chunk_rows);
   const size_t nbatches = static_cast<size_t>((n + batch - 1) / batch);
-  while (c->copy_events.size() < static_cast<size_t>(nchunks) + nbatches + 1) {
+  const size_t nev = static_cast<size_t>(nchunks) + nbatches + 1 + (score ? rects.size() : 0);
+  while (c->copy_events.size() < nev) {
     cudaEvent_t ev;
     FB_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->copy_events.push_back(ev);
@@ -1299,10 +1357,24 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
   cudaEvent_t* ev_up = c->copy_events.data();
   cudaEvent_t* ev_batch = c->copy_events.data() + nchunks;
   cudaEvent_t ev_start = c->copy_events[static_cast<size_t>(nchunks) + nbatches];
-  FB_CUDA(c, cudaMemsetAsync(maps, 0, mbytes * (host_conf ? 2 : 1), c->stream));
+  cudaEvent_t* ev_truth = c->copy_events.data() + nchunks + nbatches + 1;
+  if (!o.owned_only) FB_CUDA(c, cudaMemsetAsync(maps, 0, mbytes * (host_conf ? 2 : 1), c->stream));
   FB_CUDA(c, cudaEventRecord(ev_start, c->stream));
   FB_CUDA(c, cudaStreamWaitEvent(c->h2d_stream, ev_start, 0));
   FB_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, ev_start, 0));
+  size_t truth_sent = 0;   // rects[0 .. truth_sent) have their truth pixels on the way
+  auto send_truth = [&](int64_t upto_row) -> int {   // truth of every rectangle that starts above raster row `upto_row`
+    while (score && truth_sent < rects.size() && rects[truth_sent].y0 < upto_row) {
+      const RowRect& r = rects[truth_sent];
+      FB_CUDA(c, cudaMemcpy2DAsync(truth_dev + static_cast<size_t>(r.y0 - dev_row0) * map_w + r.x0, static_cast<size_t>(map_w),
+                                   o.host_truth + static_cast<size_t>(r.y0 - o.truth_row0) * map_w + r.x0, static_cast<size_t>(map_w),
+                                   static_cast<size_t>(r.x1 - r.x0), static_cast<size_t>(r.y1 - r.y0), cudaMemcpyHostToDevice,
+                                   c->h2d_stream));
+      FB_CUDA(c, cudaEventRecord(ev_truth[truth_sent], c->h2d_stream));
+      ++truth_sent;
+    }
+    return 0;
+  };
   for (int k = 0; k < nchunks; ++k) {
     const int64_t r0 = k * chunk_rows, nr = std::min<int64_t>(chunk_rows, rows - r0);
     if (layout == FB_LAYOUT_HWC) {
@@ -1317,9 +1389,11 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
       }
     }
     FB_CUDA(c, cudaEventRecord(ev_up[k], c->h2d_stream));
+    FB_TRY(send_truth(row0 + r0 + nr));   // truth rows travel right behind the raster rows of the same place
   }
+  FB_TRY(send_truth(INT64_MAX));
 
-  int64_t sent = map_row0;   // map rows [map_row0, sent) are already on their way to the host
+  int64_t sent = map_row0;   // whole-map mode: map rows [map_row0, sent) are already on their way to the host
   auto send_rows = [&](int64_t upto) -> int {
     if (upto <= sent) return 0;
     const size_t off = static_cast<size_t>(sent - map_row0) * map_w, len = static_cast<size_t>(upto - sent) * map_w;
@@ -1328,8 +1402,42 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
     sent = upto;
     return 0;
   };
+  size_t rect_sent = 0;      // owned-only mode: rects[0 .. rect_sent) are already on their way
+  auto finish_rects = [&](int done_tiles, cudaEvent_t ev_done) -> int {
+    // (a) score the finished rectangles on the compute stream, (b) copy them out behind ev_done on the copy stream
+    size_t upto = rect_sent;
+    while (upto < rects.size() && rects[upto].last < done_tiles) ++upto;
+    for (size_t k = rect_sent; k < upto && score; ++k) {
+      const RowRect& r = rects[k];
+      FB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_truth[k], 0));
+      const size_t doff = static_cast<size_t>(r.y0 - dev_row0) * map_w + r.x0;
+      const int rc = fb::launch_confusion_rect(maps + doff, truth_dev + doff, r.y1 - r.y0, r.x1 - r.x0, map_w, map_w, o.ncls_cm,
+                                               o.truth_sub & 0xFF, reinterpret_cast<long long*>(o.cm_dev), c->num_sms, c->stream);
+      if (rc) return fail(c, rc, "confusion launch failed");
+      c->launches++;
+    }
+    for (size_t k = rect_sent; k < upto; ++k) {
+      const RowRect& r = rects[k];
+      const size_t doff = static_cast<size_t>(r.y0 - dev_row0) * map_w + r.x0;
+      const size_t hoff = static_cast<size_t>(r.y0 - map_row0) * map_w + r.x0;
+      const size_t w = static_cast<size_t>(r.x1 - r.x0), h = static_cast<size_t>(r.y1 - r.y0);
+      if (k == rect_sent) FB_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, ev_done, 0));
+      if (w == static_cast<size_t>(map_w)) {   // full rows: one linear copy
+        FB_CUDA(c, cudaMemcpyAsync(host_cls + hoff, maps + doff, w * h, cudaMemcpyDeviceToHost, c->d2h_stream));
+        if (host_conf) FB_CUDA(c, cudaMemcpyAsync(host_conf + hoff, conf_dev + doff, w * h, cudaMemcpyDeviceToHost, c->d2h_stream));
+      } else {
+        FB_CUDA(c, cudaMemcpy2DAsync(host_cls + hoff, static_cast<size_t>(map_w), maps + doff, static_cast<size_t>(map_w), w, h,
+                                     cudaMemcpyDeviceToHost, c->d2h_stream));
+        if (host_conf)
+          FB_CUDA(c, cudaMemcpy2DAsync(host_conf + hoff, static_cast<size_t>(map_w), conf_dev + doff, static_cast<size_t>(map_w), w, h,
+                                       cudaMemcpyDeviceToHost, c->d2h_stream));
+      }
+    }
+    rect_sent = upto;
+    return 0;
+  };
   DetectSink s;
-  s.kind = 0; s.cls = maps; s.conf = conf_dev; s.map_w = map_w; s.map_row0 = map_row0;
+  s.kind = 0; s.cls = maps; s.conf = conf_dev; s.map_w = map_w; s.map_row0 = dev_row0;
   s.before_batch = [&](int i0, int nb) -> int {
     // the batch reads raster rows up to its lowest tile's bottom edge (the table is sorted by y0)
     int64_t last = static_cast<int64_t>(sorted[i0 + nb - 1].y0) + tile - 1 - row0;
@@ -1341,11 +1449,12 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
   s.after_batch = [&](int i0, int nb) -> int {
     const size_t bi = static_cast<size_t>(i0 / batch);
     FB_CUDA(c, cudaEventRecord(ev_batch[bi], c->stream));
+    if (o.owned_only) return finish_rects(i0 + nb, ev_batch[bi]);
     FB_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, ev_batch[bi], 0));
     return send_rows(low_after[i0 + nb]);
   };
   int rc = detect_loop(c, sorted.data(), n, tile, batch, s);
-  if (!rc) {
+  if (!rc && !o.owned_only) {
     // whatever no tile wrote (or an empty table): the zeroed rows still go back
     cudaError_t e = cudaEventRecord(ev_start, c->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->d2h_stream, ev_start, 0);
@@ -1359,6 +1468,121 @@ int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, 
   if (!rc && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
     rc = cuda_fail(c, e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3, "class map download");
   return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fb_detect_zone_host(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
+                        int nc, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
+                        const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
+                        uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows) {
+  return zone_host_impl(c, host_raster, bands_total, band_idx, nc, W, H, row0, rows, layout, tiles, n, tile, batch, host_cls,
+                        host_conf, map_w, map_row0, map_rows, ZoneHostOpts());
+}
+
+int fb_detect_zone_shard(fb_ctx* c, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
+                         int nc, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
+                         const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
+                         uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows,
+                         const uint8_t* host_truth, int64_t truth_row0, int truth_sub, int ncls_cm, int64_t* cm_dev) {
+  ZoneHostOpts o;
+  o.owned_only = true;
+  o.host_truth = host_truth;
+  o.truth_row0 = truth_row0;
+  o.truth_sub = truth_sub;
+  o.ncls_cm = ncls_cm;
+  o.cm_dev = cm_dev;
+  return zone_host_impl(c, host_raster, bands_total, band_idx, nc, W, H, row0, rows, layout, tiles, n, tile, batch, host_cls,
+                        host_conf, map_w, map_row0, map_rows, o);
+}
+
+int fb_confusion_rect(fb_ctx* c, const uint8_t* pred_dev, const uint8_t* truth_dev, int64_t rows, int64_t width,
+                      int64_t pred_pitch, int64_t truth_pitch, int ncls, int truth_sub, int64_t* cm_dev) {
+  if (!c) return FB_ERR_INVALID;
+  if (rows == 0 || width == 0) return 0;
+  if (!pred_dev || !truth_dev || !cm_dev || rows < 0 || width < 0 || pred_pitch < width || truth_pitch < width)
+    return fail(c, FB_ERR_INVALID, "confusion (rect): null pointer, negative size or pitch below the width");
+  if (ncls < 1 || ncls > 32) return fail(c, FB_ERR_INVALID, "confusion: ncls must be in 1..32");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  int rc = fb::launch_confusion_rect(pred_dev, truth_dev, rows, width, pred_pitch, truth_pitch, ncls, truth_sub & 0xFF,
+                                     reinterpret_cast<long long*>(cm_dev), c->num_sms, c->stream);
+  if (rc) return fail(c, rc, "confusion (rect) launch failed");
+  c->launches++;
+  return 0;
+}
+
+// Page-lock host memory the caller owns (a shared mapping of the class map): the D2H copies of fb_detect_zone_shard
+// only overlap with compute when their destination is pinned.
+int fb_host_register(void* host_ptr, int64_t bytes) {
+  if (!host_ptr || bytes <= 0) return FB_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(host_ptr, static_cast<size_t>(bytes), cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e);
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+int fb_host_unregister(void* host_ptr) {
+  if (!host_ptr) return FB_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(host_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    g_create_error = std::string("cudaHostUnregister: ") + cudaGetErrorString(e);
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+// ---- multi-GPU collectives (csrc/comm.cu): one NCCL communicator per context
+int fb_comm_unique_id(uint8_t* id128) {
+  std::string err;
+  const int rc = fb::comm_unique_id(id128, &err);
+  if (rc) g_create_error = err;
+  return rc;
+}
+
+int fb_comm_init(fb_ctx* c, const uint8_t* id128, int rank, int world) {
+  if (!c || !id128) return FB_ERR_INVALID;
+  if (c->comm) return fail(c, FB_ERR_STATE, "fb_comm_init: this context already has a communicator");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  std::string err;
+  const int rc = fb::comm_init(&c->comm, id128, rank, world, &err);
+  return rc ? fail(c, rc, err) : 0;
+}
+
+int fb_comm_destroy(fb_ctx* c) {
+  if (!c) return FB_ERR_INVALID;
+  if (c->comm) {
+    cudaStreamSynchronize(c->stream);
+    fb::comm_destroy(c->comm);
+    c->comm = nullptr;
+  }
+  return 0;
+}
+
+int fb_allreduce_confusion(fb_ctx* c, int64_t* cm_dev, int ncls) {
+  if (!c || !cm_dev || ncls < 1 || ncls > 32) return FB_ERR_INVALID;
+  if (!c->comm) return fail(c, FB_ERR_STATE, "fb_allreduce_confusion: fb_comm_init has not been called");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  std::string err;
+  const int rc = fb::comm_allreduce_i64(c->comm, reinterpret_cast<long long*>(cm_dev), static_cast<size_t>(ncls) * ncls, c->stream, &err);
+  return rc ? fail(c, rc, err) : 0;
+}
+
+int fb_gather_bytes(fb_ctx* c, const void* send_dev, int64_t send_bytes, void* recv_dev, const int64_t* offsets,
+                    const int64_t* counts, int root) {
+  if (!c || !offsets || !counts) return FB_ERR_INVALID;
+  if (!c->comm) return fail(c, FB_ERR_STATE, "fb_gather_bytes: fb_comm_init has not been called");
+  FB_CUDA(c, cudaSetDevice(c->device));
+  std::string err;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long here");
+  const int rc = fb::comm_gather_bytes(c->comm, send_dev, send_bytes, recv_dev, reinterpret_cast<const long long*>(offsets),
+                                       reinterpret_cast<const long long*>(counts), root, c->stream, &err);
+  return rc ? fail(c, rc, err) : 0;
 }
 
 int fb_predict_patches(fb_ctx* c, const uint8_t* dev_patches, const float* metadata, int n, int tile,

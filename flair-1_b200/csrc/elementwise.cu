@@ -540,6 +540,70 @@ int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, i
   return static_cast<int>(cudaGetLastError());
 }
 
+// K9 over a rectangle of two pitched uint8 maps (the write rectangles one rank owns in a sharded zone, the union of
+// which is not a contiguous byte range): work item = 512 consecutive pixels of one row (16 per lane), same warp
+// aggregation as above. 16-byte loads where the lane's addresses allow it, byte loads at ragged edges.
+__global__ void __launch_bounds__(256)
+confusion_rect_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ truth, long long rows,
+                      long long width, long long pred_pitch, long long truth_pitch, int ncls, int truth_sub,
+                      unsigned long long* __restrict__ cm) {
+  __shared__ unsigned int bins[kMaxCls * kMaxCls];
+  const int nb = ncls * ncls;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long chunks = (width + 511) >> 9;
+  const long long items = rows * chunks;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long it = warp0; it < items; it += nwarps) {
+    const long long r = it / chunks, x = ((it - r * chunks) << 9) + lane * 16;
+    const uint8_t* pp = pred + r * pred_pitch + x;
+    const uint8_t* tp = truth + r * truth_pitch + x;
+    const int valid = x >= width ? 0 : (width - x >= 16 ? 16 : static_cast<int>(width - x));
+    uint32_t pw[4] = {0, 0, 0, 0}, tw[4] = {0, 0, 0, 0};
+    if (valid == 16 && ((reinterpret_cast<uintptr_t>(pp) | reinterpret_cast<uintptr_t>(tp)) & 15) == 0) {
+      const uint4 pv = __ldg(reinterpret_cast<const uint4*>(pp)), tv = __ldg(reinterpret_cast<const uint4*>(tp));
+      pw[0] = pv.x; pw[1] = pv.y; pw[2] = pv.z; pw[3] = pv.w;
+      tw[0] = tv.x; tw[1] = tv.y; tw[2] = tv.z; tw[3] = tv.w;
+    } else {
+      for (int i = 0; i < valid; ++i) {
+        pw[i >> 2] |= static_cast<uint32_t>(pp[i]) << (8 * (i & 3));
+        tw[i >> 2] |= static_cast<uint32_t>(tp[i]) << (8 * (i & 3));
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const unsigned pb = (pw[w] >> (8 * b)) & 0xFF;
+        const unsigned tb = ((tw[w] >> (8 * b)) - truth_sub) & 0xFF;
+        const bool ok = 4 * w + b < valid && pb < static_cast<unsigned>(ncls) && tb < static_cast<unsigned>(ncls);
+        const unsigned key = ok ? tb * ncls + pb : 0xFFFFu;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (ok && lane == __ffs(peers) - 1) atomicAdd(&bins[key], __popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (bins[i] != 0) atomicAdd(&cm[i], static_cast<unsigned long long>(bins[i]));
+}
+
+int launch_confusion_rect(const uint8_t* pred, const uint8_t* truth, long long rows, long long width,
+                          long long pred_pitch, long long truth_pitch, int ncls, int truth_sub, long long* cm,
+                          int num_sms, cudaStream_t stream) {
+  if (ncls <= 0 || ncls > kMaxCls) return -2001;
+  if (rows <= 0 || width <= 0) return 0;
+  const long long items = rows * ((width + 511) >> 9);
+  long long blocks = (items + 7) / 8;   // 8 warps per block
+  const long long cap = static_cast<long long>(num_sms) * 8;
+  if (blocks > cap) blocks = cap;
+  confusion_rect_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      pred, truth, rows, width, pred_pitch, truth_pitch, ncls, truth_sub, reinterpret_cast<unsigned long long*>(cm));
+  return static_cast<int>(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------ K9b
 // Per-tile confusion matrices of the compare loop (zone_detect/main.py:349-366 -> test/metrics.py:124-163,
 // compute_metrics_patch): tile t's OWN arg-max prediction over its metric window against the truth raster, as

@@ -50,6 +50,11 @@ int launch_blend_finalize(const float* acc, const float* wsum, int method, int n
 int launch_confusion(const uint8_t* pred, const uint8_t* truth, long long npx, int ncls, int truth_sub,
                      long long* cm, int num_sms, cudaStream_t stream);
 
+// The same histogram over rows x width pixels of two pitched maps (bytes between row starts: pred_pitch / truth_pitch).
+int launch_confusion_rect(const uint8_t* pred, const uint8_t* truth, long long rows, long long width,
+                          long long pred_pitch, long long truth_pitch, int ncls, int truth_sub, long long* cm,
+                          int num_sms, cudaStream_t stream);
+
 // Per-tile confusion matrices from each tile's own arg-max over its metric window (compute_metrics_patch of the
 // compare loop). windows: int32 [n][6] = x0, y0, then the half-open window; cm: int64 [n][ncls][ncls], accumulated.
 int launch_tile_confusion(const float* logits, int ncls, int ls, int n, int T, const int* windows, const uint8_t* truth,

@@ -137,3 +137,30 @@ def split_rows_across_ranks(tiles: np.ndarray, world_size: int) -> List[np.ndarr
     y_vals = np.unique(tiles[:, 1])
     groups = np.array_split(y_vals, world_size)
     return [np.flatnonzero(np.isin(tiles[:, 1], g)) for g in groups]
+
+
+def split_tiles_across_ranks(tiles: np.ndarray, world_size: int) -> List[np.ndarray]:
+    """Shard the tile table into `world_size` contiguous ranges of the ROW-MAJOR tile order (tiles sorted by y0,
+    ties in write order, i.e. ascending x), balanced to within one tile (24 649 tiles over 8 ranks: 3082 against
+    3081.1 on average, where whole tile rows give 20 rows against 19.6). A rank's first and last tile row may be
+    shared with its neighbours; it still needs raster rows [min y0, max y0 + size) only, and what it writes is a
+    set of row bands (owned_rects) that is disjoint from every other rank's. Returns index arrays into `tiles`."""
+    order = np.argsort(tiles[:, 1], kind="stable")
+    return [np.asarray(part, dtype=np.int64) for part in np.array_split(order, world_size)]
+
+
+def owned_rects(tiles: np.ndarray) -> np.ndarray:
+    """int64 [k, 4] rows (y0, y1, x0, x1): the write rectangles of `tiles` merged into maximal runs that share
+    their rows and own adjacent columns, in y-sorted order -- the pieces of the class map one shard produces
+    (fb_detect_zone_shard sends them back, and scores them, in exactly these units)."""
+    t = np.asarray(tiles, dtype=np.int64).reshape(-1, 6)
+    t = t[np.argsort(t[:, 1], kind="stable")]
+    rects: List[List[int]] = []
+    for x0, y0, wx0, wy0, wx1, wy1 in t:
+        if wx1 <= wx0 or wy1 <= wy0:
+            continue
+        if rects and rects[-1][0] == wy0 and rects[-1][1] == wy1 and rects[-1][3] == wx0:
+            rects[-1][3] = int(wx1)
+        else:
+            rects.append([int(wy0), int(wy1), int(wx0), int(wx1)])
+    return np.asarray(rects, dtype=np.int64).reshape(-1, 4)

@@ -154,6 +154,23 @@ int fb_detect_zone_host(fb_ctx* ctx, const uint8_t* host_raster, int bands_total
                         const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
                         uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows);
 
+/* ---- the same loop for ONE SHARD of a zone whose class map is assembled by several ranks (one process per GPU;
+ *      SURVEY.md section 8e). The reference writes every tile's window into the one output raster as it goes
+ *      (main.py:421-426); here host_cls / host_conf describe that one map -- rows [map_row0, map_row0 + map_rows),
+ *      pitch map_w, typically a shared mapping that every rank has pinned -- and this call writes ONLY the write
+ *      rectangles of its own `tiles` into it (2-D copies, row band by row band as they become final), so the
+ *      ranks' pieces never pass through another rank's GPU or PCIe link. The device-side maps cover just the rows
+ *      the shard writes. With host_truth (rows [truth_row0, ...), pitch map_w, NULL to skip) the truth pixels of
+ *      the same rectangles are uploaded behind the raster and the shard's confusion matrix
+ *      (test/metrics.py:161-163, 229-231: rows = (uint8)(truth - truth_sub), columns = prediction) is added to
+ *      cm_dev (device int64 [ncls_cm][ncls_cm], zeroed by the caller, summed over ranks with
+ *      fb_allreduce_confusion). Synchronises all three streams before returning. */
+int fb_detect_zone_shard(fb_ctx* ctx, const uint8_t* host_raster, int bands_total, const int32_t* band_idx,
+                         int c, int64_t W, int64_t H, int64_t row0, int64_t rows, int layout,
+                         const fb_tile* tiles, int n, int tile, int batch, uint8_t* host_cls,
+                         uint8_t* host_conf, int64_t map_w, int64_t map_row0, int64_t map_rows,
+                         const uint8_t* host_truth, int64_t truth_row0, int truth_sub, int ncls_cm, int64_t* cm_dev);
+
 /* ---- patch predict (flair/task_module.py:206-213 + data_loader.py:130-144): n whole patches,
  *      dev_patches uint8 [n][c][tile][tile] (band-planar per patch, already restricted to the selected
  *      bands), metadata host [n][45] or NULL, cls_out_dev uint8 [n][tile][tile] (0-based classes). */
@@ -166,6 +183,37 @@ int fb_predict_patches(fb_ctx* ctx, const uint8_t* dev_patches, const float* met
  *      int64 device accumulator, caller zeroes it; ncls <= 32. */
 int fb_confusion(fb_ctx* ctx, const uint8_t* pred_dev, const uint8_t* truth_dev, int64_t npx, int ncls,
                  int truth_sub, int64_t* cm_dev);
+
+/* The same histogram over a rows x width rectangle of two pitched uint8 maps (pitch = bytes between row starts):
+ * what one rank scores when it owns a set of write rectangles rather than whole rows of the map. */
+int fb_confusion_rect(fb_ctx* ctx, const uint8_t* pred_dev, const uint8_t* truth_dev, int64_t rows, int64_t width,
+                      int64_t pred_pitch, int64_t truth_pitch, int ncls, int truth_sub, int64_t* cm_dev);
+
+/* ---- multi-GPU (one process / context per GPU). The reference is single-GPU on this path (its Lightning DDP code
+ *      only serves training, src/flair/tasks.py:83-142); sharding a zone needs exactly two collectives, both over
+ *      NCCL (resolved with dlopen at the first call: libnccl.so.2 of the process, else of the system):
+ *      fb_comm_unique_id: rank 0 creates the 128-byte rendezvous id and hands it to the other ranks by any means
+ *      (torch.distributed broadcast, a file, MPI); fb_comm_init: every rank joins (collective, blocking);
+ *      fb_allreduce_confusion: in-place sum over the ranks of cm_dev[ncls*ncls] (int64), on the context's stream
+ *      (replaces nothing in the reference -- np.sum over patches at flair/metrics.py:76 is the single-process
+ *      analogue); fb_gather_bytes: rank r's send_bytes bytes land at recv_dev + offsets[r] on `root`
+ *      (offsets / counts: host arrays of world entries, the same on every rank) -- the class_prob planes and the
+ *      blended maps travel to the writer rank this way. */
+/* Page-lock / release host memory owned by the caller (cudaHostRegister, portable): the shared class map of a
+ * sharded zone, so that fb_detect_zone_shard's copies into it run asynchronously. host_ptr and bytes are rounded
+ * by the caller to the page size. Failures are reported through fb_last_error(NULL). */
+int fb_host_register(void* host_ptr, int64_t bytes);
+int fb_host_unregister(void* host_ptr);
+
+#define FB_COMM_ID_BYTES 128
+#define FB_ERR_NCCL_MISSING (-6) /* libnccl.so.2 could not be loaded */
+#define FB_ERR_NCCL (-7)         /* an NCCL call failed; see fb_last_error */
+int fb_comm_unique_id(uint8_t* id128);
+int fb_comm_init(fb_ctx* ctx, const uint8_t* id128, int rank, int world);
+int fb_comm_destroy(fb_ctx* ctx);
+int fb_allreduce_confusion(fb_ctx* ctx, int64_t* cm_dev, int ncls);
+int fb_gather_bytes(fb_ctx* ctx, const void* send_dev, int64_t send_bytes, void* recv_dev, const int64_t* offsets,
+                    const int64_t* counts, int root);
 
 /* ---- test / profiling hooks (used by tests/ and bench.py, not by the pipelines) --------------- */
 /* Single convolution: NHWC bf16 in/out, weights [Cout][Kpad] bf16 (k = (kh*KW+kw)*Cin + c, Kpad a
