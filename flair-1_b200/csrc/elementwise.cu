@@ -324,15 +324,33 @@ argmax_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const in
     const int ty = ry - y0, tx = rx - x0;
     float v[LS];
     load_logits<LS>(logits + ((static_cast<long long>(t) * T + ty) * T + tx) * LS, v);
+    // 16 classes at a time, in the order and with the arithmetic of the head's fused sink (conv_halo.cu), which sees
+    // the logits as 16-column groups: maximum / arg-max / exponent sum of the first group, then the second group
+    // rescales that sum to the joint maximum. The two paths therefore write identical bytes for any class count.
     float best = v[0];
     int arg = 0;
 #pragma unroll
-    for (int k = 1; k < LS; ++k)
+    for (int k = 1; k < 16; ++k)
       if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
     float den = 0.f;
 #pragma unroll
-    for (int k = 0; k < LS; ++k)
+    for (int k = 0; k < 16; ++k)
       if (k < ncls) den += __expf(v[k] - best);
+    if constexpr (LS == 32) {
+      if (ncls > 16) {
+        float best2 = v[16];
+        int arg2 = 16;
+#pragma unroll
+        for (int k = 17; k < 32; ++k)
+          if (k < ncls && v[k] > best2) { best2 = v[k]; arg2 = k; }
+        const float prev = best;
+        if (best2 > best) { best = best2; arg = arg2; }   // the earlier (lower) class wins ties
+        den *= __expf(prev - best);
+#pragma unroll
+        for (int k = 16; k < 32; ++k)
+          if (k < ncls) den += __expf(v[k] - best);
+      }
+    }
     const float pmax = 1.f / den;
     const long long o = (static_cast<long long>(ry) - map_row0) * map_w + rx;
     cls_map[o] = static_cast<uint8_t>(arg);

@@ -1,10 +1,12 @@
 """`flair --conf x.yaml` on B200: the predict + metrics stages (mirrors src/flair/main.py).
 
 Training (tasks.train) is out of scope: `tasks.train: True` is rejected. The predict loop
-of the reference is a Lightning Trainer with batch_size 1 (data_module.py:97-104); here patches are
-read on the host, sent in batches of `batch_size` and predicted by one fb_predict_patches call each.
-Under torchrun the test CSV is sharded round-robin across ranks and the confusion matrices are summed
-with one NCCL all-reduce.
+of the reference is a Lightning Trainer with batch_size 1 (data_module.py:97-104); here the patches are decoded
+by a pool of host threads (the TIFF codecs release the GIL), predicted in groups by one fb_predict_patches call
+each while the next group is being read, and written (LZW) by the same pool while the GPU works on the next
+group. Under torchrun the test CSV is sharded round-robin across ranks; every rank writes its own PRED_* files
+and rank 0 computes the metrics from the files once all ranks are done (the reference's `metrics` stage also
+reads the predictions back from disk, src/flair/metrics.py:60-74).
 """
 from __future__ import annotations
 
@@ -13,6 +15,9 @@ import datetime
 import os
 import shutil
 import sys
+import time
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import torch
@@ -81,19 +86,39 @@ def get_segmentation_module(config, stage="predict", device=0):
 
 
 def predict(config, dict_test, seg_module, out_dir_predict, rank=0, world=1):
-    """src/flair/tasks.py:113-142: loop over the test patches, write PRED_* files."""
+    """src/flair/tasks.py:113-142: loop over the test patches, write PRED_* files. Three stages overlap: host threads
+    read + decode the patches of group g + 1 and encode + write the predictions of group g - 1 while the GPU predicts
+    group g. A group is `batch_size` patches, raised to `patches_per_launch` (default 148, one 512^2 patch per SM) --
+    the result of a patch does not depend on what it is batched with. Returns (patches, seconds)."""
     ds = predict_dataset(dict_files=dict_test, channels=config["channels"], num_classes=len(config["classes"]),
                          use_metadata=config["use_metadata"], norm_type=config["norm_type"],
                          means=config.get("norm_means", []), stds=config.get("norm_stds", []))
     writer = predictionwriter(config, out_dir_predict.as_posix(), write_interval="batch")
-    bs = max(1, int(config.get("batch_size", 1)))
+    group = max(1, int(config.get("batch_size", 1)), int(config.get("patches_per_launch", 148)))
     idx = list(range(rank, len(ds), world))
-    for s in range(0, len(idx), bs):
-        items = [ds[i] for i in idx[s:s + bs]]
-        batch = {"img": [it["img"] for it in items], "id": [it["id"] for it in items]}
-        if config["use_metadata"]:
-            batch["mtd"] = [it["mtd"] for it in items]
-        writer.write_on_batch_end(seg_module.predict_step(batch, s // bs))
+    groups = [idx[s:s + group] for s in range(0, len(idx), group)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(2, min(16, os.cpu_count() or 2))) as pool:
+        reads = deque()
+
+        def start_read(g):
+            reads.append([pool.submit(ds.__getitem__, i) for i in groups[g]])
+
+        writes = []
+        for g in range(min(2, len(groups))):
+            start_read(g)
+        for g in range(len(groups)):
+            items = [f.result() for f in reads.popleft()]
+            if g + 2 < len(groups):
+                start_read(g + 2)
+            batch = {"img": [it["img"] for it in items], "id": [it["id"] for it in items]}
+            if config["use_metadata"]:
+                batch["mtd"] = [it["mtd"] for it in items]
+            out = seg_module.predict_step(batch, g)
+            writes.extend(writer.write_async(out, pool))
+        for f in writes:
+            f.result()
+    return len(idx), time.perf_counter() - t0
 
 
 def predict_stage(config, dict_test, out_dir_predict, device=0, rank=0, world=1):
@@ -104,7 +129,10 @@ def predict_stage(config, dict_test, out_dir_predict, device=0, rank=0, world=1)
     load_checkpoint(config, seg_module.model)   # every rank loads (the reference's rank_zero_only here is a bug)
     if not seg_module.model.loaded:
         raise SystemExit("no usable checkpoint: refusing to predict with uninitialised weights")
-    predict(config, dict_test, seg_module, out_dir_predict, rank, world)
+    n, seconds = predict(config, dict_test, seg_module, out_dir_predict, rank, world)
+    if rank == 0:
+        print(f"    [x] predicted {n} patches in {seconds:.2f} s ({n / max(seconds, 1e-9):.1f} patches/s incl. read + write"
+              + (f", rank 0 of {world}" if world > 1 else "") + ")")
     return seg_module
 
 

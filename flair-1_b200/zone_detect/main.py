@@ -3,12 +3,16 @@
 Same CLI flags, same YAML keys, same log tee, same output raster (uint8, LZW, tiled at
 img_pixels_detection, 2 bands for `argmax`: class index and max probability), same "never overwrite"
 file naming. The hot loop of the reference (main.py:398-426: DataLoader -> H2D -> forward -> softmax ->
-D2H of all probabilities -> numpy argmax -> per-tile GDAL write) becomes: read the raster once, upload,
-one `fb_detect_strip` per rank, download the uint8 maps, write the GeoTIFF.
+D2H of all probabilities -> numpy argmax -> per-tile GDAL write) becomes: read the raster rows once into pinned
+memory, one pipelined `fb_detect_zone_shard` call per rank (chunked upload, compute and row-band download
+overlapped; with `-m` the truth rows ride along and the confusion matrix is accumulated on the GPU), write the
+GeoTIFF.
 
-Multi-GPU: launched under `torchrun`, every rank takes a contiguous group of tile rows (halo rows are
-re-read, no exchange), rank 0 gathers the class-map strips over NCCL and writes the file; with `-m` the
-per-rank confusion matrices are summed with one all-reduce.
+Multi-GPU: launched under `torchrun`, every rank takes a contiguous range of the row-major tile order (halo rows
+are re-read, no exchange) and copies its write rectangles straight into ONE output map in shared memory
+(shared_map.SharedHostMap) -- the reference's single output raster (main.py:421-426) -- which rank 0 writes to
+disk after a barrier; with `-m` the per-rank confusion matrices are summed with one NCCL all-reduce
+(fb_allreduce_confusion). torch.distributed only carries the rendezvous: barriers and a few small objects.
 """
 from __future__ import annotations
 
@@ -24,13 +28,15 @@ import numpy as np
 import torch
 
 from .. import geotiff
-from .compare import STITCH_METHODS, stitching, stitching_blend, stitching_class_prob
+from .compare import STITCH_METHODS, detect_zone, detect_zone_pipelined
 from .dataset import Sliced_Dataset
 from .metrics import batch_metrics, confusion_matrix_gpu, metrics_from_confmat
 from .model import load_model
-from .slicing_job import slice_extent, split_rows_across_ranks, tile_windows
+from .shared_map import SharedHostMap
+from .slicing_job import owned_rects, slice_extent, split_rows_across_ranks, split_tiles_across_ranks, tile_windows
 from .tiles import get_stride
-from .utils import gen_param_combination, open_images, setup, setup_device, setup_indiv_path, setup_out_path
+from .utils import (gen_param_combination, metrics_json_path, open_images, setup, setup_device, setup_indiv_path,
+                    setup_out_path)
 
 warnings.simplefilter(action="ignore", category=FutureWarning)
 
@@ -96,12 +102,20 @@ def prepare_tiles(config: dict, stride: int):
     """main.py:123-148."""
     tiles, profile, resolution, img_size = slice_extent(
         in_img=Path(config["input_img_path"]), patch_size=config["img_pixels_detection"], margin=config["margin"],
-        output_name=config["output_name"], output_path=Path(config["local_out"]), write_dataframe=config["write_dataframe"],
-        stride=stride)
+        output_name=config["output_name"], output_path=Path(config["local_out"]),
+        write_dataframe=config["write_dataframe"] and _rank_world()[0] == 0, stride=stride)
     if _rank_world()[0] == 0:
         conf_log(config, resolution, img_size)
         print(f"""    [x] sliced input raster to {len(tiles)} squares...""")
     return tiles, profile, resolution
+
+
+def _pipelined(config: dict) -> bool:
+    """True for the runs that go through fb_detect_zone_shard: exact clipping to a class map without per-patch
+    metrics. The blended stitchings, class_prob and the per-patch metrics of `-c -m` need every logit of a tile
+    (or their neighbours' accumulators) and keep whole tile rows per rank."""
+    per_patch = config["metrics"] and config["compare"] and "classes" in config and len(config["classes"]) == config["n_classes"]
+    return config["output_type"] == "argmax" and config.get("stitching", "exact-clipping") == "exact-clipping" and not per_patch
 
 
 def prepare_data(config: dict, stride: int):
@@ -109,7 +123,7 @@ def prepare_data(config: dict, stride: int):
     the GPU)."""
     tiles, profile, resolution = prepare_tiles(config, stride)
     rank, world = _rank_world()
-    shard = split_rows_across_ranks(tiles, world)[rank]
+    shard = (split_tiles_across_ranks if _pipelined(config) else split_rows_across_ranks)(tiles, world)[rank]
     my_tiles = tiles[shard]
     size = config["img_pixels_detection"]
     # the margin-cropped window of every tile of this rank (per-patch metrics of the compare loop) and its
@@ -169,68 +183,54 @@ def run_from_config(config: dict) -> None:
     run_pipeline(config, device, use_gpu)
 
 
-def detect_zone(config: dict, model, dataset: Sliced_Dataset, my_tiles: np.ndarray, device: torch.device,
-                stitch: str = "exact-clipping", truth_dev: torch.Tensor | None = None):
-    """One rank's share of the hot loop. Returns (class strip, confidence strip, first row, rows) with the
-    strips on the device. With `truth_dev` (the truth rows of this rank's strip, already minus 1) and exact
-    clipping, config["_patch_cm"] receives the per-tile confusion matrices of compute_metrics_patch
-    (main.py:349-366): each tile's own prediction over its margin-cropped window."""
-    config["_patch_cm"] = None
-    size = config["img_pixels_detection"]
-    W = dataset.raster_width
-    if len(my_tiles) == 0:
-        e = torch.empty((0, W), dtype=torch.uint8, device=device)
-        return e, e.clone(), 0, 0
-    my0, my1 = config.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())))
-    raster_dev = dataset.big_image.to(device, non_blocking=True)
-    model.set_raster(raster_dev, list(range(dataset.num_bands)), W, dataset.raster_height, row0=dataset.row0)
-    # tiles per forward pass: one 512^2 tile per SM by default, scaled with the tile area so that the activation
-    # arena (~70 MB per 512^2 tile) stays near 10 GB for the 128 .. 2048 px tiles of the compare grid
-    per_launch = int(config.get("tiles_per_launch", max(1, min(1024, round(148 * (512 / size) ** 2)))))
-    batch = min(1024, max(int(config.get("batch_size", 4)), per_launch))
-    if config["output_type"] == "class_prob":
-        # main.py:409-426 always clips exactly for this output type (compare.py:68): n_classes planes, no band 2
-        prob = torch.zeros((config["n_classes"], my1 - my0, W), dtype=torch.uint8, device=device)
-        stitching_class_prob(model, my_tiles, size, batch, prob, W, my0)
-        return prob, None, my0, my1 - my0
-    cls = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
-    conf = torch.zeros((my1 - my0, W), dtype=torch.uint8, device=device)
-    if stitch == "exact-clipping" and truth_dev is not None:
-        # a window may reach above / below the rows this rank owns (clamped last row): score what lies inside
-        win = np.array(config["_my_windows"], dtype=np.int32)
-        win[:, 3] = np.clip(win[:, 3], my0, my1)
-        win[:, 5] = np.clip(win[:, 5], my0, my1)
-        config["_patch_cm"] = model.detect_strip_metrics(my_tiles, win, size, batch, cls, conf, W, my0, truth_dev)
-    elif stitch == "exact-clipping":
-        stitching(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
-    else:
-        stitching_blend(model, my_tiles, size, batch, cls, conf, W, my0, stitch)
-    return cls, conf, my0, my1 - my0
+class OutputMap:
+    """The output raster of one run while it is being produced: uint8 [bands, H, W] on the host, filled by every
+    rank (shared memory when there are several, see shared_map.py), written to disk by rank 0."""
 
+    def __init__(self, bands: int, H: int, W: int) -> None:
+        rank, world = _rank_world()
+        self.shared = None
+        if world == 1:
+            self._tensor = torch.zeros((bands, H, W), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            self.array = self._tensor.numpy()
+            return
+        import torch.distributed as dist
+        box = [SharedHostMap.fresh_path(bands * H * W) if rank == 0 else None]
+        if rank == 0:
+            self.shared = SharedHostMap(box[0], bands, H, W, create=True)   # a fresh tmpfs file reads as zeros
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            self.shared = SharedHostMap(box[0], bands, H, W, create=False)
+        self.array = self.shared.array
 
-def _gather_strips(strip: torch.Tensor, row0: int, H: int, W: int, device) -> np.ndarray | None:
-    """Rank 0 receives every rank's class-map strip (NCCL gather) and returns the full [H, W] map."""
-    rank, world = _rank_world()
-    if world == 1:
-        out = np.zeros((H, W), np.uint8)
-        out[row0:row0 + strip.shape[0]] = strip.cpu().numpy()
-        return out
-    import torch.distributed as dist
-    meta = torch.tensor([row0, strip.shape[0]], dtype=torch.int64, device=device)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta)
-    rows_max = int(max(m[1].item() for m in metas))
-    padded = torch.zeros((rows_max, W), dtype=torch.uint8, device=device)
-    padded[:strip.shape[0]] = strip
-    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
-    dist.gather(padded, bufs, dst=0)
-    if rank != 0:
-        return None
-    out = np.zeros((H, W), np.uint8)
-    for m, b in zip(metas, bufs):
-        r0, n = int(m[0].item()), int(m[1].item())
-        out[r0:r0 + n] = b[:n].cpu().numpy()
-    return out
+    def pin_rows(self, row0: int, row1: int) -> None:
+        if self.shared is not None and torch.cuda.is_available() and row1 > row0:
+            self.shared.pin_rows(row0, row1)
+
+    def put_rows(self, band: int, row0: int, strip: torch.Tensor) -> None:
+        """Rows [row0, row0 + len(strip)) of `band` from a device (or host) tensor."""
+        if strip.shape[0]:
+            torch.from_numpy(self.array[band, row0:row0 + strip.shape[0]]).copy_(strip)
+
+    def finish(self) -> np.ndarray | None:
+        """Barrier; the complete map on rank 0 (None elsewhere)."""
+        rank, world = _rank_world()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        return self.array if rank == 0 else None
+
+    def close(self) -> None:
+        rank, world = _rank_world()
+        self.array = None
+        if self.shared is not None:
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()   # nobody unmaps / unlinks while the writer still reads
+            self.shared.close()
+            if rank == 0:
+                self.shared.unlink()
+            self.shared = None
 
 
 def _gather_patch_metrics(cfg: dict, method: str) -> list | None:
@@ -290,22 +290,36 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
     method: exact-clipping / average / average_weights / max). output_type "class_prob" writes n_classes
     probability bands instead of class + confidence."""
     rank, world = _rank_world()
+    stamp = datetime.datetime.now().strftime("%Y%m%d_%H%M%S")
     if world > 1:
         import torch.distributed as dist
         if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=device)
-    config = setup_out_path(config)
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", device_id=device if torch.cuda.is_available() else None)
+        box = [stamp]
+        dist.broadcast_object_list(box, src=0)   # one time stamp for all ranks: one output folder, one log name
+        stamp = box[0]
+    config = setup_out_path(config, stamp)
     local_out = Path(config["local_out"])
-    log_filename = local_out / Path(f"{config['output_name']}_{datetime.datetime.now().strftime('%Y%m%d_%H%M%S')}.log")
+    log_filename = local_out / Path(f"{config['output_name']}_{stamp}.log")
     old_out, old_err = sys.stdout, sys.stderr
     sys.stdout = Logger(filename=str(log_filename))
     sys.stderr = sys.stdout
     result = {}
+    model = None
     try:
         if rank == 0:
             print(f"    [LOGGER] Writing logs to: {log_filename}")
         model = prepare_model(config, device)
-        truth_array, metrics_json = open_images(config, local_out, config["metrics"])
+        if world > 1:
+            def exchange(ident):
+                import torch.distributed as dist
+                box = [ident]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+            model.comm_init(rank, world, exchange)   # the library's own NCCL communicator (confusion-matrix all-reduce)
+        # a single process scores against the whole truth raster; the ranks of a sharded run read their rows only
+        truth_array = open_images(config, local_out, True)[0] if (config["metrics"] and world == 1) else None
+        metrics_json = metrics_json_path(config, local_out) if config["metrics"] else Path()
 
         if config["compare"]:
             # the weighted stitchings (average / average_weights / max) run as stitching_blend() implements
@@ -320,6 +334,11 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                          "stride": get_stride(config)[0]}]
             if settings[0]["stitching"] not in STITCH_METHODS:
                 raise ValueError(f"stitching must be one of {STITCH_METHODS}")
+
+        def truth_rows_of(r0: int, r1: int) -> np.ndarray:
+            if truth_array is not None:
+                return truth_array[r0:r1]
+            return open_images(config, local_out, True, rows=(r0, r1))[0]
 
         method_metrics = []
         method_times = {}
@@ -338,32 +357,48 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                 print("""    [ ] starting inference...\n""")
             H, W = dataset.raster_height, dataset.raster_width
             want_metrics = config["metrics"] and cfg["output_type"] == "argmax"
-            truth_dev = None
-            if want_metrics and len(my_tiles):
-                r0, r1 = cfg.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max())))
-                truth_dev = torch.from_numpy(np.ascontiguousarray(truth_array[r0:r1])).to(device)
+            n_classes = len(config["classes"]) if "classes" in config else config["n_classes"]
+            cm = torch.zeros((n_classes, n_classes), dtype=torch.int64, device=device) if want_metrics else None
             per_patch = want_metrics and config["compare"] and "classes" in config and len(config["classes"]) == config["n_classes"]
-            cls, conf, row0, rows = detect_zone(cfg, model, dataset, my_tiles, device, combi["stitching"],
-                                                truth_dev if per_patch else None)
-            if want_metrics:
-                n_classes = len(config["classes"]) if "classes" in config else config["n_classes"]
-                if truth_dev is None:
-                    truth_dev = torch.empty((0, W), dtype=torch.uint8, device=device)
-                cm = confusion_matrix_gpu(model, cls, truth_dev, n_classes)
-                if world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(cm)
-                result["confmat"] = cm.cpu().numpy()
-            if cfg["output_type"] == "argmax":
-                full_cls = _gather_strips(cls, row0, H, W, device)
-                full_conf = _gather_strips(conf, row0, H, W, device)
-                if rank == 0:
-                    _write_output(path_out, np.stack([full_cls, full_conf]), out_profile)
+            out = OutputMap(out_profile["count"], H, W)
+            own0, own1 = cfg.get("_own_rows", (int(my_tiles[:, 3].min()), int(my_tiles[:, 5].max()))) if len(my_tiles) else (0, 0)
+            if _pipelined(cfg):
+                truth_rows = None
+                if want_metrics and len(my_tiles):
+                    truth_rows = torch.from_numpy(np.ascontiguousarray(truth_rows_of(own0, own1)))
+                    truth_rows = truth_rows.pin_memory() if torch.cuda.is_available() else truth_rows
+                detect_zone_pipelined(cfg, model, dataset, my_tiles, out, truth_rows, own0, cm)
             else:
-                # class_prob: `cls` holds the n_classes probability planes (band k + 1 = class k, main.py:424-426)
-                planes = [_gather_strips(cls[k], row0, H, W, device) for k in range(cls.shape[0])]
-                if rank == 0:
-                    _write_output(path_out, np.stack(planes), out_profile)
+                # rows of the device maps: what this rank owns, widened to its tiles' whole metric windows for the
+                # per-patch metrics (a clamped or overlapping window reaches into a neighbouring rank's rows)
+                span0, span1 = own0, own1
+                if per_patch and len(my_tiles):
+                    win = np.asarray(cfg["_my_windows"])
+                    span0, span1 = min(own0, int(win[:, 3].min())), max(own1, int(win[:, 5].max()))
+                truth_dev = None
+                if want_metrics and len(my_tiles):
+                    truth_dev = torch.from_numpy(np.ascontiguousarray(truth_rows_of(span0, span1))).to(device)
+                cls, conf, row0, rows = detect_zone(cfg, model, dataset, my_tiles, device, combi["stitching"],
+                                                    truth_dev if per_patch else None, (span0, span1) if len(my_tiles) else None)
+                if want_metrics and len(my_tiles):
+                    confusion_matrix_gpu(model, cls[own0 - row0:own1 - row0], truth_dev[own0 - span0:own1 - span0], n_classes, out=cm)
+                out.pin_rows(own0, own1)
+                if cfg["output_type"] == "argmax":
+                    out.put_rows(0, own0, cls[own0 - row0:own1 - row0])
+                    out.put_rows(1, own0, conf[own0 - row0:own1 - row0])
+                else:
+                    # class_prob: `cls` holds the n_classes probability planes (band k + 1 = class k, main.py:424-426)
+                    for k in range(cls.shape[0]):
+                        out.put_rows(k, own0, cls[k, own0 - row0:own1 - row0])
+            if want_metrics:
+                if world > 1:
+                    model.allreduce_confusion(cm)
+                result["confmat"] = cm.cpu().numpy()
+            t_detect = (datetime.datetime.now() - start_time).total_seconds()
+            full = out.finish()
+            if rank == 0:
+                _write_output(path_out, full, out_profile)
+            out.close()
             dataset.close_raster()
             elapsed = (datetime.datetime.now() - start_time).total_seconds()
             method_times.setdefault(method, []).append(elapsed * 1000)   # main.py:352-358 (per zone here, not per patch)
@@ -373,8 +408,11 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
                     patch_metrics[method] = got
             if rank == 0:
                 print(f"""    [X] done writing to {path_out.split('/')[-1]} raster file ({elapsed:.2f} s, {len(tiles)} tiles, """
-                      f"""{H * W / 1e6 / max(elapsed, 1e-9):.1f} Mpx/s incl. I/O).\n""")
+                      f"""{H * W / 1e6 / max(elapsed, 1e-9):.1f} Mpx/s incl. I/O; read + detect {t_detect:.2f} s = """
+                      f"""{H * W / 1e6 / max(t_detect, 1e-9):.1f} Mpx/s).\n""")
                 result.setdefault("outputs", []).append(path_out)
+                result.setdefault("mpx_per_s_incl_io", []).append(H * W / 1e6 / max(elapsed, 1e-9))
+                result.setdefault("mpx_per_s_read_detect", []).append(H * W / 1e6 / max(t_detect, 1e-9))
                 if config["metrics"] and "classes" in config:
                     method_metrics.append(metrics_from_confmat(result["confmat"], config, method))
         config["times"] = method_times   # main.py:378, read by batch_metrics
@@ -397,6 +435,8 @@ def run_pipeline(config: dict, device: torch.device, use_gpu: bool) -> dict:
             result["metrics"] = method_metrics
     finally:
         sys.stdout, sys.stderr = old_out, old_err
+        if model is not None:
+            model.close()   # frees the context (and its NCCL communicator) now rather than at garbage collection
     return result
 
 

@@ -391,28 +391,35 @@ def gold_batch(out: dict):
 
 
 def gold_metadata_forward(out: dict):
-    """The reference's own FLAIR_ModelFactory.forward / MetadataMLP (flair/model.py:52-96) on top of
-    the restated Unet: pins the MLP + `repeat(1,512,1,16)` broadcast + add semantics."""
+    """The reference's own FLAIR_ModelFactory.forward / MetadataMLP (flair/model.py:52-96) on top of the restated
+    Unet: pins the MLP + `repeat(1,512,1,16)` broadcast + add semantics. Weights and input are regenerated from
+    seeds at test time (oracle.synth.random_checkpoint / synth_raster: a 98 MB state_dict cannot be committed), so
+    the fixture holds the reference's OUTPUTS only, plus a checksum of the weights that tells the test whether torch
+    still draws the same numbers from the seed."""
+    from oracle import synth
+    from oracle.flair_ref import norm as ref_norm
     from src.flair.model import FLAIR_ModelFactory, MetadataMLP
-    torch.manual_seed(5)
     cfg = {"model_framework": {"model_provider": "SegmentationModelsPytorch",
                                "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}},
            "use_metadata": False, "channels": [1, 2, 3, 4, 5], "classes": {i: [1, str(i)] for i in range(1, 14)}}
     m = FLAIR_ModelFactory(cfg)        # use_metadata=True would hit the NameError at model.py:32
     m.enc = MetadataMLP()
     m.use_metadata = True
+    sd = synth.random_checkpoint(5, 13, seed=5, use_metadata=True)   # oracle FlairModel keys: seg_model.* / enc.enc_mlp.*
+    missing, unexpected = m.load_state_dict(sd, strict=True), None
     m.eval()
-    x = torch.randn(1, 5, 512, 512)
-    met = torch.rand(1, 45)
+    img = synth.synth_raster(5, 512, 512, seed=33)
+    x = torch.as_tensor(ref_norm(img, "custom", synth.FLAIR_MEANS, synth.FLAIR_STDS), dtype=torch.float)[None]
+    met = torch.rand((1, 45), generator=torch.Generator().manual_seed(45))
     with torch.no_grad():
         y = m(x, met)
         e = m.enc(met)
-    sd = {k: v.clone() for k, v in m.state_dict().items()}
-    torch.save({"state_dict": sd, "x": x.to(torch.float16), "met": met, "enc": e,
-                "logits_sub": y[:, :, ::16, ::16].clone(), "logits_absmax": y.abs().max()},
-               HERE / "_cache" / "metadata_forward.pt")
-    out["metadata_forward"] = {"note": "tensors in tests/golden/_cache/metadata_forward.pt (98 MB state_dict, not committed)",
-                               "enc": e.tolist(), "logits_absmax": float(y.abs().max())}
+    checksum = float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+    np.savez_compressed(HERE / "metadata_forward.npz", met=met.numpy(), enc=e.numpy(), logits_sub=y[:, :, ::16, ::16].numpy(),
+                        logits_absmax=np.float32(y.abs().max()), weights_checksum=np.float64(checksum),
+                        img_seed=np.int64(33), weight_seed=np.int64(5))
+    out["metadata_forward"] = {"note": "tests/golden/metadata_forward.npz: outputs of the reference's FLAIR_ModelFactory.forward",
+                               "enc": e.tolist(), "logits_absmax": float(y.abs().max()), "weights_checksum": checksum}
 
 
 def main():
@@ -427,8 +434,7 @@ def main():
     gold_checkpoint(out)
     gold_config(out)
     gold_batch(out)
-    if "--with-forward" in sys.argv:
-        gold_metadata_forward(out)
+    gold_metadata_forward(out)
     (HERE / "golden.json").write_text(json.dumps(_jsonable(out), indent=1))
     print("wrote", HERE / "golden.json")
 

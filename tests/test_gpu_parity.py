@@ -6,8 +6,11 @@ import numpy as np
 import pytest
 import torch
 
+from pathlib import Path
+
 pytestmark = pytest.mark.gpu
 
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 LOGIT_TOL = 2e-2        # relative to max|ref| (BASELINE.json north_star)
 AGREE_MIN = 0.999       # argmax pixel agreement
 
@@ -606,3 +609,142 @@ def test_full_size_zone_properties(ctx, trained_3_15):
     out_cls, out_conf = np.zeros((H, W), np.uint8), np.zeros((H, W), np.uint8)
     ctx.detect_zone_host(host_r, [0, 1, 2], W, H, 0, 0, tiles, T, 148, out_cls, out_conf, W, 0, H)
     assert np.array_equal(out_cls, cls.cpu().numpy()) and np.array_equal(out_conf, conf.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------ round 2: shards, collectives, goldens
+def test_fused_sink_is_bit_exact_for_19_classes(monkeypatch):
+    """The 32-column head (17..32 classes) takes its soft-max in two 16-column halves; the standalone K6 kernel uses
+    the same order and arithmetic, so class map AND confidence band are byte-identical with and without the fused
+    sink / dead-output elimination, also where the two best classes sit in different halves."""
+    from oracle import synth
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    nat = _nat()
+    sd = synth.cached_checkpoint(3, 19)
+    W, H, T, margin = 700, 560, 256, 32
+    raster = torch.from_numpy(synth.synth_raster(3, H, W, seed=19)).cuda()
+    tiles = tile_table(W, H, T, margin)
+    res = {}
+    for mode in ("plain", "fast"):
+        monkeypatch.setenv("FB_FULL_TILES", "1" if mode == "plain" else "0")
+        monkeypatch.setenv("FB_NO_FUSED_SINK", "1" if mode == "plain" else "0")
+        c = nat.Context(0)
+        c.load_weights(sd, 3, 19)
+        c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+        c.set_raster(raster, [0, 1, 2], W, H)
+        cls = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        conf = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        c.detect_strip(tiles, T, 7, cls, conf, W, 0)
+        res[mode] = (cls.cpu().numpy(), conf.cpu().numpy())
+        c.close()
+    np.testing.assert_array_equal(res["fast"][0], res["plain"][0])
+    np.testing.assert_array_equal(res["fast"][1], res["plain"][1])
+    assert (res["fast"][0] < 19).all() and (res["fast"][0] >= 16).any() and (res["fast"][0] < 16).any()
+
+
+def test_confusion_rect_bit_exact(ctx):
+    """fb_confusion_rect: the histogram over a rectangle cut out of two wider maps (ragged width, unaligned origin,
+    different pitches) equals numpy's on the same pixels, incl. the uint8 wrap of truth - 1 and dropped labels."""
+    from oracle.metrics_ref import confusion_numpy
+    rng = np.random.default_rng(3)
+    for (Hm, Wp, Wt, y0, y1, x0, x1, ncls, sub) in [(300, 1000, 1000, 7, 291, 13, 977, 15, 1), (64, 4099, 5003, 0, 64, 1, 4098, 19, 1),
+                                                    (50, 700, 700, 10, 11, 3, 5, 7, 0), (33, 2048, 2048, 0, 33, 0, 2048, 32, 0),
+                                                    (40, 600, 640, 5, 35, 16, 528, 15, 1)]:
+        pred = rng.integers(0, ncls + 2, (Hm, Wp), dtype=np.uint8)
+        truth = rng.integers(0, ncls + 3, (Hm, Wt), dtype=np.uint8)
+        pd, td = torch.from_numpy(pred).cuda(), torch.from_numpy(truth).cuda()
+        cm = ctx.confusion_rect(pd[y0:y1, x0:x1], td[y0:y1, x0:x1], ncls, truth_sub=sub).cpu().numpy()
+        ref = confusion_numpy(truth[y0:y1, x0:x1], pred[y0:y1, x0:x1], ncls, sub)
+        np.testing.assert_array_equal(cm, ref)
+    empty = torch.zeros((0, 16), dtype=torch.uint8, device="cuda")
+    assert int(ctx.confusion_rect(empty, empty, 15).sum()) == 0
+
+
+def test_zone_shards_fill_one_host_map_and_sum_to_the_whole_confusion_matrix(ctx, trained_3_15):
+    """fb_detect_zone_shard: three shards (contiguous ranges of the row-major tile order, so the first / last tile row
+    of a shard is shared with its neighbour) write ONLY their own rectangles into one host map, which ends up
+    byte-identical to fb_detect_strip over the whole tile table; the fused confusion matrices of the shards add up to
+    the matrix of the whole map (bit-exact, sklearn semantics), and cells no shard owns are never touched."""
+    from oracle import synth
+    from oracle.metrics_ref import confusion_numpy
+    from flair1_b200.zone_detect.slicing_job import owned_rects, split_tiles_across_ranks, tile_table
+    sd, _ = trained_3_15
+    W, H, T, margin = 1500, 1100, 512, 128
+    raster = synth.synth_raster(3, H, W, seed=21)
+    truth = synth.synth_mask(raster, 15, 3)
+    truth[::9, ::4] = 0
+    truth[5::13, 1::7] = 18
+    ctx.load_weights(sd, 3, 15)
+    ctx.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+    tiles = tile_table(W, H, T, margin)
+    ctx.set_raster(torch.from_numpy(raster).cuda(), [0, 1, 2], W, H)
+    ref_cls = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    ref_conf = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    ctx.detect_strip(tiles, T, 6, ref_cls, ref_conf, W, 0)
+    ref_cls, ref_conf = ref_cls.cpu().numpy(), ref_conf.cpu().numpy()
+    out = torch.full((2, H, W), 255, dtype=torch.uint8).pin_memory()
+    total = torch.zeros((15, 15), dtype=torch.int64, device="cuda")
+    for shard in split_tiles_across_ranks(tiles, 3):
+        mine = tiles[shard]
+        ry0, ry1 = max(int(mine[:, 1].min()), 0), min(int(mine[:, 1].max()) + T, H)
+        rects = owned_rects(mine)
+        my0, my1 = int(rects[:, 0].min()), int(rects[:, 1].max())
+        before = out.clone()
+        cm = torch.zeros((15, 15), dtype=torch.int64, device="cuda")
+        ctx.detect_zone_shard(torch.from_numpy(raster[:, ry0:ry1].copy()).pin_memory(), [0, 1, 2], W, H, ry0, 0, mine, T, 5,
+                              out[0].numpy(), out[1].numpy(), W, 0, H,
+                              truth=torch.from_numpy(truth[my0:my1].copy()).pin_memory(), truth_row0=my0, truth_sub=1, cm=cm)
+        mask = np.zeros((H, W), bool)
+        ref_cm = np.zeros((15, 15), np.int64)
+        for y0, y1, x0, x1 in rects:
+            mask[y0:y1, x0:x1] = True
+            ref_cm += confusion_numpy(truth[y0:y1, x0:x1], ref_cls[y0:y1, x0:x1], 15, 1)
+        np.testing.assert_array_equal(cm.cpu().numpy(), ref_cm)
+        assert np.array_equal(out.numpy()[:, ~mask], before.numpy()[:, ~mask])      # nothing outside the shard's rectangles
+        total += cm
+    np.testing.assert_array_equal(out[0].numpy(), ref_cls)
+    np.testing.assert_array_equal(out[1].numpy(), ref_conf)
+    np.testing.assert_array_equal(total.cpu().numpy(), confusion_numpy(truth, ref_cls, 15, 1))
+    # an empty shard (more ranks than tiles) is a no-op
+    ctx.detect_zone_shard(torch.from_numpy(raster[:, :T].copy()), [0, 1, 2], W, H, 0, 0, tiles[:0], T, 5, out[0].numpy(), None, W, 0, H)
+    np.testing.assert_array_equal(out[0].numpy(), ref_cls)
+
+
+def test_comm_single_rank_allreduce_and_gather(ctx):
+    """The library's own NCCL communicator (fb_comm_*, resolved with dlopen): with one rank the all-reduce and the
+    byte gather are identities; a second fb_comm_init on the same context is refused."""
+    ctx.comm_init(0, 1, lambda ident: ident)
+    cm = torch.arange(15 * 15, dtype=torch.int64, device="cuda").reshape(15, 15).contiguous()
+    ref = cm.clone()
+    ctx.allreduce_confusion(cm)
+    torch.cuda.synchronize()
+    assert torch.equal(cm, ref)
+    send = torch.arange(1000, dtype=torch.int32, device="cuda").to(torch.uint8)
+    got = ctx.gather_bytes(send, [send.numel()], root=0)
+    torch.cuda.synchronize()
+    assert torch.equal(got, send)
+    with pytest.raises(nat_error()):
+        ctx.comm_init(0, 1, lambda ident: ident)
+    ctx.comm_destroy()
+    with pytest.raises(nat_error()):
+        ctx.allreduce_confusion(cm)
+
+
+def test_metadata_forward_matches_the_references_own_forward(ctx):
+    """tests/golden/metadata_forward.npz holds the OUTPUT of the reference's FLAIR_ModelFactory.forward / MetadataMLP
+    (src/flair/model.py:52-96, run by tests/golden/make_golden.py) on seeded weights and a seeded 5-band tile: the
+    library's logits (fb_forward_tiles with metadata) stay within the bf16 tolerance of it."""
+    from oracle import synth
+    g = np.load(GOLDEN_DIR / "metadata_forward.npz")
+    sd = synth.random_checkpoint(5, 13, seed=int(g["weight_seed"]), use_metadata=True)
+    checksum = float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+    if abs(checksum - float(g["weights_checksum"])) > 1e-6 * float(g["weights_checksum"]):
+        pytest.skip("torch draws other numbers from the seed than when the golden was made")
+    sd = {k.replace("seg_model.", "", 1) if k.startswith("seg_model.") else k: v for k, v in sd.items()}
+    img = synth.synth_raster(5, 512, 512, seed=int(g["img_seed"]))
+    ctx.load_weights(sd, 5, 13, use_metadata=True)
+    ctx.set_norm("custom", synth.FLAIR_MEANS, synth.FLAIR_STDS)
+    ctx.set_raster(torch.from_numpy(img).cuda(), [0, 1, 2, 3, 4], 512, 512)
+    got = ctx.forward_tiles(np.array([[0, 0]], np.int32), 512, metadata=g["met"]).cpu().permute(0, 3, 1, 2)[:, :13, ::16, ::16].numpy()
+    rel = np.abs(got - g["logits_sub"]).max() / float(g["logits_absmax"])
+    print(f"metadata forward vs the reference's own forward(): rel err {rel:.4e}")
+    assert rel <= LOGIT_TOL

@@ -273,6 +273,35 @@ def test_row_sharding_covers_every_tile_once():
             assert np.isin(tiles[:, 1], ys).sum() == len(s)
 
 
+def test_tile_range_sharding_balances_to_one_tile_and_partitions_the_map():
+    """split_tiles_across_ranks: contiguous ranges of the row-major tile order, sizes within one tile of each other
+    (157 tile rows over 8 ranks would give 20 against 19.6 rows), and the owned rectangles of the shards partition
+    the raster exactly (each pixel written by exactly one rank)."""
+    from flair1_b200.zone_detect.slicing_job import owned_rects, split_tiles_across_ranks, tile_table
+    tiles = tile_table(40000, 40000, 512, 128)
+    for world in (1, 2, 4, 8):
+        shards = split_tiles_across_ranks(tiles, world)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(len(tiles)))
+        sizes = [len(s) for s in shards]
+        assert max(sizes) - min(sizes) <= 1
+        area = 0
+        for s in shards:
+            t = tiles[s]
+            assert (np.diff(t[:, 1]) >= 0).all()                      # y-sorted: a shard needs one contiguous row span
+            r = owned_rects(t)
+            assert len(r) <= len(np.unique(t[:, 1])) + 1
+            area += int(((r[:, 1] - r[:, 0]) * (r[:, 3] - r[:, 2])).sum())
+        assert area == 40000 * 40000
+    # small ragged zone, pixel-exact cover, also with more ranks than tile rows
+    for (W, H, T, M, world) in ((1500, 1100, 512, 128, 3), (700, 513, 256, 32, 5), (300, 300, 512, 128, 4)):
+        tiles = tile_table(W, H, T, M)
+        cover = np.zeros((H, W), np.int32)
+        for s in split_tiles_across_ranks(tiles, world):
+            for y0, y1, x0, x1 in owned_rects(tiles[s]):
+                cover[y0:y1, x0:x1] += 1
+        assert (cover == 1).all()
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
@@ -399,21 +428,29 @@ sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
 from flair1_b200.zone_detect import main as zmain
 from flair1_b200.zone_detect.metrics import metrics_from_confmat
-from flair1_b200.zone_detect.slicing_job import split_rows_across_ranks, tile_table, tile_windows
+from flair1_b200.zone_detect.slicing_job import owned_rects, split_tiles_across_ranks, tile_table, tile_windows
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 W, H, T, M, NC = 1500, 1100, 512, 128, 15
 rng = np.random.default_rng(11)
-full = rng.integers(0, NC, (H, W), dtype=np.uint8)
+full = rng.integers(0, NC, (2, H, W), dtype=np.uint8)
 tiles, wins = tile_table(W, H, T, M), tile_windows(W, H, T, M)
-shard = split_rows_across_ranks(tiles, world)[rank]
+shard = split_tiles_across_ranks(tiles, world)[rank]
 mine = tiles[shard]
-r0, r1 = int(mine[:, 3].min()), int(mine[:, 5].max())
-# the product's own strip gather (NCCL on the GPU box, gloo here)
-got = zmain._gather_strips(torch.from_numpy(full[r0:r1].copy()), r0, H, W, torch.device("cpu"))
+# the product's own output map: one [bands, H, W] array in shared memory, every rank writes the rectangles it owns
+# (on the GPU box fb_detect_zone_shard does these copies from device memory), rank 0 reads the whole map
+out = zmain.OutputMap(2, H, W)
+assert out.shared is not None
+for y0, y1, x0, x1 in owned_rects(mine):
+    out.array[:, y0:y1, x0:x1] = full[:, y0:y1, x0:x1]
+got = out.finish()
 assert (got is None) == (rank != 0)
 if rank == 0:
     assert np.array_equal(got, full)
+path = out.shared.path
+out.close()
+dist.barrier()
+assert not os.path.exists(path)
 # the product's own per-patch metric gather: every rank contributes the confusion matrices of its tiles
 classes = {{i + 1: [1 if i < 12 else 0, "class%d" % (i + 1)] for i in range(NC)}}
 all_cm = rng.integers(0, 1000, (len(tiles), NC, NC)).astype(np.int64)
@@ -431,8 +468,9 @@ sys.stdout.flush()
 
 
 def test_two_rank_strip_and_patch_metric_gather_of_the_pipeline_gloo(tmp_path):
-    """zone_detect.main._gather_strips / _gather_patch_metrics (the multi-GPU tail of run_pipeline) under gloo with two
-    ranks: rank 0 ends up with the whole class map and with every tile's metrics in write order."""
+    """zone_detect.main.OutputMap / _gather_patch_metrics (the multi-GPU tail of run_pipeline) under gloo with two
+    ranks sharded by tile ranges: rank 0 ends up with the whole class map (shared memory, no gather) and with every
+    tile's metrics in write order."""
     script = tmp_path / "worker_main.py"
     script.write_text(_WORKER_MAIN.format(root=str(ROOT)))
     env = dict(os.environ, OMP_NUM_THREADS="1")

@@ -288,3 +288,29 @@ def test_tile_windows_are_the_interiors():
         for x0, y0, a, b, c, d in w:
             cover[b:d, a:c] = True
         assert cover.all()
+
+
+def test_oracle_metadata_forward_equals_the_references_forward():
+    """oracle.unet_smp033.FlairModel.forward (the restatement of src/flair/model.py:52-70) reproduces the fixture made by
+    the reference's own FLAIR_ModelFactory.forward + MetadataMLP: same MLP, same repeat(1,512,1,16) broadcast, add."""
+    import numpy as np
+    import torch
+    from oracle import synth
+    from oracle.flair_ref import norm
+    from oracle.unet_smp033 import FlairModel
+    g = np.load(GOLDEN / "metadata_forward.npz")
+    sd = synth.random_checkpoint(5, 13, seed=int(g["weight_seed"]), use_metadata=True)
+    checksum = float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+    if abs(checksum - float(g["weights_checksum"])) > 1e-6 * float(g["weights_checksum"]):
+        import pytest
+        pytest.skip("torch draws other numbers from the seed than when the golden was made")
+    m = FlairModel(5, 13, True)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    img = synth.synth_raster(5, 512, 512, seed=int(g["img_seed"]))
+    x = torch.as_tensor(norm(img, "custom", synth.FLAIR_MEANS, synth.FLAIR_STDS), dtype=torch.float)[None]
+    with torch.no_grad():
+        y = m(x, torch.from_numpy(g["met"]))
+        e = m.enc(torch.from_numpy(g["met"]))
+    np.testing.assert_allclose(e.numpy(), g["enc"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(y[:, :, ::16, ::16].numpy(), g["logits_sub"], rtol=0, atol=1e-4 * float(g["logits_absmax"]))

@@ -148,8 +148,9 @@ def test_flair_detect_rejects_what_it_cannot_do(tmp_path, trained_3_15):
 
 
 def test_flair_predict_and_metrics_end_to_end(tmp_path, trained_3_15):
-    """flair --conf x.yaml (predict + metrics) on 6 synthetic 512 x 512 patches laid out like csv_toy: PRED_*.tif
-    files with 0-based classes, metrics/confmat.npy + metrics.json equal to the oracle's on the same files."""
+    """BASELINE config 1 at its stated size: flair --conf x.yaml (predict + metrics) on 50 synthetic 512 x 512 patches
+    laid out like csv_toy/flair-1-paths-toy-test.csv (50 rows of image,mask): PRED_*.tif files with 0-based classes,
+    metrics/confmat.npy + metrics.json equal to the oracle's on the same files; the log carries the patches/s of the run."""
     from flair1_b200 import geotiff as gt
     from flair1_b200.flair import main as fmain
     from oracle import synth
@@ -160,8 +161,9 @@ def test_flair_predict_and_metrics_end_to_end(tmp_path, trained_3_15):
     data = tmp_path / "data"
     (data / "img").mkdir(parents=True)
     (data / "msk").mkdir()
+    N = 50
     rows, imgs, msks = [], [], []
-    for i in range(6):
+    for i in range(N):
         img5 = synth.synth_raster(5, 512, 512, seed=100 + i)
         msk = synth.synth_mask(img5[:3], 15, 3)
         msk[:8] = 19                                  # labels outside 1..15 are dropped by the confusion matrix
@@ -196,8 +198,13 @@ def test_flair_predict_and_metrics_end_to_end(tmp_path, trained_3_15):
     pred_dir = tmp_path / "exp" / "run1" / "predictions_run1"
     assert (tmp_path / "exp" / "run1" / "flair-compute.log").exists()
     assert (tmp_path / "exp" / "run1" / "used_csv_and_config" / "test.csv").exists()
+    import re
+    log_text = (tmp_path / "exp" / "run1" / "flair-compute.log").read_text()
+    rate = re.search(r"predicted (\d+) patches in ([0-9.]+) s \(([0-9.]+) patches/s", log_text)
+    assert rate and int(rate.group(1)) == N
+    print(f"flair CLI, {N} patches incl. TIFF read + LZW write: {rate.group(3)} patches/s")
     agree, cms = [], []
-    for i in range(6):
+    for i in range(N):
         p = pred_dir / f"PRED_IMG_{i:06d}.tif"
         info = gt.read_info(p)
         assert (info.count, info.compression) == (1, 5) and 33922 in info.geo_tags
@@ -214,6 +221,94 @@ def test_flair_predict_and_metrics_end_to_end(tmp_path, trained_3_15):
     ref_m = flair_metrics(np.sum(cms, axis=0), CLASSES15)
     assert m["Avg_metrics"] == [float(v) for v in ref_m["Avg_metrics"]] and m["classes"] == ref_m["classes"]
     assert m["per_class_iou"] == [float(v) for v in ref_m["per_class_iou"]]
+
+
+def test_flair_predict_with_metadata_end_to_end(tmp_path):
+    """BASELINE config 3 through the CLI: flair --conf x.yaml with use_metadata: True and path_metadata_aerial. The JSON
+    goes through parsing_metadata (src/flair/tasks_utils.py:158-213) -> 45 floats per patch -> predict_dataset ->
+    fb_predict_patches (MLP + broadcast add onto the bottleneck, src/flair/model.py:52-70). PRED files against the oracle's
+    FlairModel on the same inputs (>= 99.9 % on a briefly trained 5-band / 13-class checkpoint with the metadata branch),
+    and the logits of the same patches within tolerance."""
+    from flair1_b200 import geotiff as gt
+    from flair1_b200.flair import main as fmain
+    from flair1_b200.flair.tasks_utils import parsing_metadata
+    import flair1_b200._native as nat
+    from oracle import synth
+    from oracle.flair_ref import norm, predict_step
+    from oracle.unet_smp033 import FlairModel
+    sd = synth.cached_checkpoint(5, 13, use_metadata=True)
+    model = FlairModel(5, 13, True)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    means, stds = synth.FLAIR_MEANS, synth.FLAIR_STDS
+    data = tmp_path / "data"
+    (data / "img").mkdir(parents=True)
+    (data / "msk").mkdir()
+    N = 6
+    rows, imgs, meta = [], [], {}
+    cams = ["UCE-M3-f120-s06", "UCX-2", "UCE"]
+    for i in range(N):
+        img5 = synth.synth_raster(5, 512, 512, seed=300 + i)
+        msk = synth.synth_mask(img5[:3], 13, 3)
+        ip, mp = data / "img" / f"IMG_{i:06d}.tif", data / "msk" / f"MSK_{i:06d}.tif"
+        gt.write(ip, img5, compress="deflate", tiled=False, blocksize=64)
+        gt.write(mp, msk, compress="lzw", tiled=False, blocksize=64)
+        rows.append(f"{ip},{mp}")
+        imgs.append(img5)
+        meta[f"IMG_{i:06d}"] = {"patch_centroid_x": 489212.4 + 51234.5 * i, "patch_centroid_y": 6222222.2 + 77777.7 * i,
+                               "patch_centroid_z": 137.5 * i, "camera": cams[i % 3], "date": f"{2018 + i % 4}-{1 + i:02d}-{3 + 4 * i:02d}",
+                               "time": f"{8 + i:02d}h{7 * i:02d}"}
+    csv = tmp_path / "test.csv"
+    csv.write_text("\n".join(rows) + "\n")
+    (tmp_path / "meta.json").write_text(json.dumps(meta))
+    classes13 = {i + 1: [1, f"class{i + 1}"] for i in range(13)}
+    # Lightning checkpoint layout of the flair CLI: model.seg_model.*, model.enc.enc_mlp.*, criterion.weight
+    torch.save({"state_dict": {**{"model." + k: v for k, v in sd.items()}, "criterion.weight": torch.ones(13)}}, tmp_path / "model.ckpt")
+    cfg = {"paths": {"out_folder": str(tmp_path / "exp"), "out_model_name": "meta", "train_csv": None, "val_csv": None,
+                     "test_csv": str(csv), "ckpt_model_path": str(tmp_path / "model.ckpt"), "path_metadata_aerial": str(tmp_path / "meta.json")},
+           "tasks": {"train": False, "train_tasks": {"init_weights_only_from_ckpt": False, "resume_training_from_ckpt": False},
+                     "predict": True, "metrics": True, "delete_preds": False},
+           "model_framework": {"model_provider": "SegmentationModelsPytorch",
+                               "SegmentationModelsPytorch": {"encoder_decoder": "resnet34_unet"}},
+           "use_augmentation": False, "use_metadata": True, "channels": [1, 2, 3, 4, 5], "norm_type": "custom",
+           "norm_means": means, "norm_stds": stds, "seed": 2022, "batch_size": 4, "classes": classes13,
+           "georeferencing_output": False, "cp_csv_and_conf_to_output": False, "accelerator": "gpu", "num_nodes": 1,
+           "gpus_per_node": 1, "strategy": "auto", "num_workers": 0}
+    conf = tmp_path / "flair.yaml"
+    conf.write_text(yaml.safe_dump(cfg))
+    old = sys.argv
+    sys.argv = ["flair", "--conf", str(conf)]
+    try:
+        fmain.main()
+    finally:
+        sys.argv = old
+    mtd = np.asarray(parsing_metadata([r.split(",")[0] for r in rows], cfg), dtype=np.float32)
+    assert mtd.shape == (N, 45)
+    x = torch.stack([torch.as_tensor(norm(im, "custom", means, stds), dtype=torch.float) for im in imgs])
+    ref_cls = predict_step(model, x, torch.from_numpy(mtd)).numpy().astype(np.uint8)
+    pred_dir = tmp_path / "exp" / "meta" / "predictions_meta"
+    got = np.stack([gt.read(pred_dir / f"PRED_IMG_{i:06d}.tif")[0] for i in range(N)])
+    agree = (got == ref_cls).mean()
+    print(f"flair predict with metadata: agreement {agree * 100:.4f}%, classes present {np.unique(ref_cls).size}")
+    assert agree >= 0.999
+    # the metadata really matters for this checkpoint: other metadata, other logits (guards against a silently ignored MTD)
+    with torch.no_grad():
+        ref_logits = model(x[:2], torch.from_numpy(mtd[:2]))
+        other = model(x[:2], torch.from_numpy(mtd[2:4]))
+    assert (ref_logits - other).abs().max() > 1e-3
+    # logits of the same patches through the library, with the vectors parsing_metadata produced
+    ctx = nat.Context(0)
+    ctx.load_weights({k.replace("seg_model.", "", 1) if k.startswith("seg_model.") else k: v for k, v in sd.items()}, 5, 13, use_metadata=True)
+    ctx.set_norm("custom", means, stds)
+    raster = torch.from_numpy(np.concatenate(imgs[:2], axis=1)).cuda()
+    ctx.set_raster(raster, [0, 1, 2, 3, 4], 512, 1024)
+    lg = ctx.forward_tiles(np.array([[0, 0], [0, 512]], np.int32), 512, metadata=mtd[:2]).cpu().permute(0, 3, 1, 2)[:, :13]
+    rel = (lg - ref_logits).abs().max().item() / ref_logits.abs().max().item()
+    print(f"flair predict with metadata: logits rel err {rel:.4e}")
+    assert rel <= 2e-2
+    ctx.close()
+    m = json.loads((tmp_path / "exp" / "meta" / "metrics" / "metrics.json").read_text())
+    assert len(m["per_class_iou"]) == 13
 
 
 def test_load_checkpoint_class_count_surgery(tmp_path, trained_3_15):
