@@ -24,7 +24,8 @@ constexpr int kMmaWarp = 3;
 template <int KH, int STRIDE, int NCH, int MB, int BN = 64>
 struct Geo {
   static constexpr int TW = 8 * MB;
-  static constexpr int PAD = KH / 2;
+  // 4x4 stride 2 = the 2x2-cell form of a 3x3 stride-1 conv (D2S): cell (Y, X) reads pixels 2Y-1 .. 2Y+2
+  static constexpr int PAD = (KH == 4 && STRIDE == 2) ? 1 : KH / 2;
   static constexpr int NP = STRIDE;                                    // w-parity planes
   static constexpr int PH = STRIDE * (kTH - 1) + KH + (NCH == 1 ? 1 : 0);  // +1: stem pairs taps vertically
   static constexpr int SPANW = STRIDE * (TW - 1) + KH;
@@ -37,8 +38,8 @@ struct Geo {
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
   // ring depth (= stages of loads in flight) / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
   // memory (filter bank + stages + 18 KB epilogue staging): the 16/32-channel layers run two CTAs per SM
-  static constexpr bool TWO = KH == 3 && NCH <= 4;
-  static constexpr int STAGES = (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
+  static constexpr bool TWO = (KH == 3 && NCH <= 4) || (KH == 4 && STRIDE == 2);
+  static constexpr int STAGES = (KH == 4 && STRIDE == 2) ? 3 : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
   static constexpr int OCC = TWO ? 2 : 1;
 };
 
@@ -50,10 +51,17 @@ struct Geo {
 // 4-7 drain the even ones (direct-store mode only; a warp may only touch the TMEM lanes of its quarter, warp % 4,
 // so a group is always four warps). Used for the one-CTA-per-SM configurations, whose drain (64 accumulator
 // columns + residual per block) otherwise outlasts the MMAs of the next tile.
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1>
+// D2S = depth-to-space output: the BN = 64 accumulator columns of a tile row are the 2x2 output pixels of one CELL
+// (column (py*2 + px)*16 + co -> pixel (2Y + py, 2X + px), channel co of a 16-channel tensor), the tile grid is the
+// cell grid. Serves the 16-channel layers at full resolution, whose N = 16 MMAs are bound by the fetch of the A
+// operand (4 KB per 128 pixels and tap): as a 4x4 stride-2 conv over cells (head, dec4.conv2: 16 taps with N = 64 per
+// 512 pixels instead of 4 x 9 taps with N = 16) or as the 3x3 conv on the low-res input whose 64 outputs are the four
+// phases of the x2-upsampled conv (dec4.conv1: 18 MMAs with N = 64 instead of 32 with N = 16).
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false>
 __global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  static_assert(!D2S || (BN == 64 && !PH && EPI == 1), "depth-to-space output: 4 pixels x 16 channels per tile row");
   static_assert(EPI == 1 || (G::OCC == 1 && !PH && MB % 2 == 0), "two epilogue groups: one CTA per SM, even block count");
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   static_assert(!PH || (MB == 4 && KH == 3 && STRIDE == 1), "phase form: 4 accumulators on a 3x3 stride-1 halo");
@@ -113,7 +121,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   pdl_launch_dependents();
   pdl_wait();
 
-  const int tiles_w = (PH ? p.Win : p.Wout) / G::TW, tiles_h = (PH ? p.Hin : p.Hout) / kTH;
+  const int tiles_w = (PH ? p.Win : D2S ? p.Wout / 2 : p.Wout) / G::TW, tiles_h = (PH ? p.Hin : D2S ? p.Hout / 2 : p.Hout) / kTH;
   // position i of this launch's schedule -> tile of the full grid (identity unless an active-tile list is given)
   auto tile_of = [&](int i) { return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i; };
 
@@ -268,7 +276,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         int sink_x0 = 0, sink_y0 = 0, sink_wx0 = 0, sink_wy0 = 0, sink_wx1 = 0, sink_wy1 = 0;
         float sink_best = 0.f, sink_den = 0.f;
         int sink_arg = 0;
-        if (!PH && (BN == 16 || BN == 32) && p.sink_cls != nullptr) {
+        if (!PH && (BN == 16 || BN == 32 || D2S) && p.sink_cls != nullptr) {
           const int* st = p.sink_tiles + 6 * tb;
           sink_x0 = __ldg(st); sink_y0 = __ldg(st + 1); sink_wx0 = __ldg(st + 2); sink_wy0 = __ldg(st + 3);
           sink_wx1 = __ldg(st + 4); sink_wy1 = __ldg(st + 5);
@@ -308,6 +316,33 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
           auto direct = [&](int col0, const auto& regs) {
             if (p.debug_skip & 4) return;
+            if constexpr (D2S) {
+              // columns col0 .. col0 + 15 = the 16 channels of pixel (2*oh + py, 2*(ow + 8m) + px) of the cell
+              const int grp = col0 >> 4;
+              const int y = 2 * oh + (grp >> 1), x = 2 * (ow + 8 * m) + (grp & 1);
+              if constexpr (sizeof(regs) == 64) {
+                if (p.sink_cls != nullptr) {
+                  // fused K6 (see below), one pixel per 16-column group
+                  const int rx = sink_x0 + x, ry = sink_y0 + y;
+                  if (!(rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1)) return;
+                  float best = regs[0];
+                  int arg = 0;
+#pragma unroll
+                  for (int k = 1; k < 16; ++k)
+                    if (k < p.sink_ncls && regs[k] > best) { best = regs[k]; arg = k; }
+                  float den = 0.f;
+#pragma unroll
+                  for (int k = 0; k < 16; ++k)
+                    if (k < p.sink_ncls) den += __expf(regs[k] - best);
+                  const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
+                  p.sink_cls[o] = static_cast<uint8_t>(arg);
+                  if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);
+                  return;
+                }
+              }
+              store_regs(out_bytes + ((static_cast<size_t>(tb) * p.Hout + y) * p.Wout + x) * (16 * elem), regs);
+              return;
+            }
             if constexpr (!PH && (BN == 16 || BN == 32) && sizeof(regs) == 64) {
               if (p.sink_cls != nullptr) {
                 // fused K6: the fp32 logits of pixel (oh, ow + 8m) of image tb arrive 16 at a time. Arg-max = first
@@ -465,26 +500,27 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   }
 }
 
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1>
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   const int groups = a.groups1 + a.groups2;
   const int wbytes = (PH ? MB : 1) * groups * a.nsteps * 2 * BN * 16;
+  // (the depth-to-space kernels only store from registers: no copy-out staging)
   const int smem = ((wbytes + 127) / 128) * 128 + 256 + G::STAGES * G::STAGE +
-                   ((2 * G::STAGES + 4) * 8 + 16 + 127) / 128 * 128 + 4 * kStgWarpBytes;
+                   ((2 * G::STAGES + 4) * 8 + 16 + 127) / 128 * 128 + (D2S ? 0 : 4 * kStgWarpBytes);
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>, kThreadsK, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>, kThreadsK, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
@@ -495,7 +531,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
-  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI>, dim3(grid), dim3(kThreadsK),
+  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>, dim3(grid), dim3(kThreadsK),
                                            static_cast<size_t>(smem), stream, pdl, a);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }

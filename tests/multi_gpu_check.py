@@ -3,12 +3,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
         tests/multi_gpu_check.py > gpurun_out/multi_gpu_check.log 2>&1
 
-Every rank runs flair-detect (`run_pipeline`, `-m`, then `-c -m` over exact-clipping / average / max) on the same
-synthetic zone with the tile rows sharded over the ranks: NCCL all-reduce of the confusion matrices, NCCL gather of
-the class-map strips to rank 0. Rank 0 then repeats everything alone on one context (`fb_detect_strip` over the whole
-tile table, blended stitchings over the whole table) and requires the outputs to be identical byte for byte: class
-map, confidence band, confusion matrix, per-patch metrics ("allreduced confmat ==
-single-GPU confmat bit-exact")."""
+Every rank runs flair-detect (`run_pipeline`, `-m`, then `-c -m` over exact-clipping / average / max, then `-c -m` with
+an overlapping stride) on the same synthetic zone sharded over the ranks: the `-m` run goes through the pipelined
+fb_detect_zone_shard with tile-range sharding and the shared-memory output map, the confusion matrices are summed by
+the library's own NCCL communicator (fb_allreduce_confusion), the compare runs keep whole tile rows per rank. Rank 0
+then repeats everything alone on one context (`fb_detect_strip` over the whole tile table, blended stitchings over the
+whole table) and requires the outputs to be identical byte for byte: class map, confidence band, confusion matrix,
+per-patch metrics -- also where a tile's metric window reaches into the rows of the neighbouring rank (stride below
+the interior) -- ("allreduced confmat == single-GPU confmat bit-exact")."""
 import json
 import os
 import sys
@@ -69,6 +71,14 @@ conf = tmp / f"detect_{rank}.yaml"
 conf.write_text(yaml.safe_dump(cfg))
 res = zmain.run_pipeline(read_config(SimpleNamespace(conf=str(conf), metrics=True, batch_mode=False, compare=False)), dev, True)
 res_c = zmain.run_pipeline(read_config(SimpleNamespace(conf=str(conf), metrics=True, batch_mode=False, compare=True)), dev, True)
+# stride 192 < interior 256: the margin-cropped windows of neighbouring tile rows overlap, so a window at a shard
+# boundary reaches into rows the other rank owns
+cfg_s = dict(cfg, overlap_strat=True,
+             strategies={"tiling": {"enabled": False, "size_range": [], "stride_range": [0.375]},
+                         "stitching": {"enabled": True, "methods": ["exact-clipping"], "margin": [0.25]}, "padding_overall": None})
+conf_s = tmp / f"detect_s_{rank}.yaml"
+conf_s.write_text(yaml.safe_dump(cfg_s))
+res_s = zmain.run_pipeline(read_config(SimpleNamespace(conf=str(conf_s), metrics=True, batch_mode=False, compare=True)), dev, True)
 dist.barrier()
 
 if rank == 0:
@@ -94,6 +104,14 @@ if rank == 0:
     method = "size=512_stride=256_margin=128_padding=no-padding_stitching=exact-clipping"
     ref_patch = [metrics_from_confmat(c, cfg, f"{method}_{int(w[2])}_{int(w[3])}") for w, c in zip(wins, cm_tiles)]
     checks["per-patch metrics == single GPU"] = json.loads(json.dumps(res_c["patch_metrics"][method])) == json.loads(json.dumps(ref_patch))
+    tiles_s, wins_s = tile_table(W, H, T, M, 192), tile_windows(W, H, T, M, 192)
+    cls_s = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    cnf_s = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    cm_tiles_s = ctx.detect_strip_metrics(tiles_s, wins_s, T, 37, cls_s, cnf_s, W, 0, truth_dev).cpu().numpy()
+    method_s = "size=512_stride=192_margin=128_padding=no-padding_stitching=exact-clipping"
+    ref_patch_s = [metrics_from_confmat(c, cfg, f"{method_s}_{int(w[2])}_{int(w[3])}") for w, c in zip(wins_s, cm_tiles_s)]
+    checks["stride 192: per-patch metrics == single GPU"] = json.loads(json.dumps(res_s["patch_metrics"][method_s])) == json.loads(json.dumps(ref_patch_s))
+    checks["stride 192: class map == single GPU"] = bool(np.array_equal(gt.read(res_s["outputs"][0])[0], cls_s.cpu().numpy()))
     for path in res_c["outputs"]:
         stitch = Path(path).stem.split("stitching=")[1]
         g = gt.read(path)
