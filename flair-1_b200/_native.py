@@ -466,7 +466,9 @@ class Context:
         Cout = w_oihw.shape[0]
         pad = KH // 2
         Hout, Wout = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KH) // stride + 1
-        m = 2 if up2_out else 1  # up2_out == 2: phase form (conv of the upsampled x1), also twice the input size
+        # up2_out == 2: phase form (conv of the upsampled x1), also twice the input size; 3 / 4: the depth-to-space
+        # forms (3: same size, 4: conv of the upsampled x1); the output always has Cout channels (<= 16 there)
+        m = 1 if up2_out == 3 else 2 if up2_out else 1
         out = torch.empty((B, Hout * m, Wout * m, Cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
         w = np.ascontiguousarray(w_oihw.detach().cpu().float().numpy())
         self._check(self._lib.fb_conv2d_halo(self._h, x1.data_ptr(), _ptr(x2), C1, C2, B, H, W, KH, stride, Cout, w.ctypes.data,

@@ -35,6 +35,9 @@ struct ConvLayer {
   int Kp_phase = 0;
   __nv_bfloat16* w_halo_phase = nullptr;  // device, phase form for the halo-staged kernel (32 -> 16 channels) (or null)
   __nv_bfloat16* w_s2d = nullptr;         // device, the stem as a 4x4 filter on the 2x2 space-to-depth image (<= 4 bands)
+  __nv_bfloat16* w_d2s = nullptr;         // device, depth-to-space form of a 16-output-channel layer (conv_halo.cuh, HaloArgs::d2s)
+  float* bias_d2s = nullptr;              // device [64]: bias[co] at (py*2+px)*16 + co
+  int d2s_mode = 0;                       // 1: 16 -> 16 as a 4x4 stride-2 conv over cells, 2: upsampled 32 -> 16 on the low-res grid
   float* bias = nullptr;            // device [Cout]
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
@@ -88,6 +91,9 @@ struct fb_ctx {
   bool stem_s2d = false;      // decided by arena_plan: x0 is stored in space-to-depth form
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
+  bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
+  bool d2s_all = false;       // FB_D2S_ALL=1: also dec4.conv2 (bf16 output) in depth-to-space form
+  bool no_sb = false;         // FB_NO_SB=1: the 128 -> 128 layers on the im2col implicit GEMM instead of the halo kernel with streamed weights
   double flops = 0;           // algorithmic FLOPs of the conv outputs actually computed since creation
   int* list_dev = nullptr;    // active-tile lists of the current network pass
   size_t list_cap = 0;        // in ints
@@ -331,6 +337,26 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
     c->owned.push_back(L.w_halo_phase);
     FB_CUDA(c, cudaMemcpy(L.w_halo_phase, hp.data(), n * 2, cudaMemcpyHostToDevice));
   }
+  // the 16-output-channel layers at full resolution (dec4, head) in depth-to-space form
+  {
+    const int mode = (KH == 3 && stride == 1 && CoutPad == 16 && Cin == CinPad)
+                         ? ((!decoder_conv1 && Cin == 16) ? 1 : (decoder_conv1 && L.C1 == 32 && L.C2 == 0) ? 2 : 0) : 0;
+    if (mode) {
+      const size_t n = fb::pack_halo_weights_d2s(mode, folded.data(), Cout, Cin, nullptr);
+      std::vector<uint16_t> hp(n);
+      fb::pack_halo_weights_d2s(mode, folded.data(), Cout, Cin, hp.data());
+      FB_CUDA(c, cudaMalloc(&L.w_d2s, n * 2));
+      c->owned.push_back(L.w_d2s);
+      FB_CUDA(c, cudaMemcpy(L.w_d2s, hp.data(), n * 2, cudaMemcpyHostToDevice));
+      std::vector<float> b64(64, 0.f);
+      for (int q = 0; q < 4; ++q)
+        for (int o = 0; o < Cout; ++o) b64[q * 16 + o] = bias[o];
+      FB_CUDA(c, cudaMalloc(&L.bias_d2s, 64 * 4));
+      c->owned.push_back(L.bias_d2s);
+      FB_CUDA(c, cudaMemcpy(L.bias_d2s, b64.data(), 64 * 4, cudaMemcpyHostToDevice));
+      L.d2s_mode = mode;
+    }
+  }
   FB_CUDA(c, cudaMalloc(&L.w, packed.size() * 2));
   c->owned.push_back(L.w);
   FB_CUDA(c, cudaMalloc(&L.bias, bias.size() * 4));
@@ -544,6 +570,40 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
   const int* list = nullptr;
   long long active = 0;
   int rc;
+  // depth-to-space form (16 output channels at full resolution): 64 accumulator columns = the 2x2 pixels of a cell
+  // (measured per 148 tiles: head 368 -> 304 us, dec4.conv1 211 -> 200 us, dec4.conv2 301 -> 491 us: its bf16 stores
+  // are the slower part there, so the 16 -> 16 bf16 layer keeps the N = 16 kernel unless FB_D2S_ALL=1)
+  if (L.d2s_mode && !c->no_d2s && !c->force_gather && !c->no_halo && !x2 && !res && !rowbias && !out.up2 && !up1 &&
+      (L.d2s_mode == 2) == phase && (L.d2s_mode == 2 || out.elem == 4 || c->d2s_all) && fb::halo_d2s_supported(L.d2s_mode, C1, 0, L.Cout, Hout, Wout) &&
+      (L.d2s_mode == 1 ? (x1.H == Hout && x1.W == Wout && !x1.up2) : (x1.H * 2 == Hout && x1.W * 2 == Wout))) {
+    fb::HaloArgs h;
+    memset(&h, 0, sizeof h);
+    h.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
+    h.C1 = C1;
+    h.B = x1.B; h.Hin = x1.H; h.Win = x1.W; h.Hout = Hout; h.Wout = Wout;
+    h.bias = L.bias_d2s;
+    h.relu = relu ? 1 : 0;
+    if (out.elem == 4) h.out_f32 = static_cast<float*>(out.ptr); else h.out = static_cast<__nv_bfloat16*>(out.ptr);
+    h.wpacked = L.w_d2s;
+    fb::halo_fill_steps_d2s(h, L.d2s_mode);
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 16, Hout / 32, Wout / 32, &list, &active));
+    if (c->plan_mode == 1) return 0;
+    if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
+    c->flops += static_cast<double>(active) * (32 * 32) * L.flops_px;
+    if (sink && need && out.elem == 4) {
+      h.sink_tiles = need->tiles_dev;
+      h.sink_cls = sink->cls;
+      h.sink_conf = sink->conf;
+      h.sink_map_w = sink->map_w;
+      h.sink_map_row0 = sink->map_row0;
+      h.sink_ncls = c->ncls;
+      if (sunk) *sunk = true;
+    }
+    rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
+    if (rc != 0) return fail(c, rc, "depth-to-space conv launch failed (code " + std::to_string(rc) + ")");
+    c->launches++;
+    return 0;
+  }
   if (phase) {
     // decoder conv1 in sub-pixel phase form: x1 at half the output resolution, x2 (skip) at full resolution
     if ((!L.w_phase && !L.w_halo_phase) || x1.H * 2 != Hout || x1.W * 2 != Wout || (x2 && (x2->H != Hout || x2->W != Wout)) || res || rowbias)
@@ -602,8 +662,8 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
   } else if (x2 && (x2->H != x1.H || x2->W != x1.W)) {
     return fail(c, FB_ERR_INVALID, "internal: skip tensor shape mismatch");
   }
-  if (up1 || (!c->force_gather && !c->no_halo && L.w_halo && L.C1 == C1 && L.C2 == C2 &&
-              fb::halo_supported(L.KH, L.stride, C1, C2, L.Cout, Hout, Wout))) {
+  if (up1 || (!c->force_gather && !c->no_halo && L.w_halo && L.C1 == C1 && L.C2 == C2 && !(c->no_sb && L.Cout == 128) &&
+              !(out.up2 && L.Cout == 128) && fb::halo_supported(L.KH, L.stride, C1, C2, L.Cout, Hout, Wout))) {
     fb::HaloArgs h;
     memset(&h, 0, sizeof h);
     h.x1 = static_cast<const __nv_bfloat16*>(x1.ptr);
@@ -877,6 +937,12 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->full_tiles = ft && ft[0] == '1';
   const char* nf = getenv("FB_NO_FUSED_SINK");
   c->no_fused_sink = nf && nf[0] == '1';
+  const char* nd = getenv("FB_NO_D2S");
+  c->no_d2s = nd && nd[0] == '1';
+  const char* da = getenv("FB_D2S_ALL");
+  c->d2s_all = da && da[0] == '1';
+  const char* nsb = getenv("FB_NO_SB");
+  c->no_sb = nsb && nsb[0] == '1';
   *out = c;
   return 0;
 }
@@ -1733,6 +1799,38 @@ int fb_conv2d_halo(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, in
   h.out = static_cast<__nv_bfloat16*>(out_bf16);
   h.out_f32 = out_f32;
   h.up2_out = up2_out;
+  if (up2_out == 3 || up2_out == 4) {
+    // depth-to-space forms: 3 = 16 -> <= 16 channels as a 4x4 stride-2 conv over 2x2 cells, 4 = the conv of the
+    // x2-upsampled 32-channel x1 on the low-res grid (HaloArgs::d2s = 1 / 2)
+    const int mode = up2_out - 2;
+    if (mode == 2) { h.Hout = 2 * Hin; h.Wout = 2 * Win; }
+    if (KH != 3 || stride != 1 || x2 || residual || !fb::halo_d2s_supported(mode, C1, 0, Cout, h.Hout, h.Wout))
+      return fail(c, FB_ERR_INVALID, "conv2d_halo: no depth-to-space instantiation for this shape");
+    h.up2_out = 0;
+    const size_t n = fb::pack_halo_weights_d2s(mode, w_oihw_host, Cout, C1, nullptr);
+    std::vector<uint16_t> hp(n);
+    fb::pack_halo_weights_d2s(mode, w_oihw_host, Cout, C1, hp.data());
+    std::vector<float> bh(Cout), b64(64, 0.f);
+    FB_CUDA(c, cudaMemcpy(bh.data(), bias, Cout * 4, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 4; ++q)
+      for (int o = 0; o < Cout; ++o) b64[q * 16 + o] = bh[o];
+    __nv_bfloat16* wdev = nullptr;
+    float* bdev = nullptr;
+    FB_CUDA(c, cudaMalloc(&wdev, n * 2));
+    FB_CUDA(c, cudaMalloc(&bdev, 64 * 4));
+    cudaMemcpy(wdev, hp.data(), n * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(bdev, b64.data(), 64 * 4, cudaMemcpyHostToDevice);
+    h.wpacked = wdev;
+    h.bias = bdev;
+    fb::halo_fill_steps_d2s(h, mode);
+    const int rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(wdev);
+    cudaFree(bdev);
+    if (rc) return fail(c, rc, "conv2d_halo (depth-to-space) launch failed (code " + std::to_string(rc) + ")");
+    c->launches++;
+    return 0;
+  }
   if (up2_out == 2) {  // sub-pixel phase form: the conv of the x2-upsampled x1, computed from the low-res x1
     if (KH != 3 || stride != 1 || x2 || residual || out_f32 || !fb::halo_phase_supported(C1, 0, Cout, Hin, Win))
       return fail(c, FB_ERR_INVALID, "conv2d_halo: no phase-form instantiation for this shape");

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
 
@@ -20,6 +22,15 @@ constexpr int kTH = 16;                  // output tile: 16 rows x (8*MB) column
 constexpr int kThreads = 256;
 constexpr int kProducers = 96;
 constexpr int kMmaWarp = 3;
+
+// epilogue arguments of the depth-to-space layers (conv_epilogue.cuh reads residual / rowbias / relu / out_f32 / Cout)
+struct D2SEpiArgs {
+  static constexpr const __nv_bfloat16* residual = nullptr;
+  static constexpr const float* rowbias = nullptr;
+  int relu;
+  const float* out_f32;
+  int Cout;
+};
 
 template <int KH, int STRIDE, int NCH, int MB, int BN = 64>
 struct Geo {
@@ -38,8 +49,9 @@ struct Geo {
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
   // ring depth (= stages of loads in flight) / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
   // memory (filter bank + stages + 18 KB epilogue staging): the 16/32-channel layers run two CTAs per SM
+  // (4x4 stride 2: a stage is the whole 34 x 34 pixel halo of a 16 x 16 cell tile, 37 KB, next to a 32 KB filter bank)
   static constexpr bool TWO = (KH == 3 && NCH <= 4) || (KH == 4 && STRIDE == 2);
-  static constexpr int STAGES = (KH == 4 && STRIDE == 2) ? 3 : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
+  static constexpr int STAGES = (KH == 4 && STRIDE == 2) ? 2 : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
   static constexpr int OCC = TWO ? 2 : 1;
 };
 
@@ -57,32 +69,53 @@ struct Geo {
 // operand (4 KB per 128 pixels and tap): as a 4x4 stride-2 conv over cells (head, dec4.conv2: 16 taps with N = 64 per
 // 512 pixels instead of 4 x 9 taps with N = 16) or as the 3x3 conv on the low-res input whose 64 outputs are the four
 // phases of the x2-upsampled conv (dec4.conv1: 18 MMAs with N = 64 instead of 32 with N = 16).
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false>
+// SB = streamed filter bank: the layer's weights (295 KB for 128 -> 128 channels) do not fit in shared memory, so one
+// extra warp streams them through a ring of kSbStages stages with 1-D bulk copies (a stage = the NCH / 2 K-steps of
+// one filter tap of one channel group, contiguous in pack_halo_weights' order) while the input halo is still staged
+// once per tile: against the im2col implicit GEMM (every input pixel fetched nine times, weights fetched once per 128
+// pixels) this moves 185 KB instead of 576 KB from L2 to shared memory per 128 output pixels of layer2.
+constexpr int kSbStages = 4;
+
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false>
 __global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   static_assert(!D2S || (BN == 64 && !PH && EPI == 1), "depth-to-space output: 4 pixels x 16 channels per tile row");
   static_assert(EPI == 1 || (G::OCC == 1 && !PH && MB % 2 == 0), "two epilogue groups: one CTA per SM, even block count");
+  static_assert(!SB || (!PH && !D2S && G::OCC == 1 && NCH % 2 == 0), "streamed filter bank: plain form, one CTA per SM");
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
+  // SB: warp 2 streams the weights and warps 0-1 gather the halo (a 13th warp would cap the kernel at 128 registers:
+  // four warps on one scheduler share its 16 K registers)
+  constexpr int kBWarp = 2;
+  constexpr int kProd = SB ? 64 : kProducers;           // halo-gathering threads
+  constexpr int kCellsPerThread = (G::CELLS + kProd - 1) / kProd;
+  constexpr int kBSteps = NCH / 2;                      // K-steps per weight stage
+  constexpr int kBStage = kBSteps * 2 * BN * 16;        // bytes
   static_assert(!PH || (MB == 4 && KH == 3 && STRIDE == 1), "phase form: 4 accumulators on a 3x3 stride-1 halo");
   constexpr int S = G::STAGES;
-  constexpr int kBarBytes = ((2 * S + 4) * 8 + 16 + 127) / 128 * 128;
+  constexpr int kBars = 2 * S + 4 + (SB ? 2 * kSbStages : 0);
+  constexpr int kBarBytes = (kBars * 8 + 16 + 127) / 128 * 128;
+  constexpr int kBiasBytes = BN * 4 <= 256 ? 256 : BN * 4;
   constexpr int ACC = MB * BN;  // TMEM columns of one accumulator buffer (MB blocks of 128 x BN)
   constexpr int TMEM_COLS = (2 * ACC <= 32) ? 32 : (2 * ACC <= 64) ? 64 : (2 * ACC <= 128) ? 128 : (2 * ACC <= 256) ? 256 : 512;
+  static_assert(2 * ACC <= 512, "two accumulator buffers must fit the 512 TMEM columns");
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int groups = p.groups1 + p.groups2;
-  const int wbytes = (PH ? MB : 1) * groups * p.nsteps * 2 * BN * 16;   // phase form: one filter set per phase
+  // phase form: one filter set per phase; streamed: the ring
+  const int wbytes = SB ? kSbStages * kBStage : (PH ? MB : 1) * groups * p.nsteps * 2 * BN * 16;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t w_addr = smem_base;
   const uint32_t bias_off = ((wbytes + 127) / 128) * 128;
-  const uint32_t stage_addr0 = smem_base + bias_off + 256;             // 64 fp32 of bias
+  const uint32_t stage_addr0 = smem_base + bias_off + kBiasBytes;      // BN fp32 of bias
   const uint32_t bars = stage_addr0 + S * G::STAGE;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + (2 * S + 4) * 8);
+  auto bfull_bar = [&](int s) { return bars + 8u * (2 * S + 4 + s); };
+  auto bempty_bar = [&](int s) { return bars + 8u * (2 * S + 4 + kSbStages + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + kBars * 8);
   float* bias_s = reinterpret_cast<float*>(smem + bias_off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,19 +124,25 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.wpacked);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    if (!(p.debug_skip & 16))
+    if (!SB && !(p.debug_skip & 16))
       for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + i);
     if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(full_bar(s), kProducers);
+        mbar_init(full_bar(s), kProd);
         mbar_init(empty_bar(s), 1);
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 128 * EPI);
+      }
+      if (SB) {
+        for (int s = 0; s < kSbStages; ++s) {
+          mbar_init(bfull_bar(s), 1);
+          mbar_init(bempty_bar(s), 1);
+        }
       }
       fence_mbar_init();
     }
@@ -125,18 +164,18 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   // position i of this launch's schedule -> tile of the full grid (identity unless an active-tile list is given)
   auto tile_of = [&](int i) { return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i; };
 
-  if (warp < kMmaWarp) {
+  if (warp < (SB ? kBWarp : kMmaWarp)) {
     // ===================================================================== producers (halo gather)
     // The cells a thread copies do not depend on the tile: decode them once into one word per cell,
     // byte offset inside a stage | hh << 16 | k << 24. kProducers is a multiple of NCH, so the channel
     // chunk c of every cell of a thread is the same: tid % NCH.
     const int tid = threadIdx.x;
-    static_assert(kProducers % NCH == 0, "channel chunk must be constant per producer thread");
+    static_assert(kProd % NCH == 0, "channel chunk must be constant per producer thread");
     const int c8 = (tid % NCH) * 8;
-    uint32_t cell[G::CELLS_PER_THREAD];
+    uint32_t cell[kCellsPerThread];
 #pragma unroll
-    for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
-      const int idx = tid + j * kProducers;
+    for (int j = 0; j < kCellsPerThread; ++j) {
+      const int idx = tid + j * kProd;
       const int c = idx % NCH;
       const int k = (idx / NCH) % G::KWCELLS;
       const int hh = idx / (NCH * G::KWCELLS);
@@ -153,7 +192,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
       const int iw0 = tw * G::TW * STRIDE - G::PAD;
       const int w_lo = iw0 < 0 ? 0 : iw0, w_hi = iw0 + G::KWCELLS < p.Win ? iw0 + G::KWCELLS : p.Win;
-      for (int r = tid; r < G::PH * nsrc; r += kProducers) {
+      for (int r = tid; r < G::PH * nsrc; r += kProd) {
         const int sidx = r / G::PH, ih = th * kTH * STRIDE - G::PAD + r % G::PH;
         if (static_cast<unsigned>(ih) >= static_cast<unsigned>(p.Hin)) continue;
         const int Cs = sidx ? p.C2 : p.C1;
@@ -190,7 +229,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           const int Hlo = p.Hin >> 1, Wlo = p.Win >> 1;
           const __nv_bfloat16* lo = p.x1 + static_cast<long long>(b) * Hlo * Wlo * Cs + g * (NCH * 8) + c8;
 #pragma unroll
-          for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+          for (int j = 0; j < kCellsPerThread; ++j) {
             if (cell[j] != 0xFFFFFFFFu) {
               const int ih = ih0 + static_cast<int>((cell[j] >> 16) & 0xFF), iw = iw0 + static_cast<int>(cell[j] >> 24);
               const bool ok = static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hin) &&
@@ -201,7 +240,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           }
         } else if (interior) {
 #pragma unroll
-          for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+          for (int j = 0; j < kCellsPerThread; ++j) {
             if (cell[j] != 0xFFFFFFFFu) {
               const int hh = (cell[j] >> 16) & 0xFF, k = cell[j] >> 24;
               cp_async_16(st + (cell[j] & 0xFFFFu), src + hh * row_elems + k * Cs, 16u);
@@ -209,7 +248,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < G::CELLS_PER_THREAD; ++j) {
+          for (int j = 0; j < kCellsPerThread; ++j) {
             if (cell[j] != 0xFFFFFFFFu) {
               const int hh = (cell[j] >> 16) & 0xFF, k = cell[j] >> 24;
               const bool ok = static_cast<unsigned>(ih0 + hh) < static_cast<unsigned>(p.Hin) &&
@@ -224,6 +263,23 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         // generic -> async proxy fence after its wait)
         cp_async_mbar_arrive_noinc(full_bar(s));
       }
+    }
+  } else if (SB && warp == kBWarp) {
+    // ===================================================================== weight streamer (SB)
+    // same (tile, group, tap) order as the MMA issuer; a stage is refilled as soon as its MMAs have completed
+    if (elect_one()) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
+      const int nb = p.nsteps / kBSteps;
+      uint32_t bit = 0;
+      for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x)
+        for (int g = 0; g < groups; ++g)
+          for (int bs = 0; bs < nb; ++bs, ++bit) {
+            const int s = bit % kSbStages;
+            mbar_wait_relaxed(bempty_bar(s), ((bit / kSbStages) & 1) ^ 1);
+            mbar_expect_tx(bfull_bar(s), kBStage);
+            bulk_load_1d(w_addr + s * kBStage, wsrc + static_cast<size_t>(g * p.nsteps + bs * kBSteps) * (2 * BN * 16), kBStage,
+                         bfull_bar(s));
+          }
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
@@ -271,7 +327,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           st_global_v8(d + 32, hi);
         }
       };
-      if (p.direct_store) {
+      if (D2S || SB || p.direct_store) {
         const int oh = th * kTH + L.own_dh, ow = tw * G::TW + L.own_dw;
         int sink_x0 = 0, sink_y0 = 0, sink_wx0 = 0, sink_wy0 = 0, sink_wx1 = 0, sink_wy1 = 0;
         float sink_best = 0.f, sink_den = 0.f;
@@ -283,9 +339,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         }
         // residual rows are loaded one block ahead: block 0 before the accumulator wait, block m + 1 while
         // block m is processed (BN <= 32: everything up front)
-        constexpr int kResBuf = PH ? 1 : (MB * BN <= 64 ? MB : 2);
+        constexpr int kResBuf = (PH || D2S || SB) ? 1 : (MB * BN <= 64 ? MB : 2);
         uint32_t rbuf[kResBuf][BN / 16][8];
-        const bool has_res = !PH && p.residual != nullptr;
+        // (SB: 128 channels per pixel; the residual row is prefetched in 64-channel groups inside epilogue_tile instead)
+        const bool has_res = !PH && !D2S && !SB && p.residual != nullptr;
         const __nv_bfloat16* res_row0 = p.residual + ((static_cast<long long>(tb) * p.Hout + oh) * p.Wout + ow) * BN;
         if (EPI == 2) {
           // this group's blocks: m = grp, grp + 2, ...; residual rows one block (of the group) ahead
@@ -386,13 +443,24 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
               store_regs(d + up_row_bytes + pixel_bytes, regs);
             }
           };
-          epilogue_tile<BN, true, true, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
-                                                    tb * p.Hout + oh, direct, rbuf[(EPI == 2 ? mi : m) % kResBuf]);
+          if constexpr (D2S) {
+            // no residual / row bias in these layers: constant-null members let the compiler drop those paths
+            const D2SEpiArgs ea{p.relu, p.out_f32, p.Cout};
+            epilogue_tile<BN, true, true, true, true>(ea, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                                      0, direct, rbuf[0]);
+          } else if constexpr (SB) {
+            epilogue_tile<BN, true, true, true, false>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                                       tb * p.Hout + oh, direct);
+          } else {
+            epilogue_tile<BN, true, true, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                                      tb * p.Hout + oh, direct, rbuf[(EPI == 2 ? mi : m) % kResBuf]);
+          }
         }
         tc_fence_before_sync();
         mbar_arrive(tempty_bar(as));
         continue;
       }
+      if constexpr (D2S || SB) continue;
       if (EPI == 2 && grp == 1) {
         // staged copy-out (2x2-replicated outputs) is done by the first group alone
         mbar_wait(tfull_bar(as), aph);
@@ -447,7 +515,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     constexpr uint32_t a_hi = static_cast<uint32_t>(G::SBO16) | (1u << 14);
     constexpr uint32_t b_hi = 8u | (1u << 14);
     const uint32_t b_lo0 = (w_addr >> 4) | (static_cast<uint32_t>(BN) << 16);
-    uint32_t it = 0, tcount = 0;
+    uint32_t it = 0, tcount = 0, bit = 0;
     for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
       const int as = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
@@ -464,7 +532,27 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         // K-step outer, block inner: consecutive MMAs hit different accumulators (block m = output columns
         // 8m..8m+7 of the tile, 8 cells further in the stage) and share the step's filter slab
         uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
-        if (p.debug_skip & 2) {
+        if constexpr (SB) {
+          // one weight stage per filter tap: wait for it, issue its kBSteps x MB MMAs, hand it back
+          const int nb = p.nsteps / kBSteps;
+          for (int bs = 0; bs < nb; ++bs, ++bit) {
+            const int sb = bit % kSbStages;
+            mbar_wait(bfull_bar(sb), (bit / kSbStages) & 1);
+            tc_fence_after_sync();
+            const uint32_t wb = ((w_addr + sb * kBStage) >> 4) | (static_cast<uint32_t>(BN) << 16);
+            if (!(p.debug_skip & 2)) {
+#pragma unroll
+              for (int kk = 0; kk < kBSteps; ++kk) {
+                const int k = bs * kBSteps + kk;
+                const uint32_t a_lo = p.a_lo[k] + st16;
+                const uint32_t acc = (g | k) != 0 ? 1u : 0u;
+#pragma unroll
+                for (int m = 0; m < MB; ++m) umma_bf16_lohi(d_tmem + m * BN, a_lo + 8 * m, a_hi, wb + kk * (2 * BN), b_hi, idesc, acc);
+              }
+            }
+            umma_commit(bempty_bar(sb));
+          }
+        } else if (p.debug_skip & 2) {
         } else if (PH) {
           // step k of phase m: a_lo[m * nsteps + k], filter slab (m * nsteps + k); k outer so that consecutive
           // MMAs alternate between the four phase accumulators
@@ -500,27 +588,27 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   }
 }
 
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false>
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   const int groups = a.groups1 + a.groups2;
-  const int wbytes = (PH ? MB : 1) * groups * a.nsteps * 2 * BN * 16;
-  // (the depth-to-space kernels only store from registers: no copy-out staging)
-  const int smem = ((wbytes + 127) / 128) * 128 + 256 + G::STAGES * G::STAGE +
-                   ((2 * G::STAGES + 4) * 8 + 16 + 127) / 128 * 128 + (D2S ? 0 : 4 * kStgWarpBytes);
+  const int wbytes = SB ? kSbStages * (NCH / 2) * 2 * BN * 16 : (PH ? MB : 1) * groups * a.nsteps * 2 * BN * 16;
+  // (the depth-to-space and streamed-weight kernels only store from registers: no copy-out staging)
+  const int smem = ((wbytes + 127) / 128) * 128 + (BN * 4 <= 256 ? 256 : BN * 4) + G::STAGES * G::STAGE +
+                   ((2 * G::STAGES + 4 + (SB ? 2 * kSbStages : 0)) * 8 + 16 + 127) / 128 * 128 + ((D2S || SB) ? 0 : 4 * kStgWarpBytes);
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>, kThreadsK, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>, kThreadsK, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
@@ -531,7 +619,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
-  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S>, dim3(grid), dim3(kThreadsK),
+  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>, dim3(grid), dim3(kThreadsK),
                                            static_cast<size_t>(smem), stream, pdl, a);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -579,6 +667,7 @@ bool halo_supported(int KH, int stride, int C1, int C2, int Cout, int Hout, int 
   const int nch = cg / 8;
   if ((C1 + C2) / cg > 2) return false;
   if (Wout % (8 * halo_blocks(KH, nch, Cout)) != 0) return false;
+  if (nch == 8 && Cout == 128) return C2 == 0 && C1 == 128;   // streamed filter bank (layer2, dec1.conv2)
   return (nch == 2 && (Cout == 16 || Cout == 32)) || (nch == 4 && (Cout == 16 || Cout == 32)) ||
          (nch == 8 && (Cout == 32 || Cout == 64));
 }
@@ -728,7 +817,60 @@ size_t pack_halo_weights_phase(const float* w, int Cout, int CoutPad, int Cin, i
   return total;
 }
 
+// ---- depth-to-space forms of the 16-output-channel layers (HaloArgs::d2s)
+bool halo_d2s_supported(int mode, int C1, int C2, int Cout, int Hout, int Wout) {
+  if (C2 != 0 || Cout > 16 || Hout % (2 * kTH) != 0 || Wout % 32 != 0) return false;   // tiles of 16 x 16 cells
+  return mode == 1 ? C1 == 16 : mode == 2 ? C1 == 32 : false;
+}
+
+void halo_fill_steps_d2s(HaloArgs& a, int mode) {
+  a.d2s = mode;
+  a.Cout = 64;
+  if (mode == 1) halo_fill_steps(a, 4, 2);   // 16 taps x one K = 16 step on the pixel grid, two w-parity planes
+  else halo_fill_steps(a, 3, 1);             // 9 taps x two K = 16 steps on the low-res grid
+  a.num_m_tiles = a.B * (a.Hout / (2 * kTH)) * (a.Wout / 32);
+  a.direct_store = 1;
+}
+
+size_t pack_halo_weights_d2s(int mode, const float* w, int Cout, int Cin, uint16_t* dst) {
+  const int KH = mode == 1 ? 4 : 3, stride = mode == 1 ? 2 : 1;
+  if (!dst) return pack_halo_weights(nullptr, 64, 64, Cin, Cin, KH, stride, Cin, 0, nullptr);
+  // w64[(py*2 + px)*16 + co][ci][a][b]: the weight output pixel (py, px) of the cell applies to window position (a, b)
+  std::vector<float> w64(static_cast<size_t>(64) * Cin * KH * KH, 0.f);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+          for (int a = 0; a < KH; ++a)
+            for (int b = 0; b < KH; ++b) {
+              double s = 0.0;
+              if (mode == 1) {
+                // window row a is pixel row 2Y - 1 + a; output row 2Y + py reads rows 2Y + py - 1 + kh: kh = a - py
+                const int kh = a - py, kw = b - px;
+                if (kh < 0 || kh > 2 || kw < 0 || kw > 2) continue;
+                s = w[((static_cast<size_t>(co) * Cin + ci) * 3 + kh) * 3 + kw];
+              } else {
+                // window row a is low-res row Y - 1 + a; output row 2Y + py reads upsampled rows 2Y + d, d = py - 1 + kh
+                // in -1 .. 2, i.e. low-res row Y + floor(d / 2): a = floor(d / 2) + 1 = (d + 2) >> 1
+                for (int kh = 0; kh < 3; ++kh)
+                  for (int kw = 0; kw < 3; ++kw)
+                    if (((py + 1 + kh) >> 1) == a && ((px + 1 + kw) >> 1) == b)
+                      s += w[((static_cast<size_t>(co) * Cin + ci) * 3 + kh) * 3 + kw];
+              }
+              w64[((static_cast<size_t>((py * 2 + px) * 16 + co) * Cin + ci) * KH + a) * KH + b] = static_cast<float>(s);
+            }
+  return pack_halo_weights(w64.data(), 64, 64, Cin, Cin, KH, stride, Cin, 0, dst);
+}
+
 int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream) {
+  if (a.d2s) {
+    if (!halo_d2s_supported(a.d2s, a.C1, a.C2, 16, a.Hout, a.Wout) || a.Cout != 64 || a.residual || a.rowbias || a.up2_out ||
+        a.up1 || a.phase_mode || (a.d2s == 1 ? (a.Hin != a.Hout || a.Win != a.Wout) : (2 * a.Hin != a.Hout || 2 * a.Win != a.Wout)))
+      return -3005;
+    if (a.nsteps != (a.d2s == 1 ? 16 : 18)) return -3002;
+    return a.d2s == 1 ? launch_halo_t<4, 2, 2, 64, 2, false, 1, true>(a, num_sms, stream)
+                      : launch_halo_t<3, 1, 4, 64, 2, false, 1, true>(a, num_sms, stream);
+  }
   if (a.phase_mode) {
     if (KH != 3 || stride != 1 || !halo_phase_supported(a.C1, a.C2, a.Cout, a.Hin, a.Win) || a.Hout != 2 * a.Hin ||
         a.Wout != 2 * a.Win || a.residual || a.rowbias || a.up2_out || a.out_f32)
@@ -743,6 +885,10 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // two epilogue groups for the one-CTA-per-SM configurations (FB_EPI2=0: one group, for A/B runs)
   const char* e2 = getenv("FB_EPI2");
   const bool epi2 = !(e2 && e2[0] == '0') && a.direct_store;
+  if (KH == 3 && nch == 8 && a.Cout == 128) {
+    if (a.up2_out || a.out_f32) return -3006;
+    return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true>(a, num_sms, stream);
+  }
   if (KH == 4) return epi2 ? launch_halo_t<4, 1, 2, 64, 2, false, 2>(a, num_sms, stream)
                            : launch_halo_t<4, 1, 2, 64, 2>(a, num_sms, stream);
   if (epi2) {

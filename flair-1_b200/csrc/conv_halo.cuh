@@ -50,6 +50,13 @@ struct HaloArgs {
   // upsample, out is [B, 2*Hin, 2*Win, Cout]; a_lo holds 4 phases x nsteps entries and wpacked one filter
   // set per phase (pack_halo_weights_phase)
   int phase_mode;
+  // Depth-to-space form of a 16-output-channel layer (64 accumulator columns = the 2x2 output pixels of one cell x 16
+  // channels; the tile grid is the cell grid, out is [B, Hout, Wout, 16]):
+  //   1: 3x3 stride-1 conv on [B, Hout, Wout, 16] run as a 4x4 stride-2 conv over cells (dec4.conv2, head);
+  //   2: 3x3 conv of the nearest-x2 upsample of the LOW-res x1 [B, Hin, Win, 32], Hout = 2*Hin, run as a 3x3 conv on
+  //      the low-res grid whose 64 outputs are the four output phases (dec4.conv1).
+  // wpacked / bias come from pack_halo_weights_d2s (bias replicated four times), Cout = 64.
+  int d2s;
   int no_prefetch;               // 0 only with FB_PREFETCH=1: L2 prefetch of upcoming halos (measured neutral)
   // FB_HALO_SKIP bit mask, bottleneck hunting only (results are wrong): 1 = producers copy nothing,
   // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake
@@ -97,6 +104,14 @@ void halo_fill_steps_phase(HaloArgs& a);
 // [phase = pa*2+pb][step = (di*2+dj)*(C/16) + kk][chunk 0/1][n][8]; taps of the 3x3 filter that read the same
 // low-res pixel are summed before the single bf16 rounding.
 size_t pack_halo_weights_phase(const float* w, int Cout, int CoutPad, int Cin, int CinPad, uint16_t* dst);
+
+// Depth-to-space forms (HaloArgs::d2s). mode 1: Cin == 16, mode 2: Cin == 32 (low-res source); Cout <= 16.
+bool halo_d2s_supported(int mode, int C1, int C2, int Cout, int Hout, int Wout);
+void halo_fill_steps_d2s(HaloArgs& a, int mode);
+// w: folded fp32 [Cout][Cin][3][3]. dst: the 64-output filter bank in the halo kernel's step order (mode 1: 16 taps of
+// the 4x4 cell window, mode 2: 9 low-res taps with the taps that read the same low-res pixel summed before the single
+// bf16 rounding); bias64: bias[co] at (py*2+px)*16 + co. Returns the bf16 element count (dst may be null).
+size_t pack_halo_weights_d2s(int mode, const float* w, int Cout, int Cin, uint16_t* dst);
 
 int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream);
 

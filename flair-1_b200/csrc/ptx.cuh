@@ -113,6 +113,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` (multiple of 16) from a 16-byte-aligned global address to a
+// 16-byte-aligned shared address; completion is counted in bytes on the mbarrier (pair with mbar_expect_tx).
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------- cp.async (LDGSTS)
 // 16-byte copy global->shared; src_bytes==0 zero-fills the destination (conv padding).
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {

@@ -100,10 +100,13 @@ def conv_case(ctx, name, B, H, W, C1, Cout, k, stride, pad, mode, C2=0, up1=Fals
 
 
 def halo_case(ctx, name, B, H, W, C1, Cout, KH, stride, C2=0, res=False, relu=True, up2=False, out_f32=False, seed=0,
-              identity=False, phase=False):
+              identity=False, phase=False, d2s=0):
     """Halo-staged kernel against the fp32 reference on bf16-rounded operands.
 
-    phase: the sub-pixel form; x1 is the LOW-res input, the reference is the conv of its nearest x2 upsample."""
+    phase: the sub-pixel form; x1 is the LOW-res input, the reference is the conv of its nearest x2 upsample.
+    d2s: the depth-to-space forms (1: 16 channels in, 4x4 stride-2 conv over 2x2 cells; 2: 32 channels in at low
+    resolution, the reference is the conv of the nearest x2 upsample)."""
+    phase = phase or d2s == 2
     g = torch.Generator(device="cpu").manual_seed(seed)
     dev = ctx.device
     x1 = torch.randn((B, H, W, C1), generator=g).to(torch.bfloat16).to(dev)
@@ -120,8 +123,8 @@ def halo_case(ctx, name, B, H, W, C1, Cout, KH, stride, C2=0, res=False, relu=Tr
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KH) // stride + 1
     residual = torch.randn((B, Ho, Wo, Cout), generator=g).to(torch.bfloat16).to(dev) if res else None
     try:
-        y = ctx.conv2d_halo(x1, w, bias, KH, stride, x2=x2, residual=residual, relu=relu, up2_out=2 if phase else up2,
-                            out_f32=out_f32)
+        y = ctx.conv2d_halo(x1, w, bias, KH, stride, x2=x2, residual=residual, relu=relu,
+                            up2_out=2 + d2s if d2s else 2 if phase else up2, out_f32=out_f32)
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         log(f"CASE {name}: EXCEPTION {e}")
@@ -167,6 +170,28 @@ HALO_CASES = [
     ("h_phase_ident_32_16", 1, 16, 8, 32, 16, 3, 1, dict(phase=True, identity=True, relu=False)),
     ("h_phase_32_16", 2, 32, 24, 32, 16, 3, 1, dict(phase=True)),
     ("h_phase_32_16_many", 3, 128, 128, 32, 16, 3, 1, dict(phase=True)),
+]
+
+
+# streamed filter bank (128 -> 128 channels: layer2, dec1.conv2): the halo kernel with the weights in a bulk-copy ring
+SB_CASES = [
+    ("sb_ident_128_128", 1, 16, 16, 128, 128, 3, 1, dict(identity=True, relu=False)),
+    ("sb_128_128", 2, 32, 32, 128, 128, 3, 1, dict(seed=11)),
+    ("sb_128_128_res", 2, 64, 64, 128, 128, 3, 1, dict(res=True, seed=12)),
+    ("sb_128_128_many", 37, 64, 64, 128, 128, 3, 1, dict(res=True, seed=13)),
+]
+
+
+# depth-to-space forms of the 16-output-channel layers (HaloArgs::d2s): tiles of 16 x 16 cells = 32 x 32 pixels
+D2S_CASES = [
+    ("d2s_ident_16_16", 1, 32, 32, 16, 16, 3, 1, dict(d2s=1, identity=True, relu=False)),
+    ("d2s_16_16", 1, 32, 32, 16, 16, 3, 1, dict(d2s=1)),
+    ("d2s_16_16_multi", 3, 96, 64, 16, 16, 3, 1, dict(d2s=1, seed=3)),
+    ("d2s_head_16_16_f32", 2, 64, 64, 16, 16, 3, 1, dict(d2s=1, relu=False, out_f32=True)),
+    ("d2s_many_tiles", 5, 256, 256, 16, 16, 3, 1, dict(d2s=1, seed=5)),
+    ("d2s_up_ident_32_16", 1, 16, 16, 32, 16, 3, 1, dict(d2s=2, identity=True, relu=False)),
+    ("d2s_up_32_16", 2, 32, 48, 32, 16, 3, 1, dict(d2s=2, seed=7)),
+    ("d2s_up_32_16_many", 3, 128, 128, 32, 16, 3, 1, dict(d2s=2, seed=9)),
 ]
 
 

@@ -65,6 +65,25 @@ def test_halo_conv_kernel_vs_torch_fp32(ctx, idx):
     assert gpu_probe.halo_case(ctx, case[0], *case[1:8], **case[8]), gpu_probe.RESULTS[-1]
 
 
+@pytest.mark.parametrize("idx", range(8))
+def test_halo_depth_to_space_forms_vs_torch_fp32(ctx, idx):
+    """dec4.conv2 / head as a 4x4 stride-2 conv over 2x2 cells, dec4.conv1 as a 3x3 conv on the low-res grid with the
+    four output phases as 64 accumulator columns: same results as the plain 3x3 conv (of the upsampled input)."""
+    import gpu_probe
+    case = gpu_probe.D2S_CASES[idx]
+    gpu_probe.RESULTS.clear()
+    assert gpu_probe.halo_case(ctx, case[0], *case[1:8], **case[8]), gpu_probe.RESULTS[-1]
+
+
+@pytest.mark.parametrize("idx", range(4))
+def test_halo_streamed_weights_vs_torch_fp32(ctx, idx):
+    """128 -> 128 channels (layer2, dec1.conv2): halo-staged input, filter bank streamed through a bulk-copy ring."""
+    import gpu_probe
+    case = gpu_probe.SB_CASES[idx]
+    gpu_probe.RESULTS.clear()
+    assert gpu_probe.halo_case(ctx, case[0], *case[1:8], **case[8]), gpu_probe.RESULTS[-1]
+
+
 def test_dual_source_tma_conv(ctx):
     import gpu_probe
     gpu_probe.RESULTS.clear()
