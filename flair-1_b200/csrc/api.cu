@@ -92,6 +92,7 @@ struct fb_ctx {
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
+  bool no_hpair = false;      // FB_NO_HPAIR=1: halo kernel always as single CTAs (no cta_group::2 pairs)
   bool d2s_all = false;       // FB_D2S_ALL=1: also dec4.conv2 (bf16 output) in depth-to-space form
   bool no_sb = false;         // FB_NO_SB=1: the 128 -> 128 layers on the im2col implicit GEMM instead of the halo kernel with streamed weights
   double flops = 0;           // algorithmic FLOPs of the conv outputs actually computed since creation
@@ -679,6 +680,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     if (out.elem == 4) h.out_f32 = static_cast<float*>(out.ptr); else h.out = static_cast<__nv_bfloat16*>(out.ptr);
     h.up2_out = out.up2 ? 1 : 0;
     h.wpacked = L.w_halo;
+    h.pair = c->no_hpair ? 0 : 1;
     fb::halo_fill_steps(h, L.KH, L.stride);
     const int tw = 8 * fb::halo_blocks(L.KH, fb::halo_group_channels(L.KH, C1, C2) / 8, L.Cout);
     FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active));
@@ -939,6 +941,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_fused_sink = nf && nf[0] == '1';
   const char* nd = getenv("FB_NO_D2S");
   c->no_d2s = nd && nd[0] == '1';
+  const char* nhp = getenv("FB_NO_HPAIR");
+  c->no_hpair = nhp && nhp[0] == '1';
   const char* da = getenv("FB_D2S_ALL");
   c->d2s_all = da && da[0] == '1';
   const char* nsb = getenv("FB_NO_SB");
@@ -1862,6 +1866,7 @@ int fb_conv2d_halo(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, in
   FB_CUDA(c, cudaMalloc(&wdev, n * 2));
   cudaMemcpy(wdev, hp.data(), n * 2, cudaMemcpyHostToDevice);
   h.wpacked = wdev;
+  h.pair = c->no_hpair ? 0 : 1;
   fb::halo_fill_steps(h, KH, stride);
   const int rc = fb::launch_conv_halo(h, KH, stride, c->num_sms, c->stream);
   cudaStreamSynchronize(c->stream);

@@ -45,7 +45,6 @@ struct Geo {
   static constexpr int PLANE16 = PH * PW;                              // 16-byte cells per plane
   static constexpr int STAGE = ((NCH * NP * PLANE16 * 16) + 127) / 128 * 128;
   static constexpr int CELLS = PH * KWCELLS * NCH;
-  static constexpr int CELLS_PER_THREAD = (CELLS + kProducers - 1) / kProducers;
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
   // ring depth (= stages of loads in flight) / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
   // memory (filter bank + stages + 18 KB epilogue staging): the 16/32-channel layers run two CTAs per SM
@@ -75,11 +74,25 @@ struct Geo {
 // once per tile: against the im2col implicit GEMM (every input pixel fetched nine times, weights fetched once per 128
 // pixels) this moves 185 KB instead of 576 KB from L2 to shared memory per 128 output pixels of layer2.
 constexpr int kSbStages = 4;
+#ifndef FB_ACC_DEEP
+#define FB_ACC_DEEP 2
+#endif
+constexpr int kAccDeep = FB_ACC_DEEP;   // accumulator buffers of the 64-channel one-CTA-per-SM configurations (2 or 4)
 
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false>
+// PAIR = two CTAs of a cluster (one TPC) run every MMA together (tcgen05.mma.cta_group::2, M = 256): each CTA stages
+// the halo of its own 16-row tile (the pair covers two vertically adjacent tiles) and holds HALF of the filter bank
+// (BN / 2 output channels), so a K = 16 step costs each SM 4 KB + BN * 16 B of shared-memory operand reads instead of
+// 4 KB + BN * 32 B -- the bound of the single-CTA form. The leader (cluster rank 0) issues the
+// MMAs and multicasts the commits to both CTAs' barriers; the peer's MMA warp only forwards "my stage has landed"
+// (its halo is written by cp.async, which can only signal a barrier of its own CTA) to the leader. Encoder layers
+// only: no active-tile lists.
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
+          bool PAIR = false>
 __global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  static_assert(!PAIR || (!PH && !D2S && G::OCC == 1 && EPI == 2 && BN % 32 == 0), "CTA pairs: plain form, one CTA per SM");
+  constexpr int BNH = PAIR ? BN / 2 : BN;               // filter-bank columns held by this CTA
   static_assert(!D2S || (BN == 64 && !PH && EPI == 1), "depth-to-space output: 4 pixels x 16 channels per tile row");
   static_assert(EPI == 1 || (G::OCC == 1 && !PH && MB % 2 == 0), "two epilogue groups: one CTA per SM, even block count");
   static_assert(!SB || (!PH && !D2S && G::OCC == 1 && NCH % 2 == 0), "streamed filter bank: plain form, one CTA per SM");
@@ -89,22 +102,29 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   constexpr int kBWarp = 2;
   constexpr int kProd = SB ? 64 : kProducers;           // halo-gathering threads
   constexpr int kCellsPerThread = (G::CELLS + kProd - 1) / kProd;
-  constexpr int kBSteps = NCH / 2;                      // K-steps per weight stage
-  constexpr int kBStage = kBSteps * 2 * BN * 16;        // bytes
+  constexpr int kBSteps = NCH >= 2 ? NCH / 2 : 1;       // K-steps per weight stage
+  constexpr int kBStage = kBSteps * 2 * BNH * 16;       // bytes (of this CTA's half in a pair)
   static_assert(!PH || (MB == 4 && KH == 3 && STRIDE == 1), "phase form: 4 accumulators on a 3x3 stride-1 halo");
   constexpr int S = G::STAGES;
-  constexpr int kBars = 2 * S + 4 + (SB ? 2 * kSbStages : 0);
+  // pairs: + "the peer's halo stage / weight stage has landed", used in the leader only
+  constexpr int ACC = MB * BN;  // TMEM columns of one accumulator buffer (MB blocks of 128 x BN)
+  // accumulator buffers: two. Four (FB_ACC_DEEP=4: where they fit the 512 TMEM columns of a one-CTA-per-SM
+  // configuration, i.e. the 64-channel layers) measured neutral (104.0 vs 103.9 ms per zone, alternating runs): the
+  // epilogue warps already spend most of their time waiting for the next accumulator
+  constexpr int NACC = (G::OCC == 1 && 4 * ACC <= 512 && !PH) ? kAccDeep : 2;
+  constexpr int kBars = 2 * S + 2 * NACC + (SB ? 2 * kSbStages : 0) + (PAIR ? S + (SB ? kSbStages : 0) : 0);
   constexpr int kBarBytes = (kBars * 8 + 16 + 127) / 128 * 128;
   constexpr int kBiasBytes = BN * 4 <= 256 ? 256 : BN * 4;
-  constexpr int ACC = MB * BN;  // TMEM columns of one accumulator buffer (MB blocks of 128 x BN)
-  constexpr int TMEM_COLS = (2 * ACC <= 32) ? 32 : (2 * ACC <= 64) ? 64 : (2 * ACC <= 128) ? 128 : (2 * ACC <= 256) ? 256 : 512;
-  static_assert(2 * ACC <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  constexpr int TMEM_COLS = (NACC * ACC <= 32) ? 32 : (NACC * ACC <= 64) ? 64 : (NACC * ACC <= 128) ? 128 : (NACC * ACC <= 256) ? 256 : 512;
+  static_assert(NACC * ACC <= 512, "the accumulator buffers must fit the 512 TMEM columns");
 
   extern __shared__ __align__(128) uint8_t smem[];
   const int groups = p.groups1 + p.groups2;
   // phase form: one filter set per phase; streamed: the ring
-  const int wbytes = SB ? kSbStages * kBStage : (PH ? MB : 1) * groups * p.nsteps * 2 * BN * 16;
+  const int wbytes = SB ? kSbStages * kBStage : (PH ? MB : 1) * groups * p.nsteps * 2 * BNH * 16;
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const uint32_t w_addr = smem_base;
   const uint32_t bias_off = ((wbytes + 127) / 128) * 128;
   const uint32_t stage_addr0 = smem_base + bias_off + kBiasBytes;      // BN fp32 of bias
@@ -112,9 +132,11 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto bfull_bar = [&](int s) { return bars + 8u * (2 * S + 4 + s); };
-  auto bempty_bar = [&](int s) { return bars + 8u * (2 * S + 4 + kSbStages + s); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + NACC + a); };
+  auto bfull_bar = [&](int s) { return bars + 8u * (2 * S + 2 * NACC + s); };
+  auto bempty_bar = [&](int s) { return bars + 8u * (2 * S + 2 * NACC + kSbStages + s); };
+  auto pfull_bar = [&](int s) { return bars + 8u * (2 * S + 2 * NACC + (SB ? 2 * kSbStages : 0) + s); };
+  auto pbfull_bar = [&](int s) { return bars + 8u * (2 * S + 2 * NACC + (SB ? 2 * kSbStages : 0) + S + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bars - smem_base) + kBars * 8);
   float* bias_s = reinterpret_cast<float*>(smem + bias_off);
 
@@ -124,8 +146,14 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.wpacked);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    if (!SB && !(p.debug_skip & 16))
-      for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + i);
+    if (!SB && !(p.debug_skip & 16)) {
+      if (PAIR) {
+        // unit i of this CTA's bank = (step-chunk sc, column n < BN / 2) <- column rank * BN / 2 + n of the full bank
+        for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + (i / BNH) * BN + rank * BNH + i % BNH);
+      } else {
+        for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + i);
+      }
+    }
     if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
   if (warp == kMmaWarp) {
@@ -134,9 +162,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         mbar_init(full_bar(s), kProd);
         mbar_init(empty_bar(s), 1);
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < NACC; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 128 * EPI);
+        mbar_init(tempty_bar(a), 128 * EPI * (PAIR ? 2 : 1));   // pairs: the leader's barrier takes both CTAs' epilogues
       }
       if (SB) {
         for (int s = 0; s < kSbStages; ++s) {
@@ -144,15 +172,26 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           mbar_init(bempty_bar(s), 1);
         }
       }
+      if (PAIR) {
+        for (int s = 0; s < S; ++s) mbar_init(pfull_bar(s), 1);
+        if (SB)
+          for (int s = 0; s < kSbStages; ++s) mbar_init(pbfull_bar(s), 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: everything above touched only this CTA's shared memory / TMEM and the static
@@ -161,8 +200,18 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   pdl_wait();
 
   const int tiles_w = (PH ? p.Win : D2S ? p.Wout / 2 : p.Wout) / G::TW, tiles_h = (PH ? p.Hin : D2S ? p.Hout / 2 : p.Hout) / kTH;
-  // position i of this launch's schedule -> tile of the full grid (identity unless an active-tile list is given)
-  auto tile_of = [&](int i) { return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i; };
+  // position i of this launch's schedule -> tile of the full grid (identity unless an active-tile list is given;
+  // pairs: position = pair (image, tile-row pair, tile column), this CTA takes tile row 2 * pair row + rank)
+  auto tile_of = [&](int i) {
+    if (PAIR) {
+      const int tw = i % tiles_w, r2 = i / tiles_w;
+      return (2 * r2 + static_cast<int>(rank)) * tiles_w + tw;   // (b * tiles_h + 2 * th2 + rank) * tiles_w + tw
+    }
+    return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i;
+  };
+  // this CTA's (pair's) schedule: positions sched0, sched0 + sched_step, ... < p.num_m_tiles
+  const int sched0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int sched_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp < (SB ? kBWarp : kMmaWarp)) {
     // ===================================================================== producers (halo gather)
@@ -200,15 +249,15 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         prefetch_l2_bulk(row, static_cast<uint32_t>((w_hi - w_lo) * Cs * 2));
       }
     };
-    for (int d = 0; d < kPrefetchDist; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);
+    for (int d = 0; d < kPrefetchDist; ++d) prefetch_tile(sched0 + d * sched_step);
     uint32_t it = 0;
     // the tile id of the NEXT iteration is loaded now, so that the list lookup (a global load) never sits on the
     // path between two tiles
-    int tile_next = blockIdx.x < p.num_m_tiles ? tile_of(blockIdx.x) : 0;
-    for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x) {
-      prefetch_tile(ti + kPrefetchDist * gridDim.x);
+    int tile_next = sched0 < p.num_m_tiles ? tile_of(sched0) : 0;
+    for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step) {
+      prefetch_tile(ti + kPrefetchDist * sched_step);
       const int tile = tile_next;
-      if (ti + static_cast<int>(gridDim.x) < p.num_m_tiles) tile_next = tile_of(ti + gridDim.x);
+      if (ti + sched_step < p.num_m_tiles) tile_next = tile_of(ti + sched_step);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
@@ -271,14 +320,22 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
       const int nb = p.nsteps / kBSteps;
       uint32_t bit = 0;
-      for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x)
+      for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step)
         for (int g = 0; g < groups; ++g)
           for (int bs = 0; bs < nb; ++bs, ++bit) {
             const int s = bit % kSbStages;
             mbar_wait_relaxed(bempty_bar(s), ((bit / kSbStages) & 1) ^ 1);
             mbar_expect_tx(bfull_bar(s), kBStage);
-            bulk_load_1d(w_addr + s * kBStage, wsrc + static_cast<size_t>(g * p.nsteps + bs * kBSteps) * (2 * BN * 16), kBStage,
-                         bfull_bar(s));
+            const uint8_t* src = wsrc + static_cast<size_t>(g * p.nsteps + bs * kBSteps) * (2 * BN * 16);
+            if (PAIR) {
+              // this CTA's BN / 2 columns of every (step, chunk) slab: 2 * kBSteps pieces of BN / 2 * 16 bytes
+#pragma unroll
+              for (int sc = 0; sc < 2 * kBSteps; ++sc)
+                bulk_load_1d(w_addr + s * kBStage + sc * (BNH * 16), src + (static_cast<size_t>(sc) * BN + rank * BNH) * 16, BNH * 16,
+                             bfull_bar(s));
+            } else {
+              bulk_load_1d(w_addr + s * kBStage, src, kBStage, bfull_bar(s));
+            }
           }
     }
   } else if (warp >= 4) {
@@ -296,19 +353,24 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                                     p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     uint32_t tcount = 0;
-    int tile_next = blockIdx.x < p.num_m_tiles ? tile_of(blockIdx.x) : 0;
-    for (int ti = blockIdx.x; ti < p.num_m_tiles; ti += gridDim.x, ++tcount) {
+    // "accumulator drained": pairs count both CTAs' epilogue threads on the leader's barrier
+    auto tempty_arrive = [&](uint32_t bar) {
+      if (PAIR) mbar_arrive_leader(bar);
+      else mbar_arrive(bar);
+    };
+    int tile_next = sched0 < p.num_m_tiles ? tile_of(sched0) : 0;
+    for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step, ++tcount) {
       const int tile = tile_next;
-      if (ti + static_cast<int>(gridDim.x) < p.num_m_tiles) tile_next = tile_of(ti + gridDim.x);
+      if (ti + sched_step < p.num_m_tiles) tile_next = tile_of(ti + sched_step);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
-      const int as = tcount & 1;
-      const uint32_t aph = (tcount >> 1) & 1;
+      const int as = tcount % NACC;
+      const uint32_t aph = (tcount / NACC) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
       if (p.debug_skip & 8) {
         mbar_wait(tfull_bar(as), aph);
         tc_fence_after_sync();
         tc_fence_before_sync();
-        mbar_arrive(tempty_bar(as));
+        tempty_arrive(tempty_bar(as));
         continue;
       }
       // direct mode: every lane stores its own pixel straight from registers, 32 bytes (one sector) per
@@ -457,7 +519,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           }
         }
         tc_fence_before_sync();
-        mbar_arrive(tempty_bar(as));
+        tempty_arrive(tempty_bar(as));
         continue;
       }
       if constexpr (D2S || SB) continue;
@@ -466,7 +528,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         mbar_wait(tfull_bar(as), aph);
         tc_fence_after_sync();
         tc_fence_before_sync();
-        mbar_arrive(tempty_bar(as));
+        tempty_arrive(tempty_bar(as));
         continue;
       }
       if (PH) {
@@ -483,7 +545,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           epilogue_tile<BN, true, true>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, 0, 0, copy);
         }
         tc_fence_before_sync();
-        mbar_arrive(tempty_bar(as));
+        tempty_arrive(tempty_bar(as));
         continue;
       }
       const int oh = th * kTH + L.own_dh;
@@ -503,7 +565,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                                       tb * p.Hout + oh, copy);
       }
       tc_fence_before_sync();
-      mbar_arrive(tempty_bar(as));
+      tempty_arrive(tempty_bar(as));
     }
   } else if (elect_one()) {
     // ===================================================================== MMA issuer
@@ -511,14 +573,40 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     // inside a per-lane serialisation loop, which more than halves the issue interval, tests/umma_probe.cu)
     // Only the low descriptor word (start address, LBO) changes between instructions; the high word
     // (SBO, descriptor version 1, no swizzle) is a constant per operand.
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN);
     constexpr uint32_t a_hi = static_cast<uint32_t>(G::SBO16) | (1u << 14);
     constexpr uint32_t b_hi = 8u | (1u << 14);
-    const uint32_t b_lo0 = (w_addr >> 4) | (static_cast<uint32_t>(BN) << 16);
+    // filter slab of one K-step: two 8-channel chunks of BNH columns (LBO = BNH cells)
+    const uint32_t b_lo0 = (w_addr >> 4) | (static_cast<uint32_t>(BNH) << 16);
+    auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+      if (PAIR) umma_bf16_lohi_2sm(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+      else umma_bf16_lohi(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+    };
+    auto commit = [&](uint32_t bar) {
+      if (PAIR) umma_commit_2sm(bar, 0b11);   // the barrier at this offset in both CTAs
+      else umma_commit(bar);
+    };
     uint32_t it = 0, tcount = 0, bit = 0;
-    for (int tile = blockIdx.x; tile < p.num_m_tiles; tile += gridDim.x, ++tcount) {
-      const int as = tcount & 1;
-      const uint32_t aph = (tcount >> 1) & 1;
+    if (PAIR && !leader) {
+      // peer of a pair: forward "landed" of every halo stage (and weight stage) to the leader, in the order the
+      // leader's MMAs consume them; the fence makes this CTA's cp.async writes visible to the async proxy first
+      const int nb = SB ? p.nsteps / kBSteps : 0;
+      for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step)
+        for (int g = 0; g < groups; ++g, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar(s), (it / S) & 1);
+          fence_proxy_async_smem();
+          mbar_arrive_leader(pfull_bar(s));
+          for (int bs = 0; bs < nb; ++bs, ++bit) {
+            const int sb = bit % kSbStages;
+            mbar_wait(bfull_bar(sb), (bit / kSbStages) & 1);
+            mbar_arrive_leader(pbfull_bar(sb));
+          }
+        }
+    } else {
+    for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step, ++tcount) {
+      const int as = tcount % NACC;
+      const uint32_t aph = (tcount / NACC) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * ACC;
@@ -526,20 +614,22 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(full_bar(s), ph);
+        if (PAIR) mbar_wait(pfull_bar(s), ph);
         fence_proxy_async_smem();   // the stage was written by cp.async (generic proxy), tcgen05.mma reads it through the async proxy
         tc_fence_after_sync();
         const uint32_t st16 = (stage_addr0 + s * G::STAGE) >> 4;
         // K-step outer, block inner: consecutive MMAs hit different accumulators (block m = output columns
         // 8m..8m+7 of the tile, 8 cells further in the stage) and share the step's filter slab
-        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BN);
+        uint32_t b_lo = b_lo0 + static_cast<uint32_t>(g * p.nsteps) * (2 * BNH);
         if constexpr (SB) {
           // one weight stage per filter tap: wait for it, issue its kBSteps x MB MMAs, hand it back
           const int nb = p.nsteps / kBSteps;
           for (int bs = 0; bs < nb; ++bs, ++bit) {
             const int sb = bit % kSbStages;
             mbar_wait(bfull_bar(sb), (bit / kSbStages) & 1);
+            if (PAIR) mbar_wait(pbfull_bar(sb), (bit / kSbStages) & 1);
             tc_fence_after_sync();
-            const uint32_t wb = ((w_addr + sb * kBStage) >> 4) | (static_cast<uint32_t>(BN) << 16);
+            const uint32_t wb = ((w_addr + sb * kBStage) >> 4) | (static_cast<uint32_t>(BNH) << 16);
             if (!(p.debug_skip & 2)) {
 #pragma unroll
               for (int kk = 0; kk < kBSteps; ++kk) {
@@ -547,10 +637,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
                 const uint32_t a_lo = p.a_lo[k] + st16;
                 const uint32_t acc = (g | k) != 0 ? 1u : 0u;
 #pragma unroll
-                for (int m = 0; m < MB; ++m) umma_bf16_lohi(d_tmem + m * BN, a_lo + 8 * m, a_hi, wb + kk * (2 * BN), b_hi, idesc, acc);
+                for (int m = 0; m < MB; ++m) mma(d_tmem + m * BN, a_lo + 8 * m, wb + kk * (2 * BNH), acc);
               }
             }
-            umma_commit(bempty_bar(sb));
+            commit(bempty_bar(sb));
           }
         } else if (p.debug_skip & 2) {
         } else if (PH) {
@@ -570,56 +660,82 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
             const uint32_t a_lo = p.a_lo[k] + st16;
             const uint32_t acc = (g | k) != 0 ? 1u : 0u;
 #pragma unroll
-            for (int m = 0; m < MB; ++m) umma_bf16_lohi(d_tmem + m * BN, a_lo + 8 * m, a_hi, b_lo, b_hi, idesc, acc);
-            b_lo += 2 * BN;
+            for (int m = 0; m < MB; ++m) mma(d_tmem + m * BN, a_lo + 8 * m, b_lo, acc);
+            b_lo += 2 * BNH;
           }
         }
-        umma_commit(empty_bar(s));
+        commit(empty_bar(s));
       }
-      umma_commit(tfull_bar(as));
+      commit(tfull_bar(as));
+    }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the leader's MMAs read the peer's shared memory, the peer arrives on the leader's barriers
   if (warp == kMmaWarp) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false>
+template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
+          bool PAIR = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   const int groups = a.groups1 + a.groups2;
-  const int wbytes = SB ? kSbStages * (NCH / 2) * 2 * BN * 16 : (PH ? MB : 1) * groups * a.nsteps * 2 * BN * 16;
+  constexpr int BNH = PAIR ? BN / 2 : BN;
+  const int wbytes = SB ? kSbStages * (NCH / 2) * 2 * BNH * 16 : (PH ? MB : 1) * groups * a.nsteps * 2 * BNH * 16;
   // (the depth-to-space and streamed-weight kernels only store from registers: no copy-out staging)
   const int smem = ((wbytes + 127) / 128) * 128 + (BN * 4 <= 256 ? 256 : BN * 4) + G::STAGES * G::STAGE +
-                   ((2 * G::STAGES + 4 + (SB ? 2 * kSbStages : 0)) * 8 + 16 + 127) / 128 * 128 + ((D2S || SB) ? 0 : 4 * kStgWarpBytes);
+                   ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
+                   ((D2S || SB) ? 0 : 4 * kStgWarpBytes);
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>, kThreadsK, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, kThreadsK, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
     occ = G::OCC;
+  }
+  if (PAIR) {
+    // a.num_m_tiles counts pairs; clusters of two CTAs, one pair of SMs (a TPC) each
+    const int clusters = a.num_m_tiles < num_sms / 2 ? a.num_m_tiles : num_sms / 2;
+    if (clusters <= 0) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreadsK);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (getenv("FB_DEBUG")) fprintf(stderr, "[halo pair %d,%d] smem=%d clusters=%d pairs=%d\n", NCH, BN, smem, clusters, a.num_m_tiles);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, a);
+    return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
   }
   const int cap = num_sms * occ;
   const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
-  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB>, dim3(grid), dim3(kThreadsK),
+  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, dim3(grid), dim3(kThreadsK),
                                            static_cast<size_t>(smem), stream, pdl, a);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -885,6 +1001,15 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // two epilogue groups for the one-CTA-per-SM configurations (FB_EPI2=0: one group, for A/B runs)
   const char* e2 = getenv("FB_EPI2");
   const bool epi2 = !(e2 && e2[0] == '0') && a.direct_store;
+  // CTA pairs (cta_group::2) for the 64- and 128-channel layers that run whole images (no active-tile list)
+  const bool pair = a.pair && KH == 3 && nch == 8 && (a.Cout == 64 || a.Cout == 128) && a.tile_list == nullptr && !a.up2_out &&
+                    !a.out_f32 && a.Hout % (2 * kTH) == 0 && epi2 && !a.up1;
+  if (pair) {
+    HaloArgs b = a;
+    b.num_m_tiles = a.B * (a.Hout / (2 * kTH)) * (a.Wout / (8 * halo_blocks(3, 8, a.Cout)));
+    return a.Cout == 128 ? launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true, true>(b, num_sms, stream)
+                         : launch_halo_t<3, 1, 8, 64, 2, false, 2, false, false, true>(b, num_sms, stream);
+  }
   if (KH == 3 && nch == 8 && a.Cout == 128) {
     if (a.up2_out || a.out_f32) return -3006;
     return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true>(a, num_sms, stream);

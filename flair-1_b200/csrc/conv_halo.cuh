@@ -57,6 +57,9 @@ struct HaloArgs {
   //      the low-res grid whose 64 outputs are the four output phases (dec4.conv1).
   // wpacked / bias come from pack_halo_weights_d2s (bias replicated four times), Cout = 64.
   int d2s;
+  // 1: run as CTA pairs (tcgen05.mma.cta_group::2, M = 256 = two vertically adjacent 16-row tiles) where the shape has
+  // that instantiation (3x3 stride 1, 64-channel groups, 64 or 128 output channels, no tile list); see conv_halo.cu
+  int pair;
   int no_prefetch;               // 0 only with FB_PREFETCH=1: L2 prefetch of upcoming halos (measured neutral)
   // FB_HALO_SKIP bit mask, bottleneck hunting only (results are wrong): 1 = producers copy nothing,
   // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake

@@ -179,6 +179,12 @@ SB_CASES = [
     ("sb_128_128", 2, 32, 32, 128, 128, 3, 1, dict(seed=11)),
     ("sb_128_128_res", 2, 64, 64, 128, 128, 3, 1, dict(res=True, seed=12)),
     ("sb_128_128_many", 37, 64, 64, 128, 128, 3, 1, dict(res=True, seed=13)),
+    # 48 rows = three 16-row tiles: not a whole number of CTA pairs, so these run as single CTAs
+    ("sb_128_128_single", 2, 48, 32, 128, 128, 3, 1, dict(res=True, seed=14)),
+    ("h_64_64_single", 3, 48, 64, 64, 64, 3, 1, dict(res=True, seed=15)),
+    # CTA pairs, 64 channels (layer1), many tiles per cluster
+    ("h_64_64_pair_many", 40, 128, 128, 64, 64, 3, 1, dict(res=True, seed=16)),
+    ("h_64_64_pair_nores", 3, 64, 32, 64, 64, 3, 1, dict(seed=17)),
 ]
 
 

@@ -75,9 +75,11 @@ def test_halo_depth_to_space_forms_vs_torch_fp32(ctx, idx):
     assert gpu_probe.halo_case(ctx, case[0], *case[1:8], **case[8]), gpu_probe.RESULTS[-1]
 
 
-@pytest.mark.parametrize("idx", range(4))
+@pytest.mark.parametrize("idx", range(8))
 def test_halo_streamed_weights_vs_torch_fp32(ctx, idx):
-    """128 -> 128 channels (layer2, dec1.conv2): halo-staged input, filter bank streamed through a bulk-copy ring."""
+    """128 -> 128 channels (layer2, dec1.conv2): halo-staged input, filter bank streamed through a bulk-copy ring; as
+    CTA pairs (cta_group::2) where the image is a whole number of 32-row tile pairs, single CTAs otherwise; the
+    64-channel pair form of layer1."""
     import gpu_probe
     case = gpu_probe.SB_CASES[idx]
     gpu_probe.RESULTS.clear()
