@@ -44,6 +44,22 @@ def class_fscore(precision, recall):
     return fscore, np.mean(fscore)
 
 
+def _report(out: dict, classes: dict) -> None:
+    """Console report of metrics() (same text as the reference's, src/flair/metrics.py:118-160): the five averages,
+    one line per scored class, then the classes with weight 0."""
+    rule = "-" * 90
+    lines = ["", "Global Metrics: ", rule]
+    lines += [f"{name:<20s} {value:<20.4f}" for name, value in zip(out["Avg_metrics_name"], out["Avg_metrics"])]
+    lines += [rule + "\n\n", "{:<25} {:<15} {:<10} {:<10} {:<10} {:<10}".format("Class", "Weight", "IoU", "F-score", "Precision", "Recall"),
+              "-" * 65]
+    per_class = {name: i for i, name in enumerate(out["classes"])}
+    cols = ("per_class_iou", "per_class_fscore", "per_class_precision", "per_class_recall")
+    scored = [(w, n) for w, n in classes.values() if w != 0]
+    lines += ["{:<25} {:<15} ".format(n, w) + " ".join("{:<10.4f}".format(out[c][per_class[n]]) for c in cols) for w, n in scored]
+    lines += ["\nNot learned Classes:"] + ["{:<25} {:<15}".format(n, w) for w, n in classes.values() if w == 0] + ["\n\n"]
+    print("\n".join(lines))
+
+
 def metrics(config: dict, path_preds, remove_preds: bool = False, context=None) -> dict:
     """src/flair/metrics.py:43-164. `context`: a libflairb200 context (required: there is no CPU path)."""
     if context is None:
@@ -90,25 +106,7 @@ def metrics(config: dict, path_preds, remove_preds: bool = False, context=None) 
     out_folder_metrics.mkdir(exist_ok=True, parents=True)
     np.save(out_folder_metrics.as_posix() + "/confmat.npy", sum_confmat)
     json.dump(out, open(out_folder_metrics / Path("metrics.json"), "w"))
-    print("")
-    print("Global Metrics: ")
-    print("-" * 90)
-    for metric_name, metric_value in zip(out["Avg_metrics_name"], out["Avg_metrics"]):
-        print(f"{metric_name:<20s} {metric_value:<20.4f}")
-    print("-" * 90 + "\n\n")
-    print("{:<25} {:<15} {:<10} {:<10} {:<10} {:<10}".format("Class", "Weight", "IoU", "F-score", "Precision", "Recall"))
-    print("-" * 65)
-    for class_index, (class_weight, class_name) in config["classes"].items():
-        if class_weight != 0:
-            i = out["classes"].index(class_name)
-            print("{:<25} {:<15} {:<10.4f} {:<10.4f} {:<10.4f} {:<10.4f}".format(
-                class_name, class_weight, out["per_class_iou"][i], out["per_class_fscore"][i],
-                out["per_class_precision"][i], out["per_class_recall"][i]))
-    print("\nNot learned Classes:")
-    for class_index, (class_weight, class_name) in config["classes"].items():
-        if class_weight == 0:
-            print("{:<25} {:<15}".format(class_name, class_weight))
-    print("\n\n")
+    _report(out, config["classes"])
     if remove_preds:
         shutil.rmtree(path_preds)
     return out

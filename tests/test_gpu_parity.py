@@ -456,6 +456,60 @@ def test_zone_detect_vs_oracle(ctx, trained_3_15, W, H, T, margin):
     np.testing.assert_array_equal(out_cls, cls_h)
 
 
+def test_no_writes_outside_the_caller_buffers(ctx, trained_3_15):
+    """compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer_closed.txt), so the out-of-bounds check
+    is done with canaries: every buffer the caller hands in (class / confidence maps, class_prob planes, blend
+    accumulators, confusion matrix, truth, raster) sits inside a larger allocation filled with a pattern, and the
+    bytes before and after it must come back untouched from the exact-clipping loop (fused sink, CTA-pair and
+    streamed-weight convs, depth-to-space head), the class_prob loop, both blended stitchings and the confusion
+    kernel. A 637 x 509 zone: every edge tile is clamped, no dimension is a multiple of a vector width."""
+    from oracle import synth
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    sd, _ = trained_3_15
+    W, H, T, margin, G = 637, 509, 256, 32, 4096
+    raster_h = synth.synth_raster(3, H, W, seed=5)
+    ctx.load_weights(sd, 3, 15)
+    ctx.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+
+    def guarded(shape, dtype, fill=None):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((G + n + G,), 0xA5, dtype=torch.uint8, device="cuda")
+        view = raw[G:G + n].view(dtype).view(*shape)
+        if fill is not None:
+            view.copy_(fill)
+        return raw, view, n
+
+    def intact(raw, n):
+        return bool((raw[:G] == 0xA5).all()) and bool((raw[G + n:] == 0xA5).all())
+
+    bufs = {}
+    bufs["raster"] = guarded((3, H, W), torch.uint8, torch.from_numpy(raster_h).cuda())
+    ctx.set_raster(bufs["raster"][1], [0, 1, 2], W, H)
+    tiles = tile_table(W, H, T, margin)
+    bufs["cls"] = guarded((H, W), torch.uint8, 0)
+    bufs["conf"] = guarded((H, W), torch.uint8, 0)
+    ctx.detect_strip(tiles, T, 5, bufs["cls"][1], bufs["conf"][1], W, 0)
+    bufs["prob"] = guarded((15, H, W), torch.uint8, 0)
+    ctx.detect_strip_prob(tiles, T, 5, bufs["prob"][1], W, 0)
+    bufs["truth"] = guarded((H, W), torch.uint8, torch.from_numpy(synth.synth_mask(raster_h, 15, 3)).cuda())
+    bufs["cm"] = guarded((15, 15), torch.int64, 0)
+    ctx.confusion(bufs["cls"][1], bufs["truth"][1], 15, truth_sub=1, out=bufs["cm"][1])
+    ls = ctx.logit_stride
+    bufs["acc"] = guarded((H, W, ls), torch.float32, 0)
+    bufs["wsum"] = guarded((H, W), torch.float32, 0)
+    ctx.blend_strip(tiles, T, 5, "average_weights", bufs["acc"][1], bufs["wsum"][1], W, 0)
+    bufs["bcls"] = guarded((H, W), torch.uint8, 0)
+    bufs["bconf"] = guarded((H, W), torch.uint8, 0)
+    ctx.blend_finalize("average_weights", bufs["acc"][1], bufs["wsum"][1], bufs["bcls"][1], bufs["bconf"][1])
+    bufs["key"] = guarded((H, W), torch.int64, 0)
+    ctx.blend_strip(tiles, T, 5, "max", bufs["key"][1], None, W, 0)
+    ctx.blend_finalize("max", bufs["key"][1], None, bufs["bcls"][1], bufs["bconf"][1])
+    torch.cuda.synchronize()
+    broken = [k for k, (raw, _, n) in bufs.items() if not intact(raw, n)]
+    assert not broken, f"bytes outside these buffers were overwritten: {broken}"
+    assert int(bufs["cm"][1].sum()) > 0 and bool((bufs["cls"][1] < 15).all())
+
+
 @pytest.mark.parametrize("W,H,T,margin", [(1500, 1300, 512, 128), (700, 520, 256, 32), (640, 512, 512, 0)])
 def test_dead_output_elimination_and_fused_sink_are_bit_exact(trained_3_15, monkeypatch, W, H, T, margin):
     """The exact-clipping loop only computes the decoder outputs inside the receptive field of each write
