@@ -92,6 +92,7 @@ struct fb_ctx {
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
+  bool no_pool_fuse = false;  // FB_NO_POOL_FUSE=1: the stem's max-pool as a kernel of its own
   bool no_hpair = false;      // FB_NO_HPAIR=1: halo kernel always as single CTAs (no cta_group::2 pairs)
   bool d2s_all = false;       // FB_D2S_ALL=1: also dec4.conv2 (bf16 output) in depth-to-space form
   bool no_sb = false;         // FB_NO_SB=1: the 128 -> 128 layers on the im2col implicit GEMM instead of the halo kernel with streamed weights
@@ -754,30 +755,43 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
       Act x0c = x0, f1c = f1;
       x0c.B = nb; x0c.ptr = static_cast<__nv_bfloat16*>(x0.ptr) + b0 * x0_px;
       f1c.B = nb; f1c.ptr = static_cast<__nv_bfloat16*>(f1.ptr) + b0 * f1_px;
+      // the max-pool runs inside the stem's epilogue (HaloArgs::pool_out) when the stem is one of the halo kernel's two
+      // forms, the batch gives most SMs an image of their own (a CTA walks whole images there) and the rows fit the
+      // carry buffers; FB_NO_POOL_FUSE=1 keeps the separate kernel
+      const ConvLayer& S = L("stem");
+      const bool stem_halo = c->stem_s2d || (!c->force_gather && !c->no_halo && S.w_halo && fb::halo_supported(7, 2, x0.C, 0, S.Cout, f1.H, f1.W));
+      const bool fuse_pool = stem_halo && !c->no_pool_fuse && c->front_chunk <= 0 && f1.W <= 256 && f1.H % 16 == 0 && f1.W % 16 == 0 &&
+                             2 * nb >= c->num_sms;
       {
         ProfScope ps(c, 1);
-        if (c->stem_s2d) {
-          const ConvLayer& S = L("stem");
+        if (stem_halo) {
           fb::HaloArgs h;
           memset(&h, 0, sizeof h);
           h.x1 = static_cast<const __nv_bfloat16*>(x0c.ptr);
-          h.C1 = 16;
+          h.C1 = x0.C;
           h.B = nb; h.Hin = x0.H; h.Win = x0.W; h.Hout = f1.H; h.Wout = f1.W;
           h.Cout = S.Cout;
           h.bias = S.bias;
           h.relu = 1;
           h.out = static_cast<__nv_bfloat16*>(f1c.ptr);
-          h.wpacked = S.w_s2d;
-          fb::halo_fill_steps(h, 4, 1);
+          h.wpacked = c->stem_s2d ? S.w_s2d : S.w_halo;
+          fb::halo_fill_steps(h, c->stem_s2d ? 4 : 7, c->stem_s2d ? 1 : 2);
+          if (fuse_pool) {
+            h.pool_out = static_cast<__nv_bfloat16*>(pool.ptr) + b0 * pool_px;
+            if (need && need->restrict_tiles && need->n == n && b0 == 0 && nb == n) {
+              h.keep_tiles = need->tiles_dev;
+              h.keep_T = need->T;
+            }
+          }
           c->flops += static_cast<double>(nb) * f1.H * f1.W * S.flops_px;
-          const int rc = fb::launch_conv_halo(h, 4, 1, c->num_sms, c->stream);
-          if (rc != 0) return fail(c, rc, "stem (space-to-depth) launch failed (code " + std::to_string(rc) + ")");
+          const int rc = fb::launch_conv_halo(h, c->stem_s2d ? 4 : 7, c->stem_s2d ? 1 : 2, c->num_sms, c->stream);
+          if (rc != 0) return fail(c, rc, "stem launch failed (code " + std::to_string(rc) + ")");
           c->launches++;
         } else {
           FB_TRY(run_conv(c, L("stem"), x0c, nullptr, nullptr, nullptr, true, f1c));
         }
       }
-      {
+      if (!fuse_pool) {
         ProfScope ps(c, 2);
         int rc = fb::launch_maxpool3x3s2(static_cast<const __nv_bfloat16*>(f1c.ptr),
                                          static_cast<__nv_bfloat16*>(pool.ptr) + b0 * pool_px, nb, f1.H, f1.W, 64,
@@ -941,6 +955,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_fused_sink = nf && nf[0] == '1';
   const char* nd = getenv("FB_NO_D2S");
   c->no_d2s = nd && nd[0] == '1';
+  const char* npf = getenv("FB_NO_POOL_FUSE");
+  c->no_pool_fuse = npf && npf[0] == '1';
   const char* nhp = getenv("FB_NO_HPAIR");
   c->no_hpair = nhp && nhp[0] == '1';
   const char* da = getenv("FB_D2S_ALL");

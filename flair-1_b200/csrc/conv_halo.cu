@@ -9,6 +9,7 @@
 
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
+#include "tile_need.cuh"
 
 namespace fb {
 
@@ -86,11 +87,22 @@ constexpr int kAccDeep = FB_ACC_DEEP;   // accumulator buffers of the 64-channel
 // MMAs and multicasts the commits to both CTAs' barriers; the peer's MMA warp only forwards "my stage has landed"
 // (its halo is written by cp.async, which can only signal a barrier of its own CTA) to the leader. Encoder layers
 // only: no active-tile lists.
+// POOL = the stem with its 3x3 stride-2 max-pool (torchvision ResNet: MaxPool2d(3, 2, 1)) fused into the epilogue. A CTA
+// takes whole images and walks their 16 x 16 tiles in row-major order; the epilogue warps leave every finished tile in
+// shared memory as well (bf16, what the separate pool kernel would read back from HBM: 8.4 MB per 512^2 tile), pool its
+// 8 x 8 outputs from it -- the row above and the column to the left come from carry buffers filled by the tiles before
+// it (last row of every tile of the previous tile row, last column of the previous tile) -- and write the pooled
+// tensor. The stem's own output is still stored, for the decoder's skip connection: all of it, or, in the
+// exact-clipping zone loop, only the part dec3.conv1 reads (HaloArgs::keep_tiles).
+constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (128 + 16: conflict-free 16-byte stores)
+
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
-          bool PAIR = false>
+          bool PAIR = false, bool POOL = false>
 __global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  static_assert(!POOL || (EPI == 2 && MB == 2 && BN == 64 && !PH && !D2S && !SB && !PAIR && G::OCC == 1),
+                "fused max-pool: 16 x 16 tiles of 64 channels, two epilogue groups");
   static_assert(!PAIR || (!PH && !D2S && G::OCC == 1 && EPI == 2 && BN % 32 == 0), "CTA pairs: plain form, one CTA per SM");
   constexpr int BNH = PAIR ? BN / 2 : BN;               // filter-bank columns held by this CTA
   static_assert(!D2S || (BN == 64 && !PH && EPI == 1), "depth-to-space output: 4 pixels x 16 channels per tile row");
@@ -207,11 +219,19 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const int tw = i % tiles_w, r2 = i / tiles_w;
       return (2 * r2 + static_cast<int>(rank)) * tiles_w + tw;   // (b * tiles_h + 2 * th2 + rank) * tiles_w + tw
     }
+    if (POOL) {
+      // whole images per CTA (blockIdx.x, blockIdx.x + gridDim.x, ...), their tiles in row-major order
+      const int per_img = tiles_w * tiles_h;
+      return (static_cast<int>(blockIdx.x) + (i / per_img) * static_cast<int>(gridDim.x)) * per_img + i % per_img;
+    }
     return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i;
   };
-  // this CTA's (pair's) schedule: positions sched0, sched0 + sched_step, ... < p.num_m_tiles
-  const int sched0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int sched_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // this CTA's (pair's) schedule: positions sched0, sched0 + sched_step, ... < sched_end
+  const int sched0 = POOL ? 0 : PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int sched_step = POOL ? 1 : PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int sched_end = POOL ? ((p.B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) *
+                                   tiles_w * tiles_h
+                             : p.num_m_tiles;
 
   if (warp < (SB ? kBWarp : kMmaWarp)) {
     // ===================================================================== producers (halo gather)
@@ -221,22 +241,33 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     const int tid = threadIdx.x;
     static_assert(kProd % NCH == 0, "channel chunk must be constant per producer thread");
     const int c8 = (tid % NCH) * 8;
-    uint32_t cell[kCellsPerThread];
-#pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
+    // (the 4x4 stride-2 depth-to-space form runs two CTAs per SM at 128 registers with a register-hungry epilogue: a
+    // 25-word table per producer thread spilled to local memory and its reloads sat in the copy loop, so that
+    // instantiation decodes each cell on the fly -- divisions by compile-time constants -- instead)
+    constexpr bool kCellTable = !(KH == 4 && STRIDE == 2);
+    auto cell_word = [&](int j) -> uint32_t {
       const int idx = tid + j * kProd;
       const int c = idx % NCH;
       const int k = (idx / NCH) % G::KWCELLS;
       const int hh = idx / (NCH * G::KWCELLS);
       const uint32_t dst = static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
-      cell[j] = idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
+      return idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
+    };
+    uint32_t cell[kCellTable ? kCellsPerThread : 1];
+    if constexpr (kCellTable) {
+#pragma unroll
+      for (int j = 0; j < kCellsPerThread; ++j) cell[j] = cell_word(j);
     }
+    auto cellw = [&](int j) -> uint32_t {
+      if constexpr (kCellTable) return cell[j];
+      else return cell_word(j);
+    };
     // Optional (FB_PREFETCH=1; measured neutral, so off by default): pull the halo rows of the tile
     // kPrefetchDist iterations ahead into L2, one bulk prefetch per halo row and source, clipped to the image.
     constexpr int kPrefetchDist = 2;
     const int nsrc = p.C2 > 0 ? 2 : 1;
     auto prefetch_tile = [&](int t) {
-      if (t >= p.num_m_tiles || p.no_prefetch || p.up1) return;
+      if (t >= sched_end || p.no_prefetch || p.up1) return;
       t = tile_of(t);
       const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
       const int iw0 = tw * G::TW * STRIDE - G::PAD;
@@ -253,11 +284,11 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     uint32_t it = 0;
     // the tile id of the NEXT iteration is loaded now, so that the list lookup (a global load) never sits on the
     // path between two tiles
-    int tile_next = sched0 < p.num_m_tiles ? tile_of(sched0) : 0;
-    for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step) {
+    int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
+    for (int ti = sched0; ti < sched_end; ti += sched_step) {
       prefetch_tile(ti + kPrefetchDist * sched_step);
       const int tile = tile_next;
-      if (ti + sched_step < p.num_m_tiles) tile_next = tile_of(ti + sched_step);
+      if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
       const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
@@ -279,31 +310,34 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           const __nv_bfloat16* lo = p.x1 + static_cast<long long>(b) * Hlo * Wlo * Cs + g * (NCH * 8) + c8;
 #pragma unroll
           for (int j = 0; j < kCellsPerThread; ++j) {
-            if (cell[j] != 0xFFFFFFFFu) {
-              const int ih = ih0 + static_cast<int>((cell[j] >> 16) & 0xFF), iw = iw0 + static_cast<int>(cell[j] >> 24);
+            const uint32_t cw = cellw(j);
+            if (cw != 0xFFFFFFFFu) {
+              const int ih = ih0 + static_cast<int>((cw >> 16) & 0xFF), iw = iw0 + static_cast<int>(cw >> 24);
               const bool ok = static_cast<unsigned>(ih) < static_cast<unsigned>(p.Hin) &&
                               static_cast<unsigned>(iw) < static_cast<unsigned>(p.Win);
               const __nv_bfloat16* gp = ok ? lo + (static_cast<long long>(ih >> 1) * Wlo + (iw >> 1)) * Cs : p.x1;
-              cp_async_16(st + (cell[j] & 0xFFFFu), gp, ok ? 16u : 0u);
+              cp_async_16(st + (cw & 0xFFFFu), gp, ok ? 16u : 0u);
             }
           }
         } else if (interior) {
 #pragma unroll
           for (int j = 0; j < kCellsPerThread; ++j) {
-            if (cell[j] != 0xFFFFFFFFu) {
-              const int hh = (cell[j] >> 16) & 0xFF, k = cell[j] >> 24;
-              cp_async_16(st + (cell[j] & 0xFFFFu), src + hh * row_elems + k * Cs, 16u);
+            const uint32_t cw = cellw(j);
+            if (cw != 0xFFFFFFFFu) {
+              const int hh = (cw >> 16) & 0xFF, k = cw >> 24;
+              cp_async_16(st + (cw & 0xFFFFu), src + hh * row_elems + k * Cs, 16u);
             }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < kCellsPerThread; ++j) {
-            if (cell[j] != 0xFFFFFFFFu) {
-              const int hh = (cell[j] >> 16) & 0xFF, k = cell[j] >> 24;
+            const uint32_t cw = cellw(j);
+            if (cw != 0xFFFFFFFFu) {
+              const int hh = (cw >> 16) & 0xFF, k = cw >> 24;
               const bool ok = static_cast<unsigned>(ih0 + hh) < static_cast<unsigned>(p.Hin) &&
                               static_cast<unsigned>(iw0 + k) < static_cast<unsigned>(p.Win);
               const __nv_bfloat16* gp = ok ? src + hh * row_elems + k * Cs : p.x1;
-              cp_async_16(st + (cell[j] & 0xFFFFu), gp, ok ? 16u : 0u);
+              cp_async_16(st + (cw & 0xFFFFu), gp, ok ? 16u : 0u);
             }
           }
         }
@@ -320,7 +354,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpacked);
       const int nb = p.nsteps / kBSteps;
       uint32_t bit = 0;
-      for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step)
+      for (int ti = sched0; ti < sched_end; ti += sched_step)
         for (int g = 0; g < groups; ++g)
           for (int bs = 0; bs < nb; ++bs, ++bit) {
             const int s = bit % kSbStages;
@@ -352,16 +386,22 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
                                     p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
+    // fused max-pool (POOL): the finished tile, the last rows of the previous tile row (two buffers, by tile-row parity)
+    // and the last column of the previous tile (two buffers, by tile-column parity), all bf16 [pixel][64]
+    uint8_t* const pool_tile = smem + (bars - smem_base) + kBarBytes + 4 * kStgWarpBytes;
+    uint8_t* const pool_rows = pool_tile + 16 * G::TW * kPoolPitch;
+    uint8_t* const pool_cols = pool_rows + 2 * static_cast<size_t>(p.Wout) * 128;
+    const int ep = (warp - 4) * 32 + lane;   // 0 .. 255 over both epilogue groups
     uint32_t tcount = 0;
     // "accumulator drained": pairs count both CTAs' epilogue threads on the leader's barrier
     auto tempty_arrive = [&](uint32_t bar) {
       if (PAIR) mbar_arrive_leader(bar);
       else mbar_arrive(bar);
     };
-    int tile_next = sched0 < p.num_m_tiles ? tile_of(sched0) : 0;
-    for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step, ++tcount) {
+    int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
+    for (int ti = sched0; ti < sched_end; ti += sched_step, ++tcount) {
       const int tile = tile_next;
-      if (ti + sched_step < p.num_m_tiles) tile_next = tile_of(ti + sched_step);
+      if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
       const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
       const int as = tcount % NACC;
       const uint32_t aph = (tcount / NACC) & 1;
@@ -433,8 +473,29 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
             dpix = p.up2_out ? (static_cast<long long>(tb) * 2 * p.Hout + 2 * oh) * (2 * p.Wout) + 2 * (ow + 8 * m) : own_pix;
           }
           uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
+          // POOL: this pixel's slot in the shared-memory tile; its global store may be skipped (keep rectangle)
+          uint8_t* const pool_px = pool_tile + (L.own_dh * G::TW + L.own_dw + 8 * m) * kPoolPitch;
+          bool keep_px = true;
+          if constexpr (POOL) {
+            if (p.keep_tiles != nullptr) {
+              // the part of the stem's output that dec3.conv1 (layer 6 of tile_need.cuh) reads for this image: its
+              // needed region, widened to the 16 x 16 kernel tiles it runs and their one-pixel halo
+              const int* kt = p.keep_tiles + 6 * tb;
+              const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
+              const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
+              const int kx0 = (r.x0 & ~15) - 1, ky0 = (r.y0 & ~15) - 1, kx1 = ((r.x1 + 15) & ~15) + 1, ky1 = ((r.y1 + 15) & ~15) + 1;
+              const int px = ow + 8 * m;
+              keep_px = r.x1 > r.x0 && r.y1 > r.y0 && px >= kx0 && px < kx1 && oh >= ky0 && oh < ky1;
+            }
+          }
           auto direct = [&](int col0, const auto& regs) {
             if (p.debug_skip & 4) return;
+            if constexpr (POOL && sizeof(regs) == 32) {
+              uint4* d = reinterpret_cast<uint4*>(pool_px + col0 * 2);
+              d[0] = make_uint4(regs[0], regs[1], regs[2], regs[3]);
+              d[1] = make_uint4(regs[4], regs[5], regs[6], regs[7]);
+              if (!keep_px) return;
+            }
             if constexpr (D2S) {
               // columns col0 .. col0 + 15 = the 16 channels of pixel (2*oh + py, 2*(ow + 8m) + px) of the cell
               const int grp = col0 >> 4;
@@ -520,6 +581,58 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         }
         tc_fence_before_sync();
         tempty_arrive(tempty_bar(as));
+        if constexpr (POOL) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // the whole tile is in shared memory (both epilogue groups)
+          const int vec = ep & 7;
+          uint8_t* const rows_prev = pool_rows + static_cast<size_t>((th & 1) ^ 1) * p.Wout * 128;
+          uint8_t* const rows_cur = pool_rows + static_cast<size_t>(th & 1) * p.Wout * 128;
+          uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
+          uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
+          // pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero outside the image: the
+          // values are post-ReLU, so a zero never wins against the window's centre)
+          auto fetch = [&](int r, int c) -> uint4 {
+            if (r >= 0 && c >= 0) return *reinterpret_cast<const uint4*>(pool_tile + (r * G::TW + c) * kPoolPitch + vec * 16);
+            if (r < 0) {
+              if (th == 0 || (c < 0 && tw == 0)) return make_uint4(0u, 0u, 0u, 0u);
+              return *reinterpret_cast<const uint4*>(rows_prev + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16);
+            }
+            if (tw == 0) return make_uint4(0u, 0u, 0u, 0u);
+            return *reinterpret_cast<const uint4*>(cols_prev + r * 128 + vec * 16);
+          };
+          auto vmax = [](uint4 a, const uint4 b) -> uint4 {
+            auto m2 = [](uint32_t x, uint32_t y) -> uint32_t {
+              const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), *reinterpret_cast<const __nv_bfloat162*>(&y));
+              return *reinterpret_cast<const uint32_t*>(&r);
+            };
+            return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w));
+          };
+          const int Hp = p.Hout >> 1, Wp = p.Wout >> 1;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int pp = (ep >> 3) + 32 * half;      // pooled pixel 0 .. 63 of the tile's 8 x 8
+            const int pi = pp >> 3, pj = pp & 7;
+            uint4 v = fetch(2 * pi, 2 * pj);
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx)
+                if (dy != 0 || dx != 0) v = vmax(v, fetch(2 * pi + dy, 2 * pj + dx));
+            if (!(p.debug_skip & 4))
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pool_out) +
+                                        ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + pj) * 128 + vec * 16) = v;
+          }
+          // carries for the tiles to the right and below: this tile's last row / last column
+          if (ep < 128) {
+            const int c = ep >> 3;
+            *reinterpret_cast<uint4*>(rows_cur + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16) =
+                *reinterpret_cast<const uint4*>(pool_tile + (15 * G::TW + c) * kPoolPitch + vec * 16);
+          } else {
+            const int r = (ep - 128) >> 3;
+            *reinterpret_cast<uint4*>(cols_cur + r * 128 + vec * 16) =
+                *reinterpret_cast<const uint4*>(pool_tile + (r * G::TW + 15) * kPoolPitch + vec * 16);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // the tile buffer may be overwritten by the next tile
+        }
         continue;
       }
       if constexpr (D2S || SB) continue;
@@ -591,7 +704,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       // peer of a pair: forward "landed" of every halo stage (and weight stage) to the leader, in the order the
       // leader's MMAs consume them; the fence makes this CTA's cp.async writes visible to the async proxy first
       const int nb = SB ? p.nsteps / kBSteps : 0;
-      for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step)
+      for (int ti = sched0; ti < sched_end; ti += sched_step)
         for (int g = 0; g < groups; ++g, ++it) {
           const int s = it % S;
           mbar_wait(full_bar(s), (it / S) & 1);
@@ -604,7 +717,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           }
         }
     } else {
-    for (int ti = sched0; ti < p.num_m_tiles; ti += sched_step, ++tcount) {
+    for (int ti = sched0; ti < sched_end; ti += sched_step, ++tcount) {
       const int as = tcount % NACC;
       const uint32_t aph = (tcount / NACC) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);
@@ -682,7 +795,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
 }
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
-          bool PAIR = false>
+          bool PAIR = false, bool POOL = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
@@ -692,19 +805,20 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   // (the depth-to-space and streamed-weight kernels only store from registers: no copy-out staging)
   const int smem = ((wbytes + 127) / 128) * 128 + (BN * 4 <= 256 ? 256 : BN * 4) + G::STAGES * G::STAGE +
                    ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
-                   ((D2S || SB) ? 0 : 4 * kStgWarpBytes);
+                   ((D2S || SB) ? 0 : 4 * kStgWarpBytes) +
+                   (POOL ? 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, kThreadsK, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, kThreadsK, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
@@ -727,15 +841,15 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo pair %d,%d] smem=%d clusters=%d pairs=%d\n", NCH, BN, smem, clusters, a.num_m_tiles);
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, a);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, a);
     return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
   }
   const int cap = num_sms * occ;
-  const int grid = a.num_m_tiles < cap ? a.num_m_tiles : cap;
+  const int grid = POOL ? (a.B < cap ? a.B : cap) : (a.num_m_tiles < cap ? a.num_m_tiles : cap);   // POOL: whole images per CTA
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
-  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR>, dim3(grid), dim3(kThreadsK),
+  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, dim3(grid), dim3(kThreadsK),
                                            static_cast<size_t>(smem), stream, pdl, a);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -1013,6 +1127,13 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   if (KH == 3 && nch == 8 && a.Cout == 128) {
     if (a.up2_out || a.out_f32) return -3006;
     return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true>(a, num_sms, stream);
+  }
+  if (a.pool_out != nullptr) {
+    // the stem with its max-pool fused (both stem forms tile 16 x 16 outputs of 64 channels)
+    if (!epi2 || !a.relu || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 || a.Wout % 16)
+      return -3007;
+    return KH == 4 ? launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream)
+                   : KH == 7 ? launch_halo_t<7, 2, 1, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream) : -3007;
   }
   if (KH == 4) return epi2 ? launch_halo_t<4, 1, 2, 64, 2, false, 2>(a, num_sms, stream)
                            : launch_halo_t<4, 1, 2, 64, 2>(a, num_sms, stream);

@@ -60,6 +60,12 @@ struct HaloArgs {
   // 1: run as CTA pairs (tcgen05.mma.cta_group::2, M = 256 = two vertically adjacent 16-row tiles) where the shape has
   // that instantiation (3x3 stride 1, 64-channel groups, 64 or 128 output channels, no tile list); see conv_halo.cu
   int pair;
+  // Fused stem max-pool (KH = 4 or 7 stem forms only): when non-null the kernel also writes MaxPool2d(3, 2, 1) of its
+  // (post-ReLU) output to pool_out [B, Hout/2, Wout/2, 64]. keep_tiles (optional, int32 [B][6] = fb_tile of each image,
+  // tile side keep_T): only the part of `out` that dec3.conv1 reads is stored (exact-clipping zone loop).
+  __nv_bfloat16* pool_out;
+  const int* keep_tiles;
+  int keep_T;
   int no_prefetch;               // 0 only with FB_PREFETCH=1: L2 prefetch of upcoming halos (measured neutral)
   // FB_HALO_SKIP bit mask, bottleneck hunting only (results are wrong): 1 = producers copy nothing,
   // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake

@@ -555,6 +555,50 @@ def test_dead_output_elimination_and_fused_sink_are_bit_exact(trained_3_15, monk
         assert res["fast"][3] < 0.9 * res["plain"][3]
 
 
+@pytest.mark.parametrize("bands,T,margin", [(3, 128, 32), (5, 128, 32), (3, 512, 128)])
+def test_fused_stem_max_pool_is_bit_exact(trained_3_15, monkeypatch, bands, T, margin):
+    """With a batch that gives most SMs an image of their own, the stem's epilogue pools its own output (csrc/conv_halo.cu,
+    POOL) and, in the exact-clipping loop, stores only the part of it the decoder reads. Pooled tensor, logits, class map
+    and confidence band must be byte-identical to the separate max-pool kernel (FB_NO_POOL_FUSE=1), for the
+    space-to-depth stem (3 bands) and the 7x7 stride-2 stem (5 bands), on edge tiles and interior tiles."""
+    from oracle import synth
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    nat = _nat()
+    ncls = 15 if bands == 3 else 13
+    if bands == 3:
+        sd = trained_3_15[0]
+    else:
+        from oracle.unet_smp033 import Unet
+        torch.manual_seed(5)
+        sd = Unet(bands, ncls).state_dict()   # random init: this test compares two GPU paths, not the oracle
+    n = 80 if T == 128 else 76
+    W, H = (T - 2 * margin) * 10 + 37, (T - 2 * margin) * 8 + 11
+    raster = torch.from_numpy(synth.synth_raster(bands, H, W, seed=bands * T)).cuda()
+    tiles = tile_table(W, H, T, margin)[:n]
+    assert len(tiles) == n
+    res = {}
+    for mode in ("separate", "fused"):
+        monkeypatch.setenv("FB_NO_POOL_FUSE", "1" if mode == "separate" else "0")
+        c = nat.Context(0)
+        c.load_weights(sd, bands, ncls)
+        c.set_norm("custom", synth.FLAIR_MEANS[:bands], synth.FLAIR_STDS[:bands])
+        c.set_raster(raster, list(range(bands)), W, H)
+        l0 = c.launch_count
+        logits = c.forward_tiles(np.ascontiguousarray(tiles[:, :2]), T)
+        launches = c.launch_count - l0
+        pool = c.debug_activation("pool").clone()
+        f1 = c.debug_activation("f1").clone()
+        cls = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        conf = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        c.detect_strip(tiles, T, n, cls, conf, W, 0)
+        torch.cuda.synchronize()
+        res[mode] = (pool.cpu(), f1.cpu(), logits.cpu(), cls.cpu(), conf.cpu(), launches)
+        c.close()
+    assert res["fused"][5] == res["separate"][5] - 1, "the fused run must launch one kernel less (no max-pool)"
+    for k, name in enumerate(("pool", "f1 (whole-tile forward)", "logits", "class map", "confidence")):
+        assert torch.equal(res["fused"][k], res["separate"][k]), name
+
+
 def _zone_setup(ctx, trained_3_15, W, H, T, margin, seed):
     from oracle import synth
     from oracle.zone_detect_ref import GeoRaster
