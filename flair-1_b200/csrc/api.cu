@@ -39,6 +39,7 @@ struct ConvLayer {
   float* bias_d2s = nullptr;              // device [64]: bias[co] at (py*2+px)*16 + co
   int d2s_mode = 0;                       // 1: 16 -> 16 as a 4x4 stride-2 conv over cells, 2: upsampled 32 -> 16 on the low-res grid
   float* bias = nullptr;            // device [Cout]
+  std::string name;                 // "layer1.0.conv1", ... (per-layer timings)
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
   double flops_px = 0;              // algorithmic FLOPs per output pixel: 2 * Cout * Cin * KH * KW, unpadded channels
@@ -68,8 +69,9 @@ struct HeadSink {
 static_assert(sizeof(fb_tile) == 6 * sizeof(int32_t), "fb_tile is handed to the kernels as int32 [n][6]");
 
 struct ProfRec {
-  int cat;
+  int cat;               // 0 extract, 1 convs, 2 pool / MLP, 3 stitch; 9 = one conv layer (label), not part of the sums
   cudaEvent_t a, b;
+  const char* label;     // layer name (owned by the ConvLayer), or null
 };
 
 }  // namespace
@@ -145,6 +147,7 @@ struct fb_ctx {
 
   // profiling
   bool prof = false;
+  bool prof_layers = false;   // FB_LAYER_TIMES=1 at fb_profile_begin: one event pair per conv launch, table on stderr at fb_profile_end
   std::vector<ProfRec> prof_recs;
 };
 
@@ -172,9 +175,10 @@ struct ProfScope {
   fb_ctx* c;
   ProfRec r;
   bool on;
-  ProfScope(fb_ctx* c_, int cat) : c(c_), on(c_->prof) {
+  ProfScope(fb_ctx* c_, int cat, const char* label = nullptr) : c(c_), on(c_->prof && cat >= 0 && (cat != 9 || c_->prof_layers)) {
     if (on) {
       r.cat = cat;
+      r.label = label;
       cudaEventCreate(&r.a);
       cudaEventCreate(&r.b);
       cudaEventRecord(r.a, c->stream);
@@ -366,6 +370,7 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
   FB_CUDA(c, cudaMemcpyAsync(L.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, c->stream));
   FB_CUDA(c, cudaMemcpyAsync(L.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, c->stream));
   FB_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors die at scope exit
+  L.name = name;
   c->conv[name] = L;
   return 0;
 }
@@ -565,6 +570,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
              const float* rowbias, bool relu, const Act& out, bool phase = false, const NeedCtx* need = nullptr,
              int layer = -1, const HeadSink* sink = nullptr, bool* sunk = nullptr, bool up1 = false) {
   // `out` may be stored 2x2-replicated (Act::up2): the conv itself runs at half those dims
+  ProfScope layer_scope(c, c->plan_mode == 1 ? -1 : 9, L.name.c_str());
   const int Hout = out.up2 ? out.H / 2 : out.H, Wout = out.up2 ? out.W / 2 : out.W;
   const int C1 = x1.C, C2 = x2 ? x2->C : 0;
   if (C1 + C2 != L.Cin || out.C != L.Cout) return fail(c, FB_ERR_INVALID, "internal: conv channel mismatch");
@@ -764,6 +770,7 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
                              2 * nb >= c->num_sms;
       {
         ProfScope ps(c, 1);
+        ProfScope ps_layer(c, 9, fuse_pool ? "stem+pool" : "stem");
         if (stem_halo) {
           fb::HaloArgs h;
           memset(&h, 0, sizeof h);
@@ -793,6 +800,7 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
       }
       if (!fuse_pool) {
         ProfScope ps(c, 2);
+        ProfScope ps_layer(c, 9, "maxpool");
         int rc = fb::launch_maxpool3x3s2(static_cast<const __nv_bfloat16*>(f1c.ptr),
                                          static_cast<__nv_bfloat16*>(pool.ptr) + b0 * pool_px, nb, f1.H, f1.W, 64,
                                          c->num_sms, c->stream);
@@ -1909,6 +1917,8 @@ int fb_profile_begin(fb_ctx* c) {
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   c->prof_recs.clear();
   c->prof = true;
+  const char* lt = getenv("FB_LAYER_TIMES");
+  c->prof_layers = lt && lt[0] == '1';
   return 0;
 }
 
@@ -1917,13 +1927,31 @@ int fb_profile_end(fb_ctx* c, float* ms4) {
   c->prof = false;
   FB_CUDA(c, cudaStreamSynchronize(c->stream));
   double acc[4] = {0, 0, 0, 0};
+  std::vector<std::pair<std::string, std::pair<double, int>>> layers;   // first-seen order
   for (auto& r : c->prof_recs) {
     float m = 0;
-    if (cudaEventElapsedTime(&m, r.a, r.b) == cudaSuccess && r.cat >= 0 && r.cat < 4) acc[r.cat] += m;
+    const bool ok = cudaEventElapsedTime(&m, r.a, r.b) == cudaSuccess;
+    if (ok && r.cat >= 0 && r.cat < 4) acc[r.cat] += m;
+    if (ok && r.cat == 9 && r.label) {
+      size_t k = 0;
+      while (k < layers.size() && layers[k].first != r.label) ++k;
+      if (k == layers.size()) layers.push_back({r.label, {0.0, 0}});
+      layers[k].second.first += m;
+      layers[k].second.second++;
+    }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   c->prof_recs.clear();
+  if (c->prof_layers) {
+    double tot = 0;
+    for (auto& l : layers) tot += l.second.first;
+    fprintf(stderr, "[layer times] CUDA events around every conv launch, %zu layers, %.3f ms in total\n", layers.size(), tot);
+    for (auto& l : layers)
+      fprintf(stderr, "[layer times] %-22s %5d launches %9.3f ms %7.1f us/launch %5.1f %%\n", l.first.c_str(), l.second.second,
+              l.second.first, 1e3 * l.second.first / l.second.second, 100.0 * l.second.first / (tot > 0 ? tot : 1));
+  }
+  c->prof_layers = false;
   for (int i = 0; i < 4; ++i) ms4[i] = static_cast<float>(acc[i]);
   return 0;
 }

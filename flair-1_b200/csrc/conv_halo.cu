@@ -589,15 +589,18 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
           uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
           // pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero outside the image: the
-          // values are post-ReLU, so a zero never wins against the window's centre)
+          // values are post-ReLU, so a zero never wins against the window's centre). Branch-free: every load is issued
+          // from an address that is always inside the pool buffers and masked afterwards, so that the nine loads of a
+          // window are in flight together instead of one load -> max step at a time.
           auto fetch = [&](int r, int c) -> uint4 {
-            if (r >= 0 && c >= 0) return *reinterpret_cast<const uint4*>(pool_tile + (r * G::TW + c) * kPoolPitch + vec * 16);
-            if (r < 0) {
-              if (th == 0 || (c < 0 && tw == 0)) return make_uint4(0u, 0u, 0u, 0u);
-              return *reinterpret_cast<const uint4*>(rows_prev + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16);
-            }
-            if (tw == 0) return make_uint4(0u, 0u, 0u, 0u);
-            return *reinterpret_cast<const uint4*>(cols_prev + r * 128 + vec * 16);
+            const bool in_tile = r >= 0 && c >= 0;
+            const bool ok = in_tile || (r < 0 ? (th > 0 && (c >= 0 || tw > 0)) : tw > 0);
+            const uint8_t* a_tile = pool_tile + ((r < 0 ? 0 : r) * G::TW + (c < 0 ? 0 : c)) * kPoolPitch;
+            const uint8_t* a_row = rows_prev + static_cast<size_t>(tw * G::TW + c + (tw == 0 && c < 0 ? 1 : 0)) * 128;
+            const uint8_t* a_col = cols_prev + (r < 0 ? 0 : r) * 128;
+            const uint8_t* a = in_tile ? a_tile : (r < 0 ? a_row : a_col);
+            const uint4 v = *reinterpret_cast<const uint4*>(a + vec * 16);
+            return ok ? v : make_uint4(0u, 0u, 0u, 0u);
           };
           auto vmax = [](uint4 a, const uint4 b) -> uint4 {
             auto m2 = [](uint32_t x, uint32_t y) -> uint32_t {
@@ -611,12 +614,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
           for (int half = 0; half < 2; ++half) {
             const int pp = (ep >> 3) + 32 * half;      // pooled pixel 0 .. 63 of the tile's 8 x 8
             const int pi = pp >> 3, pj = pp & 7;
-            uint4 v = fetch(2 * pi, 2 * pj);
+            uint4 w[9];
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx)
-                if (dy != 0 || dx != 0) v = vmax(v, fetch(2 * pi + dy, 2 * pj + dx));
+            for (int t = 0; t < 9; ++t) w[t] = fetch(2 * pi + t / 3 - 1, 2 * pj + t % 3 - 1);
+            const uint4 v = vmax(vmax(vmax(w[0], w[1]), vmax(w[2], w[3])), vmax(vmax(w[4], w[5]), vmax(vmax(w[6], w[7]), w[8])));
             if (!(p.debug_skip & 4))
               *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pool_out) +
                                         ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + pj) * 128 + vec * 16) = v;

@@ -27,6 +27,7 @@ ap.add_argument("--rounds", type=int, default=3)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--size", type=int, default=10000)
 ap.add_argument("--batch", type=int, default=148)
+ap.add_argument("--layers", action="store_true", help="print the library's per-layer CUDA-event times of the last round (FB_LAYER_TIMES=1)")
 ap.add_argument("configs", nargs="+")
 args = ap.parse_args()
 
@@ -81,12 +82,20 @@ for rnd in range(args.rounds):
         with_env(envs, step)
         ctx.synchronize()
         f0 = ctx.flop_count
+        layers = args.layers and rnd == args.rounds - 1
+        if layers:
+            os.environ["FB_LAYER_TIMES"] = "1"
+            print(f"--- per-layer times [{envs or 'default'}], {args.steps} steps ---", file=sys.stderr, flush=True)
+            ctx.profile_begin()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(args.steps):
             with_env(envs, step)
         b.record()
         torch.cuda.synchronize()
+        if layers:
+            ctx.profile_end()
+            os.environ.pop("FB_LAYER_TIMES", None)
         ms = a.elapsed_time(b) / args.steps
         fl = (ctx.flop_count - f0) / args.steps
         print(f"round {rnd} [{envs or 'default'}]: {ms:.2f} ms/step, {W * H / 1e3 / ms:.1f} Mpx/s, "
