@@ -761,12 +761,12 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
       Act x0c = x0, f1c = f1;
       x0c.B = nb; x0c.ptr = static_cast<__nv_bfloat16*>(x0.ptr) + b0 * x0_px;
       f1c.B = nb; f1c.ptr = static_cast<__nv_bfloat16*>(f1.ptr) + b0 * f1_px;
-      // the max-pool runs inside the stem's epilogue (HaloArgs::pool_out) when the stem is one of the halo kernel's two
-      // forms, the batch gives most SMs an image of their own (a CTA walks whole images there) and the rows fit the
+      // the max-pool runs inside the stem's epilogue (HaloArgs::pool_out) when the stem is in space-to-depth form (<= 4
+      // bands), the batch gives most SMs an image of their own (a CTA walks whole images there) and the rows fit the
       // carry buffers; FB_NO_POOL_FUSE=1 keeps the separate kernel
       const ConvLayer& S = L("stem");
       const bool stem_halo = c->stem_s2d || (!c->force_gather && !c->no_halo && S.w_halo && fb::halo_supported(7, 2, x0.C, 0, S.Cout, f1.H, f1.W));
-      const bool fuse_pool = stem_halo && !c->no_pool_fuse && c->front_chunk <= 0 && f1.W <= 256 && f1.H % 16 == 0 && f1.W % 16 == 0 &&
+      const bool fuse_pool = c->stem_s2d && !c->no_pool_fuse && c->front_chunk <= 0 && f1.W <= 256 && f1.H % 16 == 0 && f1.W % 16 == 0 &&
                              2 * nb >= c->num_sms;
       {
         ProfScope ps(c, 1);

@@ -78,7 +78,22 @@ constexpr int kSbStages = 4;
 #ifndef FB_ACC_DEEP
 #define FB_ACC_DEEP 2
 #endif
-constexpr int kAccDeep = FB_ACC_DEEP;   // accumulator buffers of the 64-channel one-CTA-per-SM configurations (2 or 4)
+constexpr int kAccDeep = FB_ACC_DEEP;
+// Halo gather through registers (ld.global.nc 16 B -> st.shared 16 B, a batch of loads in flight per thread) instead of
+// cp.async. `ncu` counts 30-42 shared-memory wavefronts per warp-wide cp.async of 16 bytes per lane against 4 for the
+// same bytes stored with st.shared.v4, and switching the copies off (FB_HALO_SKIP=1) makes the halo layers 15-30 %
+// faster -- but a synchronous gather needs one L2 round trip per batch, and measured per layer (CUDA events, zone
+// loop, profiles/r02_ldg_gather.txt) it only wins where a stage is one batch: the space-to-depth stem, 8 cells per
+// thread (762 -> 642 us with the pool fused); layer1 314 -> 346 us, the streamed-weight layers 147 -> 280 us (16 loads
+// in flight). FB_LDG_PRODUCER: 1 = the stem only (default), 0 = cp.async everywhere, 2 = registers everywhere.
+#ifndef FB_LDG_PRODUCER
+#define FB_LDG_PRODUCER 1
+#endif
+#ifndef FB_LDG_BATCH
+#define FB_LDG_BATCH 8
+#endif
+constexpr int kLdgBatchMax = FB_LDG_BATCH;   // 16-byte loads a gathering thread keeps in flight (4 registers each)
+constexpr int kLdgMode = FB_LDG_PRODUCER;   // accumulator buffers of the 64-channel one-CTA-per-SM configurations (2 or 4)
 
 // PAIR = two CTAs of a cluster (one TPC) run every MMA together (tcgen05.mma.cta_group::2, M = 256): each CTA stages
 // the halo of its own 16-row tile (the pair covers two vertically adjacent tiles) and holds HALF of the filter bank
@@ -88,12 +103,12 @@ constexpr int kAccDeep = FB_ACC_DEEP;   // accumulator buffers of the 64-channel
 // (its halo is written by cp.async, which can only signal a barrier of its own CTA) to the leader. Encoder layers
 // only: no active-tile lists.
 // POOL = the stem with its 3x3 stride-2 max-pool (torchvision ResNet: MaxPool2d(3, 2, 1)) fused into the epilogue. A CTA
-// takes whole images and walks their 16 x 16 tiles in row-major order; the epilogue warps leave every finished tile in
-// shared memory as well (bf16, what the separate pool kernel would read back from HBM: 8.4 MB per 512^2 tile), pool its
-// 8 x 8 outputs from it -- the row above and the column to the left come from carry buffers filled by the tiles before
-// it (last row of every tile of the previous tile row, last column of the previous tile) -- and write the pooled
-// tensor. The stem's own output is still stored, for the decoder's skip connection: all of it, or, in the
-// exact-clipping zone loop, only the part dec3.conv1 reads (HaloArgs::keep_tiles).
+// takes whole images and walks their 16 x 16 tiles in row-major order; the first epilogue group leaves every finished
+// tile in shared memory (bf16: what the separate pool kernel would read back from HBM, 8.4 MB per 512^2 tile), the
+// second group pools its 8 x 8 outputs from there -- the row above and the column to the left come from carry buffers
+// filled by the tiles before it (last row of every tile of the previous tile row, last column of the previous tile) --
+// and writes the pooled tensor. The stem's own output is still stored, for the decoder's skip connection: all of it,
+// or, in the exact-clipping zone loop, only the part dec3.conv1 reads (HaloArgs::keep_tiles).
 constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (128 + 16: conflict-free 16-byte stores)
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
@@ -171,12 +186,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(full_bar(s), kProd);
+        mbar_init(full_bar(s), kProd);   // one arrival per gathering thread (cp.async completion or plain arrive)
         mbar_init(empty_bar(s), 1);
       }
       for (int a = 0; a < NACC; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 128 * EPI * (PAIR ? 2 : 1));   // pairs: the leader's barrier takes both CTAs' epilogues
+        // pairs: the leader's barrier takes both CTAs' epilogues; fused pool: only the first group drains accumulators
+        mbar_init(tempty_bar(a), POOL ? 128 : 128 * EPI * (PAIR ? 2 : 1));
       }
       if (SB) {
         for (int s = 0; s < kSbStages; ++s) {
@@ -244,7 +260,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     // (the 4x4 stride-2 depth-to-space form runs two CTAs per SM at 128 registers with a register-hungry epilogue: a
     // 25-word table per producer thread spilled to local memory and its reloads sat in the copy loop, so that
     // instantiation decodes each cell on the fly -- divisions by compile-time constants -- instead)
-    constexpr bool kCellTable = !(KH == 4 && STRIDE == 2);
+    constexpr bool kLdgProducer = kLdgMode == 2 || (kLdgMode == 1 && KH == 4 && STRIDE == 1);
+    constexpr bool kCellTable = !(KH == 4 && STRIDE == 2) && !kLdgProducer;   // (register gather: the registers hold data instead)
     auto cell_word = [&](int j) -> uint32_t {
       const int idx = tid + j * kProd;
       const int c = idx % NCH;
@@ -302,6 +319,43 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         const __nv_bfloat16* src = (from1 ? p.x1 : p.x2) + origin * Cs + (from1 ? g : g - p.groups1) * (NCH * 8) + c8;
         const int row_elems = p.Win * Cs;  // element distance between halo rows
         const uint32_t st = stage_addr0 + s * G::STAGE;
+        if constexpr (kLdgProducer) {
+          // loads of a batch of cells in flight together, then their stores; zero for cells outside the image
+          constexpr int kBatch = kLdgBatchMax < kCellsPerThread ? kLdgBatchMax : kCellsPerThread;
+          const int Hlo = p.Hin >> 1, Wlo = p.Win >> 1;
+          const __nv_bfloat16* lo = p.x1 + static_cast<long long>(b) * Hlo * Wlo * Cs + g * (NCH * 8) + c8;
+          const bool up = p.up1 && from1;
+          if (!(p.debug_skip & 1)) {
+#pragma unroll 1
+            for (int j0 = 0; j0 < kCellsPerThread; j0 += kBatch) {
+              uint4 v[kBatch];
+#pragma unroll
+              for (int jj = 0; jj < kBatch; ++jj) {
+                if (j0 + jj < kCellsPerThread) {
+                  const uint32_t cw = cellw(j0 + jj);
+                  v[jj] = make_uint4(0u, 0u, 0u, 0u);
+                  if (cw != 0xFFFFFFFFu) {
+                    const int hh = (cw >> 16) & 0xFF, k = cw >> 24;
+                    const bool ok = interior || (static_cast<unsigned>(ih0 + hh) < static_cast<unsigned>(p.Hin) &&
+                                                 static_cast<unsigned>(iw0 + k) < static_cast<unsigned>(p.Win));
+                    const __nv_bfloat16* gp = up ? lo + (static_cast<long long>((ih0 + hh) >> 1) * Wlo + ((iw0 + k) >> 1)) * Cs
+                                                 : src + hh * row_elems + k * Cs;
+                    if (ok) v[jj] = ld_global_nc_v4(gp);
+                  }
+                }
+              }
+#pragma unroll
+              for (int jj = 0; jj < kBatch; ++jj) {
+                if (j0 + jj < kCellsPerThread) {
+                  const uint32_t cw = cellw(j0 + jj);
+                  if (cw != 0xFFFFFFFFu) st_shared_v4(st + (cw & 0xFFFFu), v[jj]);
+                }
+              }
+            }
+          }
+          mbar_arrive(full_bar(s));   // (release: the stores above are visible to whoever sees the phase complete)
+          continue;
+        }
         if (p.debug_skip & 1) {
         } else if (p.up1 && from1) {
           // x1 is read through a nearest x2 upsample: halo pixel (ih, iw) of the conv's input grid is pixel
@@ -386,12 +440,156 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BN>::GC_F32 * 4 : EpiRun<BN>::GC_BF16 * 2,
                                     p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
-    // fused max-pool (POOL): the finished tile, the last rows of the previous tile row (two buffers, by tile-row parity)
-    // and the last column of the previous tile (two buffers, by tile-column parity), all bf16 [pixel][64]
-    uint8_t* const pool_tile = smem + (bars - smem_base) + kBarBytes + 4 * kStgWarpBytes;
-    uint8_t* const pool_rows = pool_tile + 16 * G::TW * kPoolPitch;
-    uint8_t* const pool_cols = pool_rows + 2 * static_cast<size_t>(p.Wout) * 128;
-    const int ep = (warp - 4) * 32 + lane;   // 0 .. 255 over both epilogue groups
+    if constexpr (POOL) {
+      // ---- fused max-pool: a two-stage pipeline inside the epilogue. Group 0 (warps 4-7, one per TMEM lane quarter)
+      // drains BOTH 128-pixel blocks of a tile -- bias, ReLU, one bf16 rounding -- into one of two shared-memory tile
+      // buffers; group 1 (warps 8-11) takes the buffer, stores the stem's output from it (whole 128-byte pixels,
+      // coalesced; only inside the keep rectangle), pools the tile's 8 x 8 outputs and leaves the carries for the
+      // tiles to the right and below. Hand-over by named barriers: 1 + k = "buffer k filled", 3 + k = "buffer k free".
+      uint8_t* const pool_tiles = smem + (bars - smem_base) + kBarBytes;                 // 2 x [16 x 16 px][kPoolPitch]
+      uint8_t* const pool_rows = pool_tiles + 2 * 16 * G::TW * kPoolPitch;               // 2 x [Wout px][128]: by tile-row parity
+      uint8_t* const pool_cols = pool_rows + 2 * static_cast<size_t>(p.Wout) * 128;      // 2 x [16 px][128]: by tile-column parity
+      const int et = (warp & 3) * 32 + lane;   // 0 .. 127 inside the group
+      uint32_t tc = 0;
+      if (grp == 0) {
+        const int dh = et >> 3, dw = et & 7;   // TMEM lane = pixel (dh, dw) of a 16 x 8 block
+        for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
+          const int as = tc % NACC, k = tc & 1;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
+          if (tc >= 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + k) : "memory");
+          mbar_wait_relaxed(tfull_bar(as), (tc / NACC) & 1);
+          tc_fence_after_sync();
+          uint8_t* const buf = pool_tiles + k * (16 * G::TW * kPoolPitch);
+#pragma unroll
+          for (int m = 0; m < MB; ++m) {
+            uint8_t* const px = buf + (dh * G::TW + dw + 8 * m) * kPoolPitch;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+              uint32_t r0[16], r1[16];
+              tmem_ld_x16(taddr + m * BN + c0, r0);
+              tmem_ld_x16(taddr + m * BN + c0 + 16, r1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int hlf = 0; hlf < 2; ++hlf) {
+                const uint32_t* r = hlf ? r1 : r0;
+                const float* bb = bias_s + c0 + 16 * hlf;
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float v0 = fmaxf(__uint_as_float(r[2 * i]) + bb[2 * i], 0.f);
+                  const float v1 = fmaxf(__uint_as_float(r[2 * i + 1]) + bb[2 * i + 1], 0.f);
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                  pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                uint4* d = reinterpret_cast<uint4*>(px + (c0 + 16 * hlf) * 2);
+                d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
+            }
+          }
+          tc_fence_before_sync();
+          mbar_arrive(tempty_bar(as));
+          __threadfence_block();
+          asm volatile("bar.arrive %0, 256;" ::"r"(1 + k) : "memory");
+        }
+      } else {
+        const int vec = et & 7;                 // 16-byte piece (8 channels) of a pixel
+        const int Hp = p.Hout >> 1, Wp = p.Wout >> 1;
+        auto vmax = [](uint4 a, const uint4 b) -> uint4 {
+          auto m2 = [](uint32_t x, uint32_t y) -> uint32_t {
+            const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), *reinterpret_cast<const __nv_bfloat162*>(&y));
+            return *reinterpret_cast<const uint32_t*>(&r);
+          };
+          return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w));
+        };
+        int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
+        for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
+          const int tile = tile_next;
+          if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
+          const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
+          const int k = tc & 1;
+          // the part of the stem's output that dec3.conv1 (layer 6 of tile_need.cuh) reads for this image: its needed
+          // region, widened to the 16 x 16 kernel tiles that conv runs and their one-pixel halo
+          int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout;
+          if (p.keep_tiles != nullptr) {
+            const int* kt = p.keep_tiles + 6 * tb;
+            const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
+            const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
+            const bool any = r.x1 > r.x0 && r.y1 > r.y0;
+            kx0 = any ? (r.x0 & ~15) - 1 : 0; ky0 = any ? (r.y0 & ~15) - 1 : 0;
+            kx1 = any ? ((r.x1 + 15) & ~15) + 1 : 0; ky1 = any ? ((r.y1 + 15) & ~15) + 1 : 0;
+          }
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + k) : "memory");
+          const uint8_t* const buf = pool_tiles + k * (16 * G::TW * kPoolPitch);
+          uint8_t* const rows_prev = pool_rows + static_cast<size_t>((th & 1) ^ 1) * p.Wout * 128;
+          uint8_t* const rows_cur = pool_rows + static_cast<size_t>(th & 1) * p.Wout * 128;
+          uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
+          uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
+          // (a) the stem's own output: 8 lanes per pixel, 16 pixels of a tile row per instruction = 2 KB contiguous
+          if (!(p.debug_skip & 4)) {
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+              const int r = j, c = et >> 3;      // pixel (r, c) of the tile
+              const int oy = th * kTH + r, ox = tw * G::TW + c;
+              if (oy >= ky0 && oy < ky1 && ox >= kx0 && ox < kx1)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + oy) * p.Wout + ox) * 128 + vec * 16) =
+                    *reinterpret_cast<const uint4*>(buf + (r * G::TW + c) * kPoolPitch + vec * 16);
+            }
+          }
+          // (b) pooled outputs. Pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero
+          // outside the image: the values are post-ReLU, so a zero never wins against the window's centre).
+          // Branch-free: every load comes from an address inside the pool buffers and is masked afterwards, so the nine
+          // loads of a window are in flight together.
+          auto fetch = [&](int r, int c) -> uint4 {
+            const bool in_tile = r >= 0 && c >= 0;
+            const bool ok = in_tile || (r < 0 ? (th > 0 && (c >= 0 || tw > 0)) : tw > 0);
+            const uint8_t* a_tile = buf + ((r < 0 ? 0 : r) * G::TW + (c < 0 ? 0 : c)) * kPoolPitch;
+            const uint8_t* a_row = rows_prev + static_cast<size_t>(tw * G::TW + c + (tw == 0 && c < 0 ? 1 : 0)) * 128;
+            const uint8_t* a_col = cols_prev + (r < 0 ? 0 : r) * 128;
+            const uint8_t* a = in_tile ? a_tile : (r < 0 ? a_row : a_col);
+            const uint4 v = *reinterpret_cast<const uint4*>(a + vec * 16);
+            return ok ? v : make_uint4(0u, 0u, 0u, 0u);
+          };
+          // A thread pools a 2 x 2 block of outputs from its 5 x 5 window (25 loads for four outputs instead of 36: the
+          // shared-memory reads of this stage compete with the MMAs' operand fetches), row maxima first.
+          {
+            const int bi = (et >> 3) >> 2, bj = (et >> 3) & 3;   // output block: rows 2bi, 2bi+1, columns 2bj, 2bj+1
+            uint4 h[5][2];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+              uint4 w[5];
+#pragma unroll
+              for (int c = 0; c < 5; ++c) w[c] = fetch(4 * bi - 1 + r, 4 * bj - 1 + c);
+              h[r][0] = vmax(vmax(w[0], w[1]), w[2]);
+              h[r][1] = vmax(vmax(w[2], w[3]), w[4]);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const uint4 v = vmax(vmax(h[2 * a][b], h[2 * a + 1][b]), h[2 * a + 2][b]);
+                const int pi = 2 * bi + a, pj = 2 * bj + b;
+                if (!(p.debug_skip & 4))
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pool_out) +
+                                            ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + pj) * 128 + vec * 16) = v;
+              }
+          }
+          // (c) carries: this tile's last row (for the tile below) and last column (for the tile to the right)
+          {
+            const int c = et >> 3;
+            *reinterpret_cast<uint4*>(rows_cur + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16) =
+                *reinterpret_cast<const uint4*>(buf + (15 * G::TW + c) * kPoolPitch + vec * 16);
+            *reinterpret_cast<uint4*>(cols_cur + c * 128 + vec * 16) =
+                *reinterpret_cast<const uint4*>(buf + (c * G::TW + 15) * kPoolPitch + vec * 16);
+          }
+          // hand the buffer back unless nobody will fill it again (no arrival may be left pending at exit)
+          if (ti + 2 * sched_step < sched_end) {
+            __threadfence_block();
+            asm volatile("bar.arrive %0, 256;" ::"r"(3 + k) : "memory");
+          }
+        }
+      }
+    } else {
     uint32_t tcount = 0;
     // "accumulator drained": pairs count both CTAs' epilogue threads on the leader's barrier
     auto tempty_arrive = [&](uint32_t bar) {
@@ -473,29 +671,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
             dpix = p.up2_out ? (static_cast<long long>(tb) * 2 * p.Hout + 2 * oh) * (2 * p.Wout) + 2 * (ow + 8 * m) : own_pix;
           }
           uint8_t* own_dst = out_bytes + static_cast<size_t>(dpix) * pixel_bytes;
-          // POOL: this pixel's slot in the shared-memory tile; its global store may be skipped (keep rectangle)
-          uint8_t* const pool_px = pool_tile + (L.own_dh * G::TW + L.own_dw + 8 * m) * kPoolPitch;
-          bool keep_px = true;
-          if constexpr (POOL) {
-            if (p.keep_tiles != nullptr) {
-              // the part of the stem's output that dec3.conv1 (layer 6 of tile_need.cuh) reads for this image: its
-              // needed region, widened to the 16 x 16 kernel tiles it runs and their one-pixel halo
-              const int* kt = p.keep_tiles + 6 * tb;
-              const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
-              const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
-              const int kx0 = (r.x0 & ~15) - 1, ky0 = (r.y0 & ~15) - 1, kx1 = ((r.x1 + 15) & ~15) + 1, ky1 = ((r.y1 + 15) & ~15) + 1;
-              const int px = ow + 8 * m;
-              keep_px = r.x1 > r.x0 && r.y1 > r.y0 && px >= kx0 && px < kx1 && oh >= ky0 && oh < ky1;
-            }
-          }
           auto direct = [&](int col0, const auto& regs) {
             if (p.debug_skip & 4) return;
-            if constexpr (POOL && sizeof(regs) == 32) {
-              uint4* d = reinterpret_cast<uint4*>(pool_px + col0 * 2);
-              d[0] = make_uint4(regs[0], regs[1], regs[2], regs[3]);
-              d[1] = make_uint4(regs[4], regs[5], regs[6], regs[7]);
-              if (!keep_px) return;
-            }
             if constexpr (D2S) {
               // columns col0 .. col0 + 15 = the 16 channels of pixel (2*oh + py, 2*(ow + 8m) + px) of the cell
               const int grp = col0 >> 4;
@@ -581,59 +758,6 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         }
         tc_fence_before_sync();
         tempty_arrive(tempty_bar(as));
-        if constexpr (POOL) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // the whole tile is in shared memory (both epilogue groups)
-          const int vec = ep & 7;
-          uint8_t* const rows_prev = pool_rows + static_cast<size_t>((th & 1) ^ 1) * p.Wout * 128;
-          uint8_t* const rows_cur = pool_rows + static_cast<size_t>(th & 1) * p.Wout * 128;
-          uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
-          uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
-          // pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero outside the image: the
-          // values are post-ReLU, so a zero never wins against the window's centre). Branch-free: every load is issued
-          // from an address that is always inside the pool buffers and masked afterwards, so that the nine loads of a
-          // window are in flight together instead of one load -> max step at a time.
-          auto fetch = [&](int r, int c) -> uint4 {
-            const bool in_tile = r >= 0 && c >= 0;
-            const bool ok = in_tile || (r < 0 ? (th > 0 && (c >= 0 || tw > 0)) : tw > 0);
-            const uint8_t* a_tile = pool_tile + ((r < 0 ? 0 : r) * G::TW + (c < 0 ? 0 : c)) * kPoolPitch;
-            const uint8_t* a_row = rows_prev + static_cast<size_t>(tw * G::TW + c + (tw == 0 && c < 0 ? 1 : 0)) * 128;
-            const uint8_t* a_col = cols_prev + (r < 0 ? 0 : r) * 128;
-            const uint8_t* a = in_tile ? a_tile : (r < 0 ? a_row : a_col);
-            const uint4 v = *reinterpret_cast<const uint4*>(a + vec * 16);
-            return ok ? v : make_uint4(0u, 0u, 0u, 0u);
-          };
-          auto vmax = [](uint4 a, const uint4 b) -> uint4 {
-            auto m2 = [](uint32_t x, uint32_t y) -> uint32_t {
-              const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), *reinterpret_cast<const __nv_bfloat162*>(&y));
-              return *reinterpret_cast<const uint32_t*>(&r);
-            };
-            return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w));
-          };
-          const int Hp = p.Hout >> 1, Wp = p.Wout >> 1;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int pp = (ep >> 3) + 32 * half;      // pooled pixel 0 .. 63 of the tile's 8 x 8
-            const int pi = pp >> 3, pj = pp & 7;
-            uint4 w[9];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) w[t] = fetch(2 * pi + t / 3 - 1, 2 * pj + t % 3 - 1);
-            const uint4 v = vmax(vmax(vmax(w[0], w[1]), vmax(w[2], w[3])), vmax(vmax(w[4], w[5]), vmax(vmax(w[6], w[7]), w[8])));
-            if (!(p.debug_skip & 4))
-              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pool_out) +
-                                        ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + pj) * 128 + vec * 16) = v;
-          }
-          // carries for the tiles to the right and below: this tile's last row / last column
-          if (ep < 128) {
-            const int c = ep >> 3;
-            *reinterpret_cast<uint4*>(rows_cur + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16) =
-                *reinterpret_cast<const uint4*>(pool_tile + (15 * G::TW + c) * kPoolPitch + vec * 16);
-          } else {
-            const int r = (ep - 128) >> 3;
-            *reinterpret_cast<uint4*>(cols_cur + r * 128 + vec * 16) =
-                *reinterpret_cast<const uint4*>(pool_tile + (r * G::TW + 15) * kPoolPitch + vec * 16);
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // the tile buffer may be overwritten by the next tile
-        }
         continue;
       }
       if constexpr (D2S || SB) continue;
@@ -681,6 +805,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       tc_fence_before_sync();
       tempty_arrive(tempty_bar(as));
     }
+    }   // !POOL
   } else if (elect_one()) {
     // ===================================================================== MMA issuer
     // (elect_one(), not lane == 0: each tcgen05.mma is then issued once from uniform registers instead of
@@ -806,8 +931,8 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   // (the depth-to-space and streamed-weight kernels only store from registers: no copy-out staging)
   const int smem = ((wbytes + 127) / 128) * 128 + (BN * 4 <= 256 ? 256 : BN * 4) + G::STAGES * G::STAGE +
                    ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
-                   ((D2S || SB) ? 0 : 4 * kStgWarpBytes) +
-                   (POOL ? 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
+                   ((D2S || SB || POOL) ? 0 : 4 * kStgWarpBytes) +
+                   (POOL ? 2 * 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
@@ -1130,11 +1255,12 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true>(a, num_sms, stream);
   }
   if (a.pool_out != nullptr) {
-    // the stem with its max-pool fused (both stem forms tile 16 x 16 outputs of 64 channels)
-    if (!epi2 || !a.relu || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 || a.Wout % 16)
+    // the space-to-depth stem with its max-pool fused (the 7x7 stride-2 form's filter bank and stages leave no room
+    // for the pool buffers in 227 KB of shared memory: models with more than four bands keep the separate kernel)
+    if (KH != 4 || !epi2 || !a.relu || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 ||
+        a.Wout % 16)
       return -3007;
-    return KH == 4 ? launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream)
-                   : KH == 7 ? launch_halo_t<7, 2, 1, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream) : -3007;
+    return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream);
   }
   if (KH == 4) return epi2 ? launch_halo_t<4, 1, 2, 64, 2, false, 2>(a, num_sms, stream)
                            : launch_halo_t<4, 1, 2, 64, 2>(a, num_sms, stream);

@@ -127,6 +127,15 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+// 16-byte read-only global load that does not allocate in L1, and a 16-byte shared-memory store by address
+__device__ __forceinline__ uint4 ld_global_nc_v4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // 256-bit global store (sm_100+): one full 32-byte sector per lane; `ptr` must be 32-byte aligned.
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&r)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),

@@ -559,8 +559,9 @@ def test_dead_output_elimination_and_fused_sink_are_bit_exact(trained_3_15, monk
 def test_fused_stem_max_pool_is_bit_exact(trained_3_15, monkeypatch, bands, T, margin):
     """With a batch that gives most SMs an image of their own, the stem's epilogue pools its own output (csrc/conv_halo.cu,
     POOL) and, in the exact-clipping loop, stores only the part of it the decoder reads. Pooled tensor, logits, class map
-    and confidence band must be byte-identical to the separate max-pool kernel (FB_NO_POOL_FUSE=1), for the
-    space-to-depth stem (3 bands) and the 7x7 stride-2 stem (5 bands), on edge tiles and interior tiles."""
+    and confidence band must be byte-identical to the separate max-pool kernel (FB_NO_POOL_FUSE=1) for the
+    space-to-depth stem (<= 4 bands), on edge tiles and interior tiles; a 5-band model (7x7 stride-2 stem, no room for
+    the pool buffers in shared memory) must be unaffected by the switch."""
     from oracle import synth
     from flair1_b200.zone_detect.slicing_job import tile_table
     nat = _nat()
@@ -594,7 +595,8 @@ def test_fused_stem_max_pool_is_bit_exact(trained_3_15, monkeypatch, bands, T, m
         torch.cuda.synchronize()
         res[mode] = (pool.cpu(), f1.cpu(), logits.cpu(), cls.cpu(), conf.cpu(), launches)
         c.close()
-    assert res["fused"][5] == res["separate"][5] - 1, "the fused run must launch one kernel less (no max-pool)"
+    # (the 7x7 stride-2 stem of > 4-band models has no room for the pool buffers: same launches there)
+    assert res["fused"][5] == res["separate"][5] - (1 if bands <= 4 else 0), "the fused run must launch one kernel less (no max-pool)"
     for k, name in enumerate(("pool", "f1 (whole-tile forward)", "logits", "class map", "confidence")):
         assert torch.equal(res["fused"][k], res["separate"][k]), name
 
