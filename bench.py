@@ -594,7 +594,7 @@ def run_ours(args) -> int:
                          # 88 % active), from the `ncu --set full` capture in profiles/r01_ncu_full_igemm2_256_v21.csv
                          "traffic": 114.74e6, "traffic_unit": "bytes per launch (conv_igemm2_kernel<256>, 148 tiles)",
                          "peak_source": peak_src,
-                         "kernel": "conv_igemm2_kernel / conv_igemm_kernel / conv_halo_kernel (47 launches per batch); achieved = algorithmic FLOPs "
+                         "kernel": "conv_igemm2_kernel / conv_igemm_kernel / conv_halo_kernel (47 launches per batch; the stem launch also pools); achieved = algorithmic FLOPs "
                                    "(2*MAC of the direct conv) of the outputs actually computed / summed conv time",
                          "gflop_per_tile_computed": gflop_per_tile, "gflop_per_tile_full": GFLOP_PER_TILE,
                          "note": "the decoder skips outputs that can only reach the cropped margin (bit-identical class map, "
