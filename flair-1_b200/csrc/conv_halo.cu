@@ -7,7 +7,10 @@
 
 #include <vector>
 
+#include <cuda.h>
+
 #include "conv_epilogue.cuh"
+#include "conv_igemm.cuh"
 #include "ptx.cuh"
 #include "tile_need.cuh"
 
@@ -43,7 +46,7 @@ struct Geo {
   static constexpr int SPANW = STRIDE * (TW - 1) + KH;
   static constexpr int PW = (SPANW + NP - 1) / NP;
   static constexpr int KWCELLS = NP * PW;
-  static constexpr int PLANE16 = PH * PW;                              // 16-byte cells per plane
+  static constexpr int PLANE16 = (PH * PW + 7) / 8 * 8;                // 16-byte cells per plane, padded to whole 128-byte rows (TMA destinations)
   static constexpr int STAGE = ((NCH * NP * PLANE16 * 16) + 127) / 128 * 128;
   static constexpr int CELLS = PH * KWCELLS * NCH;
   static constexpr int SBO16 = STRIDE * PW;                            // next output row, in 16-byte units
@@ -112,10 +115,14 @@ constexpr int kLdgMode = FB_LDG_PRODUCER;   // accumulator buffers of the 64-cha
 constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (128 + 16: conflict-free 16-byte stores)
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
-          bool PAIR = false, bool POOL = false>
+          bool PAIR = false, bool POOL = false, bool TMAH = false>
 __global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
-conv_halo_kernel(const __grid_constant__ HaloArgs p) {
+conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUtensorMap tm1) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  // TMAH = the halo planes are written by TMA tensor loads (one 4-D box {8 channels, PW, PH, 1} per 8-channel chunk,
+  // out-of-range pixels zero-filled = the conv padding) issued by one thread, instead of one cp.async per 16-byte cell
+  // from 64-96 threads: single-source stride-1 layers only
+  static_assert(!TMAH || (STRIDE == 1 && !PH && !D2S && !POOL && KH == 3), "TMA-staged halo: plain 3x3 stride-1 form");
   static_assert(!POOL || (EPI == 2 && MB == 2 && BN == 64 && !PH && !D2S && !SB && !PAIR && G::OCC == 1),
                 "fused max-pool: 16 x 16 tiles of 64 channels, two epilogue groups");
   static_assert(!PAIR || (!PH && !D2S && G::OCC == 1 && EPI == 2 && BN % 32 == 0), "CTA pairs: plain form, one CTA per SM");
@@ -186,7 +193,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(full_bar(s), kProd);   // one arrival per gathering thread (cp.async completion or plain arrive)
+        mbar_init(full_bar(s), TMAH ? 1 : kProd);   // TMA: expect_tx by the issuing thread; else one arrival per gathering thread
         mbar_init(empty_bar(s), 1);
       }
       for (int a = 0; a < NACC; ++a) {
@@ -255,6 +262,29 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
     // byte offset inside a stage | hh << 16 | k << 24. kProducers is a multiple of NCH, so the channel
     // chunk c of every cell of a thread is the same: tid % NCH.
     const int tid = threadIdx.x;
+    if constexpr (TMAH) {
+      if (warp == 0 && elect_one()) {
+        uint32_t it = 0;
+        for (int ti = sched0; ti < sched_end; ti += sched_step) {
+          const int tile = tile_of(ti);
+          const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
+          const int ih0 = th * kTH - G::PAD, iw0 = tw * G::TW - G::PAD;
+          for (int g = 0; g < groups; ++g, ++it) {
+            const int s = it % S;
+            mbar_wait_relaxed(empty_bar(s), ((it / S) & 1) ^ 1);
+            const uint32_t st = stage_addr0 + s * G::STAGE;
+            if (!(p.debug_skip & 1)) {
+              mbar_expect_tx(full_bar(s), NCH * G::PH * G::PW * 16);
+#pragma unroll
+              for (int c = 0; c < NCH; ++c)
+                tma_load_4d(st + c * (G::PLANE16 * 16), &tm1, full_bar(s), (g * NCH + c) * 8, iw0, ih0, b);
+            } else {
+              mbar_arrive(full_bar(s));
+            }
+          }
+        }
+      }
+    } else {
     static_assert(kProd % NCH == 0, "channel chunk must be constant per producer thread");
     const int c8 = (tid % NCH) * 8;
     // (the 4x4 stride-2 depth-to-space form runs two CTAs per SM at 128 registers with a register-hungry epilogue: a
@@ -267,7 +297,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
       const int c = idx % NCH;
       const int k = (idx / NCH) % G::KWCELLS;
       const int hh = idx / (NCH * G::KWCELLS);
-      const uint32_t dst = static_cast<uint32_t>((((c * G::NP + (k % G::NP)) * G::PH + hh) * G::PW + k / G::NP) * 16);
+      const uint32_t dst = static_cast<uint32_t>(((c * G::NP + (k % G::NP)) * G::PLANE16 + hh * G::PW + k / G::NP) * 16);
       return idx < G::CELLS ? (dst | (static_cast<uint32_t>(hh) << 16) | (static_cast<uint32_t>(k) << 24)) : 0xFFFFFFFFu;
     };
     uint32_t cell[kCellTable ? kCellsPerThread : 1];
@@ -401,6 +431,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
         cp_async_mbar_arrive_noinc(full_bar(s));
       }
     }
+    }   // !TMAH
   } else if (SB && warp == kBWarp) {
     // ===================================================================== weight streamer (SB)
     // same (tile, group, tap) order as the MMA issuer; a stage is refilled as soon as its MMAs have completed
@@ -921,7 +952,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p) {
 }
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
-          bool PAIR = false, bool POOL = false>
+          bool PAIR = false, bool POOL = false, bool TMAH = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
@@ -933,18 +964,31 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
                    ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
                    ((D2S || SB || POOL) ? 0 : 4 * kStgWarpBytes) +
                    (POOL ? 2 * 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
+  alignas(64) CUtensorMap tm1;
+  memset(&tm1, 0, sizeof tm1);
+  if (TMAH) {
+    // x1 [B, Hin, Win, C1] bf16 seen as (C, W, H, B); one box = the halo plane of an 8-channel chunk
+    const unsigned long long dims[4] = {static_cast<unsigned long long>(a.C1), static_cast<unsigned long long>(a.Win),
+                                        static_cast<unsigned long long>(a.Hin), static_cast<unsigned long long>(a.B)};
+    const unsigned long long strides[3] = {static_cast<unsigned long long>(a.C1) * 2, static_cast<unsigned long long>(a.Win) * a.C1 * 2,
+                                           static_cast<unsigned long long>(a.Hin) * a.Win * a.C1 * 2};
+    const unsigned box[4] = {8u, static_cast<unsigned>(G::PW), static_cast<unsigned>(G::PH), 1u};
+    const unsigned es[4] = {1u, 1u, 1u, 1u};
+    const int rc = encode_tma_plain_bf16(&tm1, a.x1, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
   static int configured = 0;
   static int occ = 1;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     // ask for the largest shared-memory carve-out so that two CTAs of the small configurations fit
-    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = smem;
     int nb = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, kThreadsK, smem);
+    cudaError_t qe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, kThreadsK, smem);
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo occupancy query] err=%d blocks/SM=%d\n", static_cast<int>(qe), nb);
     // CTAs are independent (static tile schedule, private TMEM columns <= 256): over-subscribing is safe,
     // so size the grid for the intended co-residency and let the hardware place what fits.
@@ -967,7 +1011,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo pair %d,%d] smem=%d clusters=%d pairs=%d\n", NCH, BN, smem, clusters, a.num_m_tiles);
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, a);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, a, tm1);
     return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
   }
   const int cap = num_sms * occ;
@@ -975,8 +1019,8 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   if (grid <= 0) return 0;
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
-  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL>, dim3(grid), dim3(kThreadsK),
-                                           static_cast<size_t>(smem), stream, pdl, a);
+  const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, dim3(grid), dim3(kThreadsK),
+                                           static_cast<size_t>(smem), stream, pdl, a, tm1);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
 
@@ -1000,7 +1044,7 @@ HaloGeom halo_geom(int KH, int stride, int nch, int bn) {
   const int spanw = stride * (kTW - 1) + KH;
   g.pw = (spanw + g.np - 1) / g.np;
   g.kw_cells = g.np * g.pw;
-  g.plane16 = g.ph * g.pw;
+  g.plane16 = (g.ph * g.pw + 7) / 8 * 8;
   g.stage_bytes = ((nch * g.np * g.plane16 * 16) + 127) / 128 * 128;
   g.nsteps = (nch == 1) ? KH * ((KH + 1) / 2) : KH * KH * (nch / 2);
   return g;
@@ -1042,7 +1086,7 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride) {
       for (int pr = 0; pr < (KH + 1) / 2; ++pr) {
         const int s = kw * ((KH + 1) / 2) + pr;
         const int par = kw % g.np;
-        const uint32_t off = static_cast<uint32_t>((par * g.ph + 2 * pr) * g.pw + kw / g.np);
+        const uint32_t off = static_cast<uint32_t>(par * g.plane16 + 2 * pr * g.pw + kw / g.np);
         const uint32_t lbo = static_cast<uint32_t>(g.pw);
         a.a_lo[s] = off | (lbo << 16);
       }
@@ -1110,7 +1154,7 @@ size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int Cin
 
 // ---- sub-pixel phase form (32 -> 16 channels): tile = 16 x 8 low-res pixels, halo 18 x 10 cells per chunk
 namespace {
-constexpr int kPhNch = 4, kPhPw = 10, kPhPlane16 = 18 * kPhPw;
+constexpr int kPhNch = 4, kPhPw = 10, kPhPlane16 = (18 * kPhPw + 7) / 8 * 8;   // = Geo<3, 1, 4, 1, 16>::PLANE16
 // original filter taps that read low-res tap d (0/1) for output parity `parity`
 int phase_taps(int parity, int d, int* out) {
   if (parity == 0) { if (d == 0) { out[0] = 0; return 1; } out[0] = 1; out[1] = 2; return 2; }
@@ -1244,16 +1288,26 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // CTA pairs (cta_group::2) for the 64- and 128-channel layers that run whole images (no active-tile list)
   const bool pair = a.pair && KH == 3 && nch == 8 && (a.Cout == 64 || a.Cout == 128) && a.tile_list == nullptr && !a.up2_out &&
                     !a.out_f32 && a.Hout % (2 * kTH) == 0 && epi2 && !a.up1;
+  // TMA-staged halo for the single-source 64-channel layers (layer1, dec2.conv2): 313 -> 216 us per launch against
+  // cp.async; the streamed-weight 128-channel form measured 141 -> 161 us with it, so it keeps cp.async unless FB_TMAH=2.
+  // FB_TMAH=0: cp.async everywhere.
+  static const int tmah_mode = getenv("FB_TMAH") ? atoi(getenv("FB_TMAH")) : 1;
+  const bool tmah = tmah_mode > 0 && KH == 3 && nch == 8 && a.C2 == 0 && !a.up1 && epi2 && (a.Cout == 64 || (a.Cout == 128 && tmah_mode >= 2));
   if (pair) {
     HaloArgs b = a;
     b.num_m_tiles = a.B * (a.Hout / (2 * kTH)) * (a.Wout / (8 * halo_blocks(3, 8, a.Cout)));
+    if (tmah)
+      return a.Cout == 128 ? launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true, true, false, true>(b, num_sms, stream)
+                           : launch_halo_t<3, 1, 8, 64, 2, false, 2, false, false, true, false, true>(b, num_sms, stream);
     return a.Cout == 128 ? launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true, true>(b, num_sms, stream)
                          : launch_halo_t<3, 1, 8, 64, 2, false, 2, false, false, true>(b, num_sms, stream);
   }
   if (KH == 3 && nch == 8 && a.Cout == 128) {
     if (a.up2_out || a.out_f32) return -3006;
+    if (tmah) return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true, false, false, true>(a, num_sms, stream);
     return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true>(a, num_sms, stream);
   }
+  if (tmah && a.Cout == 64 && !a.up2_out) return launch_halo_t<3, 1, 8, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
   if (a.pool_out != nullptr) {
     // the space-to-depth stem with its max-pool fused (the 7x7 stride-2 form's filter bank and stages leave no room
     // for the pool buffers in 227 KB of shared memory: models with more than four bands keep the separate kernel)

@@ -549,6 +549,19 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorM
 
 }  // namespace
 
+int encode_tma_plain_bf16(void* tensor_map, const void* base, int rank, const unsigned long long* dims,
+                          const unsigned long long* strides, const unsigned* box, const unsigned* es) {
+  if (init_tma_encoder() != 0) return -1001;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; e[i] = es[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
+  const CUresult r = g_encode(static_cast<CUtensorMap*>(tensor_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                              const_cast<void*>(base), d, st, bx, e, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1300 - static_cast<int>(r);
+}
+
 int init_tma_encoder() {
   if (g_encode != nullptr) return 0;
   void* fn = nullptr;

@@ -82,5 +82,10 @@ int launch_conv(const ConvArgs& a, const __nv_bfloat16* weights /*[Cout][Kpad] b
 
 // Resolve cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency).
 int init_tma_encoder();
+// cuTensorMapEncodeTiled for a bf16 tensor without swizzle / interleave, out-of-range elements read as zero (the halo
+// kernel's TMA-staged input planes). dims / box / es: `rank` entries, innermost first; strides: rank - 1 entries in bytes.
+// Returns 0 or a negative code.
+int encode_tma_plain_bf16(void* tensor_map, const void* base, int rank, const unsigned long long* dims,
+                          const unsigned long long* strides, const unsigned* box, const unsigned* es);
 
 }  // namespace fb
