@@ -122,7 +122,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
   // TMAH = the halo planes are written by TMA tensor loads (one 4-D box {8 channels, PW, PH, 1} per 8-channel chunk,
   // out-of-range pixels zero-filled = the conv padding) issued by one thread, instead of one cp.async per 16-byte cell
   // from 64-96 threads: single-source stride-1 layers only
-  static_assert(!TMAH || (STRIDE == 1 && !PH && !D2S && !POOL && KH == 3), "TMA-staged halo: plain 3x3 stride-1 form");
+  // (stride 2: one box per w-parity plane, every second pixel through the map's element stride)
+  static_assert(!TMAH || !PH, "TMA-staged halo: not for the four-phase form");
   static_assert(!POOL || (EPI == 2 && MB == 2 && BN == 64 && !PH && !D2S && !SB && !PAIR && G::OCC == 1),
                 "fused max-pool: 16 x 16 tiles of 64 channels, two epilogue groups");
   static_assert(!PAIR || (!PH && !D2S && G::OCC == 1 && EPI == 2 && BN % 32 == 0), "CTA pairs: plain form, one CTA per SM");
@@ -268,16 +269,18 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         for (int ti = sched0; ti < sched_end; ti += sched_step) {
           const int tile = tile_of(ti);
           const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
-          const int ih0 = th * kTH - G::PAD, iw0 = tw * G::TW - G::PAD;
+          const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
           for (int g = 0; g < groups; ++g, ++it) {
             const int s = it % S;
             mbar_wait_relaxed(empty_bar(s), ((it / S) & 1) ^ 1);
             const uint32_t st = stage_addr0 + s * G::STAGE;
             if (!(p.debug_skip & 1)) {
-              mbar_expect_tx(full_bar(s), NCH * G::PH * G::PW * 16);
+              mbar_expect_tx(full_bar(s), NCH * G::NP * G::PH * G::PW * 16);
 #pragma unroll
               for (int c = 0; c < NCH; ++c)
-                tma_load_4d(st + c * (G::PLANE16 * 16), &tm1, full_bar(s), (g * NCH + c) * 8, iw0, ih0, b);
+#pragma unroll
+                for (int par = 0; par < G::NP; ++par)
+                  tma_load_4d(st + (c * G::NP + par) * (G::PLANE16 * 16), &tm1, full_bar(s), (g * NCH + c) * 8, iw0 + par, ih0, b);
             } else {
               mbar_arrive(full_bar(s));
             }
@@ -972,8 +975,9 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
                                         static_cast<unsigned long long>(a.Hin), static_cast<unsigned long long>(a.B)};
     const unsigned long long strides[3] = {static_cast<unsigned long long>(a.C1) * 2, static_cast<unsigned long long>(a.Win) * a.C1 * 2,
                                            static_cast<unsigned long long>(a.Hin) * a.Win * a.C1 * 2};
-    const unsigned box[4] = {8u, static_cast<unsigned>(G::PW), static_cast<unsigned>(G::PH), 1u};
-    const unsigned es[4] = {1u, 1u, 1u, 1u};
+    // stride 2: a plane holds every second pixel of a row (w-parity planes); rows are staged in full
+    const unsigned box[4] = {8u, static_cast<unsigned>(G::NP * G::PW), static_cast<unsigned>(G::PH), 1u};
+    const unsigned es[4] = {1u, static_cast<unsigned>(G::NP), 1u, 1u};
     const int rc = encode_tma_plain_bf16(&tm1, a.x1, 4, dims, strides, box, es);
     if (rc) return rc;
   }
@@ -1263,11 +1267,18 @@ size_t pack_halo_weights_d2s(int mode, const float* w, int Cout, int Cin, uint16
 }
 
 int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream) {
+  // TMA-staged halo (the input planes written by tensor loads from one thread instead of one cp.async per 16-byte cell):
+  // FB_TMAH=0 never, 1 (default) wherever it measured faster, 2 also the streamed-weight 128-channel form
+  static const int tmah_mode = getenv("FB_TMAH") ? atoi(getenv("FB_TMAH")) : 1;
+  const bool tma_ok = tmah_mode > 0 && a.C2 == 0 && !a.up1;
   if (a.d2s) {
     if (!halo_d2s_supported(a.d2s, a.C1, a.C2, 16, a.Hout, a.Wout) || a.Cout != 64 || a.residual || a.rowbias || a.up2_out ||
         a.up1 || a.phase_mode || (a.d2s == 1 ? (a.Hin != a.Hout || a.Win != a.Wout) : (2 * a.Hin != a.Hout || 2 * a.Win != a.Wout)))
       return -3005;
     if (a.nsteps != (a.d2s == 1 ? 16 : 18)) return -3002;
+    if (tma_ok)
+      return a.d2s == 1 ? launch_halo_t<4, 2, 2, 64, 2, false, 1, true, false, false, false, true>(a, num_sms, stream)
+                        : launch_halo_t<3, 1, 4, 64, 2, false, 1, true, false, false, false, true>(a, num_sms, stream);
     return a.d2s == 1 ? launch_halo_t<4, 2, 2, 64, 2, false, 1, true>(a, num_sms, stream)
                       : launch_halo_t<3, 1, 4, 64, 2, false, 1, true>(a, num_sms, stream);
   }
@@ -1288,11 +1299,8 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // CTA pairs (cta_group::2) for the 64- and 128-channel layers that run whole images (no active-tile list)
   const bool pair = a.pair && KH == 3 && nch == 8 && (a.Cout == 64 || a.Cout == 128) && a.tile_list == nullptr && !a.up2_out &&
                     !a.out_f32 && a.Hout % (2 * kTH) == 0 && epi2 && !a.up1;
-  // TMA-staged halo for the single-source 64-channel layers (layer1, dec2.conv2): 313 -> 216 us per launch against
-  // cp.async; the streamed-weight 128-channel form measured 141 -> 161 us with it, so it keeps cp.async unless FB_TMAH=2.
-  // FB_TMAH=0: cp.async everywhere.
-  static const int tmah_mode = getenv("FB_TMAH") ? atoi(getenv("FB_TMAH")) : 1;
-  const bool tmah = tmah_mode > 0 && KH == 3 && nch == 8 && a.C2 == 0 && !a.up1 && epi2 && (a.Cout == 64 || (a.Cout == 128 && tmah_mode >= 2));
+  // (64-channel layers: 313 -> 216 us per launch with TMA staging; the streamed-weight 128-channel form 141 -> 161 us)
+  const bool tmah = tma_ok && KH == 3 && nch == 8 && epi2 && (a.Cout == 64 || (a.Cout == 128 && tmah_mode >= 2));
   if (pair) {
     HaloArgs b = a;
     b.num_m_tiles = a.B * (a.Hout / (2 * kTH)) * (a.Wout / (8 * halo_blocks(3, 8, a.Cout)));
@@ -1314,14 +1322,21 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     if (KH != 4 || !epi2 || !a.relu || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 ||
         a.Wout % 16)
       return -3007;
+    if (tma_ok) return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true, true>(a, num_sms, stream);
     return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream);
   }
+  if (KH == 4 && epi2 && tma_ok) return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
+  if (KH == 7 && epi2 && tma_ok) return launch_halo_t<7, 2, 1, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
   if (KH == 4) return epi2 ? launch_halo_t<4, 1, 2, 64, 2, false, 2>(a, num_sms, stream)
                            : launch_halo_t<4, 1, 2, 64, 2>(a, num_sms, stream);
   if (epi2) {
     if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2, false, 2>(a, num_sms, stream);
     if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32, 2, false, 2>(a, num_sms, stream);
     if (nch == 8 && a.Cout == 64) return launch_halo_t<3, 1, 8, 64, 2, false, 2>(a, num_sms, stream);
+  }
+  if (tma_ok && !a.up2_out) {
+    if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4, false, 1, false, false, false, false, true>(a, num_sms, stream);
+    if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32, 2, false, 1, false, false, false, false, true>(a, num_sms, stream);
   }
   if (KH == 7) return launch_halo_t<7, 2, 1, 64, 2>(a, num_sms, stream);
   if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4>(a, num_sms, stream);
