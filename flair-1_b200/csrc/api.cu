@@ -87,7 +87,7 @@ struct fb_ctx {
   bool no_phase = false;      // FB_NO_PHASE=1: decoder conv1 on the materialised upsample instead of sub-pixel phases
   bool dec_phase[6] = {false, false, false, false, false, false};  // per decoder block, decided by arena_plan
   bool dec_up1[6] = {false, false, false, false, false, false};    // block reads its low-res x1 through the halo kernel's x2 upsample
-  bool no_up1 = false;        // FB_NO_UP1=1: such blocks read a 2x2-replicated x1 written by the producer instead
+  bool no_up1 = true;         // FB_NO_UP1=0: such blocks read their low-res x1 through the halo kernel's x2 up-sampling gather
   int front_chunk = 0;        // FB_FRONT_CHUNK: tiles per stem + max-pool chunk (0 = the whole batch)
   bool no_s2d = false;        // FB_NO_S2D=1: 7x7 stride-2 stem on the 8-channel-padded tile also for <= 4 bands
   bool stem_s2d = false;      // decided by arena_plan: x0 is stored in space-to-depth form
@@ -951,8 +951,11 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_halo = nh && nh[0] == '1';
   const char* np = getenv("FB_NO_PHASE");
   c->no_phase = np && np[0] == '1';
+  // default since the halo planes are staged by TMA (which cannot up-sample while it copies): dec2.conv2 writes its
+  // output 2x2-replicated again (120 -> 193 us) and dec3.conv1 becomes a plain two-source conv with TMA-staged planes
+  // (621 -> 410 us). FB_NO_UP1=0: dec3.conv1 reads the low-res tensor through the cp.async up-sampling gather.
   const char* nu = getenv("FB_NO_UP1");
-  c->no_up1 = nu && nu[0] == '1';
+  c->no_up1 = !(nu && nu[0] == '0');
   const char* fc = getenv("FB_FRONT_CHUNK");
   c->front_chunk = fc ? atoi(fc) : 0;
   const char* ns = getenv("FB_NO_S2D");

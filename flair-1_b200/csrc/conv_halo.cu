@@ -117,7 +117,7 @@ constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
           bool PAIR = false, bool POOL = false, bool TMAH = false>
 __global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
-conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUtensorMap tm1) {
+conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2) {
   using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
   // TMAH = the halo planes are written by TMA tensor loads (one 4-D box {8 channels, PW, PH, 1} per 8-channel chunk,
   // out-of-range pixels zero-filled = the conv padding) issued by one thread, instead of one cp.async per 16-byte cell
@@ -280,7 +280,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
               for (int c = 0; c < NCH; ++c)
 #pragma unroll
                 for (int par = 0; par < G::NP; ++par)
-                  tma_load_4d(st + (c * G::NP + par) * (G::PLANE16 * 16), &tm1, full_bar(s), (g * NCH + c) * 8, iw0 + par, ih0, b);
+                  tma_load_4d(st + (c * G::NP + par) * (G::PLANE16 * 16), g < p.groups1 ? &tm1 : &tm2, full_bar(s),
+                              ((g < p.groups1 ? g : g - p.groups1) * NCH + c) * 8, iw0 + par, ih0, b);
             } else {
               mbar_arrive(full_bar(s));
             }
@@ -967,19 +968,23 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
                    ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
                    ((D2S || SB || POOL) ? 0 : 4 * kStgWarpBytes) +
                    (POOL ? 2 * 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
-  alignas(64) CUtensorMap tm1;
+  alignas(64) CUtensorMap tm1, tm2;
   memset(&tm1, 0, sizeof tm1);
+  memset(&tm2, 0, sizeof tm2);
   if (TMAH) {
-    // x1 [B, Hin, Win, C1] bf16 seen as (C, W, H, B); one box = the halo plane of an 8-channel chunk
-    const unsigned long long dims[4] = {static_cast<unsigned long long>(a.C1), static_cast<unsigned long long>(a.Win),
-                                        static_cast<unsigned long long>(a.Hin), static_cast<unsigned long long>(a.B)};
-    const unsigned long long strides[3] = {static_cast<unsigned long long>(a.C1) * 2, static_cast<unsigned long long>(a.Win) * a.C1 * 2,
-                                           static_cast<unsigned long long>(a.Hin) * a.Win * a.C1 * 2};
-    // stride 2: a plane holds every second pixel of a row (w-parity planes); rows are staged in full
-    const unsigned box[4] = {8u, static_cast<unsigned>(G::NP * G::PW), static_cast<unsigned>(G::PH), 1u};
-    const unsigned es[4] = {1u, static_cast<unsigned>(G::NP), 1u, 1u};
-    const int rc = encode_tma_plain_bf16(&tm1, a.x1, 4, dims, strides, box, es);
-    if (rc) return rc;
+    // a source [B, Hin, Win, C] bf16 seen as (C, W, H, B); one box = the halo plane of an 8-channel chunk
+    for (int src = 0; src < (a.C2 > 0 ? 2 : 1); ++src) {
+      const unsigned long long C = static_cast<unsigned long long>(src ? a.C2 : a.C1);
+      const unsigned long long dims[4] = {C, static_cast<unsigned long long>(a.Win), static_cast<unsigned long long>(a.Hin),
+                                          static_cast<unsigned long long>(a.B)};
+      const unsigned long long strides[3] = {C * 2, static_cast<unsigned long long>(a.Win) * C * 2,
+                                             static_cast<unsigned long long>(a.Hin) * a.Win * C * 2};
+      // stride 2: a plane holds every second pixel of a row (w-parity planes); rows are staged in full
+      const unsigned box[4] = {8u, static_cast<unsigned>(G::NP * G::PW), static_cast<unsigned>(G::PH), 1u};
+      const unsigned es[4] = {1u, static_cast<unsigned>(G::NP), 1u, 1u};
+      const int rc = encode_tma_plain_bf16(src ? &tm2 : &tm1, src ? a.x2 : a.x1, 4, dims, strides, box, es);
+      if (rc) return rc;
+    }
   }
   static int configured = 0;
   static int occ = 1;
@@ -1015,7 +1020,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo pair %d,%d] smem=%d clusters=%d pairs=%d\n", NCH, BN, smem, clusters, a.num_m_tiles);
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, a, tm1);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, a, tm1, tm2);
     return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
   }
   const int cap = num_sms * occ;
@@ -1024,7 +1029,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
   const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, dim3(grid), dim3(kThreadsK),
-                                           static_cast<size_t>(smem), stream, pdl, a, tm1);
+                                           static_cast<size_t>(smem), stream, pdl, a, tm1, tm2);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
 
@@ -1270,7 +1275,7 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // TMA-staged halo (the input planes written by tensor loads from one thread instead of one cp.async per 16-byte cell):
   // FB_TMAH=0 never, 1 (default) wherever it measured faster, 2 also the streamed-weight 128-channel form
   static const int tmah_mode = getenv("FB_TMAH") ? atoi(getenv("FB_TMAH")) : 1;
-  const bool tma_ok = tmah_mode > 0 && a.C2 == 0 && !a.up1;
+  const bool tma_ok = tmah_mode > 0 && !a.up1;   // (a source read through the x2 up-sampling gather cannot be a TMA box)
   if (a.d2s) {
     if (!halo_d2s_supported(a.d2s, a.C1, a.C2, 16, a.Hout, a.Wout) || a.Cout != 64 || a.residual || a.rowbias || a.up2_out ||
         a.up1 || a.phase_mode || (a.d2s == 1 ? (a.Hin != a.Hout || a.Win != a.Wout) : (2 * a.Hin != a.Hout || 2 * a.Win != a.Wout)))
@@ -1300,7 +1305,7 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   const bool pair = a.pair && KH == 3 && nch == 8 && (a.Cout == 64 || a.Cout == 128) && a.tile_list == nullptr && !a.up2_out &&
                     !a.out_f32 && a.Hout % (2 * kTH) == 0 && epi2 && !a.up1;
   // (64-channel layers: 313 -> 216 us per launch with TMA staging; the streamed-weight 128-channel form 141 -> 161 us)
-  const bool tmah = tma_ok && KH == 3 && nch == 8 && epi2 && (a.Cout == 64 || (a.Cout == 128 && tmah_mode >= 2));
+  const bool tmah = tma_ok && KH == 3 && nch == 8 && epi2 && a.C2 == 0 && (a.Cout == 64 || (a.Cout == 128 && tmah_mode >= 2));
   if (pair) {
     HaloArgs b = a;
     b.num_m_tiles = a.B * (a.Hout / (2 * kTH)) * (a.Wout / (8 * halo_blocks(3, 8, a.Cout)));
@@ -1315,7 +1320,10 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     if (tmah) return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true, false, false, true>(a, num_sms, stream);
     return launch_halo_t<3, 1, 8, 128, 2, false, 2, false, true>(a, num_sms, stream);
   }
-  if (tmah && a.Cout == 64 && !a.up2_out) return launch_halo_t<3, 1, 8, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
+  if (tmah && a.Cout == 64) return launch_halo_t<3, 1, 8, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
+  // two-source 64 + 64 -> 32 (dec3.conv1 on a materialised up-sample, FB_NO_UP1=1)
+  if (tma_ok && KH == 3 && nch == 8 && epi2 && a.Cout == 32)
+    return launch_halo_t<3, 1, 8, 32, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
   if (a.pool_out != nullptr) {
     // the space-to-depth stem with its max-pool fused (the 7x7 stride-2 form's filter bank and stages leave no room
     // for the pool buffers in 227 KB of shared memory: models with more than four bands keep the separate kernel)
@@ -1334,6 +1342,8 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     if (nch == 8 && a.Cout == 32) return launch_halo_t<3, 1, 8, 32, 2, false, 2>(a, num_sms, stream);
     if (nch == 8 && a.Cout == 64) return launch_halo_t<3, 1, 8, 64, 2, false, 2>(a, num_sms, stream);
   }
+  // (2x2-replicated outputs use the staged copy-out of the one-group epilogue)
+  if (tma_ok && nch == 8 && a.Cout == 64 && a.C2 == 0) return launch_halo_t<3, 1, 8, 64, 2, false, 1, false, false, false, false, true>(a, num_sms, stream);
   if (tma_ok && !a.up2_out) {
     if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4, false, 1, false, false, false, false, true>(a, num_sms, stream);
     if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32, 2, false, 1, false, false, false, false, true>(a, num_sms, stream);
