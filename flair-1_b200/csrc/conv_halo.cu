@@ -79,7 +79,7 @@ struct Geo {
 // pixels) this moves 185 KB instead of 576 KB from L2 to shared memory per 128 output pixels of layer2.
 constexpr int kSbStages = 4;
 #ifndef FB_ACC_DEEP
-#define FB_ACC_DEEP 2
+#define FB_ACC_DEEP 4
 #endif
 constexpr int kAccDeep = FB_ACC_DEEP;
 // Halo gather through registers (ld.global.nc 16 B -> st.shared 16 B, a batch of loads in flight per thread) instead of
@@ -143,9 +143,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
   constexpr int S = G::STAGES;
   // pairs: + "the peer's halo stage / weight stage has landed", used in the leader only
   constexpr int ACC = MB * BN;  // TMEM columns of one accumulator buffer (MB blocks of 128 x BN)
-  // accumulator buffers: two. Four (FB_ACC_DEEP=4: where they fit the 512 TMEM columns of a one-CTA-per-SM
-  // configuration, i.e. the 64-channel layers) measured neutral (104.0 vs 103.9 ms per zone, alternating runs): the
-  // epilogue warps already spend most of their time waiting for the next accumulator
+  // accumulator buffers: four where they fit the 512 TMEM columns of a one-CTA-per-SM configuration (the 64-channel
+  // layers), two otherwise. Neutral while the halo was staged by cp.async (104.0 vs 103.9 ms per zone); with TMA
+  // staging the MMAs run closer to their ceiling and the deeper ring is worth 0.5 % (91.6 vs 92.1 ms, three
+  // alternating pairs). FB_ACC_DEEP=2: two everywhere.
   constexpr int NACC = (G::OCC == 1 && 4 * ACC <= 512 && !PH) ? kAccDeep : 2;
   constexpr int kBars = 2 * S + 2 * NACC + (SB ? 2 * kSbStages : 0) + (PAIR ? S + (SB ? kSbStages : 0) : 0);
   constexpr int kBarBytes = (kBars * 8 + 16 + 127) / 128 * 128;
