@@ -562,13 +562,17 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
           uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
           // (a) the stem's own output: 8 lanes per pixel, 16 pixels of a tile row per instruction = 2 KB contiguous
-          if (!(p.debug_skip & 4)) {
+          // (most tiles of the exact-clipping loop lie wholly outside the keep rectangle: one test per tile for those)
+          const bool tile_kept = th * kTH < ky1 && th * kTH + kTH > ky0 && tw * G::TW < kx1 && tw * G::TW + G::TW > kx0;
+          if (tile_kept && !(p.debug_skip & 4)) {
+            const int c = et >> 3, ox = tw * G::TW + c;
+            const bool col_ok = ox >= kx0 && ox < kx1;
+            uint8_t* const gcol = reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + th * kTH) * p.Wout + ox) * 128 + vec * 16;
 #pragma unroll 4
-            for (int j = 0; j < 16; ++j) {
-              const int r = j, c = et >> 3;      // pixel (r, c) of the tile
-              const int oy = th * kTH + r, ox = tw * G::TW + c;
-              if (oy >= ky0 && oy < ky1 && ox >= kx0 && ox < kx1)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + oy) * p.Wout + ox) * 128 + vec * 16) =
+            for (int r = 0; r < 16; ++r) {
+              const int oy = th * kTH + r;
+              if (col_ok && oy >= ky0 && oy < ky1)
+                *reinterpret_cast<uint4*>(gcol + static_cast<size_t>(r) * p.Wout * 128) =
                     *reinterpret_cast<const uint4*>(buf + (r * G::TW + c) * kPoolPitch + vec * 16);
             }
           }
