@@ -31,6 +31,7 @@ std::string g_create_error;
 struct ConvLayer {
   __nv_bfloat16* w = nullptr;       // device [Cout][Kpad] (im2col order, TMA / gather producers)
   __nv_bfloat16* w_halo = nullptr;  // device, K-step order of the halo-staged kernel (or null)
+  __nv_bfloat16* w_halo_pair = nullptr;  // device, the same bank in CTA-pair stage order (128 -> 128 layers; or null)
   __nv_bfloat16* w_phase = nullptr; // device [4][Cout][Kp_phase]: sub-pixel phase form of a decoder conv1 (or null)
   int Kp_phase = 0;
   __nv_bfloat16* w_halo_phase = nullptr;  // device, phase form for the halo-staged kernel (32 -> 16 channels) (or null)
@@ -274,6 +275,13 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
     FB_CUDA(c, cudaMalloc(&L.w_halo, n * 2));
     c->owned.push_back(L.w_halo);
     FB_CUDA(c, cudaMemcpy(L.w_halo, hp.data(), n * 2, cudaMemcpyHostToDevice));
+    if (KH == 3 && stride == 1 && CoutPad == 128 && L.C1 == 128 && L.C2 == 0) {
+      std::vector<uint16_t> pp(n);
+      fb::pack_halo_weights_pair128(hp.data(), n, pp.data());
+      FB_CUDA(c, cudaMalloc(&L.w_halo_pair, n * 2));
+      c->owned.push_back(L.w_halo_pair);
+      FB_CUDA(c, cudaMemcpy(L.w_halo_pair, pp.data(), n * 2, cudaMemcpyHostToDevice));
+    }
   }
   // the stem on the 2x2 space-to-depth image (conv_halo.cuh): w2[o][(py*2+px)*Cin + c][a][b] = w[o][c][2a+py-1][2b+px-1]
   if (name == "stem" && KH == 7 && stride == 2 && Cin <= 4 && Cout == 64) {
@@ -687,6 +695,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     if (out.elem == 4) h.out_f32 = static_cast<float*>(out.ptr); else h.out = static_cast<__nv_bfloat16*>(out.ptr);
     h.up2_out = out.up2 ? 1 : 0;
     h.wpacked = L.w_halo;
+    h.wpacked_pair = L.w_halo_pair;
     h.pair = c->no_hpair ? 0 : 1;
     fb::halo_fill_steps(h, L.KH, L.stride);
     const int tw = 8 * fb::halo_blocks(L.KH, fb::halo_group_channels(L.KH, C1, C2) / 8, L.Cout);
@@ -1890,14 +1899,23 @@ int fb_conv2d_halo(fb_ctx* c, const void* x1, const void* x2, int C1, int C2, in
   std::vector<uint16_t> hp(n);
   fb::pack_halo_weights(w_oihw_host, Cout, Cout, Cin, Cin, KH, stride, h.C1, h.C2, hp.data());
   __nv_bfloat16* wdev = nullptr;
+  __nv_bfloat16* wpair = nullptr;
   FB_CUDA(c, cudaMalloc(&wdev, n * 2));
   cudaMemcpy(wdev, hp.data(), n * 2, cudaMemcpyHostToDevice);
+  if (KH == 3 && stride == 1 && Cout == 128 && h.C1 == 128 && h.C2 == 0) {
+    std::vector<uint16_t> pp(n);
+    fb::pack_halo_weights_pair128(hp.data(), n, pp.data());
+    FB_CUDA(c, cudaMalloc(&wpair, n * 2));
+    cudaMemcpy(wpair, pp.data(), n * 2, cudaMemcpyHostToDevice);
+  }
   h.wpacked = wdev;
+  h.wpacked_pair = wpair;
   h.pair = c->no_hpair ? 0 : 1;
   fb::halo_fill_steps(h, KH, stride);
   const int rc = fb::launch_conv_halo(h, KH, stride, c->num_sms, c->stream);
   cudaStreamSynchronize(c->stream);
   cudaFree(wdev);
+  if (wpair) cudaFree(wpair);
   if (rc) return fail(c, rc, "conv2d_halo launch failed (code " + std::to_string(rc) + ")");
   c->launches++;
   return 0;

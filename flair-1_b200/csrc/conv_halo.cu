@@ -451,7 +451,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
             mbar_wait_relaxed(bempty_bar(s), ((bit / kSbStages) & 1) ^ 1);
             mbar_expect_tx(bfull_bar(s), kBStage);
             const uint8_t* src = wsrc + static_cast<size_t>(g * p.nsteps + bs * kBSteps) * (2 * BN * 16);
-            if (PAIR) {
+            if (PAIR && p.wpacked_pair != nullptr) {
+              // pair-ordered bank: this CTA's half of the stage is contiguous
+              bulk_load_1d(w_addr + s * kBStage,
+                           reinterpret_cast<const uint8_t*>(p.wpacked_pair) +
+                               (static_cast<size_t>(g * nb + bs) * 2 + rank) * kBStage,
+                           kBStage, bfull_bar(s));
+            } else if (PAIR) {
               // this CTA's BN / 2 columns of every (step, chunk) slab: 2 * kBSteps pieces of BN / 2 * 16 bytes
 #pragma unroll
               for (int sc = 0; sc < 2 * kBSteps; ++sc)
@@ -1164,6 +1170,18 @@ size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int Cin
             dst[(((static_cast<size_t>(grp) * g.nsteps + s) * 2 + j) * CoutPad + n) * 8 + e] = bf16_rne(W(n, ci, kh, kw));
           }
   return total;
+}
+
+void pack_halo_weights_pair128(const uint16_t* packed, size_t total, uint16_t* dst) {
+  // packed: [step (all groups)][chunk j][n < 128][8]; a stage = 4 consecutive steps (one filter tap of a 64-channel group)
+  const size_t step_elems = 2 * 128 * 8, stage_elems = 4 * step_elems;
+  for (size_t st = 0; st * stage_elems < total; ++st)
+    for (int r = 0; r < 2; ++r)
+      for (int kk = 0; kk < 4; ++kk)
+        for (int j = 0; j < 2; ++j)
+          for (int n = 0; n < 64; ++n)
+            memcpy(dst + st * stage_elems + ((static_cast<size_t>(r) * 4 + kk) * 2 + j) * 64 * 8 + n * 8,
+                   packed + st * stage_elems + (static_cast<size_t>(kk) * 2 + j) * 128 * 8 + (r * 64 + n) * 8, 8 * sizeof(uint16_t));
 }
 
 // ---- sub-pixel phase form (32 -> 16 channels): tile = 16 x 8 low-res pixels, halo 18 x 10 cells per chunk

@@ -40,6 +40,10 @@ struct HaloArgs {
   int up2_out;
   // filter bank packed by pack_halo_weights(): [group][step][chunk 0/1][n][8] bf16
   const __nv_bfloat16* wpacked;
+  // streamed filter bank of a CTA pair (optional): the same bank with each stage's two 64-column halves contiguous,
+  // [group][tap][half][step in tap][chunk 0/1][n < 64][8] (pack_halo_weights_pair128), so that a CTA fetches its half of
+  // a stage with ONE bulk copy instead of eight 1 KB pieces
+  const __nv_bfloat16* wpacked_pair;
   int groups1, groups2;          // channel groups (of NCH*8 channels) taken from x1 / x2
   int nsteps;                    // K=16 MMA steps per group
   // low word of the A descriptor of each K-step, relative to the stage base: start offset of the
@@ -106,6 +110,10 @@ void halo_fill_steps(HaloArgs& a, int KH, int stride);
 // Returns the number of bf16 elements written to `dst` (dst may be null to query the size).
 size_t pack_halo_weights(const float* w, int Cout, int CoutPad, int Cin, int CinPad, int KH, int stride,
                          int C1pad, int C2pad, uint16_t* dst);
+
+// Re-orders a bank packed by pack_halo_weights for 128 output channels and 64-channel groups (`total` bf16 elements) into
+// the CTA-pair stage order (HaloArgs::wpacked_pair); dst holds `total` elements.
+void pack_halo_weights_pair128(const uint16_t* packed, size_t total, uint16_t* dst);
 
 // Phase form (HaloArgs::phase_mode): single source of 32 channels -> 16 output channels.
 bool halo_phase_supported(int C1, int C2, int Cout, int Hlo, int Wlo);

@@ -601,6 +601,37 @@ def test_fused_stem_max_pool_is_bit_exact(trained_3_15, monkeypatch, bands, T, m
         assert torch.equal(res["fused"][k], res["separate"][k]), name
 
 
+def test_fused_sink_for_more_than_16_classes(monkeypatch):
+    """19-class nomenclature (32 logit columns): the head's fused sink takes the soft-max in two halves of 16 columns and
+    rescales the first half's exponent sum, K6 sums once against the global maximum. The class byte must be identical;
+    the confidence byte (round-half-up of the max probability) may only differ where that probability sits within
+    rounding of 0.5."""
+    from oracle import synth
+    from flair1_b200.zone_detect.slicing_job import tile_table
+    nat = _nat()
+    sd = synth.cached_checkpoint(3, 19)
+    W, H, T, margin = 900, 700, 256, 32
+    raster = torch.from_numpy(synth.synth_raster(3, H, W, seed=19)).cuda()
+    tiles = tile_table(W, H, T, margin)
+    res = {}
+    for mode in ("separate", "fused"):
+        monkeypatch.setenv("FB_NO_FUSED_SINK", "1" if mode == "separate" else "0")
+        c = nat.Context(0)
+        c.load_weights(sd, 3, 19)
+        c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+        c.set_raster(raster, [0, 1, 2], W, H)
+        cls = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        conf = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+        c.detect_strip(tiles, T, 6, cls, conf, W, 0)
+        torch.cuda.synchronize()
+        res[mode] = (cls.cpu(), conf.cpu())
+        c.close()
+    assert torch.equal(res["fused"][0], res["separate"][0])
+    assert int(res["fused"][0].max()) < 19
+    differ = int((res["fused"][1] != res["separate"][1]).sum())
+    assert differ <= W * H // 100000, f"{differ} confidence bytes differ"
+
+
 def _zone_setup(ctx, trained_3_15, W, H, T, margin, seed):
     from oracle import synth
     from oracle.zone_detect_ref import GeoRaster
