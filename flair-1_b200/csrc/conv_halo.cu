@@ -485,9 +485,11 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
     if constexpr (POOL) {
       // ---- fused max-pool: a two-stage pipeline inside the epilogue. Group 0 (warps 4-7, one per TMEM lane quarter)
       // drains BOTH 128-pixel blocks of a tile -- bias, ReLU, one bf16 rounding -- into one of two shared-memory tile
-      // buffers; group 1 (warps 8-11) takes the buffer, stores the stem's output from it (whole 128-byte pixels,
-      // coalesced; only inside the keep rectangle), pools the tile's 8 x 8 outputs and leaves the carries for the
-      // tiles to the right and below. Hand-over by named barriers: 1 + k = "buffer k filled", 3 + k = "buffer k free".
+      // buffers and stores the stem's own output from its registers (only inside the keep rectangle); group 1 (warps
+      // 8-11) takes the buffer, pools the tile's 8 x 8 outputs and leaves the carries for the tiles to the right and
+      // below. (ncu stall sampling of the first split -- stores in group 1 -- showed group 0 waiting for a free buffer
+      // two thirds of its time: the pooling group is the slower stage.) Hand-over by named barriers: 1 + k = "buffer k
+      // filled", 3 + k = "buffer k free".
       uint8_t* const pool_tiles = smem + (bars - smem_base) + kBarBytes;                 // 2 x [16 x 16 px][kPoolPitch]
       uint8_t* const pool_rows = pool_tiles + 2 * 16 * G::TW * kPoolPitch;               // 2 x [Wout px][128]: by tile-row parity
       uint8_t* const pool_cols = pool_rows + 2 * static_cast<size_t>(p.Wout) * 128;      // 2 x [16 px][128]: by tile-column parity
@@ -495,9 +497,28 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       uint32_t tc = 0;
       if (grp == 0) {
         const int dh = et >> 3, dw = et & 7;   // TMEM lane = pixel (dh, dw) of a 16 x 8 block
+        int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
         for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
+          const int tile = tile_next;
+          if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
+          const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
           const int as = tc % NACC, k = tc & 1;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
+          // The stem's own output goes to global memory from this group's registers (the pooling group is the slower
+          // stage of the pipeline). In the exact-clipping loop only the part that dec3.conv1 (layer 6 of tile_need.cuh)
+          // reads for this image is stored: its needed region, widened to the 16 x 16 kernel tiles that conv runs and
+          // their one-pixel halo.
+          int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout;
+          if (p.keep_tiles != nullptr) {
+            const int* kt = p.keep_tiles + 6 * tb;
+            const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
+            const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
+            const bool any = r.x1 > r.x0 && r.y1 > r.y0;
+            kx0 = any ? (r.x0 & ~15) - 1 : 0; ky0 = any ? (r.y0 & ~15) - 1 : 0;
+            kx1 = any ? ((r.x1 + 15) & ~15) + 1 : 0; ky1 = any ? ((r.y1 + 15) & ~15) + 1 : 0;
+          }
+          const int oy = th * kTH + dh;
+          const bool row_kept = oy >= ky0 && oy < ky1 && !(p.debug_skip & 4);
           if (tc >= 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + k) : "memory");
           mbar_wait_relaxed(tfull_bar(as), (tc / NACC) & 1);
           tc_fence_after_sync();
@@ -505,6 +526,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
 #pragma unroll
           for (int m = 0; m < MB; ++m) {
             uint8_t* const px = buf + (dh * G::TW + dw + 8 * m) * kPoolPitch;
+            const int ox = tw * G::TW + dw + 8 * m;
+            const bool kept = row_kept && ox >= kx0 && ox < kx1;
+            uint8_t* const gpx = reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + oy) * p.Wout + ox) * 128;
 #pragma unroll
             for (int c0 = 0; c0 < BN; c0 += 32) {
               uint32_t r0[16], r1[16];
@@ -526,6 +550,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                 uint4* d = reinterpret_cast<uint4*>(px + (c0 + 16 * hlf) * 2);
                 d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if (kept) st_global_v8(gpx + (c0 + 16 * hlf) * 2, pk);
               }
             }
           }
@@ -550,39 +575,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
           const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
           const int k = tc & 1;
-          // the part of the stem's output that dec3.conv1 (layer 6 of tile_need.cuh) reads for this image: its needed
-          // region, widened to the 16 x 16 kernel tiles that conv runs and their one-pixel halo
-          int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout;
-          if (p.keep_tiles != nullptr) {
-            const int* kt = p.keep_tiles + 6 * tb;
-            const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
-            const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
-            const bool any = r.x1 > r.x0 && r.y1 > r.y0;
-            kx0 = any ? (r.x0 & ~15) - 1 : 0; ky0 = any ? (r.y0 & ~15) - 1 : 0;
-            kx1 = any ? ((r.x1 + 15) & ~15) + 1 : 0; ky1 = any ? ((r.y1 + 15) & ~15) + 1 : 0;
-          }
           asm volatile("bar.sync %0, 256;" ::"r"(1 + k) : "memory");
           const uint8_t* const buf = pool_tiles + k * (16 * G::TW * kPoolPitch);
           uint8_t* const rows_prev = pool_rows + static_cast<size_t>((th & 1) ^ 1) * p.Wout * 128;
           uint8_t* const rows_cur = pool_rows + static_cast<size_t>(th & 1) * p.Wout * 128;
           uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
           uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
-          // (a) the stem's own output: 8 lanes per pixel, 16 pixels of a tile row per instruction = 2 KB contiguous
-          // (most tiles of the exact-clipping loop lie wholly outside the keep rectangle: one test per tile for those)
-          const bool tile_kept = th * kTH < ky1 && th * kTH + kTH > ky0 && tw * G::TW < kx1 && tw * G::TW + G::TW > kx0;
-          if (tile_kept && !(p.debug_skip & 4)) {
-            const int c = et >> 3, ox = tw * G::TW + c;
-            const bool col_ok = ox >= kx0 && ox < kx1;
-            uint8_t* const gcol = reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + th * kTH) * p.Wout + ox) * 128 + vec * 16;
-#pragma unroll 4
-            for (int r = 0; r < 16; ++r) {
-              const int oy = th * kTH + r;
-              if (col_ok && oy >= ky0 && oy < ky1)
-                *reinterpret_cast<uint4*>(gcol + static_cast<size_t>(r) * p.Wout * 128) =
-                    *reinterpret_cast<const uint4*>(buf + (r * G::TW + c) * kPoolPitch + vec * 16);
-            }
-          }
-          // (b) pooled outputs. Pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero
+          // pooled outputs. Pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero
           // outside the image: the values are post-ReLU, so a zero never wins against the window's centre).
           // Branch-free: every load comes from an address inside the pool buffers and is masked afterwards, so the nine
           // loads of a window are in flight together.
@@ -620,7 +619,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                                             ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + pj) * 128 + vec * 16) = v;
               }
           }
-          // (c) carries: this tile's last row (for the tile below) and last column (for the tile to the right)
+          // carries: this tile's last row (for the tile below) and last column (for the tile to the right)
           {
             const int c = et >> 3;
             *reinterpret_cast<uint4*>(rows_cur + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16) =
