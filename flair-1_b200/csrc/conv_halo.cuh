@@ -13,7 +13,13 @@
 // of the same UMMA shared-memory descriptor: 8 consecutive output columns are 8 consecutive 16-byte
 // cells (the descriptor's 8-row core matrix), the next output row is `stride` plane rows further (SBO)
 // and the second 8-channel chunk of a K=16 step is one plane (or, for the stem, one input row) further
-// (LBO). The whole filter bank stays resident in shared memory for the CTA's lifetime.
+// (LBO). The planes are written by TMA tensor loads (one 4-D box of 8 channels x halo width x halo height per
+// plane, out-of-range pixels zero-filled = the conv padding, every second pixel through the map's element stride
+// for the stride-2 forms), issued by one thread; by one cp.async per cell where a source is read through the x2
+// up-sampling gather or the TMA unit already streams the filter bank. The filter bank stays resident in shared
+// memory for the CTA's lifetime, or -- 128 -> 128 channels, 295 KB -- is streamed through a ring of bulk copies.
+// Further forms (template parameters of conv_halo_kernel, conv_halo.cu): CTA pairs (tcgen05.mma.cta_group::2),
+// depth-to-space output for the 16-channel layers, the stem with its max-pool fused into the epilogue.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
