@@ -498,6 +498,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       if (grp == 0) {
         const int dh = et >> 3, dw = et & 7;   // TMEM lane = pixel (dh, dw) of a 16 x 8 block
         int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
+        int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout, keep_tb = -1;
         for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
           const int tile = tile_next;
           if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
@@ -508,8 +509,10 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           // stage of the pipeline). In the exact-clipping loop only the part that dec3.conv1 (layer 6 of tile_need.cuh)
           // reads for this image is stored: its needed region, widened to the 16 x 16 kernel tiles that conv runs and
           // their one-pixel halo.
-          int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout;
-          if (p.keep_tiles != nullptr) {
+          // (recomputed when the image changes, i.e. once per 256 tiles: the table look-up and the walk through the
+          // decoder's regions were a third of this group's time when done per tile)
+          if (p.keep_tiles != nullptr && tb != keep_tb) {
+            keep_tb = tb;
             const int* kt = p.keep_tiles + 6 * tb;
             const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
             const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
