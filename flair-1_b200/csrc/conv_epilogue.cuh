@@ -22,6 +22,41 @@
 
 namespace fb {
 
+// Soft-max maximum of one pixel over the classes col0 .. col0 + 15 (those below ncls): first maximum (numpy arg-max
+// semantics: the lower index wins ties) and the sum of exp(v - max), both as balanced trees over the 16 values --
+// four dependent levels instead of fifteen, which is what paces the head's epilogue (ncu: its warps sit in fixed-latency
+// dependency stalls). Shared by the fused class-map sinks of the halo kernel and by K6 (argmax_stitch_kernel), so the
+// two paths keep writing identical bytes.
+__device__ __forceinline__ void softmax_max16(const float (&v)[16], int ncls, int col0, float& best, int& arg, float& den) {
+  float m[16];
+  int ix[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    m[k] = col0 + k < ncls ? v[k] : -3.0e38f;
+    ix[k] = col0 + k;
+  }
+#pragma unroll
+  for (int w = 1; w < 16; w <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2 * w) {
+      const bool right = m[k + w] > m[k];   // strictly greater: the earlier class keeps a tie
+      m[k] = right ? m[k + w] : m[k];
+      ix[k] = right ? ix[k + w] : ix[k];
+    }
+  }
+  best = m[0];
+  arg = ix[0];
+  float e[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) e[k] = col0 + k < ncls ? __expf(v[k] - best) : 0.f;
+#pragma unroll
+  for (int w = 1; w < 16; w <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2 * w) e[k] += e[k + w];
+  }
+  den = e[0];
+}
+
 constexpr int kStgPitch = 144;                 // bytes per staged pixel row (128 + 16: conflict-free 16 B stores)
 constexpr int kStgWarpBytes = 32 * kStgPitch;  // staging bytes per epilogue warp
 

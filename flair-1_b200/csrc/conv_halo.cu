@@ -730,15 +730,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                   // fused K6 (see below), one pixel per 16-column group
                   const int rx = sink_x0 + x, ry = sink_y0 + y;
                   if (!(rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1)) return;
-                  float best = regs[0];
-                  int arg = 0;
-#pragma unroll
-                  for (int k = 1; k < 16; ++k)
-                    if (k < p.sink_ncls && regs[k] > best) { best = regs[k]; arg = k; }
-                  float den = 0.f;
-#pragma unroll
-                  for (int k = 0; k < 16; ++k)
-                    if (k < p.sink_ncls) den += __expf(regs[k] - best);
+                  float best, den;
+                  int arg;
+                  softmax_max16(regs, p.sink_ncls, 0, best, arg, den);
                   const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
                   p.sink_cls[o] = static_cast<uint8_t>(arg);
                   if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);
@@ -756,23 +750,18 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                 // pixels of an active kernel tile that lie outside the write rectangle are not worth the exponentials
                 const int rx = sink_x0 + ow + 8 * m, ry = sink_y0 + oh;
                 if (!(rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1)) return;
-                float best = regs[0];
-                int arg = col0;
-#pragma unroll
-                for (int k = 1; k < 16; ++k)
-                  if (col0 + k < p.sink_ncls && regs[k] > best) { best = regs[k]; arg = col0 + k; }
-                float den = 0.f;
+                float best, den;
+                int arg;
+                softmax_max16(regs, p.sink_ncls, col0, best, arg, den);
                 if (BN == 32 && col0 != 0) {
-                  if (col0 >= p.sink_ncls || !(best > sink_best)) {   // the earlier (lower) class wins ties
-                    if (col0 >= p.sink_ncls) best = sink_best;
-                    else best = fmaxf(best, sink_best);
-                    arg = sink_arg;
-                  }
-                  den = sink_den * __expf(sink_best - best);
+                  // second half of a 17 .. 32-class head: join with the first half's maximum / arg-max / exponent sum
+                  // (the earlier, lower class wins ties); both sums are rescaled to the joint maximum
+                  const float joint = (col0 < p.sink_ncls && best > sink_best) ? best : sink_best;
+                  const float den2 = col0 < p.sink_ncls ? den * __expf(best - joint) : 0.f;
+                  if (!(col0 < p.sink_ncls && best > sink_best)) arg = sink_arg;
+                  den = sink_den * __expf(sink_best - joint) + den2;
+                  best = joint;
                 }
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                  if (col0 + k < p.sink_ncls) den += __expf(regs[k] - best);
                 if (BN == 32 && col0 == 0) {
                   sink_best = best; sink_arg = arg; sink_den = den;
                   return;

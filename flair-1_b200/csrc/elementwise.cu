@@ -5,6 +5,7 @@
 //   K6  softmax-max / argmax / margin clip / stitch (src/zone_detect/compare.py:35,66-82, dataset.py:11-34)
 //   K9  confusion-matrix histogram                  (src/flair/metrics.py:60-74, src/zone_detect/test/metrics.py:146-163)
 #include "elementwise.cuh"
+#include "conv_epilogue.cuh"
 #include "tile_need.cuh"
 
 #include <cuda_bf16.h>
@@ -344,28 +345,26 @@ argmax_stitch_kernel(const float* __restrict__ logits, int ncls, int T, const in
     // 16 classes at a time, in the order and with the arithmetic of the head's fused sink (conv_halo.cu), which sees
     // the logits as 16-column groups: maximum / arg-max / exponent sum of the first group, then the second group
     // rescales that sum to the joint maximum. The two paths therefore write identical bytes for any class count.
-    float best = v[0];
-    int arg = 0;
+    float best, den;
+    int arg;
+    {
+      float lo[16];
 #pragma unroll
-    for (int k = 1; k < 16; ++k)
-      if (k < ncls && v[k] > best) { best = v[k]; arg = k; }
-    float den = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k)
-      if (k < ncls) den += __expf(v[k] - best);
+      for (int k = 0; k < 16; ++k) lo[k] = v[k];
+      softmax_max16(lo, ncls, 0, best, arg, den);
+    }
     if constexpr (LS == 32) {
       if (ncls > 16) {
-        float best2 = v[16];
-        int arg2 = 16;
+        float hi[16], best2, den2;
+        int arg2;
 #pragma unroll
-        for (int k = 17; k < 32; ++k)
-          if (k < ncls && v[k] > best2) { best2 = v[k]; arg2 = k; }
-        const float prev = best;
-        if (best2 > best) { best = best2; arg = arg2; }   // the earlier (lower) class wins ties
-        den *= __expf(prev - best);
-#pragma unroll
-        for (int k = 16; k < 32; ++k)
-          if (k < ncls) den += __expf(v[k] - best);
+        for (int k = 0; k < 16; ++k) hi[k] = v[16 + k];
+        softmax_max16(hi, ncls, 16, best2, arg2, den2);
+        const bool second = best2 > best;   // the earlier (lower) class wins ties
+        const float joint = second ? best2 : best;
+        den = den * __expf(best - joint) + den2 * __expf(best2 - joint);
+        if (second) arg = arg2;
+        best = joint;
       }
     }
     const float pmax = 1.f / den;
