@@ -36,7 +36,7 @@ struct D2SEpiArgs {
   int Cout;
 };
 
-template <int KH, int STRIDE, int NCH, int MB, int BN = 64>
+template <int KH, int STRIDE, int NCH, int MB, int BN = 64, int EPI = 1>
 struct Geo {
   static constexpr int TW = 8 * MB;
   // 4x4 stride 2 = the 2x2-cell form of a 3x3 stride-1 conv (D2S): cell (Y, X) reads pixels 2Y-1 .. 2Y+2
@@ -53,8 +53,11 @@ struct Geo {
   // ring depth (= stages of loads in flight) / CTAs per SM, sized so that OCC CTAs fit 227 KB of shared
   // memory (filter bank + stages + 18 KB epilogue staging): the 16/32-channel layers run two CTAs per SM
   // (4x4 stride 2: a stage is the whole 34 x 34 pixel halo of a 16 x 16 cell tile, 37 KB, next to a 32 KB filter bank)
-  static constexpr bool TWO = (KH == 3 && NCH <= 4) || (KH == 4 && STRIDE == 2);
-  static constexpr int STAGES = (KH == 4 && STRIDE == 2) ? 2 : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
+  // (with two epilogue groups a configuration runs one CTA per SM and spends the room on a deeper ring)
+  static constexpr bool TWO = ((KH == 3 && NCH <= 4) || (KH == 4 && STRIDE == 2)) && EPI == 1;
+  static constexpr int STAGES = (KH == 4 && STRIDE == 2) ? (EPI == 2 ? 4 : 2)
+                                : (KH == 3 && NCH <= 4 && EPI == 2) ? 6
+                                : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
   static constexpr int OCC = TWO ? 2 : 1;
 };
 
@@ -116,9 +119,9 @@ constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
           bool PAIR = false, bool POOL = false, bool TMAH = false>
-__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>::OCC)
+__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2) {
-  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI>;
   // TMAH = the halo planes are written by TMA tensor loads (one 4-D box {8 channels, PW, PH, 1} per 8-channel chunk,
   // out-of-range pixels zero-filled = the conv padding) issued by one thread, instead of one cp.async per 16-byte cell
   // from 64-96 threads: single-source stride-1 layers only
@@ -128,7 +131,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                 "fused max-pool: 16 x 16 tiles of 64 channels, two epilogue groups");
   static_assert(!PAIR || (!PH && !D2S && G::OCC == 1 && EPI == 2 && BN % 32 == 0), "CTA pairs: plain form, one CTA per SM");
   constexpr int BNH = PAIR ? BN / 2 : BN;               // filter-bank columns held by this CTA
-  static_assert(!D2S || (BN == 64 && !PH && EPI == 1), "depth-to-space output: 4 pixels x 16 channels per tile row");
+  static_assert(!D2S || (BN == 64 && !PH), "depth-to-space output: 4 pixels x 16 channels per tile row");
   static_assert(EPI == 1 || (G::OCC == 1 && !PH && MB % 2 == 0), "two epilogue groups: one CTA per SM, even block count");
   static_assert(!SB || (!PH && !D2S && G::OCC == 1 && NCH % 2 == 0), "streamed filter bank: plain form, one CTA per SM");
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
@@ -961,7 +964,7 @@ template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI 
           bool PAIR = false, bool POOL = false, bool TMAH = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
-  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI>;
   const int groups = a.groups1 + a.groups2;
   constexpr int BNH = PAIR ? BN / 2 : BN;
   const int wbytes = SB ? kSbStages * (NCH / 2) * 2 * BNH * 16 : (PH ? MB : 1) * groups * a.nsteps * 2 * BNH * 16;
@@ -1290,11 +1293,18 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   // FB_TMAH=0 never, 1 (default) wherever it measured faster, 2 also the streamed-weight 128-channel form
   static const int tmah_mode = getenv("FB_TMAH") ? atoi(getenv("FB_TMAH")) : 1;
   const bool tma_ok = tmah_mode > 0 && !a.up1;   // (a source read through the x2 up-sampling gather cannot be a TMA box)
+  static const bool one_cta = !(getenv("FB_ONE_CTA") && getenv("FB_ONE_CTA")[0] == '0');
   if (a.d2s) {
     if (!halo_d2s_supported(a.d2s, a.C1, a.C2, 16, a.Hout, a.Wout) || a.Cout != 64 || a.residual || a.rowbias || a.up2_out ||
         a.up1 || a.phase_mode || (a.d2s == 1 ? (a.Hin != a.Hout || a.Win != a.Wout) : (2 * a.Hin != a.Hout || 2 * a.Win != a.Wout)))
       return -3005;
     if (a.nsteps != (a.d2s == 1 ? 16 : 18)) return -3002;
+    // With TMA staging one thread feeds a CTA, so the 16 / 32-channel layers no longer need two CTAs per SM for
+    // their copy threads: one CTA with two epilogue groups and a ring twice as deep measured 350 -> 300 us for the
+    // head (FB_ONE_CTA=0: two CTAs per SM, one epilogue group each).
+    if (tma_ok && one_cta)
+      return a.d2s == 1 ? launch_halo_t<4, 2, 2, 64, 2, false, 2, true, false, false, false, true>(a, num_sms, stream)
+                        : launch_halo_t<3, 1, 4, 64, 2, false, 2, true, false, false, false, true>(a, num_sms, stream);
     if (tma_ok)
       return a.d2s == 1 ? launch_halo_t<4, 2, 2, 64, 2, false, 1, true, false, false, false, true>(a, num_sms, stream)
                         : launch_halo_t<3, 1, 4, 64, 2, false, 1, true, false, false, false, true>(a, num_sms, stream);
@@ -1358,6 +1368,13 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   }
   // (2x2-replicated outputs use the staged copy-out of the one-group epilogue)
   if (tma_ok && nch == 8 && a.Cout == 64 && a.C2 == 0) return launch_halo_t<3, 1, 8, 64, 2, false, 1, false, false, false, false, true>(a, num_sms, stream);
+  // (one CTA per SM with two epilogue groups, per 148 tiles: head 349 -> 296 us, dec3.conv2 152 -> 144, dec4.conv1 the
+  // same; dec4.conv2 233 -> 242, so that one keeps two CTAs per SM unless FB_ONE_CTA=2)
+  static const bool one_cta_all = getenv("FB_ONE_CTA") && getenv("FB_ONE_CTA")[0] == '2';
+  if (tma_ok && !a.up2_out && one_cta && a.direct_store && a.sink_cls == nullptr) {
+    if (nch == 2 && a.Cout == 16 && one_cta_all) return launch_halo_t<3, 1, 2, 16, 4, false, 2, false, false, false, false, true>(a, num_sms, stream);
+    if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
+  }
   if (tma_ok && !a.up2_out) {
     if (nch == 2 && a.Cout == 16) return launch_halo_t<3, 1, 2, 16, 4, false, 1, false, false, false, false, true>(a, num_sms, stream);
     if (nch == 4 && a.Cout == 32) return launch_halo_t<3, 1, 4, 32, 2, false, 1, false, false, false, false, true>(a, num_sms, stream);
