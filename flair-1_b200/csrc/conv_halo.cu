@@ -36,7 +36,7 @@ struct D2SEpiArgs {
   int Cout;
 };
 
-template <int KH, int STRIDE, int NCH, int MB, int BN = 64, int EPI = 1>
+template <int KH, int STRIDE, int NCH, int MB, int BN = 64, int EPI = 1, bool DEEP = false>
 struct Geo {
   static constexpr int TW = 8 * MB;
   // 4x4 stride 2 = the 2x2-cell form of a 3x3 stride-1 conv (D2S): cell (Y, X) reads pixels 2Y-1 .. 2Y+2
@@ -55,9 +55,10 @@ struct Geo {
   // (4x4 stride 2: a stage is the whole 34 x 34 pixel halo of a 16 x 16 cell tile, 37 KB, next to a 32 KB filter bank)
   // (with two epilogue groups a configuration runs one CTA per SM and spends the room on a deeper ring)
   static constexpr bool TWO = ((KH == 3 && NCH <= 4) || (KH == 4 && STRIDE == 2)) && EPI == 1;
+  // (DEEP: the CTA-pair forms store from registers only, the 18 KB of copy-out staging buy a fourth stage)
   static constexpr int STAGES = (KH == 4 && STRIDE == 2) ? (EPI == 2 ? 4 : 2)
                                 : (KH == 3 && NCH <= 4 && EPI == 2) ? 6
-                                : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : 3;
+                                : (KH == 7 || NCH == 2 || (NCH == 4 && BN == 16)) ? 4 : (DEEP ? 4 : 3);
   static constexpr int OCC = TWO ? 2 : 1;
 };
 
@@ -119,9 +120,9 @@ constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
           bool PAIR = false, bool POOL = false, bool TMAH = false>
-__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI>::OCC)
+__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2) {
-  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR>;
   // TMAH = the halo planes are written by TMA tensor loads (one 4-D box {8 channels, PW, PH, 1} per 8-channel chunk,
   // out-of-range pixels zero-filled = the conv padding) issued by one thread, instead of one cp.async per 16-byte cell
   // from 64-96 threads: single-source stride-1 layers only
@@ -964,14 +965,14 @@ template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI 
           bool PAIR = false, bool POOL = false, bool TMAH = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
-  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR>;
   const int groups = a.groups1 + a.groups2;
   constexpr int BNH = PAIR ? BN / 2 : BN;
   const int wbytes = SB ? kSbStages * (NCH / 2) * 2 * BNH * 16 : (PH ? MB : 1) * groups * a.nsteps * 2 * BNH * 16;
   // (the depth-to-space and streamed-weight kernels only store from registers: no copy-out staging)
   const int smem = ((wbytes + 127) / 128) * 128 + (BN * 4 <= 256 ? 256 : BN * 4) + G::STAGES * G::STAGE +
                    ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
-                   ((D2S || SB || POOL) ? 0 : 4 * kStgWarpBytes) +
+                   ((D2S || SB || POOL || PAIR) ? 0 : 4 * kStgWarpBytes) +
                    (POOL ? 2 * 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
   alignas(64) CUtensorMap tm1, tm2;
   memset(&tm1, 0, sizeof tm1);
