@@ -111,33 +111,18 @@ extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc,
       const long long ry = ty0 + 2 * Y + py;
       const bool row_ok = ry >= 0 && ry < H && ry >= row0 && ry < row0 + rows;
       const long long ly = ry - row0;
-      // band-planar raster, the four pixels inside the row: two aligned 32-bit loads and a funnel shift per band instead
-      // of four byte loads (the kernel is bound by load instructions, not bytes: 2.3 of 6.5 TB/s before)
-      // (rx + 8 <= W: the second word of an unaligned read stays inside the row, hence inside the caller's buffer)
-      const bool fast = !layout_hwc && row_ok && rx >= 0 && rx + 8 <= W;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        if (ch < c && fast) {
-          const uint8_t* pa = raster + (static_cast<long long>(s_band[ch]) * rows + ly) * W + rx;
-          const unsigned long long addr = reinterpret_cast<unsigned long long>(pa);
-          const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~3ull);
-          const unsigned sh = static_cast<unsigned>(addr & 3ull) * 8;
-          const uint32_t lo = __ldg(wp);
-          // (the second word is only touched when the four bytes straddle it: never reads past the last needed byte)
-          const uint32_t hi = sh ? __ldg(wp + 1) : 0u;
-          const uint32_t w4 = __funnelshift_r(lo, hi, sh);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) raw[ch][py][j] = (w4 >> (8 * j)) & 0xFFu;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            raw[ch][py][j] = 0;
-            if (ch < c && row_ok && rx + j >= 0 && rx + j < W)
-              raw[ch][py][j] = layout_hwc ? raster[(ly * W + rx + j) * bands_total + s_band[ch]]
-                                          : raster[(static_cast<long long>(s_band[ch]) * rows + ly) * W + rx + j];
-          }
+        for (int j = 0; j < 4; ++j) {
+          raw[ch][py][j] = 0;
+          if (ch < c && row_ok && rx + j >= 0 && rx + j < W)
+            raw[ch][py][j] = layout_hwc ? raster[(ly * W + rx + j) * bands_total + s_band[ch]]
+                                        : raster[(static_cast<long long>(s_band[ch]) * rows + ly) * W + rx + j];
         }
       }
+      // (aligned 32-bit loads + funnel shift instead of the byte loads measured 1.66 -> 1.95 ms per zone: the kernel is
+      // not bound by load instructions; the look-ups in the shared-memory table are the likelier limit)
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {                       // the two space-to-depth pixels
