@@ -26,7 +26,10 @@ constexpr int kNumThreads = 288;          // + warp 8 (MMA issuer / TMEM owner)
 template <int BN, int EPI = 1>
 struct Cfg {
   static constexpr int kThreads = EPI == 2 ? 416 : kNumThreads;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 && EPI == 2) ? 5 : 6;
+#ifndef FB_IGEMM64_STAGES
+#define FB_IGEMM64_STAGES 6
+#endif
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 && EPI == 2) ? 5 : (BN == 64 ? FB_IGEMM64_STAGES : 6);
   static constexpr int kABytes = kBM * kBK * 2;  // 16384
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
