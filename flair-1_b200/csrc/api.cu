@@ -95,6 +95,7 @@ struct fb_ctx {
   bool full_tiles = false;    // FB_FULL_TILES=1: no dead-output elimination in the exact-clipping zone loop
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
+  bool aligned_tiles = false; // FB_ALIGNED_TILES=1: active kernel tiles on the fixed tile grid instead of origin-shifted (tile_need.cuh)
   bool no_pool_fuse = false;  // FB_NO_POOL_FUSE=1: the stem's max-pool as a kernel of its own
   bool no_hpair = false;      // FB_NO_HPAIR=1: halo kernel always as single CTAs (no cta_group::2 pairs)
   bool d2s_all = false;       // FB_D2S_ALL=1: also dec4.conv2 (bf16 output) in depth-to-space form
@@ -532,14 +533,18 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 // regions of all eleven layers, then the real walk, in which every launch picks up its list.
 // *list stays null when every tile is active.
 int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, int th, int tw, int gh, int gw,
-                   const int** list, long long* active) {
+                   const int** list, long long* active, int* shifted) {
   *list = nullptr;
+  *shifted = 0;
   const long long full = static_cast<long long>(B) * gh * gw;
   *active = full;
   if (!need || !need->restrict_tiles || layer < 0 || layer >= fb::kNeedLayers || need->n != B) return 0;
   fb::TileListSpec& sp = c->list_plan.spec[layer];
   if (c->plan_mode == 1) {
-    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, th, tw);
+    // origin-shifted tiles (tile_need.cuh, need_span) unless switched off or the packed entry cannot hold the launch
+    const bool sh = !c->aligned_tiles && B <= (1 << 10) && gh * th < (1 << fb::kTileOriginBits) && gw * tw < (1 << fb::kTileOriginBits);
+    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, th, tw, sh);
+    sp.shifted = sh ? 1 : 0;
     sp.layer = layer; sp.scale = scale; sp.th = th; sp.tw = tw; sp.gh = gh; sp.gw = gw;
     sp.count = static_cast<int>(cnt);
     sp.offset = static_cast<int>(c->list_plan_ints);
@@ -550,7 +555,7 @@ int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, 
   if (sp.scale != scale || sp.th != th || sp.tw != tw || sp.gh != gh || sp.gw != gw)
     return fail(c, FB_ERR_INVALID, "internal: tile list planned for another kernel tiling");
   *active = sp.count;
-  if (sp.use) *list = c->list_dev + sp.offset;
+  if (sp.use) { *list = c->list_dev + sp.offset; *shifted = sp.shifted; }
   return 0;
 }
 
@@ -585,6 +590,7 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
   if (sunk) *sunk = false;
   const int* list = nullptr;
   long long active = 0;
+  int shifted = 0;
   int rc;
   // depth-to-space form (16 output channels at full resolution): 64 accumulator columns = the 2x2 pixels of a cell
   // (measured per 148 tiles: head 368 -> 304 us, dec4.conv1 211 -> 200 us, dec4.conv2 301 -> 491 us: its bf16 stores
@@ -602,9 +608,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     if (out.elem == 4) h.out_f32 = static_cast<float*>(out.ptr); else h.out = static_cast<__nv_bfloat16*>(out.ptr);
     h.wpacked = L.w_d2s;
     fb::halo_fill_steps_d2s(h, L.d2s_mode);
-    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 16, Hout / 32, Wout / 32, &list, &active));
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 16, Hout / 32, Wout / 32, &list, &active, &shifted));
     if (c->plan_mode == 1) return 0;
-    if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
+    if (list) { h.tile_list = list; h.tile_packed = shifted; h.num_m_tiles = static_cast<int>(active); }
     c->flops += static_cast<double>(active) * (32 * 32) * L.flops_px;
     if (sink && need && out.elem == 4) {
       h.sink_tiles = need->tiles_dev;
@@ -637,9 +643,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
       h.wpacked = L.w_halo_phase;
       h.phase_mode = 1;
       fb::halo_fill_steps_phase(h);
-      FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 8, x1.H / 16, x1.W / 8, &list, &active));
+      FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 8, x1.H / 16, x1.W / 8, &list, &active, &shifted));
       if (c->plan_mode == 1) return 0;
-      if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
+      if (list) { h.tile_list = list; h.tile_packed = shifted; h.num_m_tiles = static_cast<int>(active); }
       c->flops += static_cast<double>(active) * (16 * 8 * 4) * L.flops_px;
       rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
       if (rc != 0) return fail(c, rc, "phase conv (halo) launch failed (code " + std::to_string(rc) + ")");
@@ -662,9 +668,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     a.up2_out = 0;
     a.phase_mode = 1;
     if (out.up2 || out.elem != 2 || !fb::conv_tma_eligible(a)) return fail(c, FB_ERR_INVALID, "internal: phase-form conv not eligible");
-    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 8, 16, Hout / 16, Wout / 32, &list, &active));
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 8, 16, Hout / 16, Wout / 32, &list, &active, &shifted));
     if (c->plan_mode == 1) return 0;
-    if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }
+    if (list) { a.tile_list = list; a.tile_packed = shifted; a.tile_list_len = static_cast<int>(active); }
     c->flops += static_cast<double>(active) * (8 * 16 * 4) * L.flops_px;
     rc = fb::launch_conv(a, L.w_phase, L.Kp_phase, true, c->num_sms, c->stream);
     if (rc != 0) return fail(c, rc, "phase conv launch failed (code " + std::to_string(rc) + ")");
@@ -699,9 +705,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     h.pair = c->no_hpair ? 0 : 1;
     fb::halo_fill_steps(h, L.KH, L.stride);
     const int tw = 8 * fb::halo_blocks(L.KH, fb::halo_group_channels(L.KH, C1, C2) / 8, L.Cout);
-    FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active));
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active, &shifted));
     if (c->plan_mode == 1) return 0;
-    if (list) { h.tile_list = list; h.num_m_tiles = static_cast<int>(active); }
+    if (list) { h.tile_list = list; h.tile_packed = shifted; h.num_m_tiles = static_cast<int>(active); }
     c->flops += static_cast<double>(active) * (16 * tw) * L.flops_px;
     if (sink && need && out.elem == 4 && (L.Cout == 16 || L.Cout == 32) && h.direct_store && !out.up2) {
       h.sink_tiles = need->tiles_dev;
@@ -738,9 +744,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     const bool pair_layer = (pair_sel == 1 || pair_sel == fb::conv_pick_bn(L.Cout)) && L.KH == 3 && L.stride == 1 && Hout % 16 == 0 &&
                             fb::conv_pick_bn(L.Cout) >= 64;
     if (tma && !pair_layer) {
-      FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active));
+      FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active, &shifted));
       if (c->plan_mode == 1) return 0;
-      if (list) { a.tile_list = list; a.tile_list_len = static_cast<int>(active); }
+      if (list) { a.tile_list = list; a.tile_packed = shifted; a.tile_list_len = static_cast<int>(active); }
       c->flops += static_cast<double>(active) * (8 * 16) * L.flops_px;
     } else {
       if (c->plan_mode == 1) return 0;
@@ -977,6 +983,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_d2s = nd && nd[0] == '1';
   const char* npf = getenv("FB_NO_POOL_FUSE");
   c->no_pool_fuse = npf && npf[0] == '1';
+  const char* alt = getenv("FB_ALIGNED_TILES");
+  c->aligned_tiles = alt && alt[0] == '1';
   const char* nhp = getenv("FB_NO_HPAIR");
   c->no_hpair = nhp && nhp[0] == '1';
   const char* da = getenv("FB_D2S_ALL");

@@ -255,6 +255,14 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
     }
     return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i;
   };
+  // tile -> image and origin (row, column) on the tile grid; packed entries carry the origin themselves (tile_need.cuh)
+  auto tile_pos = [&](int tile, int& b, int& ty0, int& tx0) {
+    if (!PAIR && !POOL && p.tile_packed) {
+      unpack_tile_origin(static_cast<uint32_t>(tile), b, ty0, tx0);
+    } else {
+      tx0 = (tile % tiles_w) * G::TW; ty0 = ((tile / tiles_w) % tiles_h) * kTH; b = tile / (tiles_w * tiles_h);
+    }
+  };
   // this CTA's (pair's) schedule: positions sched0, sched0 + sched_step, ... < sched_end
   const int sched0 = POOL ? 0 : PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int sched_step = POOL ? 1 : PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -273,8 +281,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         uint32_t it = 0;
         for (int ti = sched0; ti < sched_end; ti += sched_step) {
           const int tile = tile_of(ti);
-          const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
-          const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
+          int b, ty0, tx0;
+          tile_pos(tile, b, ty0, tx0);
+          const int ih0 = ty0 * STRIDE - G::PAD, iw0 = tx0 * STRIDE - G::PAD;
           for (int g = 0; g < groups; ++g, ++it) {
             const int s = it % S;
             mbar_wait_relaxed(empty_bar(s), ((it / S) & 1) ^ 1);
@@ -325,11 +334,12 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
     auto prefetch_tile = [&](int t) {
       if (t >= sched_end || p.no_prefetch || p.up1) return;
       t = tile_of(t);
-      const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
-      const int iw0 = tw * G::TW * STRIDE - G::PAD;
+      int b, ty0, tx0;
+      tile_pos(t, b, ty0, tx0);
+      const int iw0 = tx0 * STRIDE - G::PAD;
       const int w_lo = iw0 < 0 ? 0 : iw0, w_hi = iw0 + G::KWCELLS < p.Win ? iw0 + G::KWCELLS : p.Win;
       for (int r = tid; r < G::PH * nsrc; r += kProd) {
-        const int sidx = r / G::PH, ih = th * kTH * STRIDE - G::PAD + r % G::PH;
+        const int sidx = r / G::PH, ih = ty0 * STRIDE - G::PAD + r % G::PH;
         if (static_cast<unsigned>(ih) >= static_cast<unsigned>(p.Hin)) continue;
         const int Cs = sidx ? p.C2 : p.C1;
         const __nv_bfloat16* row = (sidx ? p.x2 : p.x1) + ((static_cast<long long>(b) * p.Hin + ih) * p.Win + w_lo) * Cs;
@@ -345,8 +355,9 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       prefetch_tile(ti + kPrefetchDist * sched_step);
       const int tile = tile_next;
       if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
-      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
-      const int ih0 = th * kTH * STRIDE - G::PAD, iw0 = tw * G::TW * STRIDE - G::PAD;
+      int b, ty0, tx0;
+      tile_pos(tile, b, ty0, tx0);
+      const int ih0 = ty0 * STRIDE - G::PAD, iw0 = tx0 * STRIDE - G::PAD;
       const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + G::PH <= p.Hin && iw0 + G::KWCELLS <= p.Win;
       const long long origin = (static_cast<long long>(b) * p.Hin + ih0) * p.Win + iw0;  // may be "negative"
       for (int g = 0; g < groups; ++g, ++it) {
@@ -511,8 +522,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
           // The stem's own output goes to global memory from this group's registers (the pooling group is the slower
           // stage of the pipeline). In the exact-clipping loop only the part that dec3.conv1 (layer 6 of tile_need.cuh)
-          // reads for this image is stored: its needed region, widened to the 16 x 16 kernel tiles that conv runs and
-          // their one-pixel halo.
+          // reads for this image's live outputs is stored: its needed region and the one-pixel halo of the 3x3 window
+          // (the dead outputs of that conv's edge tiles read stale pixels; nothing live depends on them).
           // (recomputed when the image changes, i.e. once per 256 tiles: the table look-up and the walk through the
           // decoder's regions were a third of this group's time when done per tile)
           if (p.keep_tiles != nullptr && tb != keep_tb) {
@@ -521,8 +532,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
             const int x0 = __ldg(kt), y0 = __ldg(kt + 1);
             const NeedRect r = need_rect(p.keep_T, 6, __ldg(kt + 2) - x0, __ldg(kt + 3) - y0, __ldg(kt + 4) - x0, __ldg(kt + 5) - y0);
             const bool any = r.x1 > r.x0 && r.y1 > r.y0;
-            kx0 = any ? (r.x0 & ~15) - 1 : 0; ky0 = any ? (r.y0 & ~15) - 1 : 0;
-            kx1 = any ? ((r.x1 + 15) & ~15) + 1 : 0; ky1 = any ? ((r.y1 + 15) & ~15) + 1 : 0;
+            kx0 = any ? r.x0 - 1 : 0; ky0 = any ? r.y0 - 1 : 0;
+            kx1 = any ? r.x1 + 1 : 0; ky1 = any ? r.y1 + 1 : 0;
           }
           const int oy = th * kTH + dh;
           const bool row_kept = oy >= ky0 && oy < ky1 && !(p.debug_skip & 4);
@@ -652,7 +663,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
     for (int ti = sched0; ti < sched_end; ti += sched_step, ++tcount) {
       const int tile = tile_next;
       if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
-      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
+      int tb, ty0, tx0;
+      tile_pos(tile, tb, ty0, tx0);
       const int as = tcount % NACC;
       const uint32_t aph = (tcount / NACC) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
@@ -680,7 +692,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         }
       };
       if (D2S || SB || p.direct_store) {
-        const int oh = th * kTH + L.own_dh, ow = tw * G::TW + L.own_dw;
+        const int oh = ty0 + L.own_dh, ow = tx0 + L.own_dw;
         int sink_x0 = 0, sink_y0 = 0, sink_wx0 = 0, sink_wy0 = 0, sink_wx1 = 0, sink_wy1 = 0;
         float sink_best = 0.f, sink_den = 0.f;
         int sink_arg = 0;
@@ -815,8 +827,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
           const int pa = m >> 1, pb = m & 1;
-          uint8_t* blk_dst = out_bytes + static_cast<size_t>((static_cast<long long>(tb) * p.Hout + 2 * th * kTH + pa) * p.Wout +
-                                                             2 * tw * G::TW + pb) * pixel_bytes;
+          uint8_t* blk_dst = out_bytes + static_cast<size_t>((static_cast<long long>(tb) * p.Hout + 2 * ty0 + pa) * p.Wout +
+                                                             2 * tx0 + pb) * pixel_bytes;
           auto copy = [&](auto run, int col0, int el) {
             if (p.debug_skip & 4) return;
             warp_copy_out_fast<decltype(run)::value>(stg, lane, L, blk_dst + static_cast<size_t>(col0) * el, pixel_bytes, 0, 0);
@@ -827,11 +839,11 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         tempty_arrive(tempty_bar(as));
         continue;
       }
-      const int oh = th * kTH + L.own_dh;
-      const long long pix0 = (static_cast<long long>(tb) * p.Hout + th * kTH) * p.Wout + tw * G::TW;
-      const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * kTH * 2) * (2 * p.Wout) + tw * G::TW * 2;
+      const int oh = ty0 + L.own_dh;
+      const long long pix0 = (static_cast<long long>(tb) * p.Hout + ty0) * p.Wout + tx0;
+      const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + ty0 * 2) * (2 * p.Wout) + tx0 * 2;
       uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
-      const long long own_pix0 = (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + tw * G::TW + L.own_dw;
+      const long long own_pix0 = (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + tx0 + L.own_dw;
 #pragma unroll
       for (int m = 0; m < MB; ++m) {  // block m = columns 8m..8m+7 of the tile
         uint8_t* blk_dst = tile_dst + static_cast<size_t>(p.up2_out ? 16 * m : 8 * m) * pixel_bytes;

@@ -84,6 +84,7 @@ struct HaloArgs {
   // Active-tile list (tile_need.cuh): when non-null the kernel walks tile_list[0 .. num_m_tiles) instead of the
   // full tile grid; every entry is a linear (image, tile row, tile column) index of the full grid.
   const int* tile_list;
+  int tile_packed;               // 1: the entries are pack_tile_origin() words of origin-shifted tiles (tile_need.cuh, need_span)
   // Fused class-map sink of the segmentation head (Cout == 16 or 32, out_f32 set but never written): instead of
   // storing the fp32 logits of its pixel, a lane takes their soft-max maximum / arg-max (first maximum, numpy
   // semantics; confidence byte = round-half-up of the max probability) and, when the pixel lies inside the write

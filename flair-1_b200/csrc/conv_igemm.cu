@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "conv_epilogue.cuh"
+#include "tile_need.cuh"
 #include "ptx.cuh"
 
 namespace fb {
@@ -115,8 +116,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int m_tile = m_next;
           if (tile + static_cast<int>(gridDim.x) < num_tiles) m_next = m_tile_of(tile + gridDim.x);
           const int pa = p.phase_mode ? (phase >> 1) : 0, pb = p.phase_mode ? (phase & 1) : 0;
-          const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h;
-          const int b = m_tile / (tiles_w * tiles_h);
+          int b, ty0, tx0;   // image and box origin on the tile grid
+          if (p.tile_packed) {
+            unpack_tile_origin(static_cast<uint32_t>(m_tile), b, ty0, tx0);
+          } else {
+            tx0 = (m_tile % tiles_w) * 16; ty0 = ((m_tile / tiles_w) % tiles_h) * 8; b = m_tile / (tiles_w * tiles_h);
+          }
           for (int kit = 0; kit < nk; ++kit, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
@@ -127,7 +132,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int dx = static_cast<int>((e >> 8) & 15) - 8 + pb, dy = static_cast<int>((e >> 12) & 15) - 8 + pa;
             const int sc = p.tm_scale[src];
             const uint32_t a_dst = base + s * C::kStageBytes;
-            tma_load_4d(a_dst, src ? &tmA2 : &tmA, full_bar(s), cc * 64, tw * 16 * sc + dx, th * 8 * sc + dy, b);
+            tma_load_4d(a_dst, src ? &tmA2 : &tmA, full_bar(s), cc * 64, tx0 * sc + dx, ty0 * sc + dy, b);
             tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, phase * p.Cout + n_tile * BN);
           }
         }
@@ -228,12 +233,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + grp * BNE;
       const int n0 = n_tile * BN + grp * BNE;   // first output channel this warp drains
       if (TMA_A) {
-        const int tw = m_tile % tiles_w, th = (m_tile / tiles_w) % tiles_h, tb = m_tile / (tiles_w * tiles_h);
+        int tb, ty0, tx0;
+        if (p.tile_packed) {
+          unpack_tile_origin(static_cast<uint32_t>(m_tile), tb, ty0, tx0);
+        } else {
+          tx0 = (m_tile % tiles_w) * 16; ty0 = ((m_tile / tiles_w) % tiles_h) * 8; tb = m_tile / (tiles_w * tiles_h);
+        }
         const int pa = phase >> 1, pb = phase & 1;
         const int psc = phases == 4 ? 2 : 1;   // output pixel = psc * tile-grid pixel + (pa, pb)
-        const int oh = psc * (th * 8 + L.own_dh) + pa, ow = psc * (tw * 16 + L.own_dw) + pb;
-        const long long pix0 = (static_cast<long long>(tb) * p.Hout + psc * th * 8 + pa) * p.Wout + psc * tw * 16 + pb;
-        const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + th * 16) * (2 * p.Wout) + tw * 32;
+        const int oh = psc * (ty0 + L.own_dh) + pa, ow = psc * (tx0 + L.own_dw) + pb;
+        const long long pix0 = (static_cast<long long>(tb) * p.Hout + psc * ty0 + pa) * p.Wout + psc * tx0 + pb;
+        const long long up0 = (static_cast<long long>(tb) * 2 * p.Hout + ty0 * 2) * (2 * p.Wout) + tx0 * 2;
         uint8_t* tile_dst = out_bytes + static_cast<size_t>(p.up2_out ? up0 : pix0) * pixel_bytes;
         if (p.direct_store) {
           // every lane stores its own pixel from registers, one 32-byte sector per instruction (no staging)

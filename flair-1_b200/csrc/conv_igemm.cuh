@@ -69,6 +69,7 @@ struct ConvArgs {
   // boxes tile_list[i] = (b * tgrid_h/8 + th) * tgrid_w/16 + tw instead of the full tile grid.
   const int* tile_list;
   int tile_list_len;
+  int tile_packed;   // 1: entries are pack_tile_origin() words of origin-shifted boxes (tile_need.cuh, need_span)
 };
 
 // Launch one convolution. `use_tma_a` requires conv_tma_eligible(a). Returns cudaError_t as int.

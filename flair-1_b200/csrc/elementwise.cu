@@ -688,11 +688,20 @@ build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __gri
   for (int b = threadIdx.x; b < n; b += blockDim.x) {
     const int* t = tiles + 6 * b;
     const NeedRect r = need_rect(T, sp.layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
-    NeedRect k = need_tile_range(r, sp.scale, sp.th, sp.tw);
-    if (k.x1 > sp.gw) k.x1 = sp.gw;
-    if (k.y1 > sp.gh) k.y1 = sp.gh;
+    NeedRect k;
+    if (sp.shifted) {
+      // rng = origin (x0, y0) and tile counts (x1, y1) of the shifted cover
+      const NeedRect g = need_on_tile_grid(r, sp.scale);
+      const NeedSpan sx = need_span(g.x0, g.x1, sp.tw, sp.gw * sp.tw), sy = need_span(g.y0, g.y1, sp.th, sp.gh * sp.th);
+      k.x0 = sx.o; k.y0 = sy.o; k.x1 = sx.n; k.y1 = sy.n;
+      off[b + 1] = sx.n * sy.n;
+    } else {
+      k = need_tile_range(r, sp.scale, sp.th, sp.tw);
+      if (k.x1 > sp.gw) k.x1 = sp.gw;
+      if (k.y1 > sp.gh) k.y1 = sp.gh;
+      off[b + 1] = (k.x1 - k.x0) * (k.y1 - k.y0);
+    }
     rng[b] = k;
-    off[b + 1] = (k.x1 - k.x0) * (k.y1 - k.y0);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -703,8 +712,10 @@ build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = warp; b < n; b += blockDim.x >> 5) {
     const NeedRect k = rng[b];
-    const int nx = k.x1 - k.x0, cnt = off[b + 1] - off[b];
-    for (int i = lane; i < cnt; i += 32) list[off[b] + i] = (b * sp.gh + k.y0 + i / nx) * sp.gw + k.x0 + i % nx;
+    const int nx = sp.shifted ? k.x1 : k.x1 - k.x0, cnt = off[b + 1] - off[b];
+    for (int i = lane; i < cnt; i += 32)
+      list[off[b] + i] = sp.shifted ? static_cast<int>(pack_tile_origin(b, k.y0 + (i / nx) * sp.th, k.x0 + (i % nx) * sp.tw))
+                                    : (b * sp.gh + k.y0 + i / nx) * sp.gw + k.x0 + i % nx;
   }
 }
 
@@ -716,13 +727,18 @@ int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPl
   return static_cast<int>(cudaGetLastError());
 }
 
-long long count_active_tiles(const int* tiles, int n, int T, int layer, int scale, int th, int tw) {
+long long count_active_tiles(const int* tiles, int n, int T, int layer, int scale, int th, int tw, bool shifted) {
   const int S = layer >= 10 ? T : (T / 16) << (layer / 2);
   const int gh = (S / scale) / th, gw = (S / scale) / tw;
   long long total = 0;
   for (int b = 0; b < n; ++b) {
     const int* t = tiles + 6 * b;
     const NeedRect r = need_rect(T, layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
+    if (shifted) {
+      const NeedRect g = need_on_tile_grid(r, scale);
+      total += static_cast<long long>(need_span(g.x0, g.x1, tw, gw * tw).n) * need_span(g.y0, g.y1, th, gh * th).n;
+      continue;
+    }
     NeedRect k = need_tile_range(r, scale, th, tw);
     if (k.x1 > gw) k.x1 = gw;
     if (k.y1 > gh) k.y1 = gh;

@@ -65,12 +65,46 @@ __host__ __device__ inline NeedRect need_tile_range(NeedRect r, int scale, int t
   return t;
 }
 
+// Origin-shifted tiling of one axis. The fixed tile grid wastes up to a tile on each side of a needed span (an
+// interior zone tile needs 258 of dec4's 512 columns = 9 kernel tiles of 32, but the grid-aligned cover is 10; for
+// the deep decoder layers 68 of 128 -> 5 tiles of 16 instead of 6, 36 of 64 -> 3 of 16 instead of 4). The kernels
+// take their tile ORIGINS from the list, so the cover may start at the span itself: n = ceil(len / t) tiles from
+// origin o = min(lo, extent - n * t) -- pulled back at the far edge so that no tile leaves the grid (extent is a
+// multiple of t) and no store needs masking. lo / hi / extent in tile-grid units.
+struct NeedSpan { int o, n; };
+__host__ __device__ inline NeedSpan need_span(int lo, int hi, int t, int extent) {
+  NeedSpan s;
+  s.n = hi > lo ? (hi - lo + t - 1) / t : 0;
+  s.o = lo < extent - s.n * t ? lo : extent - s.n * t;
+  return s;
+}
+// rect r of a layer's output grid -> [lo, hi) on the tile grid (= output grid / scale) of each axis
+__host__ __device__ inline NeedRect need_on_tile_grid(NeedRect r, int scale) {
+  if (r.x1 <= r.x0 || r.y1 <= r.y0) { r.x0 = r.y0 = r.x1 = r.y1 = 0; return r; }
+  const int sh = scale == 2 ? 1 : 0;
+  r.x0 >>= sh; r.y0 >>= sh;
+  r.x1 = ((r.x1 - 1) >> sh) + 1; r.y1 = ((r.y1 - 1) >> sh) + 1;
+  return r;
+}
+// list entry of an origin-shifted tile: image | origin row | origin column on the tile grid
+constexpr int kTileOriginBits = 11;   // grids up to 2047; 10 bits of image index
+__host__ __device__ inline uint32_t pack_tile_origin(int b, int y0, int x0) {
+  return (static_cast<uint32_t>(b) << (2 * kTileOriginBits)) | (static_cast<uint32_t>(y0) << kTileOriginBits) | static_cast<uint32_t>(x0);
+}
+__host__ __device__ inline void unpack_tile_origin(uint32_t e, int& b, int& y0, int& x0) {
+  x0 = static_cast<int>(e & ((1u << kTileOriginBits) - 1));
+  y0 = static_cast<int>((e >> kTileOriginBits) & ((1u << kTileOriginBits) - 1));
+  b = static_cast<int>(e >> (2 * kTileOriginBits));
+}
+
 // One conv launch's kernel tiling: tiles of th x tw pixels on the tile grid (= output grid / scale), gh x gw of them
-// per image; its active tiles go to list[offset .. offset + count), entries (b * gh + ty) * gw + tx, images in order.
+// per image; its active tiles go to list[offset .. offset + count), images in order. Entries: (b * gh + ty) * gw + tx
+// of the fixed grid, or -- shifted != 0 -- pack_tile_origin() of origin-shifted tiles (need_span).
 struct TileListSpec {
   int layer, scale, th, tw, gh, gw;
   int offset, count;
   int use;   // 0: every tile is active, no list is built
+  int shifted;
 };
 struct TileListPlan {
   TileListSpec spec[kNeedLayers];
@@ -81,6 +115,6 @@ struct TileListPlan {
 int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPlan& plan, int* list_dev,
                             cudaStream_t stream);
 // The count of one list on the host (tiles = host copy of the same table).
-long long count_active_tiles(const int* tiles_host, int n, int T, int layer, int scale, int th, int tw);
+long long count_active_tiles(const int* tiles_host, int n, int T, int layer, int scale, int th, int tw, bool shifted);
 
 }  // namespace fb
