@@ -95,6 +95,7 @@ _SIGNATURES = {
     "fb_flop_count": (C.c_double, [C.c_void_p]),
     "fb_logit_stride": (C.c_int, [C.c_void_p]),
     "fb_debug_need_rect": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    "fb_debug_tile_cover": (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int32)]),
     "fb_lzw_bound": (C.c_int64, [C.c_int64]),
     "fb_lzw_encode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "fb_lzw_decode": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),

@@ -96,6 +96,7 @@ struct fb_ctx {
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
   bool aligned_tiles = false; // FB_ALIGNED_TILES=1: active kernel tiles on the fixed tile grid instead of origin-shifted (tile_need.cuh)
+  bool dec_pair = false;      // FB_DEC_PAIR=1: dec0 stays on the CTA-pair kernel (no tile lists) under origin-shifted tiles
   bool no_pool_fuse = false;  // FB_NO_POOL_FUSE=1: the stem's max-pool as a kernel of its own
   bool no_hpair = false;      // FB_NO_HPAIR=1: halo kernel always as single CTAs (no cta_group::2 pairs)
   bool d2s_all = false;       // FB_D2S_ALL=1: also dec4.conv2 (bf16 output) in depth-to-space form
@@ -743,7 +744,10 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     const int pair_sel = pair_env ? atoi(pair_env) : 256;
     const bool pair_layer = (pair_sel == 1 || pair_sel == fb::conv_pick_bn(L.Cout)) && L.KH == 3 && L.stride == 1 && Hout % 16 == 0 &&
                             fb::conv_pick_bn(L.Cout) >= 64;
-    if (tma && !pair_layer) {
+    // ... except dec0 under origin-shifted tiles: an interior zone tile needs 22 of its 32 rows / columns = 3 x 2 boxes of
+    // 8 x 16 instead of 4 x 2, which the single-CTA kernel can skip and the pair kernel (16 x 16 per pair) cannot
+    const bool listed = need && need->restrict_tiles && layer >= 0 && !c->aligned_tiles && !c->dec_pair;
+    if (tma && (!pair_layer || listed)) {
       FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active, &shifted));
       if (c->plan_mode == 1) return 0;
       if (list) { a.tile_list = list; a.tile_packed = shifted; a.tile_list_len = static_cast<int>(active); }
@@ -983,6 +987,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_d2s = nd && nd[0] == '1';
   const char* npf = getenv("FB_NO_POOL_FUSE");
   c->no_pool_fuse = npf && npf[0] == '1';
+  const char* dpr = getenv("FB_DEC_PAIR");
+  c->dec_pair = dpr && dpr[0] == '1';
   const char* alt = getenv("FB_ALIGNED_TILES");
   c->aligned_tiles = alt && alt[0] == '1';
   const char* nhp = getenv("FB_NO_HPAIR");
@@ -1035,6 +1041,17 @@ int fb_debug_need_rect(int tile, int layer, int ax0, int ay0, int ax1, int ay1, 
   if (!rect4 || tile <= 0 || tile % 32 != 0 || layer < 0 || layer >= fb::kNeedLayers) return FB_ERR_INVALID;
   const fb::NeedRect r = fb::need_rect(tile, layer, ax0, ay0, ax1, ay1);
   rect4[0] = r.x0; rect4[1] = r.y0; rect4[2] = r.x1; rect4[3] = r.y1;
+  return 0;
+}
+
+int fb_debug_tile_cover(int tile, int layer, int scale, int th, int tw, int ax0, int ay0, int ax1, int ay1, int32_t* cover4) {
+  if (!cover4 || tile <= 0 || tile % 32 != 0 || layer < 0 || layer >= fb::kNeedLayers || (scale != 1 && scale != 2) || th <= 0 || tw <= 0)
+    return FB_ERR_INVALID;
+  const int S = (layer >= 10 ? tile : (tile / 16) << (layer / 2)) / scale;   // tile-grid extent of the layer
+  if (S % th != 0 || S % tw != 0) return FB_ERR_INVALID;
+  const fb::NeedRect g = fb::need_on_tile_grid(fb::need_rect(tile, layer, ax0, ay0, ax1, ay1), scale);
+  const fb::NeedSpan sx = fb::need_span(g.x0, g.x1, tw, S), sy = fb::need_span(g.y0, g.y1, th, S);
+  cover4[0] = sx.o; cover4[1] = sy.o; cover4[2] = sx.n; cover4[3] = sy.n;
   return 0;
 }
 

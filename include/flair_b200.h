@@ -258,6 +258,10 @@ double fb_flop_count(const fb_ctx* ctx);
  * dec<d>.conv2, 10 = segmentation head) that a tile x tile input needs when only [ax0,ax1) x [ay0,ay1) of its
  * logits is used (csrc/tile_need.cuh, dead-output elimination). rect4 = x0, y0, x1, y1 in that layer's output grid. */
 int fb_debug_need_rect(int tile, int layer, int ax0, int ay0, int ax1, int ay1, int32_t* rect4);
+/* Origin-shifted kernel-tile cover of that region (csrc/tile_need.cuh, need_span): kernel tiles of th x tw on the tile
+ * grid (= the layer's output grid / scale, scale 1 or 2). cover4 = origin column, origin row, tile columns, tile rows,
+ * in tile-grid units; the cover contains the region, stays inside the grid and uses the fewest tiles per axis. */
+int fb_debug_tile_cover(int tile, int layer, int scale, int th, int tw, int ax0, int ay0, int ax1, int ay1, int32_t* cover4);
 
 /* ---- host-side TIFF LZW codec (compression 5, libtiff/GDAL-compatible) used by the GeoTIFF
  *      reader/writer that stands in for rasterio (main.py:218-232, 421-426; writer.py:38-50).

@@ -524,9 +524,10 @@ def test_dead_output_elimination_and_fused_sink_are_bit_exact(trained_3_15, monk
     raster = torch.from_numpy(synth.synth_raster(3, H, W, seed=W * 3 + H)).cuda()
     tiles = tile_table(W, H, T, margin)
     res = {}
-    for mode in ("plain", "fast"):
+    for mode in ("plain", "fast", "aligned"):   # aligned: active kernel tiles on the fixed tile grid (FB_ALIGNED_TILES=1)
         monkeypatch.setenv("FB_FULL_TILES", "1" if mode == "plain" else "0")
         monkeypatch.setenv("FB_NO_FUSED_SINK", "1" if mode == "plain" else "0")
+        monkeypatch.setenv("FB_ALIGNED_TILES", "1" if mode == "aligned" else "0")
         c = nat.Context(0)
         c.load_weights(sd, 3, 15)
         c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
@@ -544,10 +545,14 @@ def test_dead_output_elimination_and_fused_sink_are_bit_exact(trained_3_15, monk
     np.testing.assert_array_equal(res["fast"][0], res["plain"][0])
     np.testing.assert_array_equal(res["fast"][1], res["plain"][1])
     np.testing.assert_array_equal(res["fast"][2], res["plain"][2])
+    for k in range(3):
+        np.testing.assert_array_equal(res["aligned"][k], res["plain"][k])
+    assert res["fast"][3] <= res["aligned"][3]   # origin-shifted tiles never compute more than grid-aligned ones
     assert (res["fast"][0] < 15).all()
     per_tile = res["plain"][3] / len(tiles) / 1e9
     print(f"zone {W}x{H} T={T} m={margin}: {len(tiles)} tiles, {per_tile:.3f} GFLOP per tile in full, "
-          f"{res['fast'][3] / len(tiles) / 1e9:.3f} with dead-output elimination")
+          f"{res['aligned'][3] / len(tiles) / 1e9:.3f} with dead-output elimination on the fixed tile grid, "
+          f"{res['fast'][3] / len(tiles) / 1e9:.3f} with origin-shifted tiles")
     if T == 512:
         assert abs(per_tile - 63.569) < 0.01
     assert res["fast"][3] <= res["plain"][3]
@@ -776,9 +781,10 @@ def test_fused_sink_is_bit_exact_for_19_classes(monkeypatch):
     raster = torch.from_numpy(synth.synth_raster(3, H, W, seed=19)).cuda()
     tiles = tile_table(W, H, T, margin)
     res = {}
-    for mode in ("plain", "fast"):
+    for mode in ("plain", "fast", "aligned"):   # aligned: active kernel tiles on the fixed tile grid (FB_ALIGNED_TILES=1)
         monkeypatch.setenv("FB_FULL_TILES", "1" if mode == "plain" else "0")
         monkeypatch.setenv("FB_NO_FUSED_SINK", "1" if mode == "plain" else "0")
+        monkeypatch.setenv("FB_ALIGNED_TILES", "1" if mode == "aligned" else "0")
         c = nat.Context(0)
         c.load_weights(sd, 3, 19)
         c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])

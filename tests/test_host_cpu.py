@@ -405,6 +405,51 @@ def test_dead_output_regions_cover_the_receptive_field():
     assert lib.fb_debug_need_rect(512, 3, 10, 10, 10, 40, r) == 0 and list(r) == [0, 0, 0, 0]   # empty write rectangle
 
 
+def test_origin_shifted_tile_cover_contains_the_region_with_the_fewest_tiles():
+    """csrc/tile_need.cuh need_span (host half): the kernel tiles of a launch start at the needed region instead of on
+    the fixed tile grid. For every decoder layer, kernel tiling the library uses and random write rectangles the cover
+    must contain the region, stay inside the grid (no store masking in the kernels) and use ceil(len / tile) tiles
+    per axis -- never more than the grid-aligned cover."""
+    import ctypes as C
+    import flair1_b200._native as nat
+    lib = nat.load_library(build_if_missing=False)
+    rng = np.random.default_rng(3)
+    tilings = [(1, 16, 16), (1, 16, 8), (1, 16, 32), (1, 8, 16), (2, 16, 16), (2, 16, 8), (2, 8, 16)]
+    cases = [(512, 128, 128, 384, 384), (512, 0, 0, 384, 384), (512, 128, 128, 512, 512), (512, 0, 128, 512, 384), (256, 64, 64, 192, 192)]
+    for _ in range(40):
+        T = int(rng.choice([256, 512, 1024]))
+        x0, y0 = int(rng.integers(0, T - 1)), int(rng.integers(0, T - 1))
+        cases.append((T, x0, y0, int(rng.integers(x0 + 1, T + 1)), int(rng.integers(y0 + 1, T + 1))))
+    fewer = 0
+    for T, ax0, ay0, ax1, ay1 in cases:
+        for layer in range(11):
+            S_out = T if layer >= 10 else (T // 16) << (layer // 2)
+            r = (C.c_int32 * 4)()
+            assert lib.fb_debug_need_rect(T, layer, ax0, ay0, ax1, ay1, r) == 0
+            for scale, th, tw in tilings:
+                S = S_out // scale
+                cov = (C.c_int32 * 4)()
+                rc = lib.fb_debug_tile_cover(T, layer, scale, th, tw, ax0, ay0, ax1, ay1, cov)
+                if S % th or S % tw:
+                    assert rc != 0
+                    continue
+                assert rc == 0
+                ox, oy, nx, ny = cov
+                lo_x, hi_x = r[0] // scale, (r[2] - 1) // scale + 1
+                lo_y, hi_y = r[1] // scale, (r[3] - 1) // scale + 1
+                assert 0 <= ox <= lo_x and hi_x <= ox + nx * tw <= S, (T, layer, scale, tw, list(r), list(cov))
+                assert 0 <= oy <= lo_y and hi_y <= oy + ny * th <= S, (T, layer, scale, th, list(r), list(cov))
+                assert nx == -(-(hi_x - lo_x) // tw) and ny == -(-(hi_y - lo_y) // th)
+                aligned = ((hi_x - 1) // tw - lo_x // tw + 1) * ((hi_y - 1) // th - lo_y // th + 1)
+                assert nx * ny <= aligned
+                fewer += nx * ny < aligned
+    assert fewer > 0
+    # the interior tile of the bench zone: dec2.conv2 (128^2 grid, 16 x 16 tiles) needs 68 pixels = 5 tiles from column 30
+    cov = (C.c_int32 * 4)()
+    assert lib.fb_debug_tile_cover(512, 5, 1, 16, 16, 128, 128, 384, 384, cov) == 0 and list(cov) == [30, 30, 5, 5]
+    assert lib.fb_debug_tile_cover(512, 5, 1, 16, 16, 256, 256, 512, 512, cov) == 0 and list(cov) == [48, 48, 5, 5]   # pulled back at the far edge
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """bench.py --impl reference (the CPU path: the oracle port on the host cores) on a two-tile sample: exactly one
     line on stdout, carrying the keys of the measurement contract."""
