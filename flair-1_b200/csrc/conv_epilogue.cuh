@@ -27,12 +27,13 @@ namespace fb {
 // four dependent levels instead of fifteen, which is what paces the head's epilogue (ncu: its warps sit in fixed-latency
 // dependency stalls). Shared by the fused class-map sinks of the halo kernel and by K6 (argmax_stitch_kernel), so the
 // two paths keep writing identical bytes.
-__device__ __forceinline__ void softmax_max16(const float (&v)[16], int ncls, int col0, float& best, int& arg, float& den) {
+// (unmasked core: every one of the 16 values takes part)
+__device__ __forceinline__ void softmax_max16_all(const float (&v)[16], int col0, float& best, int& arg, float& den) {
   float m[16];
   int ix[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    m[k] = col0 + k < ncls ? v[k] : -3.0e38f;
+    m[k] = v[k];
     ix[k] = col0 + k;
   }
 #pragma unroll
@@ -48,13 +49,23 @@ __device__ __forceinline__ void softmax_max16(const float (&v)[16], int ncls, in
   arg = ix[0];
   float e[16];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) e[k] = col0 + k < ncls ? __expf(v[k] - best) : 0.f;
+  for (int k = 0; k < 16; ++k) e[k] = __expf(v[k] - best);
 #pragma unroll
   for (int w = 1; w < 16; w <<= 1) {
 #pragma unroll
     for (int k = 0; k < 16; k += 2 * w) e[k] += e[k + w];
   }
   den = e[0];
+}
+// Columns at or beyond ncls are replaced by kSoftmaxMasked: they never win the maximum and their exponential is exactly
+// zero, so a caller that already holds kSoftmaxMasked in those columns (the depth-to-space head folds it into its bias
+// vector) gets the same bytes from softmax_max16_all without the 32 selects.
+constexpr float kSoftmaxMasked = -3.0e38f;
+__device__ __forceinline__ void softmax_max16(const float (&v)[16], int ncls, int col0, float& best, int& arg, float& den) {
+  float m[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) m[k] = col0 + k < ncls ? v[k] : kSoftmaxMasked;
+  softmax_max16_all(m, col0, best, arg, den);
 }
 
 constexpr int kStgPitch = 144;                 // bytes per staged pixel row (128 + 16: conflict-free 16 B stores)

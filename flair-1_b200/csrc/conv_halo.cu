@@ -194,7 +194,11 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + i);
       }
     }
-    if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+    // (depth-to-space head with the class-map sink: the padded class columns of every pixel carry kSoftmaxMasked, so the
+    // sink's soft-max needs no per-class selects)
+    if (threadIdx.x < BN)
+      bias_s[threadIdx.x] = (D2S && p.sink_cls != nullptr && static_cast<int>(threadIdx.x & 15) >= p.sink_ncls) ? kSoftmaxMasked
+                                                                                                         : p.bias[threadIdx.x];
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -727,6 +731,43 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           } else if (has_res && kResBuf != MB && m + 1 < MB) {
             load_residual_row<BN>(res_row0 + 8 * (m + 1) * BN, rbuf[(m + 1) % kResBuf]);
           }
+          if constexpr (D2S) {
+            if (p.sink_cls != nullptr) {
+              // Fused K6 of the depth-to-space head: the lane's cell = four pixels x 16 class columns. All 64 columns are
+              // read first and the four soft-max maxima are straight-line code without branches in between, so their
+              // dependency chains (compare trees, exponentials, sums) interleave: with two epilogue warps per scheduler
+              // the per-pixel version (one chain at a time, a branch per pixel) ran at 0.4 instructions per cycle and
+              // cost the head 180 of its 293 us per 148 tiles.
+              mbar_wait_relaxed(tfull_bar(as), aph);
+              tc_fence_after_sync();
+              uint32_t acc[4][16];
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) tmem_ld_x16(taddr + m * BN + 16 * g4, acc[g4]);
+              tmem_ld_wait();
+              if (!(p.debug_skip & 4)) {
+                int arg4[4];
+                float den4[4];
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                  float v[16], best;
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(acc[g4][k]) + bias_s[16 * g4 + k];
+                  softmax_max16_all(v, 0, best, arg4[g4], den4[g4]);
+                }
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                  // pixel (2*oh + py, 2*(ow + 8m) + px) of image tb; only inside the write rectangle
+                  const int rx = sink_x0 + 2 * (ow + 8 * m) + (g4 & 1), ry = sink_y0 + 2 * oh + (g4 >> 1);
+                  if (rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1) {
+                    const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
+                    p.sink_cls[o] = static_cast<uint8_t>(arg4[g4]);
+                    if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den4[g4] + 0.5f);
+                  }
+                }
+              }
+              continue;
+            }
+          }
           long long dpix, own_pix = 0;
           if (PH) {
             dpix = (static_cast<long long>(tb) * p.Hout + 2 * oh + (m >> 1)) * p.Wout + 2 * ow + (m & 1);
@@ -741,20 +782,6 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
               // columns col0 .. col0 + 15 = the 16 channels of pixel (2*oh + py, 2*(ow + 8m) + px) of the cell
               const int grp = col0 >> 4;
               const int y = 2 * oh + (grp >> 1), x = 2 * (ow + 8 * m) + (grp & 1);
-              if constexpr (sizeof(regs) == 64) {
-                if (p.sink_cls != nullptr) {
-                  // fused K6 (see below), one pixel per 16-column group
-                  const int rx = sink_x0 + x, ry = sink_y0 + y;
-                  if (!(rx >= sink_wx0 && rx < sink_wx1 && ry >= sink_wy0 && ry < sink_wy1)) return;
-                  float best, den;
-                  int arg;
-                  softmax_max16(regs, p.sink_ncls, 0, best, arg, den);
-                  const long long o = (static_cast<long long>(ry) - p.sink_map_row0) * p.sink_map_w + rx;
-                  p.sink_cls[o] = static_cast<uint8_t>(arg);
-                  if (p.sink_conf != nullptr) p.sink_conf[o] = static_cast<uint8_t>(1.f / den + 0.5f);
-                  return;
-                }
-              }
               store_regs(out_bytes + ((static_cast<size_t>(tb) * p.Hout + y) * p.Wout + x) * (16 * elem), regs);
               return;
             }
@@ -1311,6 +1338,7 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     if (!halo_d2s_supported(a.d2s, a.C1, a.C2, 16, a.Hout, a.Wout) || a.Cout != 64 || a.residual || a.rowbias || a.up2_out ||
         a.up1 || a.phase_mode || (a.d2s == 1 ? (a.Hin != a.Hout || a.Win != a.Wout) : (2 * a.Hin != a.Hout || 2 * a.Win != a.Wout)))
       return -3005;
+    if (a.sink_cls != nullptr && (a.relu || a.sink_ncls < 1 || a.sink_ncls > 16)) return -3006;   // the sink's class mask lives in the bias vector
     if (a.nsteps != (a.d2s == 1 ? 16 : 18)) return -3002;
     // With TMA staging one thread feeds a CTA, so the 16 / 32-channel layers no longer need two CTAs per SM for
     // their copy threads: one CTA with two epilogue groups and a ring twice as deep measured 350 -> 300 us for the
