@@ -40,6 +40,7 @@ struct ConvLayer {
   float* bias_d2s = nullptr;              // device [64]: bias[co] at (py*2+px)*16 + co
   int d2s_mode = 0;                       // 1: 16 -> 16 as a 4x4 stride-2 conv over cells, 2: upsampled 32 -> 16 on the low-res grid
   float* bias = nullptr;            // device [Cout]
+  std::vector<float> bias_host;     // the same values (HaloArgs::bias_c)
   std::string name;                 // "layer1.0.conv1", ... (per-layer timings)
   int Cin = 0, Cout = 0, KH = 0, KW = 0, stride = 1, pad = 0, Ktot = 0, Kpad = 0;
   int C1 = 0, C2 = 0;               // channel split of a two-source (decoder conv1) layer
@@ -375,6 +376,7 @@ int build_conv(fb_ctx* c, const TensorMap& tm, const std::string& name, const st
   }
   FB_CUDA(c, cudaMalloc(&L.w, packed.size() * 2));
   c->owned.push_back(L.w);
+  L.bias_host = bias;
   FB_CUDA(c, cudaMalloc(&L.bias, bias.size() * 4));
   c->owned.push_back(L.bias);
   FB_CUDA(c, cudaMemcpyAsync(L.w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, c->stream));
@@ -803,6 +805,8 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
           h.wpacked = c->stem_s2d ? S.w_s2d : S.w_halo;
           fb::halo_fill_steps(h, c->stem_s2d ? 4 : 7, c->stem_s2d ? 1 : 2);
           if (fuse_pool) {
+            h.bias_in_args = 1;
+            for (int i = 0; i < 64; ++i) h.bias_c[i] = i < static_cast<int>(S.bias_host.size()) ? S.bias_host[i] : 0.f;
             h.pool_out = static_cast<__nv_bfloat16*>(pool.ptr) + b0 * pool_px;
             if (need && need->restrict_tiles && need->n == n && b0 == 0 && nb == n) {
               h.keep_tiles = need->tiles_dev;

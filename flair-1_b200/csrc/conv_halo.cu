@@ -541,39 +541,47 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           }
           const int oy = th * kTH + dh;
           const bool row_kept = oy >= ky0 && oy < ky1 && !(p.debug_skip & 4);
-          if (tc >= 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + k) : "memory");
           mbar_wait_relaxed(tfull_bar(as), (tc / NACC) & 1);
           tc_fence_after_sync();
           uint8_t* const buf = pool_tiles + k * (16 * G::TW * kPoolPitch);
+          // Rounds of 32 columns (block m = j / kRoundsPerBlock), software-pipelined: the TMEM read port moves 64 bytes per
+          // cycle, a round of the group's four warps is 16 KB = 256 cycles of it, and with load -> wait -> convert -> store
+          // in sequence those cycles (and the queueing behind them) were 62 % of this group's time (ncu stall sampling:
+          // the first FADD after tcgen05.wait::ld). The loads of round j + 1 are issued before round j is processed.
+          constexpr int kRoundsPerBlock = BN / 32, kRounds = MB * kRoundsPerBlock;
+          uint32_t rr[2][2][16];
+          tmem_ld_x16(taddr, rr[0][0]);
+          tmem_ld_x16(taddr + 16, rr[0][1]);
+          if (tc >= 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + k) : "memory");   // buffer k free (the first loads are already in flight)
 #pragma unroll
-          for (int m = 0; m < MB; ++m) {
+          for (int j = 0; j < kRounds; ++j) {
+            const int m = j / kRoundsPerBlock, c0 = (j % kRoundsPerBlock) * 32;
+            tmem_ld_wait();
+            if (j + 1 < kRounds) {
+              const int mn = (j + 1) / kRoundsPerBlock, cn = ((j + 1) % kRoundsPerBlock) * 32;
+              tmem_ld_x16(taddr + mn * BN + cn, rr[(j + 1) & 1][0]);
+              tmem_ld_x16(taddr + mn * BN + cn + 16, rr[(j + 1) & 1][1]);
+            }
             uint8_t* const px = buf + (dh * G::TW + dw + 8 * m) * kPoolPitch;
             const int ox = tw * G::TW + dw + 8 * m;
             const bool kept = row_kept && ox >= kx0 && ox < kx1;
             uint8_t* const gpx = reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + oy) * p.Wout + ox) * 128;
 #pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-              uint32_t r0[16], r1[16];
-              tmem_ld_x16(taddr + m * BN + c0, r0);
-              tmem_ld_x16(taddr + m * BN + c0 + 16, r1);
-              tmem_ld_wait();
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              const uint32_t* r = rr[j & 1][hlf];
+              uint32_t pk[8];
 #pragma unroll
-              for (int hlf = 0; hlf < 2; ++hlf) {
-                const uint32_t* r = hlf ? r1 : r0;
-                const float* bb = bias_s + c0 + 16 * hlf;
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float v0 = fmaxf(__uint_as_float(r[2 * i]) + bb[2 * i], 0.f);
-                  const float v1 = fmaxf(__uint_as_float(r[2 * i + 1]) + bb[2 * i + 1], 0.f);
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                  pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
-                }
-                uint4* d = reinterpret_cast<uint4*>(px + (c0 + 16 * hlf) * 2);
-                d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                if (kept) st_global_v8(gpx + (c0 + 16 * hlf) * 2, pk);
+              for (int i = 0; i < 8; ++i) {
+                // (bias from the kernel parameters = constant-bank operands, HaloArgs::bias_c)
+                const float v0 = fmaxf(__uint_as_float(r[2 * i]) + p.bias_c[(c0 + 16 * hlf + 2 * i) & 63], 0.f);
+                const float v1 = fmaxf(__uint_as_float(r[2 * i + 1]) + p.bias_c[(c0 + 16 * hlf + 2 * i + 1) & 63], 0.f);
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
               }
+              uint4* d = reinterpret_cast<uint4*>(px + (c0 + 16 * hlf) * 2);
+              d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              if (kept) st_global_v8(gpx + (c0 + 16 * hlf) * 2, pk);
             }
           }
           tc_fence_before_sync();
@@ -1392,7 +1400,7 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
   if (a.pool_out != nullptr) {
     // the space-to-depth stem with its max-pool fused (the 7x7 stride-2 form's filter bank and stages leave no room
     // for the pool buffers in 227 KB of shared memory: models with more than four bands keep the separate kernel)
-    if (KH != 4 || !epi2 || !a.relu || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 ||
+    if (KH != 4 || !epi2 || !a.relu || !a.bias_in_args || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 ||
         a.Wout % 16)
       return -3007;
     if (tma_ok) return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true, true>(a, num_sms, stream);

@@ -76,6 +76,12 @@ struct HaloArgs {
   __nv_bfloat16* pool_out;
   const int* keep_tiles;
   int keep_T;
+  // The first 64 bias values by value (required by the fused-pool stem): kernel parameters live in the constant bank,
+  // so the epilogue's bias add takes them as instruction operands instead of 32 shared-memory loads per tile and
+  // thread -- in the fused stem those broadcast loads were a quarter of all LSU shared-memory wavefronts of a kernel
+  // whose shared-memory pipe is saturated (ncu: LSU 60 % + tensor-core operand reads 42 %).
+  int bias_in_args;
+  float bias_c[64];
   int no_prefetch;               // 0 only with FB_PREFETCH=1: L2 prefetch of upcoming halos (measured neutral)
   // FB_HALO_SKIP bit mask, bottleneck hunting only (results are wrong): 1 = producers copy nothing,
   // 2 = no MMAs are issued, 4 = the epilogue does not store, 8 = the epilogue only does the barrier handshake
