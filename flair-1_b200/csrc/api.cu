@@ -100,7 +100,7 @@ struct fb_ctx {
   bool dec_pair = false;      // FB_DEC_PAIR=1: dec0 stays on the CTA-pair kernel (no tile lists) under origin-shifted tiles
   bool no_pool_fuse = false;  // FB_NO_POOL_FUSE=1: the stem's max-pool as a kernel of its own
   bool no_hpair = false;      // FB_NO_HPAIR=1: halo kernel always as single CTAs (no cta_group::2 pairs)
-  bool d2s_all = false;       // FB_D2S_ALL=1: also dec4.conv2 (bf16 output) in depth-to-space form
+  bool d2s_all = true;        // FB_D2S_ALL=0: dec4.conv2 (bf16 output) on the N = 16 kernel instead of the depth-to-space form
   bool no_sb = false;         // FB_NO_SB=1: the 128 -> 128 layers on the im2col implicit GEMM instead of the halo kernel with streamed weights
   double flops = 0;           // algorithmic FLOPs of the conv outputs actually computed since creation
   int* list_dev = nullptr;    // active-tile lists of the current network pass
@@ -596,8 +596,9 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
   int shifted = 0;
   int rc;
   // depth-to-space form (16 output channels at full resolution): 64 accumulator columns = the 2x2 pixels of a cell
-  // (measured per 148 tiles: head 368 -> 304 us, dec4.conv1 211 -> 200 us, dec4.conv2 301 -> 491 us: its bf16 stores
-  // are the slower part there, so the 16 -> 16 bf16 layer keeps the N = 16 kernel unless FB_D2S_ALL=1)
+  // (measured per 148 tiles: head 368 -> 304 us, dec4.conv1 211 -> 200 us; dec4.conv2 first 301 -> 491 us with a spilled
+  // producer table, then -- TMA-staged, origin-shifted tiles -- 210 -> 192 us, so it runs in this form too; FB_D2S_ALL=0
+  // puts it back on the N = 16 kernel)
   if (L.d2s_mode && !c->no_d2s && !c->force_gather && !c->no_halo && !x2 && !res && !rowbias && !out.up2 && !up1 &&
       (L.d2s_mode == 2) == phase && (L.d2s_mode == 2 || out.elem == 4 || c->d2s_all) && fb::halo_d2s_supported(L.d2s_mode, C1, 0, L.Cout, Hout, Wout) &&
       (L.d2s_mode == 1 ? (x1.H == Hout && x1.W == Wout && !x1.up2) : (x1.H * 2 == Hout && x1.W * 2 == Wout))) {
@@ -623,6 +624,13 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
       h.sink_map_row0 = sink->map_row0;
       h.sink_ncls = c->ncls;
       if (sunk) *sunk = true;
+    }
+    // bias by value (cell order: bias[co] at (py*2+px)*16 + co); the sink wants the padded class columns masked
+    h.bias_in_args = 1;
+    for (int i = 0; i < 64; ++i) {
+      const int co = i & 15;
+      h.bias_c[i] = co < L.Cout && co < static_cast<int>(L.bias_host.size()) ? L.bias_host[co] : 0.f;
+      if (h.sink_cls != nullptr && co >= c->ncls) h.bias_c[i] = -3.0e38f;
     }
     rc = fb::launch_conv_halo(h, 3, 1, c->num_sms, c->stream);
     if (rc != 0) return fail(c, rc, "depth-to-space conv launch failed (code " + std::to_string(rc) + ")");
@@ -998,7 +1006,7 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   const char* nhp = getenv("FB_NO_HPAIR");
   c->no_hpair = nhp && nhp[0] == '1';
   const char* da = getenv("FB_D2S_ALL");
-  c->d2s_all = da && da[0] == '1';
+  c->d2s_all = !(da && da[0] == '0');
   const char* nsb = getenv("FB_NO_SB");
   c->no_sb = nsb && nsb[0] == '1';
   *out = c;

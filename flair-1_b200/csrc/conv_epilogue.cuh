@@ -20,10 +20,6 @@
 
 #include "ptx.cuh"
 
-#ifndef FB_EPI_PIPE
-#define FB_EPI_PIPE 0
-#endif
-
 namespace fb {
 
 // Soft-max maximum of one pixel over the classes col0 .. col0 + 15 (those below ncls): first maximum (numpy arg-max
@@ -186,20 +182,17 @@ __device__ __forceinline__ void epilogue_tile(const Args& p, const float* bias, 
     mbar_wait_relaxed(tfull_bar, tfull_parity);
     tc_fence_after_sync();
     const bool f32x = p.out_f32 != nullptr;
-    // (FB_EPI_PIPE: the 16 columns of chunk c + 1 are requested before chunk c is processed -- the TMEM read port moves
-    // 64 bytes per cycle, so a chunk of the CTA's epilogue warps is ~128 cycles that the serial order left exposed)
-    uint32_t rbuf[FB_EPI_PIPE ? 2 : 1][16];
-    if (FB_EPI_PIPE) tmem_ld_x16(taddr, rbuf[0]);
+    // (requesting chunk c + 1 before chunk c is processed measured neutral: ptxas already overlaps the next tcgen05.ld
+    // with the current chunk's packing and stores)
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t(&r)[16] = rbuf[FB_EPI_PIPE ? (c0 / 16) & 1 : 0];
-      if (!FB_EPI_PIPE) tmem_ld_x16(taddr + c0, r);
+      uint32_t r[16];
+      tmem_ld_x16(taddr + c0, r);
       float4 bb[4];
       const float4* bp = reinterpret_cast<const float4*>(bias + n0 + c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) bb[i] = BIAS_SMEM ? bp[i] : __ldg(bp + i);
       tmem_ld_wait();
-      if (FB_EPI_PIPE && c0 + 16 < BN) tmem_ld_x16(taddr + c0 + 16, rbuf[((c0 / 16) + 1) & 1]);
       float v[16];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {

@@ -194,11 +194,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         for (int i = threadIdx.x; i < wbytes / 16; i += kThreadsK) dst[i] = __ldg(src + i);
       }
     }
-    // (depth-to-space head with the class-map sink: the padded class columns of every pixel carry kSoftmaxMasked, so the
-    // sink's soft-max needs no per-class selects)
-    if (threadIdx.x < BN)
-      bias_s[threadIdx.x] = (D2S && p.sink_cls != nullptr && static_cast<int>(threadIdx.x & 15) >= p.sink_ncls) ? kSoftmaxMasked
-                                                                                                         : p.bias[threadIdx.x];
+    if (threadIdx.x < BN) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   }
   if (warp == kMmaWarp) {
     if (lane == 0) {
@@ -745,7 +741,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
               // read first and the four soft-max maxima are straight-line code without branches in between, so their
               // dependency chains (compare trees, exponentials, sums) interleave: with two epilogue warps per scheduler
               // the per-pixel version (one chain at a time, a branch per pixel) ran at 0.4 instructions per cycle and
-              // cost the head 180 of its 293 us per 148 tiles.
+              // cost the head 180 of its 293 us per 148 tiles. The bias comes from the kernel arguments (constant bank),
+              // with kSoftmaxMasked in the padded class columns, so the soft-max needs no per-class selects.
               mbar_wait_relaxed(tfull_bar(as), aph);
               tc_fence_after_sync();
               uint32_t acc[4][16];
@@ -759,7 +756,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                 for (int g4 = 0; g4 < 4; ++g4) {
                   float v[16], best;
 #pragma unroll
-                  for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(acc[g4][k]) + bias_s[16 * g4 + k];
+                  for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(acc[g4][k]) + p.bias_c[(16 * g4 + k) & 63];
                   softmax_max16_all(v, 0, best, arg4[g4], den4[g4]);
                 }
 #pragma unroll
@@ -834,8 +831,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           if constexpr (D2S) {
             // no residual / row bias in these layers: constant-null members let the compiler drop those paths
             const D2SEpiArgs ea{p.relu, p.out_f32, p.Cout};
-            epilogue_tile<BN, true, true, true, true>(ea, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
-                                                      0, direct, rbuf[0]);
+            // (bias from the kernel arguments when the caller put it there: constant-bank loads instead of shared-memory ones)
+            if (p.bias_in_args)
+              epilogue_tile<BN, true, true, true, true>(ea, p.bias_c, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                                        0, direct, rbuf[0]);
+            else
+              epilogue_tile<BN, true, true, true, true>(ea, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
+                                                        0, direct, rbuf[0]);
           } else if constexpr (SB) {
             epilogue_tile<BN, true, true, true, false>(p, bias_s, taddr + m * BN, tfull_bar(as), aph, lane, 0, stg, true, own_pix,
                                                        tb * p.Hout + oh, direct);
@@ -1346,7 +1348,8 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     if (!halo_d2s_supported(a.d2s, a.C1, a.C2, 16, a.Hout, a.Wout) || a.Cout != 64 || a.residual || a.rowbias || a.up2_out ||
         a.up1 || a.phase_mode || (a.d2s == 1 ? (a.Hin != a.Hout || a.Win != a.Wout) : (2 * a.Hin != a.Hout || 2 * a.Win != a.Wout)))
       return -3005;
-    if (a.sink_cls != nullptr && (a.relu || a.sink_ncls < 1 || a.sink_ncls > 16)) return -3006;   // the sink's class mask lives in the bias vector
+    // (the sink's class mask lives in the bias vector, which it takes from the kernel arguments)
+    if (a.sink_cls != nullptr && (a.relu || a.sink_ncls < 1 || a.sink_ncls > 16 || !a.bias_in_args)) return -3006;
     if (a.nsteps != (a.d2s == 1 ? 16 : 18)) return -3002;
     // With TMA staging one thread feeds a CTA, so the 16 / 32-channel layers no longer need two CTAs per SM for
     // their copy threads: one CTA with two epilogue groups and a ring twice as deep measured 350 -> 300 us for the
