@@ -795,7 +795,7 @@ int run_network(fb_ctx* c, int n, int T, const float* menc_dev, const NeedCtx* n
       // carry buffers; FB_NO_POOL_FUSE=1 keeps the separate kernel
       const ConvLayer& S = L("stem");
       const bool stem_halo = c->stem_s2d || (!c->force_gather && !c->no_halo && S.w_halo && fb::halo_supported(7, 2, x0.C, 0, S.Cout, f1.H, f1.W));
-      const bool fuse_pool = c->stem_s2d && !c->no_pool_fuse && c->front_chunk <= 0 && f1.W <= 256 && f1.H % 16 == 0 && f1.W % 16 == 0 &&
+      const bool fuse_pool = c->stem_s2d && !c->no_pool_fuse && fb::halo_pool_fusable() && c->front_chunk <= 0 && f1.W <= 256 && f1.H % 16 == 0 && f1.W % 16 == 0 &&
                              2 * nb >= c->num_sms;
       {
         ProfScope ps(c, 1);

@@ -36,12 +36,14 @@ struct D2SEpiArgs {
   int Cout;
 };
 
-template <int KH, int STRIDE, int NCH, int MB, int BN = 64, int EPI = 1, bool DEEP = false>
+template <int KH, int STRIDE, int NCH, int MB, int BN = 64, int EPI = 1, bool DEEP = false, bool PARB = false>
 struct Geo {
   static constexpr int TW = 8 * MB;
   // 4x4 stride 2 = the 2x2-cell form of a 3x3 stride-1 conv (D2S): cell (Y, X) reads pixels 2Y-1 .. 2Y+2
   static constexpr int PAD = (KH == 4 && STRIDE == 2) ? 1 : KH / 2;
-  static constexpr int NP = STRIDE;                                    // w-parity planes
+  // w-parity planes: one per column parity for the stride-2 forms; PARB (the fused-pool stem) splits the planes of a
+  // stride-1 conv the same way so that the two 8-column blocks of a tile can be its even and its odd columns
+  static constexpr int NP = PARB ? 2 : STRIDE;
   static constexpr int PH = STRIDE * (kTH - 1) + KH + (NCH == 1 ? 1 : 0);  // +1: stem pairs taps vertically
   static constexpr int SPANW = STRIDE * (TW - 1) + KH;
   static constexpr int PW = (SPANW + NP - 1) / NP;
@@ -110,26 +112,26 @@ constexpr int kLdgMode = FB_LDG_PRODUCER;   // accumulator buffers of the 64-cha
 // (its halo is written by cp.async, which can only signal a barrier of its own CTA) to the leader. Encoder layers
 // only: no active-tile lists.
 // POOL = the stem with its 3x3 stride-2 max-pool (torchvision ResNet: MaxPool2d(3, 2, 1)) fused into the epilogue. A CTA
-// takes whole images and walks their 16 x 16 tiles in row-major order; the first epilogue group leaves every finished
-// tile in shared memory (bf16: what the separate pool kernel would read back from HBM, 8.4 MB per 512^2 tile), the
-// second group pools its 8 x 8 outputs from there -- the row above and the column to the left come from carry buffers
-// filled by the tiles before it (last row of every tile of the previous tile row, last column of the previous tile) --
-// and writes the pooled tensor. The stem's own output is still stored, for the decoder's skip connection: all of it,
-// or, in the exact-clipping zone loop, only the part dec3.conv1 reads (HaloArgs::keep_tiles).
+// takes whole images and walks their 16 x 16 tiles in row-major order; the first epilogue group takes the horizontal
+// 3-maximum of every finished tile in registers and leaves it in shared memory (bf16; the separate pool kernel would
+// read the full-resolution tensor back from HBM, 8.4 MB per 512^2 tile), the second group finishes the pool vertically
+// from there -- the row above comes from a carry buffer filled by the tile row before it, the column to the left from
+// the previous tile -- and writes the pooled tensor. The stem's own output is still stored, for the decoder's skip
+// connection: all of it, or, in the exact-clipping zone loop, only the part dec3.conv1 reads (HaloArgs::keep_tiles).
 constexpr int kPoolPitch = 144;   // bytes per pixel of the shared-memory tile (128 + 16: conflict-free 16-byte stores)
 
 template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI = 1, bool D2S = false, bool SB = false,
           bool PAIR = false, bool POOL = false, bool TMAH = false>
-__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR>::OCC)
+__global__ void __launch_bounds__(kThreads + 128 * (EPI - 1), Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR, POOL>::OCC)
 conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2) {
-  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR, POOL>;
   // TMAH = the halo planes are written by TMA tensor loads (one 4-D box {8 channels, PW, PH, 1} per 8-channel chunk,
   // out-of-range pixels zero-filled = the conv padding) issued by one thread, instead of one cp.async per 16-byte cell
   // from 64-96 threads: single-source stride-1 layers only
   // (stride 2: one box per w-parity plane, every second pixel through the map's element stride)
   static_assert(!TMAH || !PH, "TMA-staged halo: not for the four-phase form");
-  static_assert(!POOL || (EPI == 2 && MB == 2 && BN == 64 && !PH && !D2S && !SB && !PAIR && G::OCC == 1),
-                "fused max-pool: 16 x 16 tiles of 64 channels, two epilogue groups");
+  static_assert(!POOL || (EPI == 2 && MB == 2 && BN == 64 && !PH && !D2S && !SB && !PAIR && G::OCC == 1 && TMAH && STRIDE == 1),
+                "fused max-pool: 16 x 16 tiles of 64 channels, two epilogue groups, TMA-staged parity planes");
   static_assert(!PAIR || (!PH && !D2S && G::OCC == 1 && EPI == 2 && BN % 32 == 0), "CTA pairs: plain form, one CTA per SM");
   constexpr int BNH = PAIR ? BN / 2 : BN;               // filter-bank columns held by this CTA
   static_assert(!D2S || (BN == 64 && !PH), "depth-to-space output: 4 pixels x 16 channels per tile row");
@@ -498,20 +500,30 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                                     p.up2_out ? 2 * p.Wout : p.Wout, (p.up2_out || PH) ? 2 : 1,
                                     [](int r, int& dh, int& dw) { dh = r >> 3; dw = r & 7; });
     if constexpr (POOL) {
-      // ---- fused max-pool: a two-stage pipeline inside the epilogue. Group 0 (warps 4-7, one per TMEM lane quarter)
-      // drains BOTH 128-pixel blocks of a tile -- bias, ReLU, one bf16 rounding -- into one of two shared-memory tile
-      // buffers and stores the stem's own output from its registers (only inside the keep rectangle); group 1 (warps
-      // 8-11) takes the buffer, pools the tile's 8 x 8 outputs and leaves the carries for the tiles to the right and
-      // below. (ncu stall sampling of the first split -- stores in group 1 -- showed group 0 waiting for a free buffer
-      // two thirds of its time: the pooling group is the slower stage.) Hand-over by named barriers: 1 + k = "buffer k
-      // filled", 3 + k = "buffer k free".
-      uint8_t* const pool_tiles = smem + (bars - smem_base) + kBarBytes;                 // 2 x [16 x 16 px][kPoolPitch]
-      uint8_t* const pool_rows = pool_tiles + 2 * 16 * G::TW * kPoolPitch;               // 2 x [Wout px][128]: by tile-row parity
-      uint8_t* const pool_cols = pool_rows + 2 * static_cast<size_t>(p.Wout) * 128;      // 2 x [16 px][128]: by tile-column parity
+      // ---- fused max-pool: a two-stage pipeline inside the epilogue. The two 128-row blocks of a tile are its EVEN and
+      // its ODD columns (parity planes, halo_fill_steps_pool), so a thread of group 0 (warps 4-7, one per TMEM lane
+      // quarter) owns the horizontally adjacent pixels (dh, 2d) and (dh, 2d + 1). It drains both -- bias, ReLU, one bf16
+      // rounding --, stores the stem's own output from its registers (only inside the keep rectangle) and takes the
+      // horizontal 3-maximum H(dh, d) = max(x[2d - 1], x[2d], x[2d + 1]) in registers: the pair's own maximum and the odd
+      // pixel of the lane to its left (one shuffle per register; lane d = 0 takes the previous tile's last column from a
+      // carry its own warp wrote). Only H goes to shared memory (16 x 8 cells, half the tile). Group 1 (warps 8-11) takes
+      // the buffer and finishes the pool vertically: a thread loads nine rows of one H column for four outputs (row -1 =
+      // the carry of the tile above). Against the first version (full tile to shared memory, 25 loads per thread for a
+      // 2 x 2 block of outputs) this moves 36 KB instead of 91 KB per tile through a shared-memory pipe that ncu showed
+      // saturated (LSU wavefronts 60 % + tensor-core operand reads 42 % of peak). Hand-over by named barriers:
+      // 1 + k = "buffer k filled", 3 + k = "buffer k free".
+      constexpr int kHCols = G::TW / 2;                                                   // H cells per tile row
+      uint8_t* const pool_tiles = smem + (bars - smem_base) + kBarBytes;                 // 2 x [16 x 8 cells][kPoolPitch]
+      uint8_t* const pool_rows = pool_tiles + 2 * 16 * kHCols * kPoolPitch;              // 2 x [Wout / 2 cells][128]: by tile-row parity
+      uint8_t* const pool_cols = pool_rows + static_cast<size_t>(p.Wout) * 128;          // 2 x [16 px][128]: by tile parity
       const int et = (warp & 3) * 32 + lane;   // 0 .. 127 inside the group
       uint32_t tc = 0;
+      auto hmax2 = [](uint32_t x, uint32_t y) -> uint32_t {
+        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), *reinterpret_cast<const __nv_bfloat162*>(&y));
+        return *reinterpret_cast<const uint32_t*>(&r);
+      };
       if (grp == 0) {
-        const int dh = et >> 3, dw = et & 7;   // TMEM lane = pixel (dh, dw) of a 16 x 8 block
+        const int dh = et >> 3, d = et & 7;   // TMEM lane = row dh, column pair d of the tile
         int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
         int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout, keep_tb = -1;
         for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
@@ -520,8 +532,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
           const int as = tc % NACC, k = tc & 1;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
-          // The stem's own output goes to global memory from this group's registers (the pooling group is the slower
-          // stage of the pipeline). In the exact-clipping loop only the part that dec3.conv1 (layer 6 of tile_need.cuh)
+          // In the exact-clipping loop only the part of the stem's output that dec3.conv1 (layer 6 of tile_need.cuh)
           // reads for this image's live outputs is stored: its needed region and the one-pixel halo of the 3x3 window
           // (the dead outputs of that conv's edge tiles read stale pixels; nothing live depends on them).
           // (recomputed when the image changes, i.e. once per 256 tiles: the table look-up and the walk through the
@@ -535,65 +546,81 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
             kx0 = any ? r.x0 - 1 : 0; ky0 = any ? r.y0 - 1 : 0;
             kx1 = any ? r.x1 + 1 : 0; ky1 = any ? r.y1 + 1 : 0;
           }
-          const int oy = th * kTH + dh;
+          const int oy = th * kTH + dh, ox = tw * G::TW + 2 * d;
           const bool row_kept = oy >= ky0 && oy < ky1 && !(p.debug_skip & 4);
+          const bool kept_e = row_kept && ox >= kx0 && ox < kx1, kept_o = row_kept && ox + 1 >= kx0 && ox + 1 < kx1;
+          uint8_t* const gpx = reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + oy) * p.Wout + ox) * 128;
           mbar_wait_relaxed(tfull_bar(as), (tc / NACC) & 1);
           tc_fence_after_sync();
-          uint8_t* const buf = pool_tiles + k * (16 * G::TW * kPoolPitch);
-          // Rounds of 32 columns (block m = j / kRoundsPerBlock), software-pipelined: the TMEM read port moves 64 bytes per
-          // cycle, a round of the group's four warps is 16 KB = 256 cycles of it, and with load -> wait -> convert -> store
-          // in sequence those cycles (and the queueing behind them) were 62 % of this group's time (ncu stall sampling:
-          // the first FADD after tcgen05.wait::ld). The loads of round j + 1 are issued before round j is processed.
-          constexpr int kRoundsPerBlock = BN / 32, kRounds = MB * kRoundsPerBlock;
-          uint32_t rr[2][2][16];
-          tmem_ld_x16(taddr, rr[0][0]);
-          tmem_ld_x16(taddr + 16, rr[0][1]);
-          if (tc >= 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + k) : "memory");   // buffer k free (the first loads are already in flight)
+          uint8_t* const hpx = pool_tiles + k * (16 * kHCols * kPoolPitch) + (dh * kHCols + d) * kPoolPitch;
+          // last-column carry: written by the d = 7 lanes of tile tc, read by the d = 0 lanes (same warp) of tile tc + 1
+          uint8_t* const carry_w = pool_cols + (tc & 1) * (16 * 128) + dh * 128;
+          const uint8_t* const carry_r = pool_cols + ((tc & 1) ^ 1) * (16 * 128) + dh * 128;
+          bool buf_free = tc < 2;
 #pragma unroll
-          for (int j = 0; j < kRounds; ++j) {
-            const int m = j / kRoundsPerBlock, c0 = (j % kRoundsPerBlock) * 32;
-            tmem_ld_wait();
-            if (j + 1 < kRounds) {
-              const int mn = (j + 1) / kRoundsPerBlock, cn = ((j + 1) % kRoundsPerBlock) * 32;
-              tmem_ld_x16(taddr + mn * BN + cn, rr[(j + 1) & 1][0]);
-              tmem_ld_x16(taddr + mn * BN + cn + 16, rr[(j + 1) & 1][1]);
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t re[2][16], ro[2][16];   // even pixel = block 0, odd pixel = block 1
+            tmem_ld_x16(taddr + c0, re[0]);
+            tmem_ld_x16(taddr + c0 + 16, re[1]);
+            tmem_ld_x16(taddr + BN + c0, ro[0]);
+            tmem_ld_x16(taddr + BN + c0 + 16, ro[1]);
+            if (!buf_free) {   // buffer k free (the loads are already in flight)
+              asm volatile("bar.sync %0, 256;" ::"r"(3 + k) : "memory");
+              buf_free = true;
             }
-            uint8_t* const px = buf + (dh * G::TW + dw + 8 * m) * kPoolPitch;
-            const int ox = tw * G::TW + dw + 8 * m;
-            const bool kept = row_kept && ox >= kx0 && ox < kx1;
-            uint8_t* const gpx = reinterpret_cast<uint8_t*>(p.out) + ((static_cast<size_t>(tb) * p.Hout + oy) * p.Wout + ox) * 128;
+            tmem_ld_wait();
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
-              const uint32_t* r = rr[j & 1][hlf];
-              uint32_t pk[8];
+              const int cb = c0 + 16 * hlf;   // first channel of this 16-channel piece
+              uint32_t pe[8], po[8], h[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 // (bias from the kernel parameters = constant-bank operands, HaloArgs::bias_c)
-                const float v0 = fmaxf(__uint_as_float(r[2 * i]) + p.bias_c[(c0 + 16 * hlf + 2 * i) & 63], 0.f);
-                const float v1 = fmaxf(__uint_as_float(r[2 * i + 1]) + p.bias_c[(c0 + 16 * hlf + 2 * i + 1) & 63], 0.f);
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                pk[i] = *reinterpret_cast<const uint32_t*>(&b2);
+                const float b0 = p.bias_c[(cb + 2 * i) & 63], b1 = p.bias_c[(cb + 2 * i + 1) & 63];
+                const __nv_bfloat162 e2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(re[hlf][2 * i]) + b0, 0.f),
+                                                               fmaxf(__uint_as_float(re[hlf][2 * i + 1]) + b1, 0.f));
+                const __nv_bfloat162 o2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(ro[hlf][2 * i]) + b0, 0.f),
+                                                               fmaxf(__uint_as_float(ro[hlf][2 * i + 1]) + b1, 0.f));
+                pe[i] = *reinterpret_cast<const uint32_t*>(&e2);
+                po[i] = *reinterpret_cast<const uint32_t*>(&o2);
               }
-              uint4* d = reinterpret_cast<uint4*>(px + (c0 + 16 * hlf) * 2);
-              d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-              if (kept) st_global_v8(gpx + (c0 + 16 * hlf) * 2, pk);
+              if (kept_e) st_global_v8(gpx + cb * 2, pe);
+              if (kept_o) st_global_v8(gpx + 128 + cb * 2, po);
+              // the odd pixel to the left: lane - 1, or the carry of the previous tile (zero at the image's left edge:
+              // the values are post-ReLU, so a zero never wins against the window's centre)
+              uint32_t lf[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) lf[i] = __shfl_up_sync(0xffffffffu, po[i], 1);
+              if (d == 0) {
+                const uint4 c0v = *reinterpret_cast<const uint4*>(carry_r + cb * 2), c1v = *reinterpret_cast<const uint4*>(carry_r + cb * 2 + 16);
+                const bool has = tw > 0;
+                lf[0] = has ? c0v.x : 0u; lf[1] = has ? c0v.y : 0u; lf[2] = has ? c0v.z : 0u; lf[3] = has ? c0v.w : 0u;
+                lf[4] = has ? c1v.x : 0u; lf[5] = has ? c1v.y : 0u; lf[6] = has ? c1v.z : 0u; lf[7] = has ? c1v.w : 0u;
+              }
+              if (d == 7) {
+                *reinterpret_cast<uint4*>(carry_w + cb * 2) = make_uint4(po[0], po[1], po[2], po[3]);
+                *reinterpret_cast<uint4*>(carry_w + cb * 2 + 16) = make_uint4(po[4], po[5], po[6], po[7]);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = hmax2(hmax2(pe[i], po[i]), lf[i]);
+              uint4* dst = reinterpret_cast<uint4*>(hpx + cb * 2);
+              dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+              dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
             }
           }
+          __syncwarp();   // the carry written above is read by this warp's d = 0 lanes in the next tile
           tc_fence_before_sync();
           mbar_arrive(tempty_bar(as));
           __threadfence_block();
           asm volatile("bar.arrive %0, 256;" ::"r"(1 + k) : "memory");
         }
       } else {
-        const int vec = et & 7;                 // 16-byte piece (8 channels) of a pixel
+        const int vec = et & 7;                 // 16-byte piece (8 channels) of a cell
+        const int j = (et >> 3) & 7;            // H column = pooled output column of the tile
+        const int half = et >> 6;               // output rows 4 * half .. 4 * half + 3
         const int Hp = p.Hout >> 1, Wp = p.Wout >> 1;
-        auto vmax = [](uint4 a, const uint4 b) -> uint4 {
-          auto m2 = [](uint32_t x, uint32_t y) -> uint32_t {
-            const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&x), *reinterpret_cast<const __nv_bfloat162*>(&y));
-            return *reinterpret_cast<const uint32_t*>(&r);
-          };
-          return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w));
+        auto vmax = [&](uint4 a, const uint4 b) -> uint4 {
+          return make_uint4(hmax2(a.x, b.x), hmax2(a.y, b.y), hmax2(a.z, b.z), hmax2(a.w, b.w));
         };
         int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
         for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
@@ -602,57 +629,31 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
           const int k = tc & 1;
           asm volatile("bar.sync %0, 256;" ::"r"(1 + k) : "memory");
-          const uint8_t* const buf = pool_tiles + k * (16 * G::TW * kPoolPitch);
-          uint8_t* const rows_prev = pool_rows + static_cast<size_t>((th & 1) ^ 1) * p.Wout * 128;
-          uint8_t* const rows_cur = pool_rows + static_cast<size_t>(th & 1) * p.Wout * 128;
-          uint8_t* const cols_prev = pool_cols + ((tw & 1) ^ 1) * (16 * 128);
-          uint8_t* const cols_cur = pool_cols + (tw & 1) * (16 * 128);
-          // pooled outputs. Pixel (r, c) of the tile, r / c = -1: the row above / the column to the left (zero
-          // outside the image: the values are post-ReLU, so a zero never wins against the window's centre).
+          const uint8_t* const buf = pool_tiles + k * (16 * kHCols * kPoolPitch);
+          const uint8_t* const rows_prev = pool_rows + static_cast<size_t>((th & 1) ^ 1) * Wp * 128;
+          uint8_t* const rows_cur = pool_rows + static_cast<size_t>(th & 1) * Wp * 128;
+          // H rows 8 * half - 1 .. 8 * half + 7 of column j; row -1 = last H row of the tile above (zero above the image).
           // Branch-free: every load comes from an address inside the pool buffers and is masked afterwards, so the nine
-          // loads of a window are in flight together.
-          auto fetch = [&](int r, int c) -> uint4 {
-            const bool in_tile = r >= 0 && c >= 0;
-            const bool ok = in_tile || (r < 0 ? (th > 0 && (c >= 0 || tw > 0)) : tw > 0);
-            const uint8_t* a_tile = buf + ((r < 0 ? 0 : r) * G::TW + (c < 0 ? 0 : c)) * kPoolPitch;
-            const uint8_t* a_row = rows_prev + static_cast<size_t>(tw * G::TW + c + (tw == 0 && c < 0 ? 1 : 0)) * 128;
-            const uint8_t* a_col = cols_prev + (r < 0 ? 0 : r) * 128;
-            const uint8_t* a = in_tile ? a_tile : (r < 0 ? a_row : a_col);
-            const uint4 v = *reinterpret_cast<const uint4*>(a + vec * 16);
-            return ok ? v : make_uint4(0u, 0u, 0u, 0u);
-          };
-          // A thread pools a 2 x 2 block of outputs from its 5 x 5 window (25 loads for four outputs instead of 36: the
-          // shared-memory reads of this stage compete with the MMAs' operand fetches), row maxima first.
-          {
-            const int bi = (et >> 3) >> 2, bj = (et >> 3) & 3;   // output block: rows 2bi, 2bi+1, columns 2bj, 2bj+1
-            uint4 h[5][2];
+          // loads are in flight together.
+          uint4 v[9];
 #pragma unroll
-            for (int r = 0; r < 5; ++r) {
-              uint4 w[5];
-#pragma unroll
-              for (int c = 0; c < 5; ++c) w[c] = fetch(4 * bi - 1 + r, 4 * bj - 1 + c);
-              h[r][0] = vmax(vmax(w[0], w[1]), w[2]);
-              h[r][1] = vmax(vmax(w[2], w[3]), w[4]);
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-              for (int b = 0; b < 2; ++b) {
-                const uint4 v = vmax(vmax(h[2 * a][b], h[2 * a + 1][b]), h[2 * a + 2][b]);
-                const int pi = 2 * bi + a, pj = 2 * bj + b;
-                if (!(p.debug_skip & 4))
-                  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pool_out) +
-                                            ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + pj) * 128 + vec * 16) = v;
-              }
+          for (int qq = 0; qq < 9; ++qq) {
+            const int r = 8 * half - 1 + qq;
+            const uint8_t* a_tile = buf + ((r < 0 ? 0 : r) * kHCols + j) * kPoolPitch;
+            const uint8_t* a_row = rows_prev + static_cast<size_t>(tw * kHCols + j) * 128;
+            const uint4 x = *reinterpret_cast<const uint4*>((qq == 0 && half == 0 ? a_row : a_tile) + vec * 16);
+            v[qq] = (qq == 0 && half == 0 && th == 0) ? make_uint4(0u, 0u, 0u, 0u) : x;
           }
-          // carries: this tile's last row (for the tile below) and last column (for the tile to the right)
-          {
-            const int c = et >> 3;
-            *reinterpret_cast<uint4*>(rows_cur + static_cast<size_t>(tw * G::TW + c) * 128 + vec * 16) =
-                *reinterpret_cast<const uint4*>(buf + (15 * G::TW + c) * kPoolPitch + vec * 16);
-            *reinterpret_cast<uint4*>(cols_cur + c * 128 + vec * 16) =
-                *reinterpret_cast<const uint4*>(buf + (c * G::TW + 15) * kPoolPitch + vec * 16);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const uint4 o = vmax(vmax(v[2 * a], v[2 * a + 1]), v[2 * a + 2]);
+            const int pi = 4 * half + a;
+            if (!(p.debug_skip & 4))
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.pool_out) +
+                                        ((static_cast<size_t>(tb) * Hp + th * 8 + pi) * Wp + tw * 8 + j) * 128 + vec * 16) = o;
           }
+          // carry: this tile's last H row, for the tile below
+          if (half == 1) *reinterpret_cast<uint4*>(rows_cur + static_cast<size_t>(tw * kHCols + j) * 128 + vec * 16) = v[8];
           // hand the buffer back unless nobody will fill it again (no arrival may be left pending at exit)
           if (ti + 2 * sched_step < sched_end) {
             __threadfence_block();
@@ -989,7 +990,11 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
             const uint32_t a_lo = p.a_lo[k] + st16;
             const uint32_t acc = (g | k) != 0 ? 1u : 0u;
 #pragma unroll
-            for (int m = 0; m < MB; ++m) mma(d_tmem + m * BN, a_lo + 8 * m, b_lo, acc);
+            for (int m = 0; m < MB; ++m) {
+              // POOL: block m = the tile's columns of parity m, with a step table of its own (halo_fill_steps_pool)
+              if (POOL) mma(d_tmem + m * BN, p.a_lo[m * p.nsteps + k] + st16, b_lo, acc);
+              else mma(d_tmem + m * BN, a_lo + 8 * m, b_lo, acc);
+            }
             b_lo += 2 * BNH;
           }
         }
@@ -1014,7 +1019,7 @@ template <int KH, int STRIDE, int NCH, int BN, int MB, bool PH = false, int EPI 
           bool PAIR = false, bool POOL = false, bool TMAH = false>
 int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   constexpr int kThreadsK = kThreads + 128 * (EPI - 1);
-  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR>;
+  using G = Geo<KH, STRIDE, NCH, (PH ? 1 : MB), BN, EPI, PAIR, POOL>;
   const int groups = a.groups1 + a.groups2;
   constexpr int BNH = PAIR ? BN / 2 : BN;
   const int wbytes = SB ? kSbStages * (NCH / 2) * 2 * BNH * 16 : (PH ? MB : 1) * groups * a.nsteps * 2 * BNH * 16;
@@ -1022,7 +1027,22 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   const int smem = ((wbytes + 127) / 128) * 128 + (BN * 4 <= 256 ? 256 : BN * 4) + G::STAGES * G::STAGE +
                    ((2 * G::STAGES + 2 * kAccDeep + (SB ? 2 * kSbStages : 0) + (PAIR ? G::STAGES + (SB ? kSbStages : 0) : 0)) * 8 + 16 + 127) / 128 * 128 +
                    ((D2S || SB || POOL || PAIR) ? 0 : 4 * kStgWarpBytes) +
-                   (POOL ? 2 * 16 * G::TW * kPoolPitch + 2 * a.Wout * 128 + 2 * 16 * 128 : 0);
+                   (POOL ? 2 * 16 * (G::TW / 2) * kPoolPitch + a.Wout * 128 + 2 * 16 * 128 : 0);
+  HaloArgs pool_args;
+  const HaloArgs* argp = &a;
+  if (POOL) {
+    // step tables of the fused-pool stem: block m = the tile's columns of parity m. Output column 2d + m reads halo
+    // column 2d + m + kw = cell d + (m + kw) / 2 of parity plane (m + kw) % 2; the second 8-channel chunk is NP planes on
+    pool_args = a;
+    for (int m = 0; m < 2; ++m)
+      for (int tap = 0; tap < KH * KH; ++tap) {
+        const int kh = tap / KH, kw = tap % KH;
+        const uint32_t off = static_cast<uint32_t>(((m + kw) & 1) * G::PLANE16 + kh * G::PW + ((m + kw) >> 1));
+        pool_args.a_lo[m * (KH * KH) + tap] = off | (static_cast<uint32_t>(G::NP * G::PLANE16) << 16);
+      }
+    if (a.nsteps != KH * KH || NCH != 2) return -3008;
+    argp = &pool_args;
+  }
   alignas(64) CUtensorMap tm1, tm2;
   memset(&tm1, 0, sizeof tm1);
   memset(&tm2, 0, sizeof tm2);
@@ -1075,7 +1095,7 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (getenv("FB_DEBUG")) fprintf(stderr, "[halo pair %d,%d] smem=%d clusters=%d pairs=%d\n", NCH, BN, smem, clusters, a.num_m_tiles);
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, a, tm1, tm2);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, *argp, tm1, tm2);
     return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
   }
   const int cap = num_sms * occ;
@@ -1084,11 +1104,15 @@ int launch_halo_t(const HaloArgs& a, int num_sms, cudaStream_t stream) {
   if (getenv("FB_DEBUG")) fprintf(stderr, "[halo %d,%d,%d,%d,%d] smem=%d occ=%d grid=%d tiles=%d\n", KH, STRIDE, NCH, BN, MB, smem, occ, grid, a.num_m_tiles);
   static const bool pdl = !(getenv("FB_NO_PDL") && getenv("FB_NO_PDL")[0] == '1');
   const cudaError_t le = launch_kernel_pdl(conv_halo_kernel<KH, STRIDE, NCH, BN, MB, PH, EPI, D2S, SB, PAIR, POOL, TMAH>, dim3(grid), dim3(kThreadsK),
-                                           static_cast<size_t>(smem), stream, pdl, a, tm1, tm2);
+                                           static_cast<size_t>(smem), stream, pdl, *argp, tm1, tm2);
   return static_cast<int>(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 }  // namespace
+
+bool halo_pool_fusable() {
+  return !(getenv("FB_TMAH") && atoi(getenv("FB_TMAH")) <= 0);
+}
 
 int halo_blocks(int KH, int nch, int bn) {
   if (KH == 7 || KH == 4) return 2;
@@ -1406,8 +1430,8 @@ int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStr
     if (KH != 4 || !epi2 || !a.relu || !a.bias_in_args || a.residual || a.rowbias || a.up2_out || a.out_f32 || a.tile_list || a.Wout > 256 || a.Hout % 16 ||
         a.Wout % 16)
       return -3007;
-    if (tma_ok) return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true, true>(a, num_sms, stream);
-    return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true>(a, num_sms, stream);
+    if (!tma_ok) return -3007;   // (the fused form stages parity planes by TMA only; callers ask halo_pool_fusable() first)
+    return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, true, true>(a, num_sms, stream);
   }
   if (KH == 4 && epi2 && tma_ok) return launch_halo_t<4, 1, 2, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);
   if (KH == 7 && epi2 && tma_ok) return launch_halo_t<7, 2, 1, 64, 2, false, 2, false, false, false, false, true>(a, num_sms, stream);

@@ -143,6 +143,9 @@ void halo_fill_steps_d2s(HaloArgs& a, int mode);
 // bf16 rounding); bias64: bias[co] at (py*2+px)*16 + co. Returns the bf16 element count (dst may be null).
 size_t pack_halo_weights_d2s(int mode, const float* w, int Cout, int Cin, uint16_t* dst);
 
+// The stem's max-pool can run inside its epilogue (HaloArgs::pool_out) only while the TMA-staged halo is on (FB_TMAH).
+bool halo_pool_fusable();
+
 int launch_conv_halo(const HaloArgs& a, int KH, int stride, int num_sms, cudaStream_t stream);
 
 }  // namespace fb
