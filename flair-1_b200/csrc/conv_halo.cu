@@ -524,12 +524,15 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       };
       if (grp == 0) {
         const int dh = et >> 3, d = et & 7;   // TMEM lane = row dh, column pair d of the tile
-        int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
         int kx0 = 0, ky0 = 0, kx1 = p.Wout, ky1 = p.Hout, keep_tb = -1;
+        // (a CTA walks whole images in row-major tile order: the tile coordinates are counted, not divided out of the
+        // tile index -- the three runtime divisions per tile were ~15 % of this group's instructions)
+        int tw = 0, th = 0, tb = static_cast<int>(blockIdx.x);
         for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
-          const int tile = tile_next;
-          if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
-          const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
+          if (tc != 0 && ++tw == tiles_w) {
+            tw = 0;
+            if (++th == tiles_h) { th = 0; tb += static_cast<int>(gridDim.x); }
+          }
           const int as = tc % NACC, k = tc & 1;
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
           // In the exact-clipping loop only the part of the stem's output that dec3.conv1 (layer 6 of tile_need.cuh)
@@ -576,13 +579,12 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 // (bias from the kernel parameters = constant-bank operands, HaloArgs::bias_c)
+                // ReLU on the packed pair: rounding to bf16 is monotonic and keeps zero, so max(round(v), 0) = round(max(v, 0))
                 const float b0 = p.bias_c[(cb + 2 * i) & 63], b1 = p.bias_c[(cb + 2 * i + 1) & 63];
-                const __nv_bfloat162 e2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(re[hlf][2 * i]) + b0, 0.f),
-                                                               fmaxf(__uint_as_float(re[hlf][2 * i + 1]) + b1, 0.f));
-                const __nv_bfloat162 o2 = __floats2bfloat162_rn(fmaxf(__uint_as_float(ro[hlf][2 * i]) + b0, 0.f),
-                                                               fmaxf(__uint_as_float(ro[hlf][2 * i + 1]) + b1, 0.f));
-                pe[i] = *reinterpret_cast<const uint32_t*>(&e2);
-                po[i] = *reinterpret_cast<const uint32_t*>(&o2);
+                const __nv_bfloat162 e2 = __floats2bfloat162_rn(__uint_as_float(re[hlf][2 * i]) + b0, __uint_as_float(re[hlf][2 * i + 1]) + b1);
+                const __nv_bfloat162 o2 = __floats2bfloat162_rn(__uint_as_float(ro[hlf][2 * i]) + b0, __uint_as_float(ro[hlf][2 * i + 1]) + b1);
+                pe[i] = hmax2(*reinterpret_cast<const uint32_t*>(&e2), 0u);
+                po[i] = hmax2(*reinterpret_cast<const uint32_t*>(&o2), 0u);
               }
               if (kept_e) st_global_v8(gpx + cb * 2, pe);
               if (kept_o) st_global_v8(gpx + 128 + cb * 2, po);
@@ -592,10 +594,13 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) lf[i] = __shfl_up_sync(0xffffffffu, po[i], 1);
               if (d == 0) {
-                const uint4 c0v = *reinterpret_cast<const uint4*>(carry_r + cb * 2), c1v = *reinterpret_cast<const uint4*>(carry_r + cb * 2 + 16);
-                const bool has = tw > 0;
-                lf[0] = has ? c0v.x : 0u; lf[1] = has ? c0v.y : 0u; lf[2] = has ? c0v.z : 0u; lf[3] = has ? c0v.w : 0u;
-                lf[4] = has ? c1v.x : 0u; lf[5] = has ? c1v.y : 0u; lf[6] = has ? c1v.z : 0u; lf[7] = has ? c1v.w : 0u;
+                uint4 c0v = make_uint4(0u, 0u, 0u, 0u), c1v = c0v;
+                if (tw > 0) {
+                  c0v = *reinterpret_cast<const uint4*>(carry_r + cb * 2);
+                  c1v = *reinterpret_cast<const uint4*>(carry_r + cb * 2 + 16);
+                }
+                lf[0] = c0v.x; lf[1] = c0v.y; lf[2] = c0v.z; lf[3] = c0v.w;
+                lf[4] = c1v.x; lf[5] = c1v.y; lf[6] = c1v.z; lf[7] = c1v.w;
               }
               if (d == 7) {
                 *reinterpret_cast<uint4*>(carry_w + cb * 2) = make_uint4(po[0], po[1], po[2], po[3]);
@@ -622,11 +627,12 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
         auto vmax = [&](uint4 a, const uint4 b) -> uint4 {
           return make_uint4(hmax2(a.x, b.x), hmax2(a.y, b.y), hmax2(a.z, b.z), hmax2(a.w, b.w));
         };
-        int tile_next = sched0 < sched_end ? tile_of(sched0) : 0;
+        int tw = 0, th = 0, tb = static_cast<int>(blockIdx.x);
         for (int ti = sched0; ti < sched_end; ti += sched_step, ++tc) {
-          const int tile = tile_next;
-          if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
-          const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, tb = tile / (tiles_w * tiles_h);
+          if (tc != 0 && ++tw == tiles_w) {
+            tw = 0;
+            if (++th == tiles_h) { th = 0; tb += static_cast<int>(gridDim.x); }
+          }
           const int k = tc & 1;
           asm volatile("bar.sync %0, 256;" ::"r"(1 + k) : "memory");
           const uint8_t* const buf = pool_tiles + k * (16 * kHCols * kPoolPitch);
