@@ -102,6 +102,8 @@ extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc,
   raster += static_cast<long long>(t) * tile_stride;
   const long long tx0 = tile_xy[tile_stride ? 0 : 2 * t], ty0 = tile_xy[tile_stride ? 1 : 2 * t + 1];
   __nv_bfloat16* tile_out = out + static_cast<long long>(t) * T2 * T2 * 16;
+  // rx = tx0 + 4 * (q % TQ): every row address of a band plane is a multiple of four when base, W and tx0 are
+  const bool quad_ok = !layout_hwc && (W & 3) == 0 && (tx0 & 3) == 0 && (reinterpret_cast<uintptr_t>(raster) & 3) == 0;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < items; q += gridDim.x * blockDim.x) {
     const int Y = q / TQ, X = (q - Y * TQ) << 1;        // space-to-depth pixels (Y, X) and (Y, X + 1)
     const long long rx = tx0 + 2 * X;
@@ -111,6 +113,18 @@ extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc,
       const long long ry = ty0 + 2 * Y + py;
       const bool row_ok = ry >= 0 && ry < H && ry >= row0 && ry < row0 + rows;
       const long long ly = ry - row0;
+      if (quad_ok && row_ok && rx >= 0 && rx + 3 < W) {
+        // band-planar raster, the four pixels inside the row and their address a multiple of four: one 32-bit load per
+        // band and row instead of four byte loads with a bounds test each (the kernel is bound by its instruction count)
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          unsigned w = 0;
+          if (ch < c) w = __ldg(reinterpret_cast<const unsigned*>(raster + (static_cast<long long>(s_band[ch]) * rows + ly) * W + rx));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) raw[ch][py][j] = (w >> (8 * j)) & 0xFFu;
+        }
+        continue;
+      }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
@@ -121,8 +135,8 @@ extract_normalise_s2d_kernel(const uint8_t* __restrict__ raster, int layout_hwc,
                                         : raster[(static_cast<long long>(s_band[ch]) * rows + ly) * W + rx + j];
         }
       }
-      // (aligned 32-bit loads + funnel shift instead of the byte loads measured 1.66 -> 1.95 ms per zone: the kernel is
-      // not bound by load instructions; the look-ups in the shared-memory table are the likelier limit)
+      // (unaligned 32-bit loads emulated with two aligned loads + funnel shift measured slower than the byte loads,
+      // 1.66 -> 1.95 ms per zone; only the aligned case above takes words)
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {                       // the two space-to-depth pixels
