@@ -906,3 +906,49 @@ def test_metadata_forward_matches_the_references_own_forward(ctx):
     rel = np.abs(got - g["logits_sub"]).max() / float(g["logits_absmax"])
     print(f"metadata forward vs the reference's own forward(): rel err {rel:.4e}")
     assert rel <= LOGIT_TOL
+
+
+_FALLBACK_SNIPPET = r"""
+import hashlib, sys
+sys.path.insert(0, {root!r})
+import torch
+import flair1_b200._native as nat
+from flair1_b200.zone_detect.slicing_job import tile_table
+from oracle import synth
+W = H = 896
+T, margin = 128, 32
+raster = torch.from_numpy(synth.synth_raster(3, H, W, seed=5)).cuda()
+tiles = tile_table(W, H, T, margin)
+c = nat.Context(0)
+c.load_weights(synth.cached_checkpoint(3, 15), 3, 15)
+c.set_norm("custom", synth.FLAIR_MEANS[:3], synth.FLAIR_STDS[:3])
+c.set_raster(raster, [0, 1, 2], W, H)
+cls = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+conf = torch.full((H, W), 255, dtype=torch.uint8, device="cuda")
+c.detect_strip(tiles, T, 148, cls, conf, W, 0)
+torch.cuda.synchronize()
+print("tiles", len(tiles), "digest", hashlib.sha256(cls.cpu().numpy().tobytes() + conf.cpu().numpy().tobytes()).hexdigest())
+"""
+
+
+def test_cp_async_halo_fallback_writes_the_same_maps():
+    """FB_TMAH=0 (read once per process, hence the two subprocesses) switches every halo layer back from TMA-staged planes
+    to cp.async gathers; the fused stem, which exists only in the TMA-staged form, then runs as stem + separate max-pool
+    kernel. A zone of 169 tiles in batches of 148 (large enough for the fused stem in the default run) must give the
+    same class and confidence bytes either way."""
+    import os
+    import subprocess
+    import sys
+    code = _FALLBACK_SNIPPET.format(root=str(Path(__file__).resolve().parent.parent))
+    out = {}
+    for mode in ("default", "cp.async"):
+        env = dict(os.environ)
+        env.pop("FB_TMAH", None)
+        if mode == "cp.async":
+            env["FB_TMAH"] = "0"
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("tiles")][-1]
+        assert int(line.split()[1]) >= 148
+        out[mode] = line.split()[-1]
+    assert out["default"] == out["cp.async"]
