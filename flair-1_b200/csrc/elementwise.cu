@@ -731,6 +731,11 @@ build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __gri
       list[off[b] + i] = sp.shifted ? static_cast<int>(pack_tile_origin(b, k.y0 + (i / nx) * sp.th, k.x0 + (i % nx) * sp.tw))
                                     : (b * sp.gh + k.y0 + i / nx) * sp.gw + k.x0 + i % nx;
   }
+  if (sp.sub) {
+    // half boxes are consumed in pairs: an odd list ends with a copy of its last entry (computed and stored twice)
+    __syncthreads();
+    if (threadIdx.x == 0 && (off[n] & 1) && off[n] > 0) list[off[n]] = list[off[n] - 1];
+  }
 }
 
 int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPlan& plan, int* list_dev,

@@ -105,6 +105,7 @@ struct TileListSpec {
   int offset, count;
   int use;   // 0: every tile is active, no list is built
   int shifted;
+  int sub;   // 1: entries are half boxes (th = half a kernel tile), two per kernel tile: an odd list is padded with a copy of its last entry
 };
 struct TileListPlan {
   TileListSpec spec[kNeedLayers];
