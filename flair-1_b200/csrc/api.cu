@@ -97,7 +97,7 @@ struct fb_ctx {
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
   bool aligned_tiles = false; // FB_ALIGNED_TILES=1: active kernel tiles on the fixed tile grid instead of origin-shifted (tile_need.cuh)
-  bool no_half_tiles = false; // FB_NO_HALF_TILES=1: the implicit GEMM's list entries stay whole 8 x 16 boxes (A/B)
+  int sub_tiles = 2;          // FB_SUB_TILES=0 / 1: the implicit GEMM's list entries stay whole 8 x 16 boxes / halves of 4 x 16 (default: quarters of 4 x 8)
   bool dec_pair = false;      // FB_DEC_PAIR=1: dec0 stays on the CTA-pair kernel (no tile lists) under origin-shifted tiles
   bool no_pool_fuse = false;  // FB_NO_POOL_FUSE=1: the stem's max-pool as a kernel of its own
   bool no_hpair = false;      // FB_NO_HPAIR=1: halo kernel always as single CTAs (no cta_group::2 pairs)
@@ -536,40 +536,51 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 // = output grid / scale, gh x gw of them per image) so that ONE build_tile_lists launch can expand the needed
 // regions of all eleven layers, then the real walk, in which every launch picks up its list.
 // *list stays null when every tile is active.
-// sub (optional, in/out): the caller's kernel can take HALF tiles (th / 2 rows, two list entries per kernel tile); set
-// to 1 on return when the list was built that way -- *active then counts half tiles.
+// sub (optional, in/out): the caller's kernel can take sub-boxes -- in: 1 = halves (th / 2 rows, two list entries per kernel
+// tile), 2 = quarters (th / 2 rows x tw / 2 columns, four entries); out: the mode the list was built in (0 = whole tiles).
+// *active then counts sub-boxes.
 int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, int th, int tw, int gh, int gw,
                    const int** list, long long* active, int* shifted, int* sub = nullptr) {
   *list = nullptr;
   *shifted = 0;
-  const bool want_sub = sub && *sub;
+  const int want_sub = sub ? *sub : 0;
   if (sub) *sub = 0;
   const long long full = static_cast<long long>(B) * gh * gw;
   *active = full;
   if (!need || !need->restrict_tiles || layer < 0 || layer >= fb::kNeedLayers || need->n != B) return 0;
   fb::TileListSpec& sp = c->list_plan.spec[layer];
+  auto sub_tiling = [&](int mode, int& lth, int& ltw, int& lgh, int& lgw) {
+    lth = mode ? th / 2 : th; lgh = mode ? gh * 2 : gh;
+    ltw = mode == 2 ? tw / 2 : tw; lgw = mode == 2 ? gw * 2 : gw;
+  };
   if (c->plan_mode == 1) {
     // origin-shifted tiles (tile_need.cuh, need_span) unless switched off or the packed entry cannot hold the launch
     const bool sh = !c->aligned_tiles && B <= (1 << 10) && gh * th < (1 << fb::kTileOriginBits) && gw * tw < (1 << fb::kTileOriginBits);
-    const bool half = want_sub && sh && !c->no_half_tiles && th % 2 == 0;
-    const int lth = half ? th / 2 : th, lgh = half ? gh * 2 : gh;
-    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, lth, tw, sh);
+    int mode = (sh && th % 2 == 0 && tw % 2 == 0) ? want_sub : 0;
+    if (mode > c->sub_tiles) mode = c->sub_tiles;
+    int lth, ltw, lgh, lgw;
+    sub_tiling(mode, lth, ltw, lgh, lgw);
+    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, lth, ltw, sh);
+    const int per = mode == 2 ? 4 : mode == 1 ? 2 : 1;
     sp.shifted = sh ? 1 : 0;
-    sp.sub = half ? 1 : 0;
-    sp.layer = layer; sp.scale = scale; sp.th = lth; sp.tw = tw; sp.gh = lgh; sp.gw = gw;
+    sp.sub = per;
+    sp.layer = layer; sp.scale = scale; sp.th = lth; sp.tw = ltw; sp.gh = lgh; sp.gw = lgw;
     sp.count = static_cast<int>(cnt);
     sp.offset = static_cast<int>(c->list_plan_ints);
-    sp.use = cnt < static_cast<long long>(B) * lgh * gw ? 1 : 0;
-    if (sp.use) c->list_plan_ints += static_cast<size_t>(cnt + (half ? (cnt & 1) : 0));
+    sp.use = cnt < static_cast<long long>(B) * lgh * lgw ? 1 : 0;
+    if (sp.use) c->list_plan_ints += static_cast<size_t>((cnt + per - 1) / per * per);
     return 0;
   }
-  if (sp.scale != scale || sp.th != (sp.sub ? th / 2 : th) || sp.tw != tw || sp.gh != (sp.sub ? gh * 2 : gh) || sp.gw != gw)
+  const int mode = sp.sub == 4 ? 2 : sp.sub == 2 ? 1 : 0;
+  int lth, ltw, lgh, lgw;
+  sub_tiling(mode, lth, ltw, lgh, lgw);
+  if (sp.scale != scale || sp.th != lth || sp.tw != ltw || sp.gh != lgh || sp.gw != lgw)
     return fail(c, FB_ERR_INVALID, "internal: tile list planned for another kernel tiling");
   if (sp.use) {
     *list = c->list_dev + sp.offset;
     *shifted = sp.shifted;
     *active = sp.count;
-    if (sub) *sub = sp.sub;
+    if (sub) *sub = mode;
   }
   return 0;
 }
@@ -691,14 +702,15 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     a.up2_out = 0;
     a.phase_mode = 1;
     if (out.up2 || out.elem != 2 || !fb::conv_tma_eligible(a)) return fail(c, FB_ERR_INVALID, "internal: phase-form conv not eligible");
-    int sub = 1;   // the implicit GEMM takes half boxes (4 x 16) under origin-shifted lists
+    int sub = 2;   // the implicit GEMM takes quarter boxes (4 x 8) under origin-shifted lists
     FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 8, 16, Hout / 16, Wout / 32, &list, &active, &shifted, &sub));
     if (c->plan_mode == 1) return 0;
+    const int per = sub == 2 ? 4 : sub == 1 ? 2 : 1;
     if (list) {
       a.tile_list = list; a.tile_packed = shifted; a.tile_sub = sub;
-      a.tile_list_len = static_cast<int>(sub ? (active + 1) / 2 : active);
+      a.tile_list_len = static_cast<int>((active + per - 1) / per);
     }
-    c->flops += static_cast<double>(active) * ((sub ? 4 : 8) * 16 * 4) * L.flops_px;
+    c->flops += static_cast<double>(active) * (8 * 16 * 4 / per) * L.flops_px;
     rc = fb::launch_conv(a, L.w_phase, L.Kp_phase, true, c->num_sms, c->stream);
     if (rc != 0) return fail(c, rc, "phase conv launch failed (code " + std::to_string(rc) + ")");
     c->launches++;
@@ -774,14 +786,15 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     // 8 x 16 instead of 4 x 2, which the single-CTA kernel can skip and the pair kernel (16 x 16 per pair) cannot
     const bool listed = need && need->restrict_tiles && layer >= 0 && !c->aligned_tiles && !c->dec_pair;
     if (tma && (!pair_layer || listed)) {
-      int sub = 1;
+      int sub = 2;
       FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 8, 16, Hout / 8, Wout / 16, &list, &active, &shifted, &sub));
       if (c->plan_mode == 1) return 0;
+      const int per = sub == 2 ? 4 : sub == 1 ? 2 : 1;
       if (list) {
         a.tile_list = list; a.tile_packed = shifted; a.tile_sub = sub;
-        a.tile_list_len = static_cast<int>(sub ? (active + 1) / 2 : active);
+        a.tile_list_len = static_cast<int>((active + per - 1) / per);
       }
-      c->flops += static_cast<double>(active) * ((sub ? 4 : 8) * 16) * L.flops_px;
+      c->flops += static_cast<double>(active) * (8 * 16 / per) * L.flops_px;
     } else {
       if (c->plan_mode == 1) return 0;
       c->flops += static_cast<double>(x1.B) * Hout * Wout * L.flops_px;
@@ -1019,8 +1032,9 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_d2s = nd && nd[0] == '1';
   const char* npf = getenv("FB_NO_POOL_FUSE");
   c->no_pool_fuse = npf && npf[0] == '1';
-  const char* nht = getenv("FB_NO_HALF_TILES");
-  c->no_half_tiles = nht && nht[0] == '1';
+  const char* sbt = getenv("FB_SUB_TILES");
+  c->sub_tiles = sbt ? atoi(sbt) : 2;
+  if (c->sub_tiles < 0 || c->sub_tiles > 2) c->sub_tiles = 2;
   const char* dpr = getenv("FB_DEC_PAIR");
   c->dec_pair = dpr && dpr[0] == '1';
   const char* alt = getenv("FB_ALIGNED_TILES");

@@ -104,28 +104,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int phases = p.phase_mode ? 4 : 1;
         uint32_t it = 0;
         // list lookups run one iteration ahead (a global load must not sit between two tiles)
-        const int sub = p.tile_sub;   // two half boxes per tile
+        // list entries per tile: 1 whole box, 2 half boxes (4 x 16) or 4 quarter boxes (4 x 8)
+        const int sub_n = p.tile_sub == 2 ? 4 : p.tile_sub == 1 ? 2 : 1;
         auto m_tile_of = [&](int t, int e) {
           const int idx = (t / p.num_n_tiles) / phases;
-          return p.tile_list != nullptr ? __ldg(p.tile_list + (sub ? 2 * idx + e : idx)) : idx;
+          return p.tile_list != nullptr ? __ldg(p.tile_list + sub_n * idx + e) : idx;
         };
-        int m_next = blockIdx.x < num_tiles ? m_tile_of(blockIdx.x, 0) : 0;
-        int m_next1 = (sub && blockIdx.x < num_tiles) ? m_tile_of(blockIdx.x, 1) : 0;
+        int m_next = 0, m_nexts[3] = {0, 0, 0};
+        if (static_cast<int>(blockIdx.x) < num_tiles) {
+          m_next = m_tile_of(blockIdx.x, 0);
+#pragma unroll
+          for (int e = 1; e < 4; ++e)
+            if (e < sub_n) m_nexts[e - 1] = m_tile_of(blockIdx.x, e);
+        }
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.num_n_tiles;
           const int rest = tile / p.num_n_tiles;
           const int phase = rest % phases;
-          const int m_tile = m_next, m_tile1 = m_next1;
+          const int m_tile = m_next;
+          const int m_subs[3] = {m_nexts[0], m_nexts[1], m_nexts[2]};
           if (tile + static_cast<int>(gridDim.x) < num_tiles) {
             m_next = m_tile_of(tile + gridDim.x, 0);
-            if (sub) m_next1 = m_tile_of(tile + gridDim.x, 1);
+#pragma unroll
+            for (int e = 1; e < 4; ++e)
+              if (e < sub_n) m_nexts[e - 1] = m_tile_of(tile + gridDim.x, e);
           }
           const int pa = p.phase_mode ? (phase >> 1) : 0, pb = p.phase_mode ? (phase & 1) : 0;
           int b, ty0, tx0;   // image and box origin on the tile grid
-          int b1 = 0, ty1 = 0, tx1 = 0;   // second half box
+          int bs[3] = {0, 0, 0}, tys[3] = {0, 0, 0}, txs[3] = {0, 0, 0};   // the further sub-boxes
           if (p.tile_packed) {
             unpack_tile_origin(static_cast<uint32_t>(m_tile), b, ty0, tx0);
-            if (sub) unpack_tile_origin(static_cast<uint32_t>(m_tile1), b1, ty1, tx1);
+#pragma unroll
+            for (int e = 1; e < 4; ++e)
+              if (e < sub_n) unpack_tile_origin(static_cast<uint32_t>(m_subs[e - 1]), bs[e - 1], tys[e - 1], txs[e - 1]);
           } else {
             tx0 = (m_tile % tiles_w) * 16; ty0 = ((m_tile / tiles_w) % tiles_h) * 8; b = m_tile / (tiles_w * tiles_h);
           }
@@ -140,8 +151,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int sc = p.tm_scale[src];
             const uint32_t a_dst = base + s * C::kStageBytes;
             tma_load_4d(a_dst, src ? &tmA2 : &tmA, full_bar(s), cc * 64, tx0 * sc + dx, ty0 * sc + dy, b);
-            // (half boxes: the map's box is 4 rows high; rows 64-127 of the A tile = the second entry)
-            if (sub) tma_load_4d(a_dst + 64 * 128, src ? &tmA2 : &tmA, full_bar(s), cc * 64, tx1 * sc + dx, ty1 * sc + dy, b1);
+            // (sub-boxes: the map's box is 4 rows high and 16 or 8 pixels wide; entry e fills rows e * 128 / sub_n .. of the
+            // A tile, 128 bytes per row)
+#pragma unroll
+            for (int e = 1; e < 4; ++e)
+              if (e < sub_n)
+                tma_load_4d(a_dst + e * (128 / sub_n) * 128, src ? &tmA2 : &tmA, full_bar(s), cc * 64, txs[e - 1] * sc + dx,
+                            tys[e - 1] * sc + dy, bs[e - 1]);
             tma_load_2d(a_dst + C::kABytes, &tmB, full_bar(s), kit * kBK, phase * p.Cout + n_tile * BN);
           }
         }
@@ -222,15 +238,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // TMA tiles are 8 x 16 pixel boxes: row r of the tile is pixel (r / 16, r % 16) of the box. In phase
     // mode the box lives on the low-res grid and pixel (dh, dw) lands at (2*dh + pa, 2*dw + pb).
     const int osc = (p.up2_out || phases == 4) ? 2 : 1;
+    // (quarter boxes, tile_sub == 2: a warp's 32 rows are pixel (r / 8, r % 8) of its own 4 x 8 box)
+    const bool quarter = TMA_A && p.tile_sub == 2;
     const EpiLane L = make_epi_lane(q, lane, f32 ? EpiRun<BNE>::GC_F32 * 4 : EpiRun<BNE>::GC_BF16 * 2,
-                                    p.up2_out ? 2 * p.Wout : p.Wout, osc,
-                                    [](int r, int& dh, int& dw) { dh = r >> 4; dw = r & 15; });
+                                    p.up2_out ? 2 * p.Wout : p.Wout, osc, [quarter](int r, int& dh, int& dw) {
+                                      if (quarter) { dh = (r >> 3) & 3; dw = r & 7; }
+                                      else { dh = r >> 4; dw = r & 15; }
+                                    });
     uint32_t tcount = 0;
-    // (half boxes: warps 0-1 of a group drain rows 0-63 = entry 2i, warps 2-3 rows 64-127 = entry 2i + 1)
-    const int sub_e = (TMA_A && p.tile_sub) ? (q >> 1) : 0;
+    // (half boxes: warps 0-1 of a group drain rows 0-63 = entry 2i, warps 2-3 rows 64-127 = entry 2i + 1; quarter boxes:
+    // warp q drains entry 4i + q)
+    const int sub_n = !TMA_A ? 1 : p.tile_sub == 2 ? 4 : p.tile_sub == 1 ? 2 : 1;   // list entries per tile
+    const int sub_e = sub_n == 4 ? q : sub_n == 2 ? (q >> 1) : 0;
     auto m_tile_of = [&](int t) {
       const int idx = (t / p.num_n_tiles) / phases;
-      return (TMA_A && p.tile_list != nullptr) ? __ldg(p.tile_list + (p.tile_sub ? 2 * idx + sub_e : idx)) : idx;
+      return (TMA_A && p.tile_list != nullptr) ? __ldg(p.tile_list + sub_n * idx + sub_e) : idx;
     };
     int m_next = blockIdx.x < num_tiles ? m_tile_of(blockIdx.x) : 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
@@ -247,7 +269,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int tb, ty0, tx0;
         if (p.tile_packed) {
           unpack_tile_origin(static_cast<uint32_t>(m_tile), tb, ty0, tx0);
-          ty0 -= 4 * sub_e;   // this warp's tile rows 4 * sub_e .. are rows 0 .. 3 of its half box
+          if (sub_n == 2) ty0 -= 4 * sub_e;   // this warp's tile rows 4 * sub_e .. are rows 0 .. 3 of its half box
         } else {
           tx0 = (m_tile % tiles_w) * 16; ty0 = ((m_tile / tiles_w) % tiles_h) * 8; tb = m_tile / (tiles_w * tiles_h);
         }
@@ -719,7 +741,7 @@ int launch_conv(const ConvArgs& a_in, const __nv_bfloat16* weights, int Kpad, bo
                             static_cast<cuuint64_t>(Hs), static_cast<cuuint64_t>(a.B)};
       cuuint64_t strides[3] = {static_cast<cuuint64_t>(Cs) * 2, static_cast<cuuint64_t>(Ws) * Cs * 2,
                                static_cast<cuuint64_t>(Hs) * Ws * Cs * 2};
-      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(16 * sc), static_cast<cuuint32_t>((a.tile_sub ? 4 : 8) * sc), 1};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>((a.tile_sub == 2 ? 8 : 16) * sc), static_cast<cuuint32_t>((a.tile_sub ? 4 : 8) * sc), 1};
       cuuint32_t es[4] = {1, static_cast<cuuint32_t>(sc), static_cast<cuuint32_t>(sc), 1};
       CUresult r = g_encode(src == 0 ? &tmA : &tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                             const_cast<__nv_bfloat16*>(base), dims, strides, box, es,

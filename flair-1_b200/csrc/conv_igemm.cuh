@@ -70,9 +70,10 @@ struct ConvArgs {
   const int* tile_list;
   int tile_list_len;
   int tile_packed;   // 1: entries are pack_tile_origin() words of origin-shifted boxes (tile_need.cuh, need_span)
-  // 1 (with tile_packed): the entries are HALF boxes of 4 x 16 pixels, two per 128-row tile (rows 0-63 = entry 2i, rows
-  // 64-127 = entry 2i + 1, each fetched by a TMA box of its own), tile_list_len counts tiles = pairs. A needed region of
-  // 12 or 20 rows is then covered by 3 or 5 half boxes instead of 2 or 3 whole ones.
+  // With tile_packed: 1 = the entries are HALF boxes of 4 x 16 pixels, two per 128-row tile (rows 0-63 = entry 2i, rows
+  // 64-127 = entry 2i + 1), 2 = QUARTER boxes of 4 x 8 pixels, four per tile (rows 32e .. = entry 4i + e = one epilogue
+  // warp's rows); every entry is fetched by a TMA box of its own, tile_list_len counts tiles. A needed region of 20 x 20
+  // pixels is then covered by 5 x 3 quarter boxes (480 pixels) instead of 3 x 2 whole ones (768).
   int tile_sub;
 };
 

@@ -731,10 +731,11 @@ build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __gri
       list[off[b] + i] = sp.shifted ? static_cast<int>(pack_tile_origin(b, k.y0 + (i / nx) * sp.th, k.x0 + (i % nx) * sp.tw))
                                     : (b * sp.gh + k.y0 + i / nx) * sp.gw + k.x0 + i % nx;
   }
-  if (sp.sub) {
-    // half boxes are consumed in pairs: an odd list ends with a copy of its last entry (computed and stored twice)
+  if (sp.sub > 1) {
+    // sub-boxes are consumed sp.sub at a time: the list is padded with copies of its last entry (computed and stored again)
     __syncthreads();
-    if (threadIdx.x == 0 && (off[n] & 1) && off[n] > 0) list[off[n]] = list[off[n] - 1];
+    if (threadIdx.x == 0 && off[n] > 0)
+      for (int i = off[n]; i % sp.sub != 0; ++i) list[i] = list[off[n] - 1];
   }
 }
 

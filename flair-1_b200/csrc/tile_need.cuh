@@ -105,7 +105,7 @@ struct TileListSpec {
   int offset, count;
   int use;   // 0: every tile is active, no list is built
   int shifted;
-  int sub;   // 1: entries are half boxes (th = half a kernel tile), two per kernel tile: an odd list is padded with a copy of its last entry
+  int sub;   // n > 1: entries are sub-boxes, n per kernel tile: the list is padded to a multiple of n with copies of its last entry
 };
 struct TileListPlan {
   TileListSpec spec[kNeedLayers];

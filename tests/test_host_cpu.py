@@ -414,7 +414,8 @@ def test_origin_shifted_tile_cover_contains_the_region_with_the_fewest_tiles():
     import flair1_b200._native as nat
     lib = nat.load_library(build_if_missing=False)
     rng = np.random.default_rng(3)
-    tilings = [(1, 16, 16), (1, 16, 8), (1, 16, 32), (1, 8, 16), (2, 16, 16), (2, 16, 8), (2, 8, 16)]
+    tilings = [(1, 16, 16), (1, 16, 8), (1, 16, 32), (1, 8, 16), (2, 16, 16), (2, 16, 8), (2, 8, 16),
+               (1, 4, 16), (1, 4, 8), (2, 4, 16), (2, 4, 8)]   # the last four: half / quarter boxes of the implicit GEMM
     cases = [(512, 128, 128, 384, 384), (512, 0, 0, 384, 384), (512, 128, 128, 512, 512), (512, 0, 128, 512, 384), (256, 64, 64, 192, 192)]
     for _ in range(40):
         T = int(rng.choice([256, 512, 1024]))
