@@ -97,6 +97,7 @@ struct fb_ctx {
   bool no_fused_sink = false; // FB_NO_FUSED_SINK=1: head writes fp32 logits, K6 runs as its own kernel
   bool no_d2s = false;        // FB_NO_D2S=1: dec4 / head as N = 16 convs instead of the depth-to-space forms
   bool aligned_tiles = false; // FB_ALIGNED_TILES=1: active kernel tiles on the fixed tile grid instead of origin-shifted (tile_need.cuh)
+  bool no_narrow_tiles = false; // FB_NO_NARROW_TILES=1: halo kernel tiles of an origin-shifted list always compute both 8-column blocks
   int sub_tiles = 2;          // FB_SUB_TILES=0 / 1: the implicit GEMM's list entries stay whole 8 x 16 boxes / halves of 4 x 16 (default: quarters of 4 x 8)
   bool dec_pair = false;      // FB_DEC_PAIR=1: dec0 stays on the CTA-pair kernel (no tile lists) under origin-shifted tiles
   bool no_pool_fuse = false;  // FB_NO_POOL_FUSE=1: the stem's max-pool as a kernel of its own
@@ -540,13 +541,16 @@ int ensure_meta_buffers(fb_ctx* c, int n) {
 // tile), 2 = quarters (th / 2 rows x tw / 2 columns, four entries); out: the mode the list was built in (0 = whole tiles).
 // *active then counts sub-boxes.
 int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, int th, int tw, int gh, int gw,
-                   const int** list, long long* active, int* shifted, int* sub = nullptr) {
+                   const int** list, long long* active, int* shifted, int* sub = nullptr, long long* blocks = nullptr) {
+  // blocks (optional, halo kernels with tiles of two 8-column blocks): request narrow tiles; on return the number of
+  // active blocks (for the FLOP count)
   *list = nullptr;
   *shifted = 0;
   const int want_sub = sub ? *sub : 0;
   if (sub) *sub = 0;
   const long long full = static_cast<long long>(B) * gh * gw;
   *active = full;
+  if (blocks) *blocks = 2 * full;
   if (!need || !need->restrict_tiles || layer < 0 || layer >= fb::kNeedLayers || need->n != B) return 0;
   fb::TileListSpec& sp = c->list_plan.spec[layer];
   auto sub_tiling = [&](int mode, int& lth, int& ltw, int& lgh, int& lgw) {
@@ -555,14 +559,18 @@ int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, 
   };
   if (c->plan_mode == 1) {
     // origin-shifted tiles (tile_need.cuh, need_span) unless switched off or the packed entry cannot hold the launch
-    const bool sh = !c->aligned_tiles && B <= (1 << 10) && gh * th < (1 << fb::kTileOriginBits) && gw * tw < (1 << fb::kTileOriginBits);
+    const bool sh = !c->aligned_tiles && B <= (1 << fb::kTileImageBits) && gh * th < (1 << fb::kTileOriginBits) && gw * tw < (1 << fb::kTileOriginBits);
     int mode = (sh && th % 2 == 0 && tw % 2 == 0) ? want_sub : 0;
     if (mode > c->sub_tiles) mode = c->sub_tiles;
     int lth, ltw, lgh, lgw;
     sub_tiling(mode, lth, ltw, lgh, lgw);
-    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, lth, ltw, sh);
+    const bool half_x = blocks != nullptr && sh && !c->no_narrow_tiles && tw == 16 && B <= (1 << fb::kTileImageBits);
+    long long nblocks = 0;
+    const long long cnt = fb::count_active_tiles(need->tiles_host, B, need->T, layer, scale, lth, ltw, sh, half_x, &nblocks);
     const int per = mode == 2 ? 4 : mode == 1 ? 2 : 1;
     sp.shifted = sh ? 1 : 0;
+    sp.half_x = half_x ? 1 : 0;
+    sp.blocks = nblocks;
     sp.sub = per;
     sp.layer = layer; sp.scale = scale; sp.th = lth; sp.tw = ltw; sp.gh = lgh; sp.gw = lgw;
     sp.count = static_cast<int>(cnt);
@@ -581,6 +589,7 @@ int make_tile_list(fb_ctx* c, const NeedCtx* need, int layer, int B, int scale, 
     *shifted = sp.shifted;
     *active = sp.count;
     if (sub) *sub = mode;
+    if (blocks) *blocks = sp.blocks;
   }
   return 0;
 }
@@ -635,10 +644,11 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     if (out.elem == 4) h.out_f32 = static_cast<float*>(out.ptr); else h.out = static_cast<__nv_bfloat16*>(out.ptr);
     h.wpacked = L.w_d2s;
     fb::halo_fill_steps_d2s(h, L.d2s_mode);
-    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 16, Hout / 32, Wout / 32, &list, &active, &shifted));
+    long long blocks = 0;   // (narrow tiles: the second 8-cell block of the last tile of a row may be skipped)
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 2, 16, 16, Hout / 32, Wout / 32, &list, &active, &shifted, nullptr, &blocks));
     if (c->plan_mode == 1) return 0;
     if (list) { h.tile_list = list; h.tile_packed = shifted; h.num_m_tiles = static_cast<int>(active); }
-    c->flops += static_cast<double>(active) * (32 * 32) * L.flops_px;
+    c->flops += static_cast<double>(blocks) * (32 * 16) * L.flops_px;
     if (sink && need && out.elem == 4) {
       h.sink_tiles = need->tiles_dev;
       h.sink_cls = sink->cls;
@@ -744,10 +754,11 @@ int run_conv(fb_ctx* c, const ConvLayer& L, const Act& x1, const Act* x2, const 
     h.pair = c->no_hpair ? 0 : 1;
     fb::halo_fill_steps(h, L.KH, L.stride);
     const int tw = 8 * fb::halo_blocks(L.KH, fb::halo_group_channels(L.KH, C1, C2) / 8, L.Cout);
-    FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active, &shifted));
+    long long blocks = 0;
+    FB_TRY(make_tile_list(c, need, layer, x1.B, 1, 16, tw, Hout / 16, Wout / tw, &list, &active, &shifted, nullptr, &blocks));
     if (c->plan_mode == 1) return 0;
     if (list) { h.tile_list = list; h.tile_packed = shifted; h.num_m_tiles = static_cast<int>(active); }
-    c->flops += static_cast<double>(active) * (16 * tw) * L.flops_px;
+    c->flops += static_cast<double>(blocks) * (16 * tw / 2) * L.flops_px;
     if (sink && need && out.elem == 4 && (L.Cout == 16 || L.Cout == 32) && h.direct_store && !out.up2) {
       h.sink_tiles = need->tiles_dev;
       h.sink_cls = sink->cls;
@@ -1032,6 +1043,8 @@ int fb_create(int device, void* cuda_stream, fb_ctx** out) {
   c->no_d2s = nd && nd[0] == '1';
   const char* npf = getenv("FB_NO_POOL_FUSE");
   c->no_pool_fuse = npf && npf[0] == '1';
+  const char* nnt = getenv("FB_NO_NARROW_TILES");
+  c->no_narrow_tiles = nnt && nnt[0] == '1';
   const char* sbt = getenv("FB_SUB_TILES");
   c->sub_tiles = sbt ? atoi(sbt) : 2;
   if (c->sub_tiles < 0 || c->sub_tiles > 2) c->sub_tiles = 2;

@@ -265,6 +265,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       tx0 = (tile % tiles_w) * G::TW; ty0 = ((tile / tiles_w) % tiles_h) * kTH; b = tile / (tiles_w * tiles_h);
     }
   };
+  // packed entries may mark a tile as narrow: only its first 8-column block is computed and stored (tile_need.cuh)
+  auto tile_narrow = [&](int tile) { return !PAIR && !POOL && !PH && p.tile_packed && (static_cast<uint32_t>(tile) & kTileNarrow) != 0; };
   // this CTA's (pair's) schedule: positions sched0, sched0 + sched_step, ... < sched_end
   const int sched0 = POOL ? 0 : PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int sched_step = POOL ? 1 : PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -680,6 +682,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       if (ti + sched_step < sched_end) tile_next = tile_of(ti + sched_step);
       int tb, ty0, tx0;
       tile_pos(tile, tb, ty0, tx0);
+      const int nblk = tile_narrow(tile) ? 1 : MB;   // blocks of this tile that were computed
       const int as = tcount % NACC;
       const uint32_t aph = (tcount / NACC) & 1;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC;
@@ -734,9 +737,18 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
             load_residual_row<BN>(res_row0, rbuf[0]);
           }
         }
+        if (EPI == 2 && grp >= nblk) {
+          // narrow tile: this group's block was not computed; keep the accumulator hand-shake in step
+          mbar_wait(tfull_bar(as), aph);
+          tc_fence_after_sync();
+          tc_fence_before_sync();
+          tempty_arrive(tempty_bar(as));
+          continue;
+        }
 #pragma unroll
         for (int mi = 0; mi < MB / EPI; ++mi) {
           const int m = EPI == 2 ? 2 * mi + grp : mi;
+          if (m >= nblk) continue;
           if (EPI == 2) {
             if (has_res && mi + 1 < MB / EPI) load_residual_row<BN>(res_row0 + 8 * (m + 2) * BN, rbuf[(mi + 1) % kResBuf]);
           } else if (has_res && kResBuf != MB && m + 1 < MB) {
@@ -890,6 +902,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
       const long long own_pix0 = (static_cast<long long>(tb) * p.Hout + oh) * p.Wout + tx0 + L.own_dw;
 #pragma unroll
       for (int m = 0; m < MB; ++m) {  // block m = columns 8m..8m+7 of the tile
+        if (m >= nblk) continue;
         uint8_t* blk_dst = tile_dst + static_cast<size_t>(p.up2_out ? 16 * m : 8 * m) * pixel_bytes;
         auto copy = [&](auto run, int col0, int el) {
           if (p.debug_skip & 4) return;
@@ -940,9 +953,14 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
           }
         }
     } else {
+    const bool listed = !PAIR && !POOL && !PH && p.tile_packed && p.tile_list != nullptr;
+    int mtile_next = (listed && sched0 < sched_end) ? tile_of(sched0) : 0;
     for (int ti = sched0; ti < sched_end; ti += sched_step, ++tcount) {
       const int as = tcount % NACC;
       const uint32_t aph = (tcount / NACC) & 1;
+      // blocks of this tile: a narrow tile of an origin-shifted list has one (the entry is read one tile ahead)
+      const int nblk = (listed && tile_narrow(mtile_next)) ? 1 : MB;
+      if (listed && ti + sched_step < sched_end) mtile_next = tile_of(ti + sched_step);
       mbar_wait(tempty_bar(as), aph ^ 1);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + as * ACC;
@@ -973,7 +991,8 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
                 const uint32_t a_lo = p.a_lo[k] + st16;
                 const uint32_t acc = (g | k) != 0 ? 1u : 0u;
 #pragma unroll
-                for (int m = 0; m < MB; ++m) mma(d_tmem + m * BN, a_lo + 8 * m, wb + kk * (2 * BNH), acc);
+                for (int m = 0; m < MB; ++m)
+                  if (m < nblk) mma(d_tmem + m * BN, a_lo + 8 * m, wb + kk * (2 * BNH), acc);
               }
             }
             commit(bempty_bar(sb));
@@ -999,7 +1018,7 @@ conv_halo_kernel(const __grid_constant__ HaloArgs p, const __grid_constant__ CUt
             for (int m = 0; m < MB; ++m) {
               // POOL: block m = the tile's columns of parity m, with a step table of its own (halo_fill_steps_pool)
               if (POOL) mma(d_tmem + m * BN, p.a_lo[m * p.nsteps + k] + st16, b_lo, acc);
-              else mma(d_tmem + m * BN, a_lo + 8 * m, b_lo, acc);
+              else if (m < nblk) mma(d_tmem + m * BN, a_lo + 8 * m, b_lo, acc);
             }
             b_lo += 2 * BNH;
           }

@@ -706,9 +706,18 @@ build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __gri
     if (sp.shifted) {
       // rng = origin (x0, y0) and tile counts (x1, y1) of the shifted cover
       const NeedRect g = need_on_tile_grid(r, sp.scale);
-      const NeedSpan sx = need_span(g.x0, g.x1, sp.tw, sp.gw * sp.tw), sy = need_span(g.y0, g.y1, sp.th, sp.gh * sp.th);
+      const NeedSpan sy = need_span(g.y0, g.y1, sp.th, sp.gh * sp.th);
+      NeedSpan sx;
+      if (sp.half_x) {
+        // columns in blocks of tw / 2; k.x1 = tiles per row, bit 16 = the last one is narrow
+        const NeedSpan bx = need_span(g.x0, g.x1, sp.tw / 2, sp.gw * sp.tw);
+        sx.o = bx.o;
+        sx.n = ((bx.n + 1) / 2) | ((bx.n & 1) << 16);
+      } else {
+        sx = need_span(g.x0, g.x1, sp.tw, sp.gw * sp.tw);
+      }
       k.x0 = sx.o; k.y0 = sy.o; k.x1 = sx.n; k.y1 = sy.n;
-      off[b + 1] = sx.n * sy.n;
+      off[b + 1] = (sx.n & 0xFFFF) * sy.n;
     } else {
       k = need_tile_range(r, sp.scale, sp.th, sp.tw);
       if (k.x1 > sp.gw) k.x1 = sp.gw;
@@ -726,9 +735,11 @@ build_tile_lists_kernel(const int* __restrict__ tiles, int n, int T, const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = warp; b < n; b += blockDim.x >> 5) {
     const NeedRect k = rng[b];
-    const int nx = sp.shifted ? k.x1 : k.x1 - k.x0, cnt = off[b + 1] - off[b];
+    const int nx = sp.shifted ? (k.x1 & 0xFFFF) : k.x1 - k.x0, cnt = off[b + 1] - off[b];
+    const bool last_narrow = sp.shifted && (k.x1 >> 16) != 0;
     for (int i = lane; i < cnt; i += 32)
-      list[off[b] + i] = sp.shifted ? static_cast<int>(pack_tile_origin(b, k.y0 + (i / nx) * sp.th, k.x0 + (i % nx) * sp.tw))
+      list[off[b] + i] = sp.shifted ? static_cast<int>(pack_tile_origin(b, k.y0 + (i / nx) * sp.th, k.x0 + (i % nx) * sp.tw,
+                                                                        last_narrow && i % nx == nx - 1))
                                     : (b * sp.gh + k.y0 + i / nx) * sp.gw + k.x0 + i % nx;
   }
   if (sp.sub > 1) {
@@ -747,7 +758,9 @@ int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPl
   return static_cast<int>(cudaGetLastError());
 }
 
-long long count_active_tiles(const int* tiles, int n, int T, int layer, int scale, int th, int tw, bool shifted) {
+long long count_active_tiles(const int* tiles, int n, int T, int layer, int scale, int th, int tw, bool shifted, bool half_x,
+                             long long* blocks) {
+  if (blocks) *blocks = 0;
   const int S = layer >= 10 ? T : (T / 16) << (layer / 2);
   const int gh = (S / scale) / th, gw = (S / scale) / tw;
   long long total = 0;
@@ -756,13 +769,23 @@ long long count_active_tiles(const int* tiles, int n, int T, int layer, int scal
     const NeedRect r = need_rect(T, layer, t[2] - t[0], t[3] - t[1], t[4] - t[0], t[5] - t[1]);
     if (shifted) {
       const NeedRect g = need_on_tile_grid(r, scale);
-      total += static_cast<long long>(need_span(g.x0, g.x1, tw, gw * tw).n) * need_span(g.y0, g.y1, th, gh * th).n;
+      const long long ny = need_span(g.y0, g.y1, th, gh * th).n;
+      if (half_x) {
+        const long long nb = need_span(g.x0, g.x1, tw / 2, gw * tw).n;
+        total += (nb + 1) / 2 * ny;
+        if (blocks) *blocks += nb * ny;
+      } else {
+        const long long nx = need_span(g.x0, g.x1, tw, gw * tw).n;
+        total += nx * ny;
+        if (blocks) *blocks += 2 * nx * ny;
+      }
       continue;
     }
     NeedRect k = need_tile_range(r, scale, th, tw);
     if (k.x1 > gw) k.x1 = gw;
     if (k.y1 > gh) k.y1 = gh;
     total += static_cast<long long>(k.x1 - k.x0) * (k.y1 - k.y0);
+    if (blocks) *blocks += 2LL * (k.x1 - k.x0) * (k.y1 - k.y0);
   }
   return total;
 }

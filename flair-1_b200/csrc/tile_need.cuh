@@ -86,15 +86,18 @@ __host__ __device__ inline NeedRect need_on_tile_grid(NeedRect r, int scale) {
   r.x1 = ((r.x1 - 1) >> sh) + 1; r.y1 = ((r.y1 - 1) >> sh) + 1;
   return r;
 }
-// list entry of an origin-shifted tile: image | origin row | origin column on the tile grid
-constexpr int kTileOriginBits = 11;   // grids up to 2047; 10 bits of image index
-__host__ __device__ inline uint32_t pack_tile_origin(int b, int y0, int x0) {
-  return (static_cast<uint32_t>(b) << (2 * kTileOriginBits)) | (static_cast<uint32_t>(y0) << kTileOriginBits) | static_cast<uint32_t>(x0);
+// list entry of an origin-shifted tile: narrow flag | image | origin row | origin column on the tile grid
+constexpr int kTileOriginBits = 11;   // grids up to 2047
+constexpr int kTileImageBits = 9;     // up to 512 images per launch
+constexpr uint32_t kTileNarrow = 1u << 31;   // halo kernels: only the first 8-column block of the tile is computed
+__host__ __device__ inline uint32_t pack_tile_origin(int b, int y0, int x0, bool narrow = false) {
+  return (narrow ? kTileNarrow : 0u) | (static_cast<uint32_t>(b) << (2 * kTileOriginBits)) |
+         (static_cast<uint32_t>(y0) << kTileOriginBits) | static_cast<uint32_t>(x0);
 }
 __host__ __device__ inline void unpack_tile_origin(uint32_t e, int& b, int& y0, int& x0) {
   x0 = static_cast<int>(e & ((1u << kTileOriginBits) - 1));
   y0 = static_cast<int>((e >> kTileOriginBits) & ((1u << kTileOriginBits) - 1));
-  b = static_cast<int>(e >> (2 * kTileOriginBits));
+  b = static_cast<int>((e >> (2 * kTileOriginBits)) & ((1u << kTileImageBits) - 1));
 }
 
 // One conv launch's kernel tiling: tiles of th x tw pixels on the tile grid (= output grid / scale), gh x gw of them
@@ -105,6 +108,10 @@ struct TileListSpec {
   int offset, count;
   int use;   // 0: every tile is active, no list is built
   int shifted;
+  // 1: the kernel computes a tile as two 8-column blocks and can skip the second (halo kernels, tw = 16): the columns are
+  // covered in blocks of tw / 2, an odd block count ends every tile row with a narrow tile (kTileNarrow)
+  int half_x;
+  long long blocks;   // half_x: active blocks of the list (host bookkeeping)
   int sub;   // n > 1: entries are sub-boxes, n per kernel tile: the list is padded to a multiple of n with copies of its last entry
 };
 struct TileListPlan {
@@ -116,6 +123,8 @@ struct TileListPlan {
 int launch_build_tile_lists(const int* tiles_dev, int n, int T, const TileListPlan& plan, int* list_dev,
                             cudaStream_t stream);
 // The count of one list on the host (tiles = host copy of the same table).
-long long count_active_tiles(const int* tiles_host, int n, int T, int layer, int scale, int th, int tw, bool shifted);
+// blocks (optional): half_x lists -- the number of active 8-column blocks (tiles * 2 - narrow tiles), for the FLOP count
+long long count_active_tiles(const int* tiles_host, int n, int T, int layer, int scale, int th, int tw, bool shifted,
+                             bool half_x = false, long long* blocks = nullptr);
 
 }  // namespace fb
