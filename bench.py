@@ -654,7 +654,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=148, help="tiles per forward pass (148 = one per SM; 74 / 111 / 148 measured 906 / 907 / 922 Mpx/s)")
+    ap.add_argument("--batch", type=int, default=296, help="tiles per forward pass (296 = two per SM; round 1: 74 / 111 / 148 measured 906 / 907 / 922 Mpx/s, round 2: 148 / 222 / 296 measured 1209 / 1231 / 1233 Mpx/s)")
     ap.add_argument("--cpu-tiles", type=int, default=160, help="tiles of the zone timed on the host cores (cpu_baseline)")
     ap.add_argument("--ref-tiles", type=int, default=64, help="tiles per step of the reference arm")
     ap.add_argument("--verify-full", action="store_true", help="N = 1: run the CPU oracle on every tile of the zone and compare the whole map")
